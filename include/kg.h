@@ -1,0 +1,101 @@
+/* kg.h -- C ABI of the B200-native batched KinovaGripper env step (libkg_b200.so).
+ *
+ * The reference has no FFI for this path: its boundary is the gym API of
+ * gym_kinova_gripper.envs.kinova_gripper_env.KinovaGripper_Env (reset/step) sitting on the
+ * mujoco-py object surface.  Each entry point below names the reference interface it
+ * replaces.  All arrays are struct-of-arrays, field-major [field][n_envs], fp32 / int32.
+ * "dev" pointers are CUDA device pointers, "host" pointers are ordinary host memory.
+ * Return value: 0 on success, a negative KG_E* code otherwise; kg_last_error() gives the text.
+ * A handle is bound to one device and one stream at a time (thread-compatible, not thread-safe).
+ */
+#ifndef KG_H
+#define KG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KG_OK 0
+#define KG_EINVAL -1
+#define KG_ECUDA -2
+#define KG_EMODEL -3
+
+#define KG_NQ 16
+#define KG_NVEL 15
+#define KG_OBS 82
+#define KG_ACT 4
+
+typedef struct kg_handle_s *kg_handle;
+
+/* Replaces KinovaGripper_Env.__init__ + load_model_from_path/MjSim for n_envs environments
+ * (kinova_gripper_env.py:51-102, 878-879, 1002-1003).  model_blob = assets/model_card.bin. */
+int kg_create(int n_envs, int device, const void *model_blob, size_t nbytes, kg_handle *out);
+int kg_destroy(kg_handle h);
+const char *kg_last_error(kg_handle h);
+int kg_num_envs(kg_handle h);
+/* cudaStream_t as void*; NULL = the legacy default stream. */
+int kg_set_stream(kg_handle h, void *stream);
+int kg_sync(kg_handle h);
+
+/* Replaces KinovaGripper_Env.reset's physical part (kinova_gripper_env.py:1310-1410: write_xml with the
+ * hand euler, _set_state, sim.forward(), first _get_obs, centroid fix-up) with explicit poses.
+ * mask_dev: int[n] (non-zero = reset this env) or NULL = all.  shape_dev int[n] (0..13, model-card order),
+ * euler_dev float[3][n] hand euler (MuJoCo eulerseq xyz), objpos_dev float[3][n]. obs_dev float[82][n] or NULL. */
+int kg_reset(kg_handle h, const int *mask_dev, const int *shape_dev, const float *euler_dev,
+             const float *objpos_dev, float *obs_dev);
+
+/* Replaces select_orienation + determine_obj_hand_coords + sample_initial_object_hand_pos
+ * (kinova_gripper_env.py:1180-1283, 1008-1054): rows are drawn on the device from the with_noise tables.
+ * shape_dev: int[n] or NULL (keep each env's current shape).  orient: 0 normal, 1 rotated, 2 top,
+ * 3 random (U(0,1) thresholds 0.333/0.667).  variant 0 = code-faithful (euler of the drawn row, 5-char
+ * truncated as write_xml does); variant 1 = SURVEY 8d "variant B": object position from the 'normal' table,
+ * euler of the same row of the 'top' table.  test_table: 0 train_coords, 1 test_coords. */
+int kg_reset_sampled(kg_handle h, const int *mask_dev, const int *shape_dev, int orient, int variant,
+                     int test_table, uint64_t seed, float *obs_dev);
+
+/* Replaces KinovaGripper_Env.step (kinova_gripper_env.py:1495-1552: ctrl mapping, frame_skip x sim.step(),
+ * _get_obs, _get_reward) and gym's TimeLimit.  action_dev float[4][n] = [wrist, f1, f2, f3], or NULL to
+ * let the on-device expert (expert_data.py:610-671; mode 0 naive, 1 position-dependent, 2 combined) act.
+ * Outputs (any may be NULL): obs float[82][n], reward float[n] (= lift_reward, finger/grasp reward are 0),
+ * done int[n] (lift success OR elapsed >= max_episode_steps), action_out float[4][n]. */
+int kg_step(kg_handle h, const float *action_dev, int expert_mode, float *obs_dev, float *reward_dev,
+            int *done_dev, float *action_out_dev);
+
+/* The same call with HOST buffers (the end-to-end path a gym-style caller uses): H2D of the actions,
+ * the launch, D2H of obs/reward/done, and a stream synchronise are all inside this call. */
+int kg_step_host(kg_handle h, const float *action_host, int expert_mode, float *obs_host, float *reward_host,
+                 int *done_host);
+int kg_reset_host(kg_handle h, const int *mask_host, const int *shape_host, const float *euler_host,
+                  const float *objpos_host, float *obs_host);
+
+/* sim.data.qpos / qvel access (kinova_gripper_env.py:346-353, 692-703).  float[16][n] / float[15][n]. */
+int kg_get_state(kg_handle h, float *qpos_dev, float *qvel_dev);
+int kg_set_state(kg_handle h, const float *qpos_dev, const float *qvel_dev);
+int kg_get_state_host(kg_handle h, float *qpos_host, float *qvel_host);
+int kg_set_state_host(kg_handle h, const float *qpos_host, const float *qvel_host);
+int kg_set_max_episode_steps(kg_handle h, int steps);      /* env._max_episode_steps (MAIN:164,384) */
+int kg_set_frame_skip(kg_handle h, int frame_skip);        /* KinovaGripper_Env(frame_skip=15) */
+/* Multi-GPU sharding: this handle owns global envs [offset, offset+n).  Only the pose sampler's counter-based RNG
+ * looks at it, so that a run's draws do not depend on how many GPUs the envs are spread over. */
+int kg_set_env_offset(kg_handle h, int offset);
+/* The action the last kg_step applied (the caller's, or the on-device expert's: get_action, expert_data.py:610). float[4][n]. */
+int kg_get_last_action_host(kg_handle h, float *action_host);
+
+/* counters since the last call: [0] hull pairs sent to MPR, [1] Newton iterations, [2] substeps that
+ * overflowed the per-env contact capacity, [3] substeps executed. */
+int kg_get_stats(kg_handle h, long long stats_host[4]);
+
+/* Test hook: one mj_forward of env `env` with the given ctrl[9]; dumps intermediates to host memory.
+ * out layout (floats): M[225] bias[15] fsmooth[15] qacc_smooth[15] qacc[15] ftotal[15] ncon[1]
+ * con[23][8]{dist,pos3,n3,mu} geom_xpos[27] geom_xmat[81]  -> 225+75+1+184+108 = 593 floats. */
+#define KG_DEBUG_FLOATS 593
+int kg_forward_debug(kg_handle h, int env, const float *ctrl_host, float *out_host);
+/* Test hook: device time of the last kg_step launch in milliseconds (CUDA events on the handle's stream). */
+int kg_last_step_ms(kg_handle h, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

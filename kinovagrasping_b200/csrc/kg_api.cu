@@ -1,0 +1,375 @@
+// kg_api.cu -- kernels + the C ABI of include/kg.h.
+//
+// Built two ways from this one source:
+//   nvcc -gencode arch=compute_100a,code=sm_100a ...        -> kinovagrasping_b200/libkg_b200.so  (THE PRODUCT)
+//   g++ -x c++ -DKG_EMU ...                                 -> tests/emu/libkg_emu.so  (TEST-ONLY host emulation
+//        of the warp phases, used to debug the algorithm against the oracle without a GPU; the package
+//        never loads it and has no CPU fallback).
+#include "../../include/kg.h"
+#include "kg_core.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#ifndef KG_EMU
+#include <cuda_runtime.h>
+#define KG_WARPS 8
+__constant__ KgModel c_model;
+#endif
+
+struct kg_handle_s {
+    int n = 0, device = 0, frame_skip = 15, env_offset = 0;
+    void *stream = nullptr;
+    std::string err;
+    KgModel model;            // host copy; table pointers are device pointers (or host pointers under KG_EMU)
+    KgEnvArrays A;
+    int *ep_count = nullptr;  // [n] episodes started per env (RNG counter)
+    std::vector<void *> allocs;
+    // scratch for the *_host entry points
+    float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_euler = nullptr, *d_objp = nullptr, *d_q = nullptr;
+    int *d_done = nullptr, *d_mask = nullptr, *d_shape = nullptr;
+    float *d_debug = nullptr, *d_ctrl = nullptr;
+#ifndef KG_EMU
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+#endif
+    float last_ms = 0.f;
+#ifdef KG_EMU
+    KgHostTables tables;
+#endif
+};
+
+// ------------------------------------------------------------------------------------------------ backend helpers
+#ifdef KG_EMU
+static int be_alloc(kg_handle h, void **p, size_t bytes) { *p = calloc(1, bytes ? bytes : 1); h->allocs.push_back(*p); return *p ? 0 : -1; }
+static int be_h2d(kg_handle, void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
+static int be_d2h(kg_handle, void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
+static int be_d2d(kg_handle, void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
+static int be_sync(kg_handle) { return 0; }
+#define KG_MODEL(h) ((h)->model)
+#else
+#define CUDA_TRY(h, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { (h)->err = std::string(#x) + ": " + cudaGetErrorString(e_); return KG_ECUDA; } } while (0)
+static int be_alloc(kg_handle h, void **p, size_t bytes) {
+    CUDA_TRY(h, cudaMalloc(p, bytes ? bytes : 4));
+    CUDA_TRY(h, cudaMemset(*p, 0, bytes ? bytes : 4));
+    h->allocs.push_back(*p);
+    return 0;
+}
+static int be_h2d(kg_handle h, void *d, const void *s, size_t b) { CUDA_TRY(h, cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, (cudaStream_t)h->stream)); return 0; }
+static int be_d2h(kg_handle h, void *d, const void *s, size_t b) { CUDA_TRY(h, cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, (cudaStream_t)h->stream)); return 0; }
+static int be_d2d(kg_handle h, void *d, const void *s, size_t b) { CUDA_TRY(h, cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, (cudaStream_t)h->stream)); return 0; }
+static int be_sync(kg_handle h) { CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)h->stream)); return 0; }
+#endif
+#define TRY(x) do { int r_ = (x); if (r_ != 0) return r_ < 0 ? r_ : KG_ECUDA; } while (0)
+
+// ------------------------------------------------------------------------------------------------ device-side sampling
+KG_DEV unsigned long long kg_mix(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+struct KgSample { int shape; float euler[3], objp[3]; };
+// select_orienation (ENV:1180-1222) + sample_initial_object_hand_pos (ENV:1008-1054): the reference drops
+// file line 0 and draws randint(0, len(data)), i.e. file lines 1..rows-1.
+KG_DEV KgSample kg_sample_pose(const KgModel &m, unsigned long long seed, int env, int episode, int shape, int orient, int variant, int test_table) {
+    unsigned long long r = kg_mix(seed ^ kg_mix((unsigned long long)env * 0x100000001B3ull + (unsigned long long)episode));
+    unsigned long long r2 = kg_mix(r);
+    int rows = test_table ? m.pose_rows_test : m.pose_rows_train;
+    const float *tab = test_table ? m.pose_test : m.pose_train;
+    int o = orient;
+    if (orient == 3) {
+        float u = (float)((r2 >> 40) * (1.0 / 16777216.0));
+        o = u < 0.333f ? 0 : (u > 0.667f ? 2 : 1);
+    }
+    int row = 1 + (int)(r % (unsigned long long)(rows - 1));
+    KgSample s;
+    s.shape = shape;
+    const float *p = tab + (((size_t)shape * 3 + (variant == 1 ? 0 : o)) * rows + row) * 9;
+    s.objp[0] = p[0]; s.objp[1] = p[1]; s.objp[2] = p[2];
+    const float *e = variant == 1 ? tab + (((size_t)shape * 3 + 2) * rows + row) * 9 : p;
+    s.euler[0] = e[6]; s.euler[1] = e[7]; s.euler[2] = e[8];
+    return s;
+}
+
+// one mj_forward with a dump of the intermediates (test hook behind kg_forward_debug)
+KG_DEV void kg_debug_run(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *ctrl, float *out, int kg_lane) {
+    kg_load_env(m, ws, A, env, kg_lane);
+    KG_PHASE(l) { if (l < 9) ws.ctrl[l] = ctrl[l]; }
+    KG_SYNC();
+    kg_kinematics(m, ws, kg_lane);
+    kg_dynamics(m, ws, kg_lane);
+    kg_collision(m, ws, kg_lane);
+    kg_make_rows(m, ws, kg_lane);
+    kg_solve(m, ws, kg_lane);
+    KG_PHASE(l) {
+        for (int i = l; i < 225; i += 32) out[i] = ws.M[(i / 15) * KG_MS + (i % 15)];
+        if (l < 15) {
+            out[225 + l] = ws.bias[l]; out[240 + l] = ws.fs[l]; out[255 + l] = ws.qas[l];
+            out[270 + l] = ws.qacc[l]; out[285 + l] = ws.ftot[l];
+        }
+        if (l == 0) out[300] = (float)ws.ncon_total;
+        if (l < KG_MAXCON) {
+            float *o = out + 301 + 8 * l;
+            if (9 + l < ws.ngroup) {
+                int s = ws.gslot[9 + l];
+                o[0] = ws.st_dist[s]; o[1] = ws.st_pos[s][0]; o[2] = ws.st_pos[s][1]; o[3] = ws.st_pos[s][2];
+                o[4] = ws.st_n[s][0]; o[5] = ws.st_n[s][1]; o[6] = ws.st_n[s][2]; o[7] = ws.st_mu[s] + 10.f * ws.st_g1[s] + 100.f * ws.st_g2[s];
+            } else for (int c = 0; c < 8; c++) o[c] = 0.f;
+        }
+        for (int i = l; i < 27; i += 32) out[485 + i] = ws.gpos[i / 3][i % 3];
+        for (int i = l; i < 81; i += 32) out[512 + i] = ws.gmat[i / 9][i % 9];
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ kernels / emu loops
+#ifndef KG_EMU
+__global__ void __launch_bounds__(KG_WARPS * 32) kg_step_kernel(KgEnvArrays A, const float *action, int mode, int nsub, float *obs, float *reward, int *done, float *act_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * KG_WARPS + warp;
+    if (env >= A.N) return;
+    KgWS &ws = *(reinterpret_cast<KgWS *>(smem) + warp);
+    kg_env_step(c_model, ws, A, env, action, mode, nsub, obs, reward, done, act_out, lane);
+}
+__global__ void __launch_bounds__(KG_WARPS * 32) kg_reset_kernel(KgEnvArrays A, const int *mask, const int *shape, const float *euler, const float *objp,
+                                                                 int sampled, int orient, int variant, int test_table, unsigned long long seed, int *ep_count, int env_offset, float *obs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * KG_WARPS + warp;
+    if (env >= A.N) return;
+    if (mask && mask[env] == 0) return;
+    KgWS &ws = *(reinterpret_cast<KgWS *>(smem) + warp);
+    int sh = shape ? shape[env] : A.shape[env];
+    float e[3], p[3];
+    if (sampled) {
+        KgSample s = kg_sample_pose(c_model, seed, env + env_offset, ep_count[env], sh, orient, variant, test_table);
+        for (int c = 0; c < 3; c++) { e[c] = s.euler[c]; p[c] = s.objp[c]; }
+    } else {
+        for (int c = 0; c < 3; c++) { e[c] = euler[c * A.N + env]; p[c] = objp[c * A.N + env]; }
+    }
+    __syncwarp();
+    if (lane == 0) ep_count[env] += 1;
+    kg_env_reset(c_model, ws, A, env, sh, e, p, obs, lane);
+}
+__global__ void kg_debug_kernel(KgEnvArrays A, int env, const float *ctrl, float *out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    KgWS &ws = *reinterpret_cast<KgWS *>(smem);
+    kg_debug_run(c_model, ws, A, env, ctrl, out, threadIdx.x & 31);
+}
+#else
+static KgWS g_ws;
+#endif
+
+static size_t ws_bytes() { return sizeof(KgWS); }
+
+static int launch_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
+#ifdef KG_EMU
+    for (int env = 0; env < h->n; env++) kg_env_step(h->model, g_ws, h->A, env, action, mode, h->frame_skip, obs, reward, done, act_out, 0);
+    return 0;
+#else
+    cudaStream_t st = (cudaStream_t)h->stream;
+    int blocks = (h->n + KG_WARPS - 1) / KG_WARPS;
+    cudaEventRecord(h->ev0, st);
+    kg_step_kernel<<<blocks, KG_WARPS * 32, KG_WARPS * ws_bytes(), st>>>(h->A, action, mode, h->frame_skip, obs, reward, done, act_out);
+    cudaEventRecord(h->ev1, st);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+#endif
+}
+static int launch_reset(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, int sampled, int orient,
+                        int variant, int test_table, unsigned long long seed, float *obs) {
+#ifdef KG_EMU
+    for (int env = 0; env < h->n; env++) {
+        if (mask && mask[env] == 0) continue;
+        int sh = shape ? shape[env] : h->A.shape[env];
+        float e[3], p[3];
+        if (sampled) {
+            KgSample s = kg_sample_pose(h->model, seed, env + h->env_offset, h->ep_count[env], sh, orient, variant, test_table);
+            for (int c = 0; c < 3; c++) { e[c] = s.euler[c]; p[c] = s.objp[c]; }
+        } else for (int c = 0; c < 3; c++) { e[c] = euler[c * h->n + env]; p[c] = objp[c * h->n + env]; }
+        h->ep_count[env] += 1;
+        kg_env_reset(h->model, g_ws, h->A, env, sh, e, p, obs, 0);
+    }
+    return 0;
+#else
+    cudaStream_t st = (cudaStream_t)h->stream;
+    int blocks = (h->n + KG_WARPS - 1) / KG_WARPS;
+    kg_reset_kernel<<<blocks, KG_WARPS * 32, KG_WARPS * ws_bytes(), st>>>(h->A, mask, shape, euler, objp, sampled, orient, variant, test_table, seed, h->ep_count, h->env_offset, obs);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle *out) {
+    if (!out || n_envs <= 0 || !blob) return KG_EINVAL;
+    kg_handle h = new kg_handle_s();
+    *out = h;
+    h->n = n_envs; h->device = device;
+    KgHostTables local;
+#ifdef KG_EMU
+    KgHostTables &t = h->tables;
+#else
+    KgHostTables &t = local;
+    CUDA_TRY(h, cudaSetDevice(device));
+#endif
+    std::string e = kg_load_model(blob, nbytes, &h->model, &t);
+    if (!e.empty()) { h->err = "model card: " + e; return KG_EMODEL; }
+    KgModel &m = h->model;
+#ifdef KG_EMU
+    m.hull_vert = t.hull_vert.data(); m.adj_start = t.adj_start.data(); m.adj = t.adj.data(); m.tri = t.tri.data();
+    m.bvh_lo = t.bvh_lo.data(); m.bvh_hi = t.bvh_hi.data(); m.bvh_meta = t.bvh_meta.data();
+    m.pose_train = t.pose_train.data(); m.pose_test = t.pose_test.data();
+#else
+#define UP(field, vec) do { void *p_; TRY(be_alloc(h, &p_, (vec).size() * sizeof((vec)[0]))); CUDA_TRY(h, cudaMemcpy(p_, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice)); m.field = (decltype(m.field))p_; } while (0)
+    UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(tri, t.tri);
+    UP(bvh_lo, t.bvh_lo); UP(bvh_hi, t.bvh_hi); UP(bvh_meta, t.bvh_meta); UP(pose_train, t.pose_train); UP(pose_test, t.pose_test);
+#undef UP
+    CUDA_TRY(h, cudaMemcpyToSymbol(c_model, &m, sizeof(KgModel)));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_bytes()));
+    CUDA_TRY(h, cudaEventCreate(&h->ev0)); CUDA_TRY(h, cudaEventCreate(&h->ev1));
+#endif
+    const size_t N = (size_t)n_envs;
+    KgEnvArrays &A = h->A;
+    A.N = n_envs; A.max_steps = 30;
+    TRY(be_alloc(h, (void **)&A.qpos, 16 * N * 4)); TRY(be_alloc(h, (void **)&A.qvel, 15 * N * 4)); TRY(be_alloc(h, (void **)&A.qwarm, 15 * N * 4));
+    TRY(be_alloc(h, (void **)&A.hand_quat, 4 * N * 4)); TRY(be_alloc(h, (void **)&A.shape, N * 4)); TRY(be_alloc(h, (void **)&A.elapsed, N * 4));
+    TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
+    TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
+    TRY(be_alloc(h, (void **)&h->d_action, 4 * N * 4)); TRY(be_alloc(h, (void **)&h->d_obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&h->d_reward, N * 4));
+    TRY(be_alloc(h, (void **)&h->d_done, N * 4)); TRY(be_alloc(h, (void **)&h->d_mask, N * 4)); TRY(be_alloc(h, (void **)&h->d_shape, N * 4));
+    TRY(be_alloc(h, (void **)&h->d_euler, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_objp, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_q, 31 * N * 4));
+    TRY(be_alloc(h, (void **)&h->d_debug, KG_DEBUG_FLOATS * 4)); TRY(be_alloc(h, (void **)&h->d_ctrl, 16 * 4));
+    // a valid default state: every env reset to shape 0 at a neutral pose
+    {
+        std::vector<float> hq(4 * N, 0.f), qp(16 * N, 0.f);
+        for (size_t i = 0; i < N; i++) { hq[i] = 1.f; qp[12 * N + i] = 1.f; qp[11 * N + i] = 0.05f; }
+        TRY(be_h2d(h, A.hand_quat, hq.data(), hq.size() * 4)); TRY(be_h2d(h, A.qpos, qp.data(), qp.size() * 4));
+        TRY(be_sync(h));
+    }
+    return KG_OK;
+}
+
+int kg_destroy(kg_handle h) {
+    if (!h) return KG_EINVAL;
+#ifdef KG_EMU
+    for (void *p : h->allocs) free(p);
+#else
+    cudaSetDevice(h->device);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+#endif
+    delete h;
+    return KG_OK;
+}
+const char *kg_last_error(kg_handle h) { return h ? h->err.c_str() : "null handle"; }
+int kg_num_envs(kg_handle h) { return h ? h->n : KG_EINVAL; }
+int kg_set_stream(kg_handle h, void *stream) { if (!h) return KG_EINVAL; h->stream = stream; return KG_OK; }
+int kg_sync(kg_handle h) { if (!h) return KG_EINVAL; return be_sync(h); }
+int kg_set_max_episode_steps(kg_handle h, int steps) { if (!h || steps <= 0) return KG_EINVAL; h->A.max_steps = steps; return KG_OK; }
+int kg_set_frame_skip(kg_handle h, int fs) { if (!h || fs <= 0) return KG_EINVAL; h->frame_skip = fs; return KG_OK; }
+int kg_set_env_offset(kg_handle h, int offset) { if (!h || offset < 0) return KG_EINVAL; h->env_offset = offset; return KG_OK; }
+int kg_get_last_action_host(kg_handle h, float *act) {
+    if (!h || !act) return KG_EINVAL;
+    TRY(be_d2h(h, act, h->A.last_action, 4 * (size_t)h->n * 4));
+    return be_sync(h);
+}
+
+int kg_reset(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, float *obs) {
+    if (!h || !shape || !euler || !objp) { if (h) h->err = "kg_reset: shape/euler/objpos are required"; return KG_EINVAL; }
+    return launch_reset(h, mask, shape, euler, objp, 0, 0, 0, 0, 0ull, obs);
+}
+int kg_reset_sampled(kg_handle h, const int *mask, const int *shape, int orient, int variant, int test_table, uint64_t seed, float *obs) {
+    if (!h || orient < 0 || orient > 3 || variant < 0 || variant > 1) { if (h) h->err = "kg_reset_sampled: bad orient/variant"; return KG_EINVAL; }
+    return launch_reset(h, mask, shape, nullptr, nullptr, 1, orient, variant, test_table ? 1 : 0, (unsigned long long)seed, obs);
+}
+int kg_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
+    if (!h || mode < 0 || mode > 2) { if (h) h->err = "kg_step: expert_mode must be 0, 1 or 2"; return KG_EINVAL; }
+    return launch_step(h, action, mode, obs, reward, done, act_out);
+}
+int kg_step_host(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done) {
+    if (!h) return KG_EINVAL;
+    const size_t N = h->n;
+    if (action) TRY(be_h2d(h, h->d_action, action, 4 * N * 4));
+    TRY(kg_step(h, action ? h->d_action : nullptr, mode, obs ? h->d_obs : nullptr, reward ? h->d_reward : nullptr, done ? h->d_done : nullptr, nullptr));
+    if (obs) TRY(be_d2h(h, obs, h->d_obs, KG_NOBS * N * 4));
+    if (reward) TRY(be_d2h(h, reward, h->d_reward, N * 4));
+    if (done) TRY(be_d2h(h, done, h->d_done, N * 4));
+    return be_sync(h);
+}
+int kg_reset_host(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, float *obs) {
+    if (!h || !shape || !euler || !objp) { if (h) h->err = "kg_reset_host: shape/euler/objpos are required"; return KG_EINVAL; }
+    const size_t N = h->n;
+    if (mask) TRY(be_h2d(h, h->d_mask, mask, N * 4));
+    TRY(be_h2d(h, h->d_shape, shape, N * 4)); TRY(be_h2d(h, h->d_euler, euler, 3 * N * 4)); TRY(be_h2d(h, h->d_objp, objp, 3 * N * 4));
+    TRY(kg_reset(h, mask ? h->d_mask : nullptr, h->d_shape, h->d_euler, h->d_objp, obs ? h->d_obs : nullptr));
+    if (obs) TRY(be_d2h(h, obs, h->d_obs, KG_NOBS * N * 4));
+    return be_sync(h);
+}
+int kg_get_state(kg_handle h, float *qpos, float *qvel) {
+    if (!h) return KG_EINVAL;
+    const size_t N = h->n;
+    if (qpos) TRY(be_d2d(h, qpos, h->A.qpos, 16 * N * 4));
+    if (qvel) TRY(be_d2d(h, qvel, h->A.qvel, 15 * N * 4));
+    return KG_OK;
+}
+int kg_set_state(kg_handle h, const float *qpos, const float *qvel) {
+    if (!h) return KG_EINVAL;
+    const size_t N = h->n;
+    if (qpos) TRY(be_d2d(h, h->A.qpos, qpos, 16 * N * 4));
+    if (qvel) TRY(be_d2d(h, h->A.qvel, qvel, 15 * N * 4));
+    return KG_OK;
+}
+int kg_get_state_host(kg_handle h, float *qpos, float *qvel) {
+    if (!h) return KG_EINVAL;
+    const size_t N = h->n;
+    if (qpos) TRY(be_d2h(h, qpos, h->A.qpos, 16 * N * 4));
+    if (qvel) TRY(be_d2h(h, qvel, h->A.qvel, 15 * N * 4));
+    return be_sync(h);
+}
+int kg_set_state_host(kg_handle h, const float *qpos, const float *qvel) {
+    if (!h) return KG_EINVAL;
+    const size_t N = h->n;
+    if (qpos) TRY(be_h2d(h, h->A.qpos, qpos, 16 * N * 4));
+    if (qvel) TRY(be_h2d(h, h->A.qvel, qvel, 15 * N * 4));
+    return be_sync(h);
+}
+int kg_get_stats(kg_handle h, long long out[4]) {
+    if (!h || !out) return KG_EINVAL;
+    int s[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+    TRY(be_d2h(h, s, h->A.stats, sizeof s)); TRY(be_sync(h));
+    TRY(be_h2d(h, h->A.stats, z, sizeof z)); TRY(be_sync(h));
+    for (int i = 0; i < 4; i++) out[i] = s[i];
+    return KG_OK;
+}
+int kg_forward_debug(kg_handle h, int env, const float *ctrl, float *out) {
+    if (!h || env < 0 || env >= h->n || !ctrl || !out) return KG_EINVAL;
+    TRY(be_h2d(h, h->d_ctrl, ctrl, 9 * 4));
+#ifdef KG_EMU
+    kg_debug_run(h->model, g_ws, h->A, env, h->d_ctrl, h->d_debug, 0);
+#else
+    kg_debug_kernel<<<1, 32, ws_bytes(), (cudaStream_t)h->stream>>>(h->A, env, h->d_ctrl, h->d_debug);
+    CUDA_TRY(h, cudaGetLastError());
+#endif
+    TRY(be_d2h(h, out, h->d_debug, KG_DEBUG_FLOATS * 4));
+    return be_sync(h);
+}
+int kg_last_step_ms(kg_handle h, float *ms) {
+    if (!h || !ms) return KG_EINVAL;
+#ifdef KG_EMU
+    *ms = 0.f;
+#else
+    CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+    CUDA_TRY(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+#endif
+    return KG_OK;
+}
+
+}  // extern "C"

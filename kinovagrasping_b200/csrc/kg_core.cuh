@@ -1,0 +1,1475 @@
+// kg_core.cuh -- the batched grasp-env substep, ONE WARP PER ENVIRONMENT (fp32).
+//
+// Replaces the per-substep call chain kinova_gripper_env.py:1516-1535 -> mujoco_py MjSim.step() ->
+// mj_step for this fixed model.  Everything is written as a sequence of
+// warp-wide PHASES over a per-warp shared-memory workspace (KgWS):
+//
+//     KG_PHASE(l) { ... body executed by lane l ... }  KG_SYNC();
+//
+// A phase body may read anything written in earlier phases and must write only lane-owned
+// locations.  On the GPU a phase is straight-line code for the calling lane followed by
+// __syncwarp().  The same source also compiles for the host (tests/emu, TEST-ONLY: a debugging
+// aid that executes the lanes of a phase one after the other; it is never linked into the package),
+// which is how the algorithm is checked against the fp64 oracle inside the GPU-less container.
+//
+// Formulation notes (how this differs from the literal pipeline the oracle restates):
+//   * link_7 only translates, both hinges of a finger share one world-fixed axis  ->  CRBA/RNE are
+//     closed-form per finger (planar 2R chain on a translating base), the free body is closed-form;
+//   * hull support is hill-climbing on the hull graph, warm-started per pair across substeps;
+//   * the 4 pyramid rows of a contact are never stored: 3 frame rows J_n, J_t1, J_t2 are, and
+//     row_k = J_n +- mu J_t is expanded on the fly;
+//   * the exact line search brackets the root of the piecewise-linear phi'(alpha) with safeguarded
+//     Newton steps evaluated warp-wide.
+#pragma once
+#include "kg_model.h"
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDA_ARCH__)
+#define KG_DEV __device__ __forceinline__
+#define KG_PHASE(l) for (int l = kg_lane, kg_once_ = 0; kg_once_ < 1; ++kg_once_)
+#define KG_SYNC() __syncwarp()
+#define KG_LDG4(p) __ldg((const float4 *)(p))
+#else
+#if defined(__CUDACC__)
+#define KG_DEV __host__ __device__ inline
+#else
+#define KG_DEV inline
+#endif
+#define KG_PHASE(l) for (int l = 0; l < 32; ++l)
+#define KG_SYNC() ((void)0)
+struct kg_float4 { float x, y, z, w; };
+#define KG_LDG4(p) (*(const kg_float4 *)(p))
+#endif
+
+#define KG_NV 15
+#define KG_MS 16                       // row stride of 15x15 matrices
+#define KG_MAXCON 23                   // contact groups per env (overflow is counted and dropped)
+#define KG_NBASE (9 + 3 * KG_MAXCON)   // 3 tendon rows, 6 limit rows, 3 frame rows per contact
+#define KG_JS 17                       // row stride of J (odd: conflict-free column access)
+#define KG_NSTAGE 54                   // contact staging slots: 8 plane lanes x 4 + 22 hull lanes
+#define KG_NOBS 82
+#define KG_MPR_TOL 1e-6f
+#define KG_MPR_ITER 50
+#ifndef KG_NEWTON_MAXIT
+#define KG_NEWTON_MAXIT 20             // iteration cap; the loop exits early on the (fp32-aware) 1e-8 tests
+#endif
+#define KG_LS_MAXIT 12
+
+struct KgWS {
+    // ---- state
+    float qpos[16], qvel[16], qwarm[16], ctrl[12], sens_q[12];
+    // ---- per-episode constants
+    float Rh[9], B[3][9], fo[3][3], sax[3][3];
+    int shape, pad_;
+    // ---- kinematics
+    float hp[3], p1[3][3], p2[3][3], c1[3][3], c2[3][3];
+    float gpos[9][3], gmat[9][9];
+    float oR[9];
+    // ---- dynamics
+    float M[KG_NV * KG_MS], L[KG_NV * KG_MS];
+    float bias[16], fs[16], qas[16], qacc[16], Mdq[16], grad[16], dir[16], Md[16], ftot[16];
+    float sbias[3][3];
+    // ---- contact staging
+    float st_dist[KG_NSTAGE], st_mu[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3];
+    unsigned char st_g1[KG_NSTAGE], st_g2[KG_NSTAGE];
+    int cnt[32];
+    unsigned short cv1[32], cv2[32];   // warm-start hull vertices per pair lane
+    // ---- constraint groups: slot g<3 tendon, 3..8 limits, 9.. contacts
+    int gtype[32], gslot[32], ngroup, ncon_total;
+    float gmu[32], garef[32][4], gD[32][4];
+    float J[KG_NBASE * KG_JS];
+    float bdot[KG_NBASE + 2], bdir[KG_NBASE + 2], bw[KG_NBASE + 2];
+    float red[32], red2[32];
+    // ---- solver scalars (written by lane 0, read by all after a sync)
+    float s_alpha, s_cost, s_flag, s_lo, s_hi, s_glo, s_ghi;
+    int s_iter, s_done;
+    // ---- statistics
+    int stat_mpr, stat_newton, stat_overflow, stat_pad;
+    // ---- obs staging
+    float range[KG_NSITE + 3];
+    float obs[KG_NOBS + 2];
+};
+
+// ------------------------------------------------------------------------------------------------ small math
+KG_DEV float kg_dot(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+KG_DEV void kg_cross(float *r, const float *a, const float *b) {
+    float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    r[0] = x; r[1] = y; r[2] = z;
+}
+KG_DEV void kg_sub(float *r, const float *a, const float *b) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+KG_DEV void kg_add(float *r, const float *a, const float *b) { r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; }
+KG_DEV void kg_addscl(float *r, const float *a, const float *b, float s) { r[0] = a[0] + s * b[0]; r[1] = a[1] + s * b[1]; r[2] = a[2] + s * b[2]; }
+KG_DEV void kg_copy(float *r, const float *a) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
+KG_DEV float kg_normalize(float *a) {
+    float n = sqrtf(kg_dot(a, a));
+    if (n < 1e-30f) { a[0] = 1; a[1] = 0; a[2] = 0; return n; }
+    float inv = 1.0f / n;
+    a[0] *= inv; a[1] *= inv; a[2] *= inv;
+    return n;
+}
+KG_DEV void kg_mulmv(float *r, const float *M, const float *v) {
+    float x = M[0] * v[0] + M[1] * v[1] + M[2] * v[2];
+    float y = M[3] * v[0] + M[4] * v[1] + M[5] * v[2];
+    float z = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
+    r[0] = x; r[1] = y; r[2] = z;
+}
+KG_DEV void kg_multmv(float *r, const float *M, const float *v) {
+    float x = M[0] * v[0] + M[3] * v[1] + M[6] * v[2];
+    float y = M[1] * v[0] + M[4] * v[1] + M[7] * v[2];
+    float z = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
+    r[0] = x; r[1] = y; r[2] = z;
+}
+KG_DEV void kg_mulmm(float *r, const float *A, const float *Bm) {
+    float t[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * Bm[j] + A[3 * i + 1] * Bm[3 + j] + A[3 * i + 2] * Bm[6 + j];
+    for (int i = 0; i < 9; i++) r[i] = t[i];
+}
+KG_DEV void kg_quat2mat(float *M, const float *q) {
+    float w = q[0], x = q[1], y = q[2], z = q[3];
+    M[0] = w * w + x * x - y * y - z * z; M[1] = 2 * (x * y - w * z); M[2] = 2 * (x * z + w * y);
+    M[3] = 2 * (x * y + w * z); M[4] = w * w - x * x + y * y - z * z; M[5] = 2 * (y * z - w * x);
+    M[6] = 2 * (x * z - w * y); M[7] = 2 * (y * z + w * x); M[8] = w * w - x * x - y * y + z * z;
+}
+
+// warp total of ws.red[] (every lane wrote its partial in the previous phase)
+KG_DEV float kg_total(const float *red, int l) {
+#if defined(__CUDA_ARCH__)
+    float v = red[l];
+    v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+#else
+    (void)l;
+    float p[32];
+    for (int i = 0; i < 32; i++) p[i] = red[i];
+    for (int o = 16; o >= 1; o >>= 1) { float q[32]; for (int i = 0; i < 32; i++) q[i] = p[i] + p[i ^ o]; for (int i = 0; i < 32; i++) p[i] = q[i]; }
+    return p[0];
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ episode constants
+// hand_quat is what the reference writes into the XML at every reset (ENV:851-881); here it is data.
+KG_DEV void kg_episode_constants(const KgModel &m, KgWS &ws, const float *hand_quat, int shape, int kg_lane) {
+    KG_PHASE(l) {
+        if (l == 0) {
+            kg_quat2mat(ws.Rh, hand_quat);
+            ws.shape = shape;
+        }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        if (l < 3) {
+            kg_mulmm(ws.B[l], ws.Rh, m.finger_R + 9 * l);
+            kg_mulmv(ws.fo[l], ws.Rh, m.finger_pos + 3 * l);
+            kg_mulmv(ws.sax[l], ws.Rh, m.slide_axes + 3 * l);
+        }
+        if (l == 3) kg_mulmm(ws.gmat[1], ws.Rh, m.palm_gR);
+        ws.cv1[l] = 0; ws.cv2[l] = 0;
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ P1 kinematics
+KG_DEV void kg_kinematics(const KgModel &m, KgWS &ws, int kg_lane) {
+    KG_PHASE(l) {
+        float hp[3];
+        for (int c = 0; c < 3; c++) hp[c] = m.l7_pos[c] + ws.sax[0][c] * ws.qpos[0] + ws.sax[1][c] * ws.qpos[1] + ws.sax[2][c] * ws.qpos[2];
+        if (l < 3) {
+            const float *Bk = ws.B[l];
+            float q1 = ws.qpos[3 + 2 * l], q2 = ws.qpos[4 + 2 * l];
+            float s1, c1, s2, c2;
+            sincosf(q1, &s1, &c1);
+            sincosf(q1 + q2, &s2, &c2);
+            float R1[9], R2[9];
+            for (int r = 0; r < 3; r++) {
+                float b0 = Bk[3 * r], b1 = Bk[3 * r + 1], b2 = Bk[3 * r + 2];
+                R1[3 * r] = c1 * b0 + s1 * b1; R1[3 * r + 1] = -s1 * b0 + c1 * b1; R1[3 * r + 2] = b2;
+                R2[3 * r] = c2 * b0 + s2 * b1; R2[3 * r + 1] = -s2 * b0 + c2 * b1; R2[3 * r + 2] = b2;
+            }
+            float t[3], p1[3], p2[3];
+            kg_add(p1, hp, ws.fo[l]);
+            kg_mulmv(t, R1, m.tip_pos); kg_add(p2, p1, t);
+            kg_copy(ws.p1[l], p1); kg_copy(ws.p2[l], p2);
+            kg_mulmv(t, R1, m.link_com); kg_add(ws.c1[l], p1, t);
+            kg_mulmv(t, R2, m.link_com); kg_add(ws.c2[l], p2, t);
+            kg_mulmv(t, R1, m.prox_gpos); kg_add(ws.gpos[2 + 2 * l], p1, t);
+            kg_mulmv(t, R2, m.dist_gpos); kg_add(ws.gpos[3 + 2 * l], p2, t);
+            kg_mulmm(ws.gmat[2 + 2 * l], R1, m.prox_gR);
+            kg_mulmm(ws.gmat[3 + 2 * l], R2, m.dist_gR);
+        } else if (l == 3) {
+            float q[4] = {ws.qpos[12], ws.qpos[13], ws.qpos[14], ws.qpos[15]};
+            float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+            float inv = 1.0f / n;
+            for (int c = 0; c < 4; c++) q[c] *= inv;
+            kg_quat2mat(ws.oR, q);
+            const KgShape &sh = m.shape[ws.shape];
+            float t[3];
+            kg_mulmv(t, ws.oR, sh.gpos);
+            for (int c = 0; c < 3; c++) ws.gpos[8][c] = ws.qpos[9 + c] + t[c];
+            kg_mulmm(ws.gmat[8], ws.oR, sh.gR);
+        } else if (l == 4) {
+            float t[3];
+            kg_mulmv(t, ws.Rh, m.palm_gpos);
+            kg_add(ws.gpos[1], hp, t);
+            kg_copy(ws.hp, hp);
+        } else if (l >= 5 && l < 14) {
+            ws.sens_q[l - 5] = (l - 5) < 3 ? ws.qpos[l - 5] : ((l - 5) < 6 ? ws.qpos[3 + 2 * (l - 8)] : ws.qpos[4 + 2 * (l - 11)]);
+        }
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ P2 + P3: M, bias, smooth force
+KG_DEV void kg_dynamics(const KgModel &m, KgWS &ws, int kg_lane) {
+    KG_PHASE(l) {
+        for (int i = l; i < KG_NV * KG_MS; i += 32) ws.M[i] = 0.f;
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        const float g = m.gravity;
+        if (l < 3) {
+            const float mk = m.link_mass, Izz = m.link_Izz;
+            float a[3] = {ws.B[l][2], ws.B[l][5], ws.B[l][8]};
+            float r1[3], r2[3], r22[3], r12[3], d11[3], d12[3], d22[3];
+            kg_sub(r1, ws.c1[l], ws.p1[l]); kg_sub(r2, ws.c2[l], ws.p1[l]); kg_sub(r22, ws.c2[l], ws.p2[l]);
+            kg_sub(r12, ws.p2[l], ws.p1[l]);
+            kg_cross(d11, a, r1); kg_cross(d12, a, r2); kg_cross(d22, a, r22);
+            int h1 = 3 + 2 * l, h2 = 4 + 2 * l;
+            ws.M[h1 * KG_MS + h1] = 2 * Izz + mk * (kg_dot(d11, d11) + kg_dot(d12, d12)) + m.armature;
+            float m12 = Izz + mk * kg_dot(d12, d22);
+            ws.M[h1 * KG_MS + h2] = m12; ws.M[h2 * KG_MS + h1] = m12;
+            ws.M[h2 * KG_MS + h2] = Izz + mk * kg_dot(d22, d22) + m.armature;
+            float w1 = ws.qvel[h1], w2 = ws.qvel[h1] + ws.qvel[h2];
+            float ac1[3], ac2[3];
+            for (int c = 0; c < 3; c++) { ac1[c] = -w1 * w1 * r1[c]; ac2[c] = -w1 * w1 * r12[c] - w2 * w2 * r22[c]; }
+            float lin1[3], lin2[3];   // m * d(com)/dq summed over the links a hinge moves
+            for (int c = 0; c < 3; c++) { lin1[c] = mk * (d11[c] + d12[c]); lin2[c] = mk * d22[c]; }
+            for (int i = 0; i < 3; i++) {
+                float v1 = kg_dot(ws.sax[i], lin1), v2 = kg_dot(ws.sax[i], lin2);
+                ws.M[i * KG_MS + h1] = v1; ws.M[h1 * KG_MS + i] = v1;
+                ws.M[i * KG_MS + h2] = v2; ws.M[h2 * KG_MS + i] = v2;
+                ws.sbias[l][i] = mk * (kg_dot(ws.sax[i], ac1) + kg_dot(ws.sax[i], ac2));
+            }
+            ws.bias[h1] = mk * (kg_dot(d11, ac1) + g * d11[2]) + mk * (kg_dot(d12, ac2) + g * d12[2]);
+            ws.bias[h2] = mk * (kg_dot(d22, ac2) + g * d22[2]);
+        } else if (l == 3) {
+            const KgShape &sh = m.shape[ws.shape];
+            const float mo = m.obj_mass;
+            const float *R = ws.oR, *rl = sh.gpos;
+            for (int i = 0; i < 3; i++) ws.M[(9 + i) * KG_MS + 9 + i] = mo + m.armature;
+            // M_tr = -m R [r_l]x
+            float rx[9] = {0, -rl[2], rl[1], rl[2], 0, -rl[0], -rl[1], rl[0], 0};
+            float T[9];
+            kg_mulmm(T, R, rx);
+            for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) {
+                float v = -mo * T[3 * j + i];
+                ws.M[(9 + j) * KG_MS + 12 + i] = v; ws.M[(12 + i) * KG_MS + 9 + j] = v;
+            }
+            const float *Io = sh.Io, *Ic = sh.Ic;
+            ws.M[12 * KG_MS + 12] = Io[0] + m.armature; ws.M[13 * KG_MS + 13] = Io[1] + m.armature; ws.M[14 * KG_MS + 14] = Io[2] + m.armature;
+            ws.M[12 * KG_MS + 13] = ws.M[13 * KG_MS + 12] = Io[3];
+            ws.M[12 * KG_MS + 14] = ws.M[14 * KG_MS + 12] = Io[4];
+            ws.M[13 * KG_MS + 14] = ws.M[14 * KG_MS + 13] = Io[5];
+            float w[3] = {ws.qvel[12], ws.qvel[13], ws.qvel[14]};
+            float wr[3], wwr[3], Fl[3], Iw[3], Nc[3], rF[3], Fw[3];
+            kg_cross(wr, w, rl); kg_cross(wwr, w, wr);
+            float gz[3] = {R[6] * g, R[7] * g, R[8] * g};   // R^T (0,0,g)
+            for (int c = 0; c < 3; c++) Fl[c] = mo * (wwr[c] + gz[c]);
+            Iw[0] = Ic[0] * w[0] + Ic[3] * w[1] + Ic[4] * w[2];
+            Iw[1] = Ic[3] * w[0] + Ic[1] * w[1] + Ic[5] * w[2];
+            Iw[2] = Ic[4] * w[0] + Ic[5] * w[1] + Ic[2] * w[2];
+            kg_cross(Nc, w, Iw); kg_cross(rF, rl, Fl);
+            kg_mulmv(Fw, R, Fl);
+            for (int c = 0; c < 3; c++) { ws.bias[9 + c] = Fw[c]; ws.bias[12 + c] = Nc[c] + rF[c]; }
+        } else if (l == 4) {
+            for (int i = 0; i < 3; i++) ws.M[i * KG_MS + i] = m.m_hand_total + m.armature;
+        }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        if (l < KG_NV) {
+            float b = ws.bias[l], act = 0.f, v = ws.qvel[l];
+            if (l < 3) {
+                b = ws.sbias[0][l] + ws.sbias[1][l] + ws.sbias[2][l] + m.m_hand_total * m.gravity * ws.sax[l][2];
+                ws.bias[l] = b;
+                float c = fminf(fmaxf(ws.ctrl[2 * l], -m.ctrl_slide), m.ctrl_slide);
+                act = m.act_kv_slide * (c - v) + m.act_gear_slide * ws.ctrl[2 * l + 1];
+            } else if (l < 9 && ((l - 3) & 1) == 0) {
+                float c = fminf(fmaxf(ws.ctrl[6 + (l - 3) / 2], -m.ctrl_finger), m.ctrl_finger);
+                act = m.act_kv_finger * (c - v);
+            }
+            ws.fs[l] = -m.damping * v - b + act;
+        }
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ dense 15x15 Cholesky
+// A (stride KG_MS) -> lower factor in Lm.  Lanes own rows.
+KG_DEV void kg_cholesky(const float *A, float *Lm, float diag_add, int kg_lane) {
+    for (int j = 0; j < KG_NV; j++) {
+        KG_PHASE(l) {
+            if (l == j) {
+                float s = A[j * KG_MS + j] + diag_add;
+                for (int k = 0; k < j; k++) s -= Lm[j * KG_MS + k] * Lm[j * KG_MS + k];
+                Lm[j * KG_MS + j] = sqrtf(fmaxf(s, 1e-20f));
+            }
+        }
+        KG_SYNC();
+        KG_PHASE(l) {
+            if (l > j && l < KG_NV) {
+                float t = A[l * KG_MS + j];
+                for (int k = 0; k < j; k++) t -= Lm[l * KG_MS + k] * Lm[j * KG_MS + k];
+                Lm[l * KG_MS + j] = t / Lm[j * KG_MS + j];
+            }
+        }
+        KG_SYNC();
+    }
+}
+// x <- (L L^T)^-1 x, executed by lane 0 (latency-bound either way at n = 15)
+KG_DEV void kg_cholsolve(const float *Lm, float *x, int kg_lane) {
+    KG_PHASE(l) {
+        if (l == 0) {
+            float y[KG_NV];
+            for (int i = 0; i < KG_NV; i++) { float t = x[i]; for (int k = 0; k < i; k++) t -= Lm[i * KG_MS + k] * y[k]; y[i] = t / Lm[i * KG_MS + i]; }
+            for (int i = KG_NV - 1; i >= 0; i--) { float t = y[i]; for (int k = i + 1; k < KG_NV; k++) t -= Lm[k * KG_MS + i] * y[k]; y[i] = t / Lm[i * KG_MS + i]; x[i] = y[i]; }
+        }
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ P5 hull support (hill climbing)
+struct KgHull {
+    const float *vert;           // xyzw
+    const int *adjs;
+    const unsigned short *adj;
+    float pos[3], R[9];
+    float margin;
+    int cur;                     // warm-start vertex (kept across calls and substeps)
+};
+KG_DEV void kg_hull_init(const KgModel &m, KgHull &h, int mesh, const float *pos, const float *R, float margin, int start) {
+    const KgMesh &mi = m.mesh[mesh];
+    h.vert = m.hull_vert + 4 * (size_t)mi.vert0;
+    h.adjs = m.adj_start + mi.vert0;
+    h.adj = m.adj;
+    kg_copy(h.pos, pos);
+    for (int i = 0; i < 9; i++) h.R[i] = R[i];
+    h.margin = margin;
+    h.cur = start < mi.nvert ? start : 0;
+}
+// support point of the (margin-inflated) hull along the unit world direction dir
+KG_DEV void kg_support(KgHull &h, const float *dir, float *out) {
+    float ld[3];
+    kg_multmv(ld, h.R, dir);
+    int cur = h.cur;
+    auto v = KG_LDG4(h.vert + 4 * cur);
+    float best = v.x * ld[0] + v.y * ld[1] + v.z * ld[2];
+    float bx = v.x, by = v.y, bz = v.z;
+    for (int guard = 0; guard < 1024; guard++) {
+        int a0 = h.adjs[cur], a1 = h.adjs[cur + 1], nxt = cur;
+        for (int a = a0; a < a1; a++) {
+            int nb = h.adj[a];
+            auto w = KG_LDG4(h.vert + 4 * nb);
+            float d = w.x * ld[0] + w.y * ld[1] + w.z * ld[2];
+            if (d > best) { best = d; nxt = nb; bx = w.x; by = w.y; bz = w.z; }
+        }
+        if (nxt == cur) break;
+        cur = nxt;
+    }
+    h.cur = cur;
+    float lv[3] = {bx, by, bz}, wv[3];
+    kg_mulmv(wv, h.R, lv);
+    for (int c = 0; c < 3; c++) out[c] = wv[c] + h.pos[c] + h.margin * dir[c];
+}
+
+// ------------------------------------------------------------------------------------------------ P5 MPR (libccd's algorithm, fp32)
+struct KgSupp { float v[3], v1[3]; };   // Minkowski point and the witness on hull 1 (witness 2 = v1 - v)
+// libccd's ccdIsZero is an ABSOLUTE test against DBL_EPSILON; the reference engine runs it in double.  Keeping the
+// same absolute threshold in fp32 (2.2e-16 is representable) reproduces its branch decisions, whereas FLT_EPSILON
+// would classify every small-but-regular quantity (|v0 x v1|^2, the Gram determinant of a refined portal) as zero.
+#define KG_CCD_EPS 2.220446e-16f
+KG_DEV bool kg_iszero(float x) { return fabsf(x) < KG_CCD_EPS; }
+KG_DEV bool kg_feq(float a, float b) {
+    float ab = fabsf(a - b);
+    if (ab < FLT_EPSILON) return true;
+    float fa = fabsf(a), fb = fabsf(b);
+    return ab < FLT_EPSILON * (fb > fa ? fb : fa);
+}
+KG_DEV void kg_mink(KgHull &h1, KgHull &h2, const float *dir, KgSupp &s) {
+    float nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
+    kg_support(h1, dir, s.v1);
+    kg_support(h2, nd, v2);
+    kg_sub(s.v, s.v1, v2);
+}
+KG_DEV void kg_portal_dir(const KgSupp *p, float *dir) {
+    float a[3], b[3];
+    kg_sub(a, p[2].v, p[1].v); kg_sub(b, p[3].v, p[1].v);
+    kg_cross(dir, a, b);
+    kg_normalize(dir);
+}
+KG_DEV bool kg_reach_tol(const KgSupp *p, const KgSupp &v4, const float *dir) {
+    float dv4 = kg_dot(v4.v, dir);
+    float d1 = dv4 - kg_dot(p[1].v, dir), d2 = dv4 - kg_dot(p[2].v, dir), d3 = dv4 - kg_dot(p[3].v, dir);
+    float mn = fminf(d1, fminf(d2, d3));
+    return kg_feq(mn, KG_MPR_TOL) || mn < KG_MPR_TOL;
+}
+KG_DEV void kg_expand_portal(KgSupp *p, const KgSupp &v4) {
+    float v4v0[3];
+    kg_cross(v4v0, v4.v, p[0].v);
+    if (kg_dot(p[1].v, v4v0) > 0) {
+        if (kg_dot(p[2].v, v4v0) > 0) p[1] = v4; else p[3] = v4;
+    } else {
+        if (kg_dot(p[3].v, v4v0) > 0) p[2] = v4; else p[1] = v4;
+    }
+}
+KG_DEV float kg_seg_dist2(const float *a, const float *b, float *w) {   // closest point to the origin on [a,b]
+    float d[3];
+    kg_sub(d, b, a);
+    float t = -kg_dot(a, d) / kg_dot(d, d);
+    if (t < 0 || kg_iszero(t)) kg_copy(w, a);
+    else if (t > 1 || kg_feq(t, 1)) kg_copy(w, b);
+    else kg_addscl(w, a, d, t);
+    return kg_dot(w, w);
+}
+KG_DEV float kg_tri_dist2(const float *x0, const float *Bv, const float *C, float *w) {   // origin vs triangle
+    float d1[3], d2[3];
+    kg_sub(d1, Bv, x0); kg_sub(d2, C, x0);
+    float v = kg_dot(d1, d1), ww = kg_dot(d2, d2), p = kg_dot(x0, d1), q = kg_dot(x0, d2), r = kg_dot(d1, d2);
+    float div = ww * v - r * r, s, t = 0;
+    if (kg_iszero(div)) s = -1; else { s = (q * r - ww * p) / div; t = (-s * r - q) / ww; }
+    if ((kg_iszero(s) || s > 0) && (kg_feq(s, 1) || s < 1) && (kg_iszero(t) || t > 0) && (kg_feq(t, 1) || t < 1) && (kg_feq(t + s, 1) || t + s < 1)) {
+        kg_addscl(w, x0, d1, s); kg_addscl(w, w, d2, t);
+        return kg_dot(w, w);
+    }
+    float w2[3], dist = kg_seg_dist2(x0, Bv, w), dv;
+    dv = kg_seg_dist2(x0, C, w2); if (dv < dist) { dist = dv; kg_copy(w, w2); }
+    dv = kg_seg_dist2(Bv, C, w2); if (dv < dist) { dist = dv; kg_copy(w, w2); }
+    return dist;
+}
+// returns true when the inflated hulls overlap; coordinates are relative to hull 1's centre
+KG_DEV bool kg_mpr(KgHull &h1, KgHull &h2, float *depth, float *nrm, float *pos) {
+    KgSupp p[4], v4;
+    float dir[3], va[3], vb[3], dot;
+    kg_copy(p[0].v1, h1.pos);
+    kg_sub(p[0].v, h1.pos, h2.pos);
+    if (kg_iszero(p[0].v[0]) && kg_iszero(p[0].v[1]) && kg_iszero(p[0].v[2])) p[0].v[0] += KG_CCD_EPS * 10;
+    for (int c = 0; c < 3; c++) dir[c] = -p[0].v[c];
+    kg_normalize(dir);
+    kg_mink(h1, h2, dir, p[1]);
+    dot = kg_dot(p[1].v, dir);
+    if (kg_iszero(dot) || dot < 0) return false;
+    kg_cross(dir, p[0].v, p[1].v);
+    if (kg_iszero(kg_dot(dir, dir))) {
+        if (kg_iszero(p[1].v[0]) && kg_iszero(p[1].v[1]) && kg_iszero(p[1].v[2])) return false;   // touching, no normal
+        *depth = sqrtf(kg_dot(p[1].v, p[1].v));
+        kg_copy(nrm, p[1].v); kg_normalize(nrm);
+        for (int c = 0; c < 3; c++) pos[c] = p[1].v1[c] - 0.5f * p[1].v[c];
+        return true;
+    }
+    kg_normalize(dir);
+    kg_mink(h1, h2, dir, p[2]);
+    dot = kg_dot(p[2].v, dir);
+    if (kg_iszero(dot) || dot < 0) return false;
+    kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
+    kg_cross(dir, va, vb); kg_normalize(dir);
+    if (kg_dot(dir, p[0].v) > 0) { KgSupp t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+    for (int guard = 0;; guard++) {
+        if (guard > 100) return false;
+        kg_mink(h1, h2, dir, p[3]);
+        dot = kg_dot(p[3].v, dir);
+        if (kg_iszero(dot) || dot < 0) return false;
+        bool cont = false;
+        kg_cross(va, p[1].v, p[3].v); dot = kg_dot(va, p[0].v);
+        if (dot < 0 && !kg_iszero(dot)) { p[2] = p[3]; cont = true; }
+        if (!cont) {
+            kg_cross(va, p[3].v, p[2].v); dot = kg_dot(va, p[0].v);
+            if (dot < 0 && !kg_iszero(dot)) { p[1] = p[3]; cont = true; }
+        }
+        if (!cont) break;
+        kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
+        kg_cross(dir, va, vb); kg_normalize(dir);
+    }
+    for (int guard = 0;; guard++) {
+        if (guard > 200) return false;
+        kg_portal_dir(p, dir);
+        dot = kg_dot(dir, p[1].v);
+        if (kg_iszero(dot) || dot > 0) break;
+        kg_mink(h1, h2, dir, v4);
+        dot = kg_dot(v4.v, dir);
+        if (!(kg_iszero(dot) || dot > 0) || kg_reach_tol(p, v4, dir)) return false;
+        kg_expand_portal(p, v4);
+    }
+    for (int it = 0;; it++) {
+        kg_portal_dir(p, dir);
+        kg_mink(h1, h2, dir, v4);
+        if (kg_reach_tol(p, v4, dir) || it > KG_MPR_ITER) {
+            float w[3];
+            *depth = sqrtf(kg_tri_dist2(p[1].v, p[2].v, p[3].v, w));
+            if (kg_iszero(w[0]) && kg_iszero(w[1]) && kg_iszero(w[2])) kg_copy(w, dir);
+            kg_copy(nrm, w); kg_normalize(nrm);
+            // findPos: barycentric coordinates of the origin in the portal tetrahedron
+            float b[4], t[3], sum;
+            kg_cross(t, p[1].v, p[2].v); b[0] = kg_dot(t, p[3].v);
+            kg_cross(t, p[3].v, p[2].v); b[1] = kg_dot(t, p[0].v);
+            kg_cross(t, p[0].v, p[1].v); b[2] = kg_dot(t, p[3].v);
+            kg_cross(t, p[2].v, p[1].v); b[3] = kg_dot(t, p[0].v);
+            sum = b[0] + b[1] + b[2] + b[3];
+            if (kg_iszero(sum) || sum < 0) {
+                kg_portal_dir(p, dir);
+                b[0] = 0;
+                kg_cross(t, p[2].v, p[3].v); b[1] = kg_dot(t, dir);
+                kg_cross(t, p[3].v, p[1].v); b[2] = kg_dot(t, dir);
+                kg_cross(t, p[1].v, p[2].v); b[3] = kg_dot(t, dir);
+                sum = b[1] + b[2] + b[3];
+            }
+            float inv = 1.0f / sum;
+            for (int c = 0; c < 3; c++) {
+                float s1 = 0, sv = 0;
+                for (int i = 0; i < 4; i++) { s1 += b[i] * p[i].v1[c]; sv += b[i] * p[i].v[c]; }
+                pos[c] = (s1 - 0.5f * sv) * inv;   // (p1 + p2)/2 with p2 = p1 - v
+            }
+            return true;
+        }
+        kg_expand_portal(p, v4);
+    }
+}
+
+// mju_makeFrame on frame[0:3] = normal
+KG_DEV void kg_make_frame(const float *n, float *t1, float *t2) {
+    t1[0] = 0; t1[1] = 0; t1[2] = 0;
+    if (n[1] < 0.5f && n[1] > -0.5f) t1[1] = 1; else t1[2] = 1;
+    float d = kg_dot(n, t1);
+    kg_addscl(t1, t1, n, -d);
+    kg_normalize(t1);
+    kg_cross(t2, n, t1);
+}
+
+// ------------------------------------------------------------------------------------------------ P4 + P5 collision
+// pair table: lanes 0..7 plane vs geoms 1..8; lanes 8..13 object vs geoms 2..7; lane 14 object vs palm;
+// lanes 15..29 the dynamic pairs (palm-distal x3, finger-finger x12).  geom1 of the explicit pairs is
+// the object (XML:159-166), so their normals point from the object to the hand geom.
+KG_DEV void kg_pair_of_lane(int l, int &g1, int &g2) {
+    if (l < 8) { g1 = 0; g2 = l + 1; }
+    else if (l < 14) { g1 = 8; g2 = l - 6; }
+    else if (l == 14) { g1 = 8; g2 = 1; }
+    else {
+        const unsigned char t1[15] = {1, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3, 4, 4, 5, 5};
+        const unsigned char t2[15] = {3, 5, 7, 4, 5, 4, 5, 6, 7, 6, 7, 6, 7, 6, 7};
+        g1 = t1[l - 15]; g2 = t2[l - 15];
+    }
+}
+KG_DEV int kg_mesh_of_geom(const KgWS &ws, int g) { return g == 8 ? 3 + ws.shape : (g == 1 ? 0 : ((g & 1) ? 2 : 1)); }
+KG_DEV float kg_rbound(const KgModel &m, const KgWS &ws, int g) { return g == 8 ? m.shape[ws.shape].rbound : (g == 1 ? m.hand_rbound[0] : ((g & 1) ? m.hand_rbound[2] : m.hand_rbound[1])); }
+
+KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
+    KG_PHASE(l) {
+        int n = 0;
+        if (l < 30) {
+            int g1, g2;
+            kg_pair_of_lane(l, g1, g2);
+            const float margin = m.margin;
+            float rb2 = kg_rbound(m, ws, g2);
+            if (l < 8) {
+                const int base = 4 * l;
+                if (ws.gpos[g2][2] <= rb2 + margin) {
+                    KgHull h;
+                    kg_hull_init(m, h, kg_mesh_of_geom(ws, g2), ws.gpos[g2], ws.gmat[g2], 0.f, ws.cv2[l]);
+                    float nd[3] = {0, 0, -1}, w[3];
+                    kg_support(h, nd, w);
+                    ws.cv2[l] = (unsigned short)h.cur;
+                    if (w[2] <= margin) {
+                        const float thresh = 0.3f * rb2;
+                        int best = h.cur, a0 = h.adjs[best], a1 = h.adjs[best + 1];
+                        for (int c = -1; c < a1 - a0 && n < 4; c++) {
+                            if (c >= 0) {
+                                auto lv = KG_LDG4(h.vert + 4 * h.adj[a0 + c]);
+                                float lvv[3] = {lv.x, lv.y, lv.z};
+                                kg_mulmv(w, h.R, lvv); kg_add(w, w, h.pos);
+                            }
+                            float dist = w[2];
+                            if (dist > margin) continue;
+                            float cp[3] = {w[0], w[1], w[2] - 0.5f * dist};
+                            bool skip = false;
+                            for (int k = 0; k < n; k++) {
+                                float df[3]; kg_sub(df, cp, ws.st_pos[base + k]);
+                                if (kg_dot(df, df) < thresh * thresh) skip = true;
+                            }
+                            if (skip) continue;
+                            int s = base + n;
+                            ws.st_dist[s] = dist; ws.st_mu[s] = m.pair_mu[l]; kg_copy(ws.st_pos[s], cp);
+                            ws.st_n[s][0] = 0; ws.st_n[s][1] = 0; ws.st_n[s][2] = 1;
+                            ws.st_g1[s] = 0; ws.st_g2[s] = (unsigned char)g2;
+                            n++;
+                        }
+                    }
+                }
+            } else {
+                float rb1 = kg_rbound(m, ws, g1), df[3];
+                kg_sub(df, ws.gpos[g2], ws.gpos[g1]);
+                float lim = rb1 + rb2 + margin;
+                if (kg_dot(df, df) <= lim * lim) {
+                    KgHull h1, h2;
+                    const float zero[3] = {0, 0, 0};
+                    kg_hull_init(m, h1, kg_mesh_of_geom(ws, g1), zero, ws.gmat[g1], 0.5f * margin, ws.cv1[l]);
+                    kg_hull_init(m, h2, kg_mesh_of_geom(ws, g2), df, ws.gmat[g2], 0.5f * margin, ws.cv2[l]);
+                    float depth, nrm[3], pos[3];
+                    bool hit = kg_mpr(h1, h2, &depth, nrm, pos);
+                    ws.cv1[l] = (unsigned short)h1.cur; ws.cv2[l] = (unsigned short)h2.cur;
+                    n = 0;
+                    ws.red2[l] = 1.f;
+                    if (hit && depth > 0.f) {
+                        int s = 32 + (l - 8);
+                        ws.st_dist[s] = margin - depth; ws.st_mu[s] = m.pair_mu[l];
+                        kg_add(ws.st_pos[s], pos, ws.gpos[g1]);
+                        kg_copy(ws.st_n[s], nrm);
+                        ws.st_g1[s] = (unsigned char)g1; ws.st_g2[s] = (unsigned char)g2;
+                        n = 1;
+                    }
+                } else ws.red2[l] = 0.f;
+            }
+        }
+        if (l < 8 || l >= 30) ws.red2[l] = 0.f;
+        ws.cnt[l] = n;
+    }
+    KG_SYNC();
+    // compaction: contact groups 9.. reference staging slots
+    KG_PHASE(l) {
+        int off = 0, total = 0;
+        for (int k = 0; k < 32; k++) { int c = ws.cnt[k]; if (k < l) off += c; total += c; }
+        int base = l < 8 ? 4 * l : 32 + (l - 8);
+        for (int i = 0; i < ws.cnt[l]; i++) {
+            int g = 9 + off + i;
+            if (g < 32) { ws.gslot[g] = base + i; ws.gtype[g] = 3; }
+        }
+        if (l == 0) {
+            ws.ncon_total = total;
+            int nc = total > KG_MAXCON ? KG_MAXCON : total;
+            ws.ngroup = 9 + nc;
+            if (total > KG_MAXCON) ws.stat_overflow += 1;
+        }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        float nm = kg_total(ws.red2, l);
+        if (l == 0) ws.stat_mpr += (int)(nm + 0.5f);
+        if (l >= 9 && l >= ws.ngroup) ws.gtype[l] = 0;
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ P6 constraint rows
+KG_DEV float kg_impedance(const KgModel &m, float r) {
+    float x = fabsf(r) / m.width;
+    if (x >= 1.f) return m.dmax;
+    float y = x <= 0.5f ? 2.f * x * x : 1.f - 2.f * (1.f - x) * (1.f - x);
+    return m.dmin + y * (m.dmax - m.dmin);
+}
+// translational Jacobian row of the point p on the body carrying geom g, projected on f, ADDED with sign sg
+KG_DEV void kg_jac_add(const KgWS &ws, int g, const float *p, const float *f, float sg, float *row) {
+    if (g == 0) return;
+    if (g == 8) {
+        float r[3], t[3];
+        for (int c = 0; c < 3; c++) { row[9 + c] += sg * f[c]; r[c] = p[c] - ws.qpos[9 + c]; }
+        // rot dof i: f . ((R e_i) x r) = (R e_i) . (r x f)
+        kg_cross(t, r, f);
+        for (int i = 0; i < 3; i++) row[12 + i] += sg * (ws.oR[i] * t[0] + ws.oR[3 + i] * t[1] + ws.oR[6 + i] * t[2]);
+        return;
+    }
+    for (int i = 0; i < 3; i++) row[i] += sg * kg_dot(f, ws.sax[i]);
+    if (g == 1) return;
+    int k = (g - 2) >> 1;
+    float a[3] = {ws.B[k][2], ws.B[k][5], ws.B[k][8]}, r[3], t[3];
+    kg_sub(r, p, ws.p1[k]); kg_cross(t, a, r);
+    row[3 + 2 * k] += sg * kg_dot(f, t);
+    if (g & 1) { kg_sub(r, p, ws.p2[k]); kg_cross(t, a, r); row[4 + 2 * k] += sg * kg_dot(f, t); }
+}
+
+KG_DEV void kg_make_rows(const KgModel &m, KgWS &ws, int kg_lane) {
+    KG_PHASE(l) {
+        const float K = m.solK, Bd = m.solB;
+        if (l < 3) {
+            float *row = ws.J + l * KG_JS;
+            for (int j = 0; j < KG_NV; j++) row[j] = 0.f;
+            row[3 + 2 * l] = 1.f; row[4 + 2 * l] = -2.f;
+            float pos = ws.qpos[3 + 2 * l] - 2.f * ws.qpos[4 + 2 * l];
+            float vel = ws.qvel[3 + 2 * l] - 2.f * ws.qvel[4 + 2 * l];
+            float imp = kg_impedance(m, pos);
+            float R = fmaxf((1.f - imp) / imp * m.tendon_invw[l], 1e-15f);
+            ws.gtype[l] = 1; ws.gD[l][0] = 1.f / R; ws.garef[l][0] = -Bd * vel - K * imp * pos;
+        } else if (l < 9) {
+            int a = l - 3, j = a < 3 ? a : 3 + 2 * (a - 3);
+            float lo = a < 3 ? m.slide_range[2 * a] : m.finger_range[2 * (a - 3)];
+            float hi = a < 3 ? m.slide_range[2 * a + 1] : m.finger_range[2 * (a - 3) + 1];
+            float q = ws.qpos[j], sgn = 0.f, pos = 0.f;
+            if (q - lo < 0.f) { sgn = 1.f; pos = q - lo; } else if (hi - q < 0.f) { sgn = -1.f; pos = hi - q; }
+            float *row = ws.J + l * KG_JS;
+            for (int jj = 0; jj < KG_NV; jj++) row[jj] = 0.f;
+            if (sgn != 0.f) {
+                row[j] = sgn;
+                float imp = kg_impedance(m, pos);
+                float R = fmaxf((1.f - imp) / imp * m.dof_invw[j], 1e-15f);
+                ws.gtype[l] = 2; ws.gD[l][0] = 1.f / R; ws.garef[l][0] = -Bd * sgn * ws.qvel[j] - K * imp * pos;
+            } else ws.gtype[l] = 0;
+        } else if (l < ws.ngroup) {
+            int s = ws.gslot[l], g1 = ws.st_g1[s], g2 = ws.st_g2[s];
+            float n[3], t1[3], t2[3];
+            kg_copy(n, ws.st_n[s]);
+            kg_make_frame(n, t1, t2);
+            float *rn = ws.J + (9 + 3 * (l - 9)) * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
+            for (int j = 0; j < KG_NV; j++) { rn[j] = 0.f; r1[j] = 0.f; r2[j] = 0.f; }
+            const float *p = ws.st_pos[s];
+            kg_jac_add(ws, g2, p, n, 1.f, rn); kg_jac_add(ws, g1, p, n, -1.f, rn);
+            kg_jac_add(ws, g2, p, t1, 1.f, r1); kg_jac_add(ws, g1, p, t1, -1.f, r1);
+            kg_jac_add(ws, g2, p, t2, 1.f, r2); kg_jac_add(ws, g1, p, t2, -1.f, r2);
+            float vn = 0, v1 = 0, v2 = 0;
+            for (int j = 0; j < KG_NV; j++) { float v = ws.qvel[j]; vn += rn[j] * v; v1 += r1[j] * v; v2 += r2[j] * v; }
+            float mu = ws.st_mu[s], dist = ws.st_dist[s], r = dist - m.margin;
+            float tran = (g1 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g1]) + (g2 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g2]);
+            float imp = kg_impedance(m, r);
+            float R = fmaxf((1.f - imp) / imp * (tran + mu * mu * tran), 1e-15f);
+            float Rpy = fmaxf(2.f * mu * mu / m.impratio * R, 1e-15f);
+            float Dv = 1.f / Rpy, kr = K * imp * r;
+            ws.gmu[l] = mu;
+            for (int k = 0; k < 4; k++) ws.gD[l][k] = Dv;
+            ws.garef[l][0] = -Bd * (vn + mu * v1) - kr; ws.garef[l][1] = -Bd * (vn - mu * v1) - kr;
+            ws.garef[l][2] = -Bd * (vn + mu * v2) - kr; ws.garef[l][3] = -Bd * (vn - mu * v2) - kr;
+        }
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ P7 Newton solver
+// Scalar rows of group g at the point described by base-row products bd[]:
+//   tendon/limit: jar = bd[g] - aref ;  contact c: jar_k = bd[n] +- mu bd[t] - aref_k
+KG_DEV int kg_group_rows(const KgWS &ws, int g, const float *bd, float *jar) {
+    int tp = ws.gtype[g];
+    if (tp == 0) return 0;
+    if (tp < 3) { jar[0] = bd[g] - ws.garef[g][0]; return 1; }
+    int b = 9 + 3 * (g - 9);
+    float mu = ws.gmu[g], n = bd[b], t1 = mu * bd[b + 1], t2 = mu * bd[b + 2];
+    jar[0] = n + t1 - ws.garef[g][0]; jar[1] = n - t1 - ws.garef[g][1];
+    jar[2] = n + t2 - ws.garef[g][2]; jar[3] = n - t2 - ws.garef[g][3];
+    return 4;
+}
+KG_DEV int kg_nbase(const KgWS &ws) { return 9 + 3 * (ws.ngroup - 9); }
+
+// base-row products  out[b] = J_b . x   (lane per base row)
+KG_DEV void kg_base_dots(KgWS &ws, const float *x, float *out, int kg_lane) {
+    KG_PHASE(l) {
+        int nb = kg_nbase(ws);
+        for (int b = l; b < nb; b += 32) {
+            const float *row = ws.J + b * KG_JS;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < KG_NV; j++) s += row[j] * x[j];
+            out[b] = s;
+        }
+    }
+    KG_SYNC();
+}
+
+KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
+    const float tol = 1e-8f;
+    // ---- unconstrained acceleration
+    KG_PHASE(l) { if (l < KG_NV) ws.qas[l] = ws.fs[l]; }
+    KG_SYNC();
+    kg_cholesky(ws.M, ws.L, 0.f, kg_lane);
+    kg_cholsolve(ws.L, ws.qas, kg_lane);
+    // ---- warm start: the cheaper of qacc_warmstart and qacc_smooth
+    kg_base_dots(ws, ws.qwarm, ws.bdot, kg_lane);
+    kg_base_dots(ws, ws.qas, ws.bdir, kg_lane);
+    KG_PHASE(l) {
+        float cw = 0.f, cs = 0.f;
+        if (l < KG_NV) {
+            float s = 0.f;
+            for (int j = 0; j < KG_NV; j++) s += ws.M[l * KG_MS + j] * (ws.qwarm[j] - ws.qas[j]);
+            ws.Mdq[l] = s;
+            cw = 0.5f * s * (ws.qwarm[l] - ws.qas[l]);
+        }
+        float jar[4];
+        int n = kg_group_rows(ws, l, ws.bdot, jar);
+        for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) cw += 0.5f * ws.gD[l][k] * jar[k] * jar[k];
+        n = kg_group_rows(ws, l, ws.bdir, jar);
+        for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) cs += 0.5f * ws.gD[l][k] * jar[k] * jar[k];
+        ws.red[l] = cw; ws.red2[l] = cs;
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        float cw = kg_total(ws.red, l), cs = kg_total(ws.red2, l);
+        bool use_smooth = cs < cw;
+        if (l < KG_NV) {
+            ws.qacc[l] = use_smooth ? ws.qas[l] : ws.qwarm[l];
+            if (use_smooth) ws.Mdq[l] = 0.f;
+        }
+        if (use_smooth) { int nb = kg_nbase(ws); for (int b = l; b < nb; b += 32) ws.bdot[b] = ws.bdir[b]; }
+        if (l == 0) { ws.s_cost = 3.0e38f; ws.s_done = 0; ws.s_iter = 0; }
+    }
+    KG_SYNC();
+    const float scale = m.shape[ws.shape].scale;
+    for (int iter = 0; iter <= KG_NEWTON_MAXIT; iter++) {
+        // ---- (a) rows at the current point: cost, weights, Hessian coefficients
+        KG_PHASE(l) {
+            float c = 0.f;
+            if (l < KG_NV) c = 0.5f * ws.Mdq[l] * (ws.qacc[l] - ws.qas[l]);
+            float jar[4], w[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
+            int n = kg_group_rows(ws, l, ws.bdot, jar);
+            for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) { a[k] = ws.gD[l][k]; w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
+            if (n == 1) { ws.bw[l] = w[0]; ws.garef[l][1] = a[0]; }
+            else if (n == 4) {
+                int b = 9 + 3 * (l - 9);
+                float mu = ws.gmu[l];
+                ws.bw[b] = w[0] + w[1] + w[2] + w[3]; ws.bw[b + 1] = mu * (w[0] - w[1]); ws.bw[b + 2] = mu * (w[2] - w[3]);
+            } else if (l < 9) ws.bw[l] = 0.f;
+            // Hessian coefficients of the group are recomputed in (b) from the same activity test
+            ws.red[l] = c;
+        }
+        KG_SYNC();
+        KG_PHASE(l) {
+            float cost = kg_total(ws.red, l);
+            if (l == 0) {
+                // MuJoCo's test is scale*improvement < 1e-8; in fp32 the cost itself only carries ~2^-23 relative
+                // precision, so an "improvement" below that noise floor is treated as converged as well
+                float improvement = scale * (ws.s_cost - cost);
+                if (iter > 0 && improvement < tol + 2.4e-7f * scale * fabsf(cost)) ws.s_done = 1;
+                if (iter == KG_NEWTON_MAXIT) ws.s_done = 1;
+                ws.s_cost = cost;
+            }
+        }
+        KG_SYNC();
+        if (ws.s_done) break;
+        // ---- (b) gradient and Hessian (lane = dof / row of H)
+        KG_PHASE(l) {
+            float gsq = 0.f;
+            if (l < KG_NV) {
+                float gr = ws.Mdq[l];
+                float h[KG_NV];
+#pragma unroll
+                for (int j = 0; j < KG_NV; j++) h[j] = ws.M[l * KG_MS + j];
+                for (int g = 0; g < ws.ngroup; g++) {
+                    int tp = ws.gtype[g];
+                    if (tp == 0) continue;
+                    if (tp < 3) {
+                        const float *row = ws.J + g * KG_JS;
+                        float ji = row[l];
+                        gr += ji * ws.bw[g];
+                        float u = ji * ws.garef[g][1];   // D * active stored by (a)
+                        if (u != 0.f) {
+#pragma unroll
+                            for (int j = 0; j < KG_NV; j++) h[j] += u * row[j];
+                        }
+                    } else {
+                        int b = 9 + 3 * (g - 9);
+                        const float *rn = ws.J + b * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
+                        float jn = rn[l], j1 = r1[l], j2 = r2[l];
+                        gr += jn * ws.bw[b] + j1 * ws.bw[b + 1] + j2 * ws.bw[b + 2];
+                        float jar[4], a[4];
+                        kg_group_rows(ws, g, ws.bdot, jar);
+                        for (int k = 0; k < 4; k++) a[k] = jar[k] < 0.f ? ws.gD[g][k] : 0.f;
+                        float mu = ws.gmu[g];
+                        float A = a[0] + a[1] + a[2] + a[3], B1 = mu * (a[0] - a[1]), C1 = mu * mu * (a[0] + a[1]);
+                        float B2 = mu * (a[2] - a[3]), C2 = mu * mu * (a[2] + a[3]);
+                        if (A != 0.f) {
+                            float u = A * jn + B1 * j1 + B2 * j2, v1 = B1 * jn + C1 * j1, v2 = B2 * jn + C2 * j2;
+#pragma unroll
+                            for (int j = 0; j < KG_NV; j++) h[j] += u * rn[j] + v1 * r1[j] + v2 * r2[j];
+                        }
+                    }
+                }
+                ws.grad[l] = gr;
+                gsq = gr * gr;
+#pragma unroll
+                for (int j = 0; j < KG_NV; j++) ws.L[l * KG_MS + j] = h[j];
+            }
+            ws.red[l] = gsq;
+        }
+        KG_SYNC();
+        KG_PHASE(l) {
+            float gn = kg_total(ws.red, l);
+            if (l == 0 && scale * sqrtf(gn) < tol) ws.s_done = 1;
+            if (l < KG_NV) ws.dir[l] = -ws.grad[l];
+        }
+        KG_SYNC();
+        if (ws.s_done) break;
+        kg_cholesky(ws.L, ws.L, 0.f, kg_lane);
+        kg_cholsolve(ws.L, ws.dir, kg_lane);
+        // ---- (c) directional products
+        kg_base_dots(ws, ws.dir, ws.bdir, kg_lane);
+        KG_PHASE(l) {
+            float p1 = 0.f, p2 = 0.f;
+            if (l < KG_NV) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < KG_NV; j++) s += ws.M[l * KG_MS + j] * ws.dir[j];
+                ws.Md[l] = s;
+                p1 = ws.Mdq[l] * ws.dir[l]; p2 = s * ws.dir[l];
+            }
+            ws.red[l] = p1; ws.red2[l] = p2;
+        }
+        KG_SYNC();
+        KG_PHASE(l) {
+            float p1 = kg_total(ws.red, l), p2 = kg_total(ws.red2, l);
+            if (l == 0) { ws.s_glo = p1; ws.s_ghi = p2; }   // Gauss part of phi'(0), phi''
+        }
+        KG_SYNC();
+        // ---- (d) exact line search: root of the piecewise-linear phi'(alpha), safeguarded Newton
+        {
+            float alpha = 0.f, lo = 0.f, hi = -1.f, g0abs = 0.f, best_alpha = 0.f;
+            const float gp1 = ws.s_glo, gp2 = ws.s_ghi;
+            for (int ls = 0; ls < KG_LS_MAXIT; ls++) {
+                KG_PHASE(l) {
+                    float d1 = 0.f, d2 = 0.f, jar[4], jv[4];
+                    int n = kg_group_rows(ws, l, ws.bdot, jar);
+                    if (n == 1) jv[0] = ws.bdir[l];
+                    else if (n == 4) {
+                        int b = 9 + 3 * (l - 9);
+                        float mu = ws.gmu[l], nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
+                        jv[0] = nn + t1; jv[1] = nn - t1; jv[2] = nn + t2; jv[3] = nn - t2;
+                    }
+                    for (int k = 0; k < n; k++) {
+                        float x = jar[k] + alpha * jv[k];
+                        if (ws.gtype[l] == 1 || x < 0.f) { float dj = ws.gD[l][k] * jv[k]; d1 += dj * x; d2 += dj * jv[k]; }
+                    }
+                    ws.red[l] = d1; ws.red2[l] = d2;
+                }
+                KG_SYNC();
+                float gA = 0.f, hA = 0.f;
+                KG_PHASE(l) {
+                    float d1 = kg_total(ws.red, l), d2 = kg_total(ws.red2, l);
+                    if (l == 0) { ws.s_lo = d1; ws.s_hi = d2; }
+                }
+                KG_SYNC();
+                gA = gp1 + alpha * gp2 + ws.s_lo; hA = gp2 + ws.s_hi;
+                if (ls == 0) { g0abs = fabsf(gA); if (gA >= 0.f) { best_alpha = 0.f; break; } }
+                best_alpha = alpha;
+                if (fabsf(gA) <= 1e-6f * g0abs) break;
+                if (gA < 0.f) lo = alpha; else hi = alpha;
+                float nxt = alpha - gA / hA;
+                if (!(nxt > lo) || (hi > 0.f && !(nxt < hi))) nxt = hi > 0.f ? 0.5f * (lo + hi) : 2.f * alpha + 1.f;
+                if (fabsf(nxt - alpha) <= 1e-7f * fmaxf(1.f, fabsf(alpha))) { best_alpha = nxt; break; }
+                alpha = nxt;
+                best_alpha = alpha;
+            }
+            const float al = best_alpha;
+            KG_PHASE(l) {
+                if (l < KG_NV) { ws.qacc[l] += al * ws.dir[l]; ws.Mdq[l] += al * ws.Md[l]; }
+                int nb = kg_nbase(ws);
+                for (int b = l; b < nb; b += 32) ws.bdot[b] += al * ws.bdir[b];
+                if (l == 0) { ws.s_iter = iter + 1; }
+            }
+            KG_SYNC();
+        }
+    }
+    // ---- total force, warm start for the next substep
+    KG_PHASE(l) {
+        if (l < KG_NV) {
+            float f = ws.fs[l];
+            int nb = kg_nbase(ws);
+            for (int b = 0; b < nb; b++) {
+                if (b < 9 && ws.gtype[b] == 0) continue;
+                f -= ws.J[b * KG_JS + l] * ws.bw[b];
+            }
+            ws.ftot[l] = f;
+            ws.qwarm[l] = ws.qacc[l];
+        }
+        if (l == 0) ws.stat_newton += ws.s_iter;
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ P9 Euler
+KG_DEV void kg_euler(const KgModel &m, KgWS &ws, int kg_lane) {
+    const float h = m.timestep;
+    kg_cholesky(ws.M, ws.L, h * m.damping, kg_lane);
+    kg_cholsolve(ws.L, ws.ftot, kg_lane);
+    KG_PHASE(l) {
+        if (l < KG_NV) {
+            float v = ws.qvel[l] + h * ws.ftot[l];
+            ws.qvel[l] = v;
+            if (l < 12) ws.qpos[l] += h * v;
+        }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        if (l == 0) {
+            float w[3] = {ws.qvel[12], ws.qvel[13], ws.qvel[14]};
+            float q[4] = {ws.qpos[12], ws.qpos[13], ws.qpos[14], ws.qpos[15]};
+            float wn = sqrtf(kg_dot(w, w)), ang = h * wn;
+            if (ang > 0.f) {
+                float s, c;
+                sincosf(0.5f * ang, &s, &c);
+                float k = s / wn;
+                float r[4] = {c, w[0] * k, w[1] * k, w[2] * k};
+                float t[4] = {q[0] * r[0] - q[1] * r[1] - q[2] * r[2] - q[3] * r[3],
+                              q[0] * r[1] + q[1] * r[0] + q[2] * r[3] - q[3] * r[2],
+                              q[0] * r[2] - q[1] * r[3] + q[2] * r[0] + q[3] * r[1],
+                              q[0] * r[3] + q[1] * r[2] - q[2] * r[1] + q[3] * r[0]};
+                for (int c2 = 0; c2 < 4; c2++) q[c2] = t[c2];
+            }
+            float inv = 1.0f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+            for (int c2 = 0; c2 < 4; c2++) ws.qpos[12 + c2] = q[c2] * inv;
+        }
+    }
+    KG_SYNC();
+}
+
+// one mj_step: forward (positions -> constraints -> solve) + integrate
+KG_DEV void kg_substep(const KgModel &m, KgWS &ws, int kg_lane) {
+    kg_kinematics(m, ws, kg_lane);
+    kg_dynamics(m, ws, kg_lane);
+    kg_collision(m, ws, kg_lane);
+    kg_make_rows(m, ws, kg_lane);
+    kg_solve(m, ws, kg_lane);
+    kg_euler(m, ws, kg_lane);
+}
+
+// ------------------------------------------------------------------------------------------------ P8 rangefinder rays
+// mj_ray restated (see oracle/kgo_rays.c for the literal version): own-body geoms excluded, plane hit
+// from the front only, meshes culled by the geom_size box, then nearest raw-triangle hit via the BVH.
+KG_DEV float kg_ray_box(const float *size, const float *p, const float *v) {
+    float best = -1.f;
+    for (int ax = 0; ax < 3; ax++) {
+        if (fabsf(v[ax]) < 1e-15f) continue;
+        int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
+        for (int sg = -1; sg <= 1; sg += 2) {
+            float x = (sg * size[ax] - p[ax]) / v[ax];
+            if (x < 0.f) continue;
+            float c1 = p[a1] + x * v[a1], c2 = p[a2] + x * v[a2];
+            if (fabsf(c1) <= size[a1] && fabsf(c2) <= size[a2] && (best < 0.f || x < best)) best = x;
+        }
+    }
+    return best;
+}
+KG_DEV float kg_ray_tri(const float *t, const float *p, const float *v, const float *b0, const float *b1) {
+    float pl[3][2];
+    for (int i = 0; i < 3; i++) {
+        float dif[3] = {t[3 * i] - p[0], t[3 * i + 1] - p[1], t[3 * i + 2] - p[2]};
+        pl[i][0] = kg_dot(b0, dif); pl[i][1] = kg_dot(b1, dif);
+    }
+    for (int c = 0; c < 2; c++) {
+        if (pl[0][c] > 0 && pl[1][c] > 0 && pl[2][c] > 0) return -1.f;
+        if (pl[0][c] < 0 && pl[1][c] < 0 && pl[2][c] < 0) return -1.f;
+    }
+    float A0 = pl[0][0] - pl[2][0], A1 = pl[1][0] - pl[2][0], A2 = pl[0][1] - pl[2][1], A3 = pl[1][1] - pl[2][1];
+    float bb0 = -pl[2][0], bb1 = -pl[2][1];
+    float det = A0 * A3 - A1 * A2;
+    if (fabsf(det) < 1e-30f) return -1.f;
+    float t0 = (A3 * bb0 - A1 * bb1) / det, t1 = (-A2 * bb0 + A0 * bb1) / det;
+    if (t0 < 0 || t1 < 0 || t0 + t1 > 1) return -1.f;
+    float e0[3], e1[3], e2[3], nrm[3];
+    for (int c = 0; c < 3; c++) { e0[c] = t[c] - t[6 + c]; e1[c] = t[3 + c] - t[6 + c]; e2[c] = p[c] - t[6 + c]; }
+    kg_cross(nrm, e0, e1);
+    float den = kg_dot(v, nrm);
+    if (fabsf(den) < 1e-30f) return -1.f;
+    float x = -kg_dot(e2, nrm) / den;
+    return x >= 0.f ? x : -1.f;
+}
+KG_DEV float kg_ray_mesh(const KgModel &m, int mesh, const float *gpos, const float *gmat, const float *size, const float *pnt, const float *vec) {
+    float dp[3], lp[3], lv[3];
+    kg_sub(dp, pnt, gpos);
+    kg_multmv(lp, gmat, dp); kg_multmv(lv, gmat, vec);
+    if (kg_ray_box(size, lp, lv) < 0.f) return -1.f;
+    float b0[3], b1[3];
+    if (fabsf(lv[0]) < fabsf(lv[1]) && fabsf(lv[0]) < fabsf(lv[2])) { b0[0] = 0; b0[1] = lv[2]; b0[2] = -lv[1]; }
+    else if (fabsf(lv[1]) < fabsf(lv[2])) { b0[0] = -lv[2]; b0[1] = 0; b0[2] = lv[0]; }
+    else { b0[0] = lv[1]; b0[1] = -lv[0]; b0[2] = 0; }
+    kg_normalize(b0);
+    kg_cross(b1, b0, lv);
+    kg_normalize(b1);
+    const KgMesh &mi = m.mesh[mesh];
+    const float *tv = m.tri + 9 * (size_t)mi.tri0;
+    const float *lo = m.bvh_lo + 4 * (size_t)mi.bvh0, *hi = m.bvh_hi + 4 * (size_t)mi.bvh0;
+    const int *meta = m.bvh_meta + 2 * (size_t)mi.bvh0;
+    float inv[3];
+    for (int c = 0; c < 3; c++) inv[c] = fabsf(lv[c]) > 1e-30f ? 1.0f / lv[c] : (lv[c] >= 0 ? 1e30f : -1e30f);
+    float best = -1.f;
+    int stack[48], sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+        int n = stack[--sp];
+        auto nlo = KG_LDG4(lo + 4 * n); auto nhi = KG_LDG4(hi + 4 * n);
+        float l3[3] = {nlo.x, nlo.y, nlo.z}, h3[3] = {nhi.x, nhi.y, nhi.z};
+        float t0 = 0.f, t1 = best < 0.f ? 1e30f : best;
+        bool hit = true;
+        for (int c = 0; c < 3; c++) {
+            float a = (l3[c] - lp[c]) * inv[c], b = (h3[c] - lp[c]) * inv[c];
+            if (a > b) { float s = a; a = b; b = s; }
+            t0 = fmaxf(t0, a); t1 = fminf(t1, b);
+        }
+        if (t0 > t1 * (1.f + 1e-5f) + 1e-7f) hit = false;
+        if (!hit) continue;
+        int first = meta[2 * n], cnt = meta[2 * n + 1];
+        if (cnt == 0) { if (sp < 46) { stack[sp++] = first; stack[sp++] = first + 1; } }
+        else for (int i = 0; i < cnt; i++) {
+            float x = kg_ray_tri(tv + 9 * (size_t)(first + i), lp, lv, b0, b1);
+            if (x >= 0.f && (best < 0.f || x < best)) best = x;
+        }
+    }
+    return best;
+}
+KG_DEV void kg_site_pose(const KgModel &m, const KgWS &ws, int i, float *p, float *z) {
+    int sb = m.site_body[i];
+    float R[9], org[3];
+    if (sb == 0) { for (int c = 0; c < 9; c++) R[c] = ws.Rh[c]; kg_copy(org, ws.hp); }
+    else {
+        int k = sb <= 3 ? sb - 1 : sb - 4;
+        // body frames: recover R1 / R2 from the geom frames would need the inverse; rebuild from B and q
+        float q1 = ws.sens_q[3 + k], q2 = ws.sens_q[6 + k], s, c;
+        sincosf(sb <= 3 ? q1 : q1 + q2, &s, &c);
+        const float *Bk = ws.B[k];
+        for (int r = 0; r < 3; r++) { float b0 = Bk[3 * r], b1 = Bk[3 * r + 1]; R[3 * r] = c * b0 + s * b1; R[3 * r + 1] = -s * b0 + c * b1; R[3 * r + 2] = Bk[3 * r + 2]; }
+        kg_copy(org, sb <= 3 ? ws.p1[k] : ws.p2[k]);
+    }
+    float t[3];
+    kg_mulmv(t, R, m.site_pos + 3 * i); kg_add(p, org, t);
+    kg_mulmv(z, R, m.site_z + 3 * i);
+}
+KG_DEV void kg_rays(const KgModel &m, KgWS &ws, int kg_lane) {
+    KG_PHASE(l) {
+        if (l < KG_NSITE) {
+            float p[3], v[3];
+            kg_site_pose(m, ws, l, p, v);
+            int sb = m.site_body[l];
+            int own = sb == 0 ? 1 : (sb <= 3 ? 2 * sb : 2 * (sb - 3) + 1);
+            float best = -1.f;
+            if (v[2] < -1e-15f) {
+                float x = -p[2] / v[2];
+                if (x >= 0.f && fabsf(p[0] + x * v[0]) <= 2.f && fabsf(p[1] + x * v[1]) <= 2.f) best = x;
+            }
+            for (int g = 1; g < 9; g++) {
+                if (g == own) continue;
+                const float *size = g == 8 ? m.shape[ws.shape].size : (g == 1 ? m.hand_size : ((g & 1) ? m.hand_size + 6 : m.hand_size + 3));
+                float x = kg_ray_mesh(m, kg_mesh_of_geom(ws, g), ws.gpos[g], ws.gmat[g], size, p, v);
+                if (x >= 0.f && (best < 0.f || x < best)) best = x;
+            }
+            ws.range[l] = best;
+        }
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ O1-O9, R1: obs + reward
+// Restates _get_obs('local') / _get_reward (ENV:438-534, 631-687) on the kinematics of the LAST forward
+// pass (the one-substep staleness of SURVEY 8a O-note is reproduced: this runs before nothing else
+// touches ws.gpos / ws.sens_q).
+KG_DEV float kg_dotprod20(const float *hand, const float *p) {
+    float ox = fabsf(p[0] - hand[0]), oy = fabsf(p[1] - hand[1]);
+    float on = sqrtf(ox * ox + oy * oy);
+    float cx = fabsf(hand[0]), cy = fabsf(hand[1]);
+    float cn = sqrtf(cx * cx + cy * cy);
+    float d = (ox / on) * (cx / cn) + (oy / on) * (cy / cn);
+    float d2 = d * d, d4 = d2 * d2, d8 = d4 * d4, d16 = d8 * d8;
+    return d16 * d4;
+}
+KG_DEV float kg_tri_area(const float *a, const float *b) { float c[3]; kg_cross(c, a, b); return 0.5f * sqrtf(kg_dot(c, c)); }
+
+KG_DEV void kg_obs(const KgModel &m, KgWS &ws, int kg_lane, float *reward, int *done) {
+    // hand frame (O1): T = (R_palm C)^T, wrist = p_palm + T^T [-0.009, 0.048, 0]
+    KG_PHASE(l) {
+        const float *Rp = ws.gmat[1];
+        float T[9];   // rows of T = columns of Rp*C ; Rp*C columns: (-Rp col1, -Rp col2, Rp col0)
+        for (int c = 0; c < 3; c++) { T[c] = -Rp[3 * c + 1]; T[3 + c] = -Rp[3 * c + 2]; T[6 + c] = Rp[3 * c]; }
+        float off[3] = {-0.009f, 0.048f, 0.0f}, w[3], wrist[3], tt[3];
+        kg_multmv(w, T, off); kg_add(wrist, ws.gpos[1], w);
+        kg_mulmv(tt, T, wrist);
+        const float *obj = ws.gpos[8];
+        float *o = ws.obs;
+        const int fgeom[6] = {2, 4, 6, 3, 5, 7};
+        if (l < 6) {
+            float r[3];
+            kg_mulmv(r, T, ws.gpos[fgeom[l]]);
+            for (int c = 0; c < 3; c++) o[3 * l + c] = r[c] - tt[c];
+            o[75 + l] = kg_dotprod20(ws.hp, ws.gpos[fgeom[l]]);
+        } else if (l == 6) {
+            float r[3];
+            kg_mulmv(r, T, wrist);
+            for (int c = 0; c < 3; c++) o[18 + c] = r[c] - tt[c];
+            kg_mulmv(r, T, obj);
+            for (int c = 0; c < 3; c++) { r[c] -= tt[c]; o[21 + c] = r[c]; }
+            float n = sqrtf(kg_dot(r, r));
+            float ow[3] = {r[0] / n, r[1] / n, r[2] / n};
+            o[49] = acosf(ow[1] / sqrtf(ow[0] * ow[0] + ow[1] * ow[1]));   // z_angle
+            o[48] = acosf(ow[1] / sqrtf(ow[1] * ow[1] + ow[2] * ow[2]));   // x_angle
+            o[81] = kg_dotprod20(ws.hp, obj);
+            const float gw[3] = {0, 0, -1};
+            kg_mulmv(r, T, gw);
+            for (int c = 0; c < 3; c++) o[67 + c] = r[c];
+            const KgShape &sh = m.shape[ws.shape];
+            o[33] = sh.obs_size[0]; o[34] = sh.obs_size[1]; o[35] = sh.obs_size[2] * 2.f;
+        } else if (l == 7) {
+            for (int i = 0; i < 9; i++) o[24 + i] = (i < 2 ? -ws.sens_q[i] : ws.sens_q[i]);
+        } else if (l >= 8 && l < 20) {
+            float p[3], z[3], df[3];
+            kg_site_pose(m, ws, m.fod_site[l - 8], p, z);
+            kg_sub(df, p, obj);
+            o[36 + l - 8] = sqrtf(kg_dot(df, df));
+        }
+        if (l < KG_NSITE) { float r = ws.range[l]; o[50 + l] = (r == -1.f) ? 6.f : r; }
+    }
+    KG_SYNC();
+    // experimental_sensor (O8), reward (R1)
+    KG_PHASE(l) {
+        if (l == 0) {
+            float *o = ws.obs;
+            const float *fl = o;
+            float s1[3], s2[3];
+            kg_sub(s1, fl, fl + 6); kg_sub(s2, fl, fl + 3);
+            float front_area = kg_tri_area(s1, s2);
+            float top1 = kg_tri_area(fl, fl + 9), top2 = kg_tri_area(fl + 9, fl + 12), top3 = kg_tri_area(fl + 3, fl + 12);
+            float top4 = kg_tri_area(fl + 6, fl + 15), top5 = kg_tri_area(fl + 9, fl + 15);
+            float top_area = fmaxf(top1 + top2 + top3, top1 + top4 + top5);
+            const float *Rp = ws.gmat[1];
+            float T[9];
+            for (int c = 0; c < 3; c++) { T[c] = -Rp[3 * c + 1]; T[3 + c] = -Rp[3 * c + 2]; T[6 + c] = Rp[3 * c]; }
+            float off[3] = {-0.009f, 0.048f, 0.0f}, w[3], wrist[3], tt[3];
+            kg_multmv(w, T, off); kg_add(wrist, ws.gpos[1], w);
+            kg_mulmv(tt, T, wrist);
+            float sp[3] = {0, 0, 0}; int ns = 0;
+            for (int i = 0; i < 5; i++) {
+                float rng = o[50 + i];
+                if (rng < 0.06f) {
+                    float p[3], z[3], r[3];
+                    kg_site_pose(m, ws, i, p, z);
+                    kg_mulmv(r, T, p);
+                    sp[0] += r[0] - tt[0]; sp[1] += r[1] - tt[1] + rng; sp[2] += r[2] - tt[2];
+                    ns++;
+                }
+            }
+            if (ns == 0) { sp[0] = sp[1] = sp[2] = 0.2f; } else { float inv = 1.f / ns; sp[0] *= inv; sp[1] *= inv; sp[2] *= inv; }
+            o[70] = sp[0]; o[71] = sp[1]; o[72] = sp[2];
+            const float *sz = m.shape[ws.shape].obs_size;
+            float g0 = fabsf(o[67]), g1 = fabsf(o[68]), g2 = fabsf(o[69]);
+            int gi = 0; if (g1 > g0) gi = 1; if (g2 > (gi == 0 ? g0 : g1)) gi = 2;
+            float fp, tp;
+            if (gi == 2) { fp = fabsf(sz[0] * sz[2]) / front_area; tp = fabsf(sz[0] * sz[1]) / top_area; }
+            else if (gi == 1) { fp = fabsf(sz[0] * sz[2]) / front_area; tp = fabsf(sz[1] * sz[2]) / top_area; }
+            else { fp = fabsf(sz[0] * sz[1]) / front_area; tp = fabsf(sz[0] * sz[2]) / top_area; }
+            o[73] = fp; o[74] = tp;
+            float z = ws.gpos[8][2];
+            int dn = (fabsf(z - 0.2f) < 0.005f) || (z >= 0.2f);
+            *reward = dn ? 50.f : 0.f;
+            *done = dn;
+        }
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ S1: ctrl from the 4-d action (ENV:1501-1534)
+KG_DEV void kg_ctrl_from_action(KgWS &ws, const float *action, int kg_lane) {
+    KG_PHASE(l) {
+        if (l == 0) {
+            const float *Rp = ws.gmat[1];
+            // T z-column: T * (0,0,s) = s * (T[2], T[5], T[8]) with T rows = (-Rp col1, -Rp col2, Rp col0)
+            float tz[3] = {-Rp[7], -Rp[8], Rp[6]};
+            const float gcomp = 0.733f * 10.f / 25.f;
+            float a0 = action[0];
+            ws.ctrl[0] = -tz[0] * a0; ws.ctrl[2] = -tz[1] * a0; ws.ctrl[4] = tz[2] * a0;
+            ws.ctrl[1] = -tz[0] * gcomp; ws.ctrl[3] = -tz[1] * gcomp; ws.ctrl[5] = tz[2] * gcomp;
+            ws.ctrl[6] = action[1]; ws.ctrl[7] = action[2]; ws.ctrl[8] = action[3];
+        }
+    }
+    KG_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ C1-C3: expert controller (EXP:318-352, 367-671, 745-804)
+struct KgExpertState { float init_obj_x, init_dot, prev_fx[3]; int have_prev, num_good, total_steps; };
+KG_DEV float kg_pid_touch(float a, float b) { float e = a - b; return e + e / 15.f; }
+KG_DEV float kg_pid_velocity(float dot) { float e = 1.f - dot, v = e + e / 15.f, a = (v / 1.25f) * 0.3f; return a < 0.05f ? 0.05f : a; }
+KG_DEV void kg_pd_controller(const KgExpertState &e, const float *obs, int lift, float *a) {
+    const float cv = 0.5f, minv = 0.5f, flv = 0.5f;
+    float dot = obs[81], f1 = 0, f2 = 0, f3 = 0;
+    if (fabsf(e.init_obj_x) <= 0.03f) {
+        f1 = f2 = f3 = cv;
+        if (fabsf(dot - e.init_dot) > 0.01f) { f1 = cv; f2 = f3 = cv / 2; }
+        if (lift) { f1 = flv / 2; f2 = f3 = flv; }
+    } else if (e.init_obj_x > 0.0f) {
+        if (fabsf(dot - e.init_dot) < 0.01f) { f1 = 0; f2 = f3 = kg_pid_touch(dot, obs[79]); }
+        else {
+            if (fabsf(1.f - dot) > 0.01f) { f1 = minv; f2 = f3 = kg_pid_velocity(dot); }
+            else { f1 = kg_pid_touch(dot, obs[78]); f2 = f3 = 0; }
+            if (lift) { f1 = flv / 2; f2 = f3 = flv; }
+        }
+    } else {
+        if (fabsf(dot - e.init_dot) < 0.01f) { f1 = kg_pid_touch(dot, obs[78]); f2 = f3 = 0; }
+        else {
+            if (fabsf(1.f - dot) > 0.01f) { f1 = kg_pid_velocity(dot); f2 = f3 = minv; }
+            else { f2 = f3 = kg_pid_touch(dot, obs[79]); f1 = 0; }
+            if (lift) { f1 = flv / 2; f2 = f3 = flv; }
+        }
+    }
+    a[1] = f1; a[2] = f2; a[3] = f3;
+    for (int i = 1; i < 4; i++) { if (a[i] < 0.5f) a[i] = 0.5f; else if (a[i] > 0.8f) a[i] = 0.8f; }   // check_vel_in_range
+}
+// mode 0 naive, 1 position-dependent, 2 combined.  Advances the episode bookkeeping of EXP:745-804.
+KG_DEV void kg_expert_action(KgExpertState &e, const float *obs, int mode, float *action) {
+    int grasp = 0;
+    if (e.have_prev) {
+        float ch = fabsf(e.prev_fx[0] - obs[9]) / 15.f + fabsf(e.prev_fx[1] - obs[12]) / 15.f + fabsf(e.prev_fx[2] - obs[15]) / 15.f;
+        grasp = ch < 0.0002f;
+    }
+    if (grasp) e.num_good++;
+    int lift = (e.total_steps > 10) && (e.num_good >= 1);
+    float x = obs[21];
+    action[1] = action[2] = action[3] = 0.5f;
+    if (mode == 1) kg_pd_controller(e, obs, lift, action);
+    else if (mode == 2) {
+        if (x < -0.04f || x > 0.04f) kg_pd_controller(e, obs, lift, action);
+        else if ((-0.04f <= x && x <= -0.02f) || (0.02f <= x && x <= 0.04f)) {
+            float ex[4];
+            kg_pd_controller(e, obs, lift, ex);
+            action[1] = action[2] = action[3] = ex[2];   // np.interp quirk at EXP:654
+        }
+    }
+    action[0] = lift ? 0.6f : 0.0f;
+    if (e.total_steps > 0) { e.prev_fx[0] = obs[9]; e.prev_fx[1] = obs[12]; e.prev_fx[2] = obs[15]; e.have_prev = 1; }
+    e.total_steps++;
+}
+
+// ------------------------------------------------------------------------------------------------ env-level drivers
+// Struct-of-arrays device state: field-major [field][N] so that consecutive envs are consecutive floats.
+struct KgEnvArrays {
+    float *qpos, *qvel, *qwarm;   // [16][N], [15][N], [15][N]
+    float *hand_quat;             // [4][N]
+    int *shape, *elapsed;         // [N]
+    float *ex_f;                  // [5][N] init_obj_x, init_dot, prev_fx[3]
+    int *ex_i;                    // [3][N] have_prev, num_good, total_steps
+    float *obs;                   // [82][N] last observation (input of the expert controller)
+    float *last_action;           // [4][N] action applied by the last step (given or expert)
+    int *stats;                   // [4] mpr pairs, newton iterations, contact overflows, substeps
+    int N, max_steps;
+};
+
+KG_DEV void kg_load_env(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, int kg_lane) {
+    KG_PHASE(l) {
+        const int N = A.N;
+        if (l < 16) ws.qpos[l] = A.qpos[l * N + env];
+        if (l < 15) { ws.qvel[l] = A.qvel[l * N + env]; ws.qwarm[l] = A.qwarm[l * N + env]; }
+        if (l == 31) { ws.stat_mpr = 0; ws.stat_newton = 0; ws.stat_overflow = 0; ws.qvel[15] = 0.f; ws.qwarm[15] = 0.f; }
+    }
+    KG_SYNC();
+    float hq[4] = {A.hand_quat[env], A.hand_quat[A.N + env], A.hand_quat[2 * A.N + env], A.hand_quat[3 * A.N + env]};
+    kg_episode_constants(m, ws, hq, A.shape[env], kg_lane);
+}
+KG_DEV void kg_store_env(KgWS &ws, const KgEnvArrays &A, int env, int kg_lane) {
+    KG_PHASE(l) {
+        const int N = A.N;
+        if (l < 16) A.qpos[l * N + env] = ws.qpos[l];
+        if (l < 15) { A.qvel[l * N + env] = ws.qvel[l]; A.qwarm[l * N + env] = ws.qwarm[l]; }
+    }
+    KG_SYNC();
+}
+
+// One RL step of one env: [expert action] -> ctrl -> nsub x mj_step -> rays -> obs/reward/done (+TimeLimit).
+// action_in == nullptr selects the on-device expert (mode 0 naive, 1 position-dependent, 2 combined).
+KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *action_in, int expert_mode,
+                        int nsub, float *obs_out, float *reward_out, int *done_out, float *action_out, int kg_lane) {
+    kg_load_env(m, ws, A, env, kg_lane);
+    float act[4] = {0, 0, 0, 0};
+    if (action_in) { for (int c = 0; c < 4; c++) act[c] = action_in[c * A.N + env]; }
+    else {
+        KG_PHASE(l) { for (int i = l; i < KG_NOBS; i += 32) ws.obs[i] = A.obs[i * A.N + env]; }
+        KG_SYNC();
+        KG_PHASE(l) {
+            if (l == 0) {
+                const int N = A.N;
+                KgExpertState e;
+                e.init_obj_x = A.ex_f[env]; e.init_dot = A.ex_f[N + env];
+                e.prev_fx[0] = A.ex_f[2 * N + env]; e.prev_fx[1] = A.ex_f[3 * N + env]; e.prev_fx[2] = A.ex_f[4 * N + env];
+                e.have_prev = A.ex_i[env]; e.num_good = A.ex_i[N + env]; e.total_steps = A.ex_i[2 * N + env];
+                float a4[4];
+                kg_expert_action(e, ws.obs, expert_mode, a4);
+                A.ex_f[2 * N + env] = e.prev_fx[0]; A.ex_f[3 * N + env] = e.prev_fx[1]; A.ex_f[4 * N + env] = e.prev_fx[2];
+                A.ex_i[env] = e.have_prev; A.ex_i[N + env] = e.num_good; A.ex_i[2 * N + env] = e.total_steps;
+                for (int c = 0; c < 4; c++) ws.red[c] = a4[c];
+            }
+        }
+        KG_SYNC();
+        for (int c = 0; c < 4; c++) act[c] = ws.red[c];
+        KG_SYNC();
+    }
+    kg_ctrl_from_action(ws, act, kg_lane);
+    for (int s = 0; s < nsub; s++) kg_substep(m, ws, kg_lane);
+    kg_rays(m, ws, kg_lane);
+    float rew = 0.f; int dn = 0;
+    kg_obs(m, ws, kg_lane, &rew, &dn);
+    kg_store_env(ws, A, env, kg_lane);
+    KG_PHASE(l) {
+        const int N = A.N;
+        for (int i = l; i < KG_NOBS; i += 32) { float v = ws.obs[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
+        if (l == 0) {
+            // reward/done were produced by lane 0 of kg_obs; TimeLimit (gym_kinova_gripper/__init__.py:3-7, MAIN:164)
+            int el = A.elapsed[env] + 1;
+            A.elapsed[env] = el;
+            int d = dn || (el >= A.max_steps);
+            if (reward_out) reward_out[env] = rew;
+            if (done_out) done_out[env] = d;
+            for (int c = 0; c < 4; c++) { A.last_action[c * N + env] = act[c]; if (action_out) action_out[c * N + env] = act[c]; }
+#if defined(__CUDA_ARCH__)
+            if (A.stats) { atomicAdd(A.stats, ws.stat_mpr); atomicAdd(A.stats + 1, ws.stat_newton); atomicAdd(A.stats + 2, ws.stat_overflow); atomicAdd(A.stats + 3, nsub); }
+#else
+            if (A.stats) { A.stats[0] += ws.stat_mpr; A.stats[1] += ws.stat_newton; A.stats[2] += ws.stat_overflow; A.stats[3] += nsub; }
+#endif
+        }
+    }
+    KG_SYNC();
+}
+
+// reset of one env (ENV:1310-1410 without the file system): hand euler -> quaternion, hand joints 0, object at
+// obj_pos with identity orientation, velocities and warm start 0, forward kinematics + rays + first obs,
+// centroid fix-up (ENV:1382-1389), expert-controller episode state (EXP:367-379, 724-727).
+KG_DEV void kg_env_reset(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, int shape, const float *euler, const float *objp,
+                         float *obs_out, int kg_lane) {
+    float hq[4] = {1, 0, 0, 0};
+    for (int i = 0; i < 3; i++) {   // MuJoCo eulerseq "xyz": q = qx qy qz
+        float s, c;
+        sincosf(0.5f * euler[i], &s, &c);
+        float r[4] = {c, 0, 0, 0};
+        r[i + 1] = s;
+        float t[4] = {hq[0] * r[0] - hq[1] * r[1] - hq[2] * r[2] - hq[3] * r[3],
+                      hq[0] * r[1] + hq[1] * r[0] + hq[2] * r[3] - hq[3] * r[2],
+                      hq[0] * r[2] - hq[1] * r[3] + hq[2] * r[0] + hq[3] * r[1],
+                      hq[0] * r[3] + hq[1] * r[2] - hq[2] * r[1] + hq[3] * r[0]};
+        for (int c2 = 0; c2 < 4; c2++) hq[c2] = t[c2];
+    }
+    {
+        float n = 1.0f / sqrtf(hq[0] * hq[0] + hq[1] * hq[1] + hq[2] * hq[2] + hq[3] * hq[3]);
+        for (int c = 0; c < 4; c++) hq[c] *= n;
+    }
+    KG_PHASE(l) {
+        if (l < 16) ws.qpos[l] = 0.f;
+        if (l < 16) { ws.qvel[l] = 0.f; ws.qwarm[l] = 0.f; }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        if (l == 0) { ws.qpos[9] = objp[0]; ws.qpos[10] = objp[1]; ws.qpos[11] = objp[2]; ws.qpos[12] = 1.f; }
+    }
+    KG_SYNC();
+    kg_episode_constants(m, ws, hq, shape, kg_lane);
+    kg_kinematics(m, ws, kg_lane);
+    {
+        float d[3] = {objp[0] - ws.gpos[8][0], objp[1] - ws.gpos[8][1], objp[2] - ws.gpos[8][2]};
+        if (kg_dot(d, d) > 0.05f * 0.05f) {
+            KG_SYNC();
+            KG_PHASE(l) { if (l == 0) { ws.qpos[9] = objp[0] + d[0]; ws.qpos[10] = objp[1] + d[1]; ws.qpos[11] = objp[2] + d[2]; } }
+            KG_SYNC();
+            kg_kinematics(m, ws, kg_lane);
+        }
+    }
+    kg_rays(m, ws, kg_lane);
+    float rew; int dn;
+    kg_obs(m, ws, kg_lane, &rew, &dn);
+    kg_store_env(ws, A, env, kg_lane);
+    KG_PHASE(l) {
+        const int N = A.N;
+        for (int i = l; i < KG_NOBS; i += 32) { float v = ws.obs[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
+        if (l < 4) A.hand_quat[l * N + env] = hq[l];
+        if (l == 0) {
+            A.shape[env] = shape; A.elapsed[env] = 0;
+            A.ex_f[env] = ws.obs[21]; A.ex_f[N + env] = ws.obs[81];
+            A.ex_f[2 * N + env] = 0.f; A.ex_f[3 * N + env] = 0.f; A.ex_f[4 * N + env] = 0.f;
+            A.ex_i[env] = 0; A.ex_i[N + env] = 0; A.ex_i[2 * N + env] = 0;
+        }
+    }
+    KG_SYNC();
+}

@@ -1,0 +1,213 @@
+// kg_model.h -- fp32 device-side model card (POD) + host loader from assets/model_card.bin.
+// Replaces what mujoco_py.load_model_from_path + MjSim build on every reset
+// (kinova_gripper_env.py:878-879, 1002-1003) with one immutable table set per GPU.
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define KG_NSHAPE 14
+#define KG_NMESH 17
+#define KG_NSITE 17
+
+struct KgMesh {
+    int vert0, nvert, adj0, tri0, ntri, bvh0, nbvh, nface;
+};
+
+struct KgShape {
+    float gpos[3];        // object geom centre (mesh centre of mass) in the body frame
+    float gR[9];          // geom (mesh inertial) frame in the body frame, row-major
+    float rbound;
+    float size[3];        // geom_size (inertia-box half sizes): ray culling box
+    float obs_size[3];    // _get_obj_size() result (ENV:706-746)
+    float Ic[6];          // inertia about the centre of mass, body frame: xx,yy,zz,xy,xz,yz
+    float Io[6];          // inertia about the body origin, body frame (+ nothing else)
+    float invw_tran;      // body_invweight0 (translational)
+    float scale;          // 1 / (meaninertia * nv): Newton tolerance scaling
+};
+
+struct KgModel {
+    float timestep, impratio, margin, damping, armature, obj_mass, gravity;
+    float solK, solB, dmin, dmax, width;   // from solref (0.02,1) / solimp (0.9,0.95,0.001), refsafe applied
+    float l7_pos[3], slide_axes[9], slide_range[6], finger_range[6];
+    float m_hand_total;
+    float finger_pos[9], finger_R[27], tip_pos[3], link_com[3];
+    float link_mass, link_Izz;             // proximal == distal inertial (XML:81,90)
+    float palm_gpos[3], palm_gR[9], prox_gpos[3], prox_gR[9], dist_gpos[3], dist_gR[9];
+    float hand_rbound[3], hand_size[9];    // palm, proximal, distal
+    float site_pos[KG_NSITE * 3], site_z[KG_NSITE * 3];
+    int site_body[KG_NSITE], fod_site[12];
+    float body_invw[8];                    // translational invweight0 of geoms 0..7's bodies (ground = 0)
+    float dof_invw[9], tendon_invw[3];
+    float act_kv_slide, act_gear_slide, act_kv_finger, ctrl_slide, ctrl_finger;
+    float pair_mu[30];
+    KgShape shape[KG_NSHAPE];
+    KgMesh mesh[KG_NMESH];
+    // big read-only tables (device pointers on the GPU, host pointers in the emulation build)
+    const float *hull_vert;        // xyzw per vertex (w unused): 128-bit loads
+    const int *adj_start;
+    const unsigned short *adj;
+    const float *tri;              // 9 floats per triangle, BVH leaf order
+    const float *bvh_lo, *bvh_hi;  // xyz + pad per node
+    const int *bvh_meta;           // (left|first, count) per node
+    const float *pose_train, *pose_test;  // [shape][orient][row][9]
+    int pose_rows_train, pose_rows_test;
+};
+
+// ---------------------------------------------------------------------------------- host loader
+struct KgHostTables {
+    std::vector<float> hull_vert, tri, bvh_lo, bvh_hi, pose_train, pose_test;
+    std::vector<int> adj_start, bvh_meta;
+    std::vector<unsigned short> adj;
+};
+
+namespace kgdetail {
+struct Sec { char name[24]; uint32_t dtype, count; uint64_t offset; };
+inline const Sec *find(const unsigned char *blob, const char *name) {
+    uint32_t n = *(const uint32_t *)(blob + 8);
+    const Sec *t = (const Sec *)(blob + 16);
+    for (uint32_t i = 0; i < n; i++) if (std::strncmp(t[i].name, name, 24) == 0) return &t[i];
+    return nullptr;
+}
+inline void q2m(const double *q, double *M) {
+    double w = q[0], x = q[1], y = q[2], z = q[3];
+    M[0] = w * w + x * x - y * y - z * z; M[1] = 2 * (x * y - w * z); M[2] = 2 * (x * z + w * y);
+    M[3] = 2 * (x * y + w * z); M[4] = w * w - x * x + y * y - z * z; M[5] = 2 * (y * z - w * x);
+    M[6] = 2 * (x * z - w * y); M[7] = 2 * (y * z + w * x); M[8] = w * w - x * x - y * y + z * z;
+}
+}  // namespace kgdetail
+
+// Fills `m` (pointers left null) and `t`.  Returns "" or an error string.
+inline std::string kg_load_model(const void *blob_, size_t nbytes, KgModel *m, KgHostTables *t) {
+    using namespace kgdetail;
+    const unsigned char *blob = (const unsigned char *)blob_;
+    if (nbytes < 16 || std::memcmp(blob, "KGMC0001", 8) != 0) return "bad magic";
+    std::memset(m, 0, sizeof *m);
+    auto D = [&](const char *n, size_t expect) -> const double * {
+        const Sec *s = find(blob, n);
+        if (!s || s->dtype != 0 || (expect && s->count != expect)) return nullptr;
+        return (const double *)(blob + s->offset);
+    };
+    auto I = [&](const char *n, size_t *cnt) -> const int * {
+        const Sec *s = find(blob, n);
+        if (!s || s->dtype != 1) return nullptr;
+        if (cnt) *cnt = s->count;
+        return (const int *)(blob + s->offset);
+    };
+    auto F = [&](const char *n, size_t *cnt) -> const float * {
+        const Sec *s = find(blob, n);
+        if (!s || s->dtype != 2) return nullptr;
+        if (cnt) *cnt = s->count;
+        return (const float *)(blob + s->offset);
+    };
+#define KG_NEED(p) if (!(p)) return std::string("missing/bad section at ") + #p
+    const double *opt = D("opt", 12); KG_NEED(opt);
+    m->timestep = (float)opt[0]; m->impratio = (float)opt[1]; m->margin = (float)opt[2]; m->damping = (float)opt[3];
+    m->armature = (float)opt[4]; m->obj_mass = (float)opt[5]; m->gravity = (float)opt[6];
+    {
+        double tc = opt[7], dr = opt[8], dmax = opt[10];
+        if (tc < 2 * opt[0]) tc = 2 * opt[0];
+        m->solK = (float)(1.0 / (dmax * dmax * tc * tc * dr * dr));
+        m->solB = (float)(2.0 / (dmax * tc));
+        m->dmin = (float)opt[9]; m->dmax = (float)dmax; m->width = (float)opt[11];
+    }
+    const double *p;
+    p = D("l7_pos", 3); KG_NEED(p); for (int i = 0; i < 3; i++) m->l7_pos[i] = (float)p[i];
+    p = D("slide_axes", 9); KG_NEED(p); for (int i = 0; i < 9; i++) m->slide_axes[i] = (float)p[i];
+    p = D("slide_range", 6); KG_NEED(p); for (int i = 0; i < 6; i++) m->slide_range[i] = (float)p[i];
+    p = D("finger_range", 6); KG_NEED(p); for (int i = 0; i < 6; i++) m->finger_range[i] = (float)p[i];
+    const double *l7i = D("l7_inertial", 7); KG_NEED(l7i);
+    const double *fi = D("finger_inertial", 21); KG_NEED(fi);
+    const double *ti = D("tip_inertial", 21); KG_NEED(ti);
+    m->m_hand_total = (float)(l7i[3] + 3 * fi[3] + 3 * ti[3]);
+    m->link_mass = (float)fi[3]; m->link_Izz = (float)fi[6];
+    for (int i = 0; i < 3; i++) m->link_com[i] = (float)fi[i];
+    for (int k = 0; k < 3; k++) {  // the kernels rely on identical proximal / distal inertials
+        if (fi[7 * k + 3] != fi[3] || ti[7 * k + 3] != fi[3] || ti[7 * k + 6] != fi[6] || ti[7 * k] != fi[0]) return "finger inertials differ";
+    }
+    p = D("finger_pos", 9); KG_NEED(p); for (int i = 0; i < 9; i++) m->finger_pos[i] = (float)p[i];
+    p = D("finger_quat", 12); KG_NEED(p);
+    for (int k = 0; k < 3; k++) { double R[9]; q2m(p + 4 * k, R); for (int i = 0; i < 9; i++) m->finger_R[9 * k + i] = (float)R[i]; }
+    p = D("tip_pos", 9); KG_NEED(p); for (int i = 0; i < 3; i++) m->tip_pos[i] = (float)p[i];
+    const double *mg = D("mesh_geom", KG_NMESH * 15); KG_NEED(mg);
+    float *gp[3] = {m->palm_gpos, m->prox_gpos, m->dist_gpos};
+    float *gr[3] = {m->palm_gR, m->prox_gR, m->dist_gR};
+    for (int k = 0; k < 3; k++) {
+        const double *c = mg + 15 * k; double R[9];
+        q2m(c + 3, R);
+        for (int i = 0; i < 3; i++) { gp[k][i] = (float)c[i]; m->hand_size[3 * k + i] = (float)c[8 + i]; }
+        for (int i = 0; i < 9; i++) gr[k][i] = (float)R[i];
+        m->hand_rbound[k] = (float)c[7];
+    }
+    const double *oinv = D("obj_invw0", KG_NSHAPE * 4); KG_NEED(oinv);
+    const double *hm = D("hand_M0", 81); KG_NEED(hm);
+    double tr = 0; for (int j = 0; j < 9; j++) tr += hm[10 * j];
+    for (int s = 0; s < KG_NSHAPE; s++) {
+        const double *c = mg + 15 * (3 + s); double R[9];
+        KgShape &sh = m->shape[s];
+        q2m(c + 3, R);
+        for (int i = 0; i < 3; i++) { sh.gpos[i] = (float)c[i]; sh.size[i] = (float)c[8 + i]; }
+        for (int i = 0; i < 9; i++) sh.gR[i] = (float)R[i];
+        sh.rbound = (float)c[7];
+        double in[3], Ic[9] = {0}, Io[9];
+        for (int i = 0; i < 3; i++) in[i] = c[12 + i] * opt[5] / c[11];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) Ic[3 * i + j] += R[3 * i + k] * in[k] * R[3 * j + k];
+        double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Io[3 * i + j] = Ic[3 * i + j] + opt[5] * ((i == j ? cc : 0) - c[i] * c[j]);
+        const int ix[6] = {0, 4, 8, 1, 2, 5};
+        for (int i = 0; i < 6; i++) { sh.Ic[i] = (float)Ic[ix[i]]; sh.Io[i] = (float)Io[ix[i]]; }
+        sh.invw_tran = (float)oinv[4 * s];
+        double t = tr + 3 * (opt[5] + opt[4]);
+        for (int i = 0; i < 3; i++) t += Io[4 * i] + opt[4];
+        sh.scale = (float)(1.0 / (t / 15.0 * 15.0));
+        // _get_obj_size (ENV:706-746), single-geom object
+        double sz[3] = {c[8], c[9], c[10]};
+        if (sz[2] == 0) { sz[2] = sz[1]; sz[1] = sz[0]; }
+        double df[3] = {std::abs(sz[0] - sz[1]), std::abs(sz[1] - sz[2]), std::abs(sz[0] - sz[2])};
+        int am = 0; if (df[1] < df[am]) am = 1; if (df[2] < df[am]) am = 2;
+        if (am != 0) { double x = sz[0]; sz[0] = sz[2]; sz[2] = x; }
+        sh.obs_size[0] = (float)(sz[0] > 0 ? sz[0] : 0); sh.obs_size[1] = (float)(sz[1] > 0 ? sz[1] : 0); sh.obs_size[2] = (float)sz[2];
+    }
+    p = D("site_pos", KG_NSITE * 3); KG_NEED(p); for (int i = 0; i < KG_NSITE * 3; i++) m->site_pos[i] = (float)p[i];
+    p = D("site_zaxis", KG_NSITE * 3); KG_NEED(p); for (int i = 0; i < KG_NSITE * 3; i++) m->site_z[i] = (float)p[i];
+    const int *ip;
+    ip = I("site_body", nullptr); KG_NEED(ip); for (int i = 0; i < KG_NSITE; i++) m->site_body[i] = ip[i];
+    ip = I("fod_site", nullptr); KG_NEED(ip); for (int i = 0; i < 12; i++) m->fod_site[i] = ip[i];
+    const double *hb = D("hand_body_invw0", 14); KG_NEED(hb);
+    m->body_invw[0] = 0;
+    for (int g = 1; g < 8; g++) m->body_invw[g] = (float)hb[2 * (g - 1)];
+    p = D("hand_dof_invw0", 9); KG_NEED(p); for (int i = 0; i < 9; i++) m->dof_invw[i] = (float)p[i];
+    p = D("tendon_invw0", 3); KG_NEED(p); for (int i = 0; i < 3; i++) m->tendon_invw[i] = (float)p[i];
+    const double *kv = D("act_kv", 9), *gear = D("act_gear", 9), *cr = D("act_ctrlrange", 18);
+    KG_NEED(kv); KG_NEED(gear); KG_NEED(cr);
+    m->act_kv_slide = (float)kv[0]; m->act_gear_slide = (float)gear[1]; m->act_kv_finger = (float)kv[6];
+    m->ctrl_slide = (float)cr[1]; m->ctrl_finger = (float)cr[13];
+    const double *pf = D("pair_friction", 8); KG_NEED(pf);
+    // pair table: 0..7 plane vs geoms 1..8; 8..13 object vs geoms 2..7; 14 object vs palm; 15..29 dynamic
+    for (int i = 0; i < 30; i++) m->pair_mu[i] = 1.0f;
+    m->pair_mu[7] = (float)pf[0];
+    for (int g = 2; g <= 7; g++) m->pair_mu[8 + g - 2] = (float)pf[g - 1];
+    m->pair_mu[14] = (float)pf[7];
+    // tables
+    size_t n;
+    ip = I("mesh_index", &n); KG_NEED(ip);
+    std::memcpy(m->mesh, ip, sizeof(KgMesh) * KG_NMESH);
+    const Sec *hv = find(blob, "hull_vert"); KG_NEED(hv);
+    const double *hvd = (const double *)(blob + hv->offset);
+    t->hull_vert.assign(hv->count / 3 * 4, 0.f);
+    for (size_t i = 0; i < hv->count / 3; i++) for (int c = 0; c < 3; c++) t->hull_vert[4 * i + c] = (float)hvd[3 * i + c];
+    ip = I("hull_adj_start", &n); KG_NEED(ip); t->adj_start.assign(ip, ip + n);
+    ip = I("hull_adj", &n); KG_NEED(ip); t->adj.resize(n); for (size_t i = 0; i < n; i++) t->adj[i] = (unsigned short)ip[i];
+    const float *fp;
+    fp = F("tri_vert", &n); KG_NEED(fp); t->tri.assign(fp, fp + n);
+    fp = F("bvh_lo", &n); KG_NEED(fp); t->bvh_lo.assign(n / 3 * 4, 0.f); for (size_t i = 0; i < n / 3; i++) for (int c = 0; c < 3; c++) t->bvh_lo[4 * i + c] = fp[3 * i + c];
+    fp = F("bvh_hi", &n); KG_NEED(fp); t->bvh_hi.assign(n / 3 * 4, 0.f); for (size_t i = 0; i < n / 3; i++) for (int c = 0; c < 3; c++) t->bvh_hi[4 * i + c] = fp[3 * i + c];
+    ip = I("bvh_meta", &n); KG_NEED(ip); t->bvh_meta.assign(ip, ip + n);
+    fp = F("pose_train", &n); KG_NEED(fp); t->pose_train.assign(fp, fp + n); m->pose_rows_train = (int)(n / (KG_NSHAPE * 3 * 9));
+    fp = F("pose_test", &n); KG_NEED(fp); t->pose_test.assign(fp, fp + n); m->pose_rows_test = (int)(n / (KG_NSHAPE * 3 * 9));
+#undef KG_NEED
+    return "";
+}

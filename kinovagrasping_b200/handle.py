@@ -1,0 +1,138 @@
+"""Thin object wrapper over the C ABI (include/kg.h): error handling + numpy host-buffer helpers.
+Device-pointer entry points take raw integer addresses (e.g. torch.Tensor.data_ptr())."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .modelcard import DEFAULT_PATH
+
+
+class KgError(RuntimeError):
+    pass
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Handle:
+    """One batch of environments on one device (kg_create ... kg_destroy)."""
+
+    def __init__(self, n_envs, device=0, blob_path=DEFAULT_PATH, lib=None):
+        self.lib = lib if lib is not None else _lib.load()
+        with open(blob_path, "rb") as f:
+            blob = f.read()
+        self.n = int(n_envs)
+        self.h = C.c_void_p()
+        rc = self.lib.kg_create(self.n, int(device), blob, len(blob), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.kg_last_error(self.h).decode() if self.h else "kg_create failed"
+            raise KgError(f"kg_create: {msg} (rc={rc})")
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise KgError(f"{what}: {self.lib.kg_last_error(self.h).decode()} (rc={rc})")
+
+    def close(self):
+        if self.h:
+            self.lib.kg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device-pointer API (addresses as ints; 0/None = NULL)
+    def set_stream(self, stream_ptr):
+        self._chk(self.lib.kg_set_stream(self.h, C.c_void_p(stream_ptr or 0)), "kg_set_stream")
+
+    def sync(self):
+        self._chk(self.lib.kg_sync(self.h), "kg_sync")
+
+    def reset(self, mask, shape, euler, objpos, obs):
+        self._chk(self.lib.kg_reset(self.h, mask or None, shape, euler, objpos, obs or None), "kg_reset")
+
+    def reset_sampled(self, mask, shape, orient, variant, test_table, seed, obs):
+        self._chk(self.lib.kg_reset_sampled(self.h, mask or None, shape or None, int(orient), int(variant), int(test_table),
+                                            C.c_uint64(int(seed) & (2 ** 64 - 1)), obs or None), "kg_reset_sampled")
+
+    def step(self, action, expert_mode, obs, reward, done, action_out=None):
+        self._chk(self.lib.kg_step(self.h, action or None, int(expert_mode), obs or None, reward or None, done or None,
+                                   action_out or None), "kg_step")
+
+    def get_state(self, qpos, qvel):
+        self._chk(self.lib.kg_get_state(self.h, qpos or None, qvel or None), "kg_get_state")
+
+    def set_state(self, qpos, qvel):
+        self._chk(self.lib.kg_set_state(self.h, qpos or None, qvel or None), "kg_set_state")
+
+    def set_max_episode_steps(self, n):
+        self._chk(self.lib.kg_set_max_episode_steps(self.h, int(n)), "kg_set_max_episode_steps")
+
+    def set_frame_skip(self, n):
+        self._chk(self.lib.kg_set_frame_skip(self.h, int(n)), "kg_set_frame_skip")
+
+    def set_env_offset(self, off):
+        self._chk(self.lib.kg_set_env_offset(self.h, int(off)), "kg_set_env_offset")
+
+    def last_action_host(self):
+        a = np.zeros((4, self.n), dtype=np.float32)
+        self._chk(self.lib.kg_get_last_action_host(self.h, _np_ptr(a)), "kg_get_last_action_host")
+        return a
+
+    def last_step_ms(self):
+        ms = C.c_float()
+        self._chk(self.lib.kg_last_step_ms(self.h, C.byref(ms)), "kg_last_step_ms")
+        return ms.value
+
+    def stats(self):
+        out = (C.c_longlong * 4)()
+        self._chk(self.lib.kg_get_stats(self.h, out), "kg_get_stats")
+        return {"mpr_pairs": out[0], "newton_iters": out[1], "contact_overflow": out[2], "substeps": out[3]}
+
+    # ---- host-buffer API (numpy)
+    def reset_host(self, shape, euler, objpos, mask=None):
+        n = self.n
+        shape = np.ascontiguousarray(shape, dtype=np.int32).reshape(n)
+        euler = np.ascontiguousarray(euler, dtype=np.float32).reshape(3, n)
+        objpos = np.ascontiguousarray(objpos, dtype=np.float32).reshape(3, n)
+        obs = np.zeros((82, n), dtype=np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.int32).reshape(n)
+        self._chk(self.lib.kg_reset_host(self.h, None if m is None else _np_ptr(m), _np_ptr(shape), _np_ptr(euler), _np_ptr(objpos),
+                                         _np_ptr(obs)), "kg_reset_host")
+        return obs
+
+    def step_host(self, action=None, expert_mode=0, obs_out=None, reward_out=None, done_out=None):
+        n = self.n
+        a = None if action is None else np.ascontiguousarray(action, dtype=np.float32).reshape(4, n)
+        obs = np.zeros((82, n), dtype=np.float32) if obs_out is None else obs_out
+        rew = np.zeros(n, dtype=np.float32) if reward_out is None else reward_out
+        done = np.zeros(n, dtype=np.int32) if done_out is None else done_out
+        self._chk(self.lib.kg_step_host(self.h, None if a is None else _np_ptr(a), int(expert_mode), _np_ptr(obs), _np_ptr(rew),
+                                        _np_ptr(done)), "kg_step_host")
+        return obs, rew, done
+
+    def get_state_host(self):
+        qpos = np.zeros((16, self.n), dtype=np.float32)
+        qvel = np.zeros((15, self.n), dtype=np.float32)
+        self._chk(self.lib.kg_get_state_host(self.h, _np_ptr(qpos), _np_ptr(qvel)), "kg_get_state_host")
+        return qpos, qvel
+
+    def set_state_host(self, qpos=None, qvel=None):
+        qp = None if qpos is None else np.ascontiguousarray(qpos, dtype=np.float32).reshape(16, self.n)
+        qv = None if qvel is None else np.ascontiguousarray(qvel, dtype=np.float32).reshape(15, self.n)
+        self._chk(self.lib.kg_set_state_host(self.h, None if qp is None else _np_ptr(qp), None if qv is None else _np_ptr(qv)),
+                  "kg_set_state_host")
+
+    def forward_debug(self, env, ctrl):
+        c = np.ascontiguousarray(ctrl, dtype=np.float32).reshape(9)
+        out = np.zeros(_lib.DEBUG_FLOATS, dtype=np.float32)
+        self._chk(self.lib.kg_forward_debug(self.h, int(env), _np_ptr(c), _np_ptr(out)), "kg_forward_debug")
+        ncon = int(out[300])
+        con = out[301:301 + 8 * 23].reshape(23, 8)
+        return {"M": out[:225].reshape(15, 15), "bias": out[225:240], "fsmooth": out[240:255], "qacc_smooth": out[255:270],
+                "qacc": out[270:285], "ftotal": out[285:300], "ncon": ncon, "con": con[:min(ncon, 23)],
+                "geom_xpos": out[485:512].reshape(9, 3), "geom_xmat": out[512:593].reshape(9, 9)}
