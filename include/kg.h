@@ -87,6 +87,10 @@ int kg_get_last_action_host(kg_handle h, float *action_host);
  * overflowed the per-env contact capacity, [3] substeps executed. */
 int kg_get_stats(kg_handle h, long long stats_host[4]);
 
+/* Profiling builds (-DKG_PROF): SM cycles summed over envs per stage since the last call:
+ * [0] kinematics+dynamics [1] collision [2] constraint rows [3] solver [4] Euler [5] rays [6] obs; zeros otherwise. */
+int kg_get_prof(kg_handle h, long long cycles_host[8]);
+
 /* Test hook: one mj_forward of env `env` with the given ctrl[9]; dumps intermediates to host memory.
  * out layout (floats): M[225] bias[15] fsmooth[15] qacc_smooth[15] qacc[15] ftotal[15] ncon[1]
  * con[23][8]{dist,pos3,n3,mu} geom_xpos[27] geom_xmat[81]  -> 225+75+1+184+108 = 593 floats. */

@@ -14,7 +14,9 @@
 
 #ifndef KG_EMU
 #include <cuda_runtime.h>
+#ifndef KG_WARPS
 #define KG_WARPS 8
+#endif
 __constant__ KgModel c_model;
 #endif
 
@@ -114,7 +116,7 @@ KG_DEV void kg_debug_run(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int e
             if (9 + l < ws.ngroup) {
                 int s = ws.gslot[9 + l];
                 o[0] = ws.st_dist[s]; o[1] = ws.st_pos[s][0]; o[2] = ws.st_pos[s][1]; o[3] = ws.st_pos[s][2];
-                o[4] = ws.st_n[s][0]; o[5] = ws.st_n[s][1]; o[6] = ws.st_n[s][2]; o[7] = ws.st_mu[s] + 10.f * ws.st_g1[s] + 100.f * ws.st_g2[s];
+                o[4] = ws.st_n[s][0]; o[5] = ws.st_n[s][1]; o[6] = ws.st_n[s][2]; o[7] = ws.gmu[9 + l] + 10.f * ws.st_g1[s] + 100.f * ws.st_g2[s];
             } else for (int c = 0; c < 8; c++) o[c] = 0.f;
         }
         for (int i = l; i < 27; i += 32) out[485 + i] = ws.gpos[i / 3][i % 3];
@@ -163,6 +165,9 @@ static KgWS g_ws;
 #endif
 
 static size_t ws_bytes() { return sizeof(KgWS); }
+#ifndef KG_EMU
+static_assert(2 * (KG_WARPS * sizeof(KgWS) + 1024) <= 227 * 1024 || KG_WARPS != 8, "KgWS too large for two 8-warp CTAs per SM");
+#endif
 
 static int launch_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
 #ifdef KG_EMU
@@ -241,7 +246,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     TRY(be_alloc(h, (void **)&A.qpos, 16 * N * 4)); TRY(be_alloc(h, (void **)&A.qvel, 15 * N * 4)); TRY(be_alloc(h, (void **)&A.qwarm, 15 * N * 4));
     TRY(be_alloc(h, (void **)&A.hand_quat, 4 * N * 4)); TRY(be_alloc(h, (void **)&A.shape, N * 4)); TRY(be_alloc(h, (void **)&A.elapsed, N * 4));
     TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
-    TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
+    TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&A.prof, 8 * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
     TRY(be_alloc(h, (void **)&h->d_action, 4 * N * 4)); TRY(be_alloc(h, (void **)&h->d_obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&h->d_reward, N * 4));
     TRY(be_alloc(h, (void **)&h->d_done, N * 4)); TRY(be_alloc(h, (void **)&h->d_mask, N * 4)); TRY(be_alloc(h, (void **)&h->d_shape, N * 4));
     TRY(be_alloc(h, (void **)&h->d_euler, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_objp, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_q, 31 * N * 4));
@@ -349,6 +354,13 @@ int kg_get_stats(kg_handle h, long long out[4]) {
     for (int i = 0; i < 4; i++) out[i] = s[i];
     return KG_OK;
 }
+int kg_get_prof(kg_handle h, long long out[8]) {
+    if (!h || !out) return KG_EINVAL;
+    long long z[8] = {0};
+    TRY(be_d2h(h, out, h->A.prof, sizeof z)); TRY(be_sync(h));
+    TRY(be_h2d(h, h->A.prof, z, sizeof z)); TRY(be_sync(h));
+    return KG_OK;
+}
 int kg_forward_debug(kg_handle h, int env, const float *ctrl, float *out) {
     if (!h || env < 0 || env >= h->n || !ctrl || !out) return KG_EINVAL;
     TRY(be_h2d(h, h->d_ctrl, ctrl, 9 * 4));
@@ -361,6 +373,10 @@ int kg_forward_debug(kg_handle h, int env, const float *ctrl, float *out) {
     TRY(be_d2h(h, out, h->d_debug, KG_DEBUG_FLOATS * 4));
     return be_sync(h);
 }
+#ifdef KG_EMU
+// emulation-only: 0 = lanes of a phase run 0..31, 1 = 31..0 (tests/test_emu_race.py)
+int kg_emu_set_lane_order(int reverse) { kg_emu_lane_order = reverse ? 1 : 0; return KG_OK; }
+#endif
 int kg_last_step_ms(kg_handle h, float *ms) {
     if (!h || !ms) return KG_EINVAL;
 #ifdef KG_EMU

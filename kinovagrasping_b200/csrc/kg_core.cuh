@@ -27,16 +27,31 @@
 
 #if defined(__CUDA_ARCH__)
 #define KG_DEV __device__ __forceinline__
+#define KG_NOINL __device__ __noinline__
 #define KG_PHASE(l) for (int l = kg_lane, kg_once_ = 0; kg_once_ < 1; ++kg_once_)
 #define KG_SYNC() __syncwarp()
 #define KG_LDG4(p) __ldg((const float4 *)(p))
+// Block-wide rendezvous between pipeline stages.  Functionally unnecessary (warps never share data); it keeps the
+// 8 warps of a CTA inside the same ~10-20 KB code region so that they share instruction-cache lines (the whole
+// substep is ~100 KB of SASS, far beyond the 32 KB L1.5 I-cache; ncu showed stall_no_instruction dominating).
+#ifdef KG_STAGE_SYNC
+#define KG_STAGE() __syncthreads()
 #else
+#define KG_STAGE() ((void)0)
+#endif
+#else
+#define KG_STAGE() ((void)0)
 #if defined(__CUDACC__)
 #define KG_DEV __host__ __device__ inline
+#define KG_NOINL __host__ __device__
 #else
 #define KG_DEV inline
+#define KG_NOINL inline
 #endif
-#define KG_PHASE(l) for (int l = 0; l < 32; ++l)
+// host emulation: the lanes of a phase run one after the other, forwards or (race check) backwards.  A phase that
+// reads something another lane writes in the same phase gives different results in the two orders.
+static int kg_emu_lane_order = 0;
+#define KG_PHASE(l) for (int kg_i_ = 0, l = kg_emu_lane_order ? 31 : 0; kg_i_ < 32; ++kg_i_, l += kg_emu_lane_order ? -1 : 1)
 #define KG_SYNC() ((void)0)
 struct kg_float4 { float x, y, z, w; };
 #define KG_LDG4(p) (*(const kg_float4 *)(p))
@@ -56,6 +71,9 @@ struct kg_float4 { float x, y, z, w; };
 #endif
 #define KG_LS_MAXIT 12
 
+// obs / rangefinder staging aliases the constraint Jacobian storage (J is dead outside the substep loop)
+#define KG_WSOBS(ws) ((ws).J)
+#define KG_RANGE(ws) ((ws).J + 96)
 struct KgWS {
     // ---- state
     float qpos[16], qvel[16], qwarm[16], ctrl[12], sens_q[12];
@@ -71,24 +89,28 @@ struct KgWS {
     float bias[16], fs[16], qas[16], qacc[16], Mdq[16], grad[16], dir[16], Md[16], ftot[16];
     float sbias[3][3];
     // ---- contact staging
-    float st_dist[KG_NSTAGE], st_mu[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3];
+    float st_dist[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3];
     unsigned char st_g1[KG_NSTAGE], st_g2[KG_NSTAGE];
     int cnt[32];
     unsigned short cv1[32], cv2[32];   // warm-start hull vertices per pair lane
+    float sep[32][3];                  // cached separating axis per hull-pair lane (valid while sepok[l] != 0)
+    int sepok[32];
     // ---- constraint groups: slot g<3 tendon, 3..8 limits, 9.. contacts
     int gtype[32], gslot[32], ngroup, ncon_total;
-    float gmu[32], garef[32][4], gD[32][4];
+    float gmu[32], garef[32][4], gD[32];
     float J[KG_NBASE * KG_JS];
     float bdot[KG_NBASE + 2], bdir[KG_NBASE + 2], bw[KG_NBASE + 2];
     float red[32], red2[32];
     // ---- solver scalars (written by lane 0, read by all after a sync)
-    float s_alpha, s_cost, s_flag, s_lo, s_hi, s_glo, s_ghi;
-    int s_iter, s_done;
+    float s_alpha, s_cost, s_flag, s_lo, s_hi, s_glo, s_ghi, s_cost2;
+    int s_iter, s_done, s_exact;
+    // ---- closed-form M^-1 scratch (per finger lane)
+    float mv_S[3][6], mv_r[3][3], mv_y[3][2], mv_i[3][3], mv_xs[4], mv_red3[32];
     // ---- statistics
     int stat_mpr, stat_newton, stat_overflow, stat_pad;
-    // ---- obs staging
-    float range[KG_NSITE + 3];
-    float obs[KG_NOBS + 2];
+#ifdef KG_PROF
+    long long prof[8];                 // cycles per stage (kin+dyn, collision, rows, solve, euler, rays, obs)
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------ small math
@@ -166,7 +188,7 @@ KG_DEV void kg_episode_constants(const KgModel &m, KgWS &ws, const float *hand_q
             kg_mulmv(ws.sax[l], ws.Rh, m.slide_axes + 3 * l);
         }
         if (l == 3) kg_mulmm(ws.gmat[1], ws.Rh, m.palm_gR);
-        ws.cv1[l] = 0; ws.cv2[l] = 0;
+        ws.cv1[l] = 0; ws.cv2[l] = 0; ws.sepok[l] = 0;
     }
     KG_SYNC();
 }
@@ -308,7 +330,7 @@ KG_DEV void kg_dynamics(const KgModel &m, KgWS &ws, int kg_lane) {
 
 // ------------------------------------------------------------------------------------------------ dense 15x15 Cholesky
 // A (stride KG_MS) -> lower factor in Lm.  Lanes own rows.
-KG_DEV void kg_cholesky(const float *A, float *Lm, float diag_add, int kg_lane) {
+KG_NOINL void kg_cholesky(const float *A, float *Lm, float diag_add, int kg_lane) {
     for (int j = 0; j < KG_NV; j++) {
         KG_PHASE(l) {
             if (l == j) {
@@ -329,7 +351,7 @@ KG_DEV void kg_cholesky(const float *A, float *Lm, float diag_add, int kg_lane) 
     }
 }
 // x <- (L L^T)^-1 x, executed by lane 0 (latency-bound either way at n = 15)
-KG_DEV void kg_cholsolve(const float *Lm, float *x, int kg_lane) {
+KG_NOINL void kg_cholsolve(const float *Lm, float *x, int kg_lane) {
     KG_PHASE(l) {
         if (l == 0) {
             float y[KG_NV];
@@ -341,47 +363,36 @@ KG_DEV void kg_cholsolve(const float *Lm, float *x, int kg_lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ P5 hull support (hill climbing)
-struct KgHull {
-    const float *vert;           // xyzw
-    const int *adjs;
-    const unsigned short *adj;
-    float pos[3], R[9];
-    float margin;
-    int cur;                     // warm-start vertex (kept across calls and substeps)
-};
-KG_DEV void kg_hull_init(const KgModel &m, KgHull &h, int mesh, const float *pos, const float *R, float margin, int start) {
+// Support point of geom g's convex hull, inflated by `margin`, along the unit world direction dir, expressed relative
+// to `origin`.  The geom frame comes from the workspace (shared memory), the vertices from the read-only hull table;
+// `cur` is the warm-start vertex (kept per pair across calls and substeps).
+KG_DEV void kg_support(const KgModel &m, const KgWS &ws, int g, int mesh, int &cur, const float *dir, const float *origin, float margin, float *out) {
     const KgMesh &mi = m.mesh[mesh];
-    h.vert = m.hull_vert + 4 * (size_t)mi.vert0;
-    h.adjs = m.adj_start + mi.vert0;
-    h.adj = m.adj;
-    kg_copy(h.pos, pos);
-    for (int i = 0; i < 9; i++) h.R[i] = R[i];
-    h.margin = margin;
-    h.cur = start < mi.nvert ? start : 0;
-}
-// support point of the (margin-inflated) hull along the unit world direction dir
-KG_DEV void kg_support(KgHull &h, const float *dir, float *out) {
+    const float *vert = m.hull_vert + 4 * (size_t)mi.vert0;
+    const int *adjs = m.adj_start + mi.vert0;
+    const unsigned short *adj = m.adj;
+    const float *R = ws.gmat[g];
     float ld[3];
-    kg_multmv(ld, h.R, dir);
-    int cur = h.cur;
-    auto v = KG_LDG4(h.vert + 4 * cur);
+    kg_multmv(ld, R, dir);
+    int c = cur;
+    auto v = KG_LDG4(vert + 4 * c);
     float best = v.x * ld[0] + v.y * ld[1] + v.z * ld[2];
     float bx = v.x, by = v.y, bz = v.z;
     for (int guard = 0; guard < 1024; guard++) {
-        int a0 = h.adjs[cur], a1 = h.adjs[cur + 1], nxt = cur;
+        int a0 = adjs[c], a1 = adjs[c + 1], nxt = c;
         for (int a = a0; a < a1; a++) {
-            int nb = h.adj[a];
-            auto w = KG_LDG4(h.vert + 4 * nb);
+            int nb = adj[a];
+            auto w = KG_LDG4(vert + 4 * nb);
             float d = w.x * ld[0] + w.y * ld[1] + w.z * ld[2];
             if (d > best) { best = d; nxt = nb; bx = w.x; by = w.y; bz = w.z; }
         }
-        if (nxt == cur) break;
-        cur = nxt;
+        if (nxt == c) break;
+        c = nxt;
     }
-    h.cur = cur;
+    cur = c;
     float lv[3] = {bx, by, bz}, wv[3];
-    kg_mulmv(wv, h.R, lv);
-    for (int c = 0; c < 3; c++) out[c] = wv[c] + h.pos[c] + h.margin * dir[c];
+    kg_mulmv(wv, R, lv);
+    for (int k = 0; k < 3; k++) out[k] = wv[k] + (ws.gpos[g][k] - origin[k]) + margin * dir[k];
 }
 
 // ------------------------------------------------------------------------------------------------ P5 MPR (libccd's algorithm, fp32)
@@ -396,12 +407,6 @@ KG_DEV bool kg_feq(float a, float b) {
     if (ab < FLT_EPSILON) return true;
     float fa = fabsf(a), fb = fabsf(b);
     return ab < FLT_EPSILON * (fb > fa ? fb : fa);
-}
-KG_DEV void kg_mink(KgHull &h1, KgHull &h2, const float *dir, KgSupp &s) {
-    float nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
-    kg_support(h1, dir, s.v1);
-    kg_support(h2, nd, v2);
-    kg_sub(s.v, s.v1, v2);
 }
 KG_DEV void kg_portal_dir(const KgSupp *p, float *dir) {
     float a[3], b[3];
@@ -448,92 +453,116 @@ KG_DEV float kg_tri_dist2(const float *x0, const float *Bv, const float *C, floa
     dv = kg_seg_dist2(Bv, C, w2); if (dv < dist) { dist = dv; kg_copy(w, w2); }
     return dist;
 }
-// returns true when the inflated hulls overlap; coordinates are relative to hull 1's centre
-KG_DEV bool kg_mpr(KgHull &h1, KgHull &h2, float *depth, float *nrm, float *pos) {
-    KgSupp p[4], v4;
+// ccdMPRPenetration on the margin-inflated hulls of geoms g1, g2; coordinates are relative to geom g1's centre.
+// Written as ONE loop around ONE support evaluation (state machine over libccd's discoverPortal / refinePortal /
+// findPenetr) so that the hill-climbing support code exists once in the instruction stream.
+// On a "no overlap" exit that PROVES separation (support of A-B along dir is negative) *sep_found is set and dir is
+// returned in nrm: the caller re-tests that axis first in the next substep (two supports instead of a full MPR).
+KG_DEV bool kg_mpr(const KgModel &m, const KgWS &ws, int g1, int mesh1, int g2, int mesh2, float hmargin, int &cur1, int &cur2,
+                   float *depth, float *nrm, float *pos, int *sep_found) {
+    *sep_found = 0;
+    KgSupp p[4];
     float dir[3], va[3], vb[3], dot;
-    kg_copy(p[0].v1, h1.pos);
-    kg_sub(p[0].v, h1.pos, h2.pos);
+    const float *org = ws.gpos[g1];
+    p[0].v1[0] = p[0].v1[1] = p[0].v1[2] = 0.f;
+    kg_sub(p[0].v, ws.gpos[g1], ws.gpos[g2]);
     if (kg_iszero(p[0].v[0]) && kg_iszero(p[0].v[1]) && kg_iszero(p[0].v[2])) p[0].v[0] += KG_CCD_EPS * 10;
     for (int c = 0; c < 3; c++) dir[c] = -p[0].v[c];
     kg_normalize(dir);
-    kg_mink(h1, h2, dir, p[1]);
-    dot = kg_dot(p[1].v, dir);
-    if (kg_iszero(dot) || dot < 0) return false;
-    kg_cross(dir, p[0].v, p[1].v);
-    if (kg_iszero(kg_dot(dir, dir))) {
-        if (kg_iszero(p[1].v[0]) && kg_iszero(p[1].v[1]) && kg_iszero(p[1].v[2])) return false;   // touching, no normal
-        *depth = sqrtf(kg_dot(p[1].v, p[1].v));
-        kg_copy(nrm, p[1].v); kg_normalize(nrm);
-        for (int c = 0; c < 3; c++) pos[c] = p[1].v1[c] - 0.5f * p[1].v[c];
-        return true;
-    }
-    kg_normalize(dir);
-    kg_mink(h1, h2, dir, p[2]);
-    dot = kg_dot(p[2].v, dir);
-    if (kg_iszero(dot) || dot < 0) return false;
-    kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
-    kg_cross(dir, va, vb); kg_normalize(dir);
-    if (kg_dot(dir, p[0].v) > 0) { KgSupp t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
-    for (int guard = 0;; guard++) {
-        if (guard > 100) return false;
-        kg_mink(h1, h2, dir, p[3]);
-        dot = kg_dot(p[3].v, dir);
-        if (kg_iszero(dot) || dot < 0) return false;
-        bool cont = false;
-        kg_cross(va, p[1].v, p[3].v); dot = kg_dot(va, p[0].v);
-        if (dot < 0 && !kg_iszero(dot)) { p[2] = p[3]; cont = true; }
-        if (!cont) {
-            kg_cross(va, p[3].v, p[2].v); dot = kg_dot(va, p[0].v);
-            if (dot < 0 && !kg_iszero(dot)) { p[1] = p[3]; cont = true; }
+    int state = 0, it = 0;
+    for (int guard = 0; guard < 400; guard++) {
+        KgSupp s;
+        {
+            float nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
+            kg_support(m, ws, g1, mesh1, cur1, dir, org, hmargin, s.v1);
+            kg_support(m, ws, g2, mesh2, cur2, nd, org, hmargin, v2);
+            kg_sub(s.v, s.v1, v2);
         }
-        if (!cont) break;
-        kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
-        kg_cross(dir, va, vb); kg_normalize(dir);
-    }
-    for (int guard = 0;; guard++) {
-        if (guard > 200) return false;
-        kg_portal_dir(p, dir);
-        dot = kg_dot(dir, p[1].v);
-        if (kg_iszero(dot) || dot > 0) break;
-        kg_mink(h1, h2, dir, v4);
-        dot = kg_dot(v4.v, dir);
-        if (!(kg_iszero(dot) || dot > 0) || kg_reach_tol(p, v4, dir)) return false;
-        kg_expand_portal(p, v4);
-    }
-    for (int it = 0;; it++) {
-        kg_portal_dir(p, dir);
-        kg_mink(h1, h2, dir, v4);
-        if (kg_reach_tol(p, v4, dir) || it > KG_MPR_ITER) {
-            float w[3];
-            *depth = sqrtf(kg_tri_dist2(p[1].v, p[2].v, p[3].v, w));
-            if (kg_iszero(w[0]) && kg_iszero(w[1]) && kg_iszero(w[2])) kg_copy(w, dir);
-            kg_copy(nrm, w); kg_normalize(nrm);
-            // findPos: barycentric coordinates of the origin in the portal tetrahedron
-            float b[4], t[3], sum;
-            kg_cross(t, p[1].v, p[2].v); b[0] = kg_dot(t, p[3].v);
-            kg_cross(t, p[3].v, p[2].v); b[1] = kg_dot(t, p[0].v);
-            kg_cross(t, p[0].v, p[1].v); b[2] = kg_dot(t, p[3].v);
-            kg_cross(t, p[2].v, p[1].v); b[3] = kg_dot(t, p[0].v);
-            sum = b[0] + b[1] + b[2] + b[3];
-            if (kg_iszero(sum) || sum < 0) {
-                kg_portal_dir(p, dir);
-                b[0] = 0;
-                kg_cross(t, p[2].v, p[3].v); b[1] = kg_dot(t, dir);
-                kg_cross(t, p[3].v, p[1].v); b[2] = kg_dot(t, dir);
-                kg_cross(t, p[1].v, p[2].v); b[3] = kg_dot(t, dir);
-                sum = b[1] + b[2] + b[3];
+        bool check_portal = false;
+        if (state == 0) {
+            p[1] = s;
+            dot = kg_dot(s.v, dir);
+            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; kg_copy(nrm, dir); } return false; }
+            kg_cross(dir, p[0].v, p[1].v);
+            if (kg_iszero(kg_dot(dir, dir))) {
+                if (kg_iszero(p[1].v[0]) && kg_iszero(p[1].v[1]) && kg_iszero(p[1].v[2])) return false;   // touching, no normal
+                *depth = sqrtf(kg_dot(p[1].v, p[1].v));
+                kg_copy(nrm, p[1].v); kg_normalize(nrm);
+                for (int c = 0; c < 3; c++) pos[c] = p[1].v1[c] - 0.5f * p[1].v[c];
+                return true;
             }
-            float inv = 1.0f / sum;
-            for (int c = 0; c < 3; c++) {
-                float s1 = 0, sv = 0;
-                for (int i = 0; i < 4; i++) { s1 += b[i] * p[i].v1[c]; sv += b[i] * p[i].v[c]; }
-                pos[c] = (s1 - 0.5f * sv) * inv;   // (p1 + p2)/2 with p2 = p1 - v
+            kg_normalize(dir);
+            state = 1;
+        } else if (state == 1) {
+            p[2] = s;
+            dot = kg_dot(s.v, dir);
+            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; kg_copy(nrm, dir); } return false; }
+            kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
+            kg_cross(dir, va, vb); kg_normalize(dir);
+            if (kg_dot(dir, p[0].v) > 0) { KgSupp t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+            state = 2;
+        } else if (state == 2) {
+            p[3] = s;
+            dot = kg_dot(s.v, dir);
+            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; kg_copy(nrm, dir); } return false; }
+            bool cont = false;
+            kg_cross(va, p[1].v, p[3].v); dot = kg_dot(va, p[0].v);
+            if (dot < 0 && !kg_iszero(dot)) { p[2] = p[3]; cont = true; }
+            if (!cont) {
+                kg_cross(va, p[3].v, p[2].v); dot = kg_dot(va, p[0].v);
+                if (dot < 0 && !kg_iszero(dot)) { p[1] = p[3]; cont = true; }
             }
-            return true;
+            if (cont) {
+                kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
+                kg_cross(dir, va, vb); kg_normalize(dir);
+            } else { state = 3; check_portal = true; }
+        } else if (state == 3) {
+            dot = kg_dot(s.v, dir);
+            if (!(kg_iszero(dot) || dot > 0)) { *sep_found = 1; kg_copy(nrm, dir); return false; }
+            if (kg_reach_tol(p, s, dir)) return false;
+            kg_expand_portal(p, s);
+            check_portal = true;
+        } else {
+            if (kg_reach_tol(p, s, dir) || it > KG_MPR_ITER) {
+                float w[3];
+                *depth = sqrtf(kg_tri_dist2(p[1].v, p[2].v, p[3].v, w));
+                if (kg_iszero(w[0]) && kg_iszero(w[1]) && kg_iszero(w[2])) kg_copy(w, dir);
+                kg_copy(nrm, w); kg_normalize(nrm);
+                // findPos: barycentric coordinates of the origin in the portal tetrahedron
+                float b[4], t[3], sum;
+                kg_cross(t, p[1].v, p[2].v); b[0] = kg_dot(t, p[3].v);
+                kg_cross(t, p[3].v, p[2].v); b[1] = kg_dot(t, p[0].v);
+                kg_cross(t, p[0].v, p[1].v); b[2] = kg_dot(t, p[3].v);
+                kg_cross(t, p[2].v, p[1].v); b[3] = kg_dot(t, p[0].v);
+                sum = b[0] + b[1] + b[2] + b[3];
+                if (kg_iszero(sum) || sum < 0) {
+                    kg_portal_dir(p, dir);
+                    b[0] = 0;
+                    kg_cross(t, p[2].v, p[3].v); b[1] = kg_dot(t, dir);
+                    kg_cross(t, p[3].v, p[1].v); b[2] = kg_dot(t, dir);
+                    kg_cross(t, p[1].v, p[2].v); b[3] = kg_dot(t, dir);
+                    sum = b[1] + b[2] + b[3];
+                }
+                float inv = 1.0f / sum;
+                for (int c = 0; c < 3; c++) {
+                    float s1 = 0, sv = 0;
+                    for (int i = 0; i < 4; i++) { s1 += b[i] * p[i].v1[c]; sv += b[i] * p[i].v[c]; }
+                    pos[c] = (s1 - 0.5f * sv) * inv;   // (p1 + p2)/2 with p2 = p1 - v
+                }
+                return true;
+            }
+            kg_expand_portal(p, s);
+            it++;
+            kg_portal_dir(p, dir);
         }
-        kg_expand_portal(p, v4);
+        if (check_portal) {
+            // refinePortal's loop head: does the portal already enclose the origin ray?
+            kg_portal_dir(p, dir);
+            dot = kg_dot(dir, p[1].v);
+            if (kg_iszero(dot) || dot > 0) state = 4;   // findPenetr starts with this same portal direction
+        }
     }
+    return false;
 }
 
 // mju_makeFrame on frame[0:3] = normal
@@ -566,27 +595,32 @@ KG_DEV float kg_rbound(const KgModel &m, const KgWS &ws, int g) { return g == 8 
 KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
     KG_PHASE(l) {
         int n = 0;
+        float tried = 0.f;
         if (l < 30) {
             int g1, g2;
             kg_pair_of_lane(l, g1, g2);
             const float margin = m.margin;
-            float rb2 = kg_rbound(m, ws, g2);
+            const float rb2 = kg_rbound(m, ws, g2);
+            const int mesh2 = kg_mesh_of_geom(ws, g2);
             if (l < 8) {
                 const int base = 4 * l;
                 if (ws.gpos[g2][2] <= rb2 + margin) {
-                    KgHull h;
-                    kg_hull_init(m, h, kg_mesh_of_geom(ws, g2), ws.gpos[g2], ws.gmat[g2], 0.f, ws.cv2[l]);
-                    float nd[3] = {0, 0, -1}, w[3];
-                    kg_support(h, nd, w);
-                    ws.cv2[l] = (unsigned short)h.cur;
+                    const float nd[3] = {0, 0, -1}, zero[3] = {0, 0, 0};
+                    float w[3];
+                    int cur = ws.cv2[l];
+                    if (cur >= m.mesh[mesh2].nvert) cur = 0;
+                    kg_support(m, ws, g2, mesh2, cur, nd, zero, 0.f, w);
+                    ws.cv2[l] = (unsigned short)cur;
                     if (w[2] <= margin) {
                         const float thresh = 0.3f * rb2;
-                        int best = h.cur, a0 = h.adjs[best], a1 = h.adjs[best + 1];
+                        const float *vert = m.hull_vert + 4 * (size_t)m.mesh[mesh2].vert0;
+                        const int *adjs = m.adj_start + m.mesh[mesh2].vert0;
+                        int a0 = adjs[cur], a1 = adjs[cur + 1];
                         for (int c = -1; c < a1 - a0 && n < 4; c++) {
                             if (c >= 0) {
-                                auto lv = KG_LDG4(h.vert + 4 * h.adj[a0 + c]);
+                                auto lv = KG_LDG4(vert + 4 * m.adj[a0 + c]);
                                 float lvv[3] = {lv.x, lv.y, lv.z};
-                                kg_mulmv(w, h.R, lvv); kg_add(w, w, h.pos);
+                                kg_mulmv(w, ws.gmat[g2], lvv); kg_add(w, w, ws.gpos[g2]);
                             }
                             float dist = w[2];
                             if (dist > margin) continue;
@@ -598,7 +632,7 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
                             }
                             if (skip) continue;
                             int s = base + n;
-                            ws.st_dist[s] = dist; ws.st_mu[s] = m.pair_mu[l]; kg_copy(ws.st_pos[s], cp);
+                            ws.st_dist[s] = dist; kg_copy(ws.st_pos[s], cp);
                             ws.st_n[s][0] = 0; ws.st_n[s][1] = 0; ws.st_n[s][2] = 1;
                             ws.st_g1[s] = 0; ws.st_g2[s] = (unsigned char)g2;
                             n++;
@@ -610,27 +644,39 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
                 kg_sub(df, ws.gpos[g2], ws.gpos[g1]);
                 float lim = rb1 + rb2 + margin;
                 if (kg_dot(df, df) <= lim * lim) {
-                    KgHull h1, h2;
-                    const float zero[3] = {0, 0, 0};
-                    kg_hull_init(m, h1, kg_mesh_of_geom(ws, g1), zero, ws.gmat[g1], 0.5f * margin, ws.cv1[l]);
-                    kg_hull_init(m, h2, kg_mesh_of_geom(ws, g2), df, ws.gmat[g2], 0.5f * margin, ws.cv2[l]);
+                    const int mesh1 = kg_mesh_of_geom(ws, g1);
+                    int c1 = ws.cv1[l], c2 = ws.cv2[l];
+                    if (c1 >= m.mesh[mesh1].nvert) c1 = 0;
+                    if (c2 >= m.mesh[mesh2].nvert) c2 = 0;
                     float depth, nrm[3], pos[3];
-                    bool hit = kg_mpr(h1, h2, &depth, nrm, pos);
-                    ws.cv1[l] = (unsigned short)h1.cur; ws.cv2[l] = (unsigned short)h2.cur;
-                    n = 0;
-                    ws.red2[l] = 1.f;
+                    bool hit = false, separated = false;
+                    int sepf = 0;
+                    if (ws.sepok[l]) {
+                        // the axis that separated the inflated hulls in the previous substep: still separating?
+                        float n0[3] = {ws.sep[l][0], ws.sep[l][1], ws.sep[l][2]}, nn[3] = {-n0[0], -n0[1], -n0[2]}, s1[3], s2[3];
+                        kg_support(m, ws, g1, mesh1, c1, n0, ws.gpos[g1], 0.5f * margin, s1);
+                        kg_support(m, ws, g2, mesh2, c2, nn, ws.gpos[g1], 0.5f * margin, s2);
+                        separated = (kg_dot(s1, n0) - kg_dot(s2, n0)) < 0.f;
+                    }
+                    if (!separated) {
+                        hit = kg_mpr(m, ws, g1, mesh1, g2, mesh2, 0.5f * margin, c1, c2, &depth, nrm, pos, &sepf);
+                        tried = 1.f;
+                        ws.sepok[l] = sepf;
+                        if (sepf) { ws.sep[l][0] = nrm[0]; ws.sep[l][1] = nrm[1]; ws.sep[l][2] = nrm[2]; }
+                    }
+                    ws.cv1[l] = (unsigned short)c1; ws.cv2[l] = (unsigned short)c2;
                     if (hit && depth > 0.f) {
                         int s = 32 + (l - 8);
-                        ws.st_dist[s] = margin - depth; ws.st_mu[s] = m.pair_mu[l];
+                        ws.st_dist[s] = margin - depth;
                         kg_add(ws.st_pos[s], pos, ws.gpos[g1]);
                         kg_copy(ws.st_n[s], nrm);
                         ws.st_g1[s] = (unsigned char)g1; ws.st_g2[s] = (unsigned char)g2;
                         n = 1;
                     }
-                } else ws.red2[l] = 0.f;
+                } else ws.sepok[l] = 0;
             }
         }
-        if (l < 8 || l >= 30) ws.red2[l] = 0.f;
+        ws.red2[l] = tried;
         ws.cnt[l] = n;
     }
     KG_SYNC();
@@ -667,7 +713,7 @@ KG_DEV float kg_impedance(const KgModel &m, float r) {
     return m.dmin + y * (m.dmax - m.dmin);
 }
 // translational Jacobian row of the point p on the body carrying geom g, projected on f, ADDED with sign sg
-KG_DEV void kg_jac_add(const KgWS &ws, int g, const float *p, const float *f, float sg, float *row) {
+KG_NOINL void kg_jac_add(const KgWS &ws, int g, const float *p, const float *f, float sg, float *row) {
     if (g == 0) return;
     if (g == 8) {
         float r[3], t[3];
@@ -697,7 +743,7 @@ KG_DEV void kg_make_rows(const KgModel &m, KgWS &ws, int kg_lane) {
             float vel = ws.qvel[3 + 2 * l] - 2.f * ws.qvel[4 + 2 * l];
             float imp = kg_impedance(m, pos);
             float R = fmaxf((1.f - imp) / imp * m.tendon_invw[l], 1e-15f);
-            ws.gtype[l] = 1; ws.gD[l][0] = 1.f / R; ws.garef[l][0] = -Bd * vel - K * imp * pos;
+            ws.gtype[l] = 1; ws.gD[l] = 1.f / R; ws.garef[l][0] = -Bd * vel - K * imp * pos;
         } else if (l < 9) {
             int a = l - 3, j = a < 3 ? a : 3 + 2 * (a - 3);
             float lo = a < 3 ? m.slide_range[2 * a] : m.finger_range[2 * (a - 3)];
@@ -710,7 +756,7 @@ KG_DEV void kg_make_rows(const KgModel &m, KgWS &ws, int kg_lane) {
                 row[j] = sgn;
                 float imp = kg_impedance(m, pos);
                 float R = fmaxf((1.f - imp) / imp * m.dof_invw[j], 1e-15f);
-                ws.gtype[l] = 2; ws.gD[l][0] = 1.f / R; ws.garef[l][0] = -Bd * sgn * ws.qvel[j] - K * imp * pos;
+                ws.gtype[l] = 2; ws.gD[l] = 1.f / R; ws.garef[l][0] = -Bd * sgn * ws.qvel[j] - K * imp * pos;
             } else ws.gtype[l] = 0;
         } else if (l < ws.ngroup) {
             int s = ws.gslot[l], g1 = ws.st_g1[s], g2 = ws.st_g2[s];
@@ -725,14 +771,14 @@ KG_DEV void kg_make_rows(const KgModel &m, KgWS &ws, int kg_lane) {
             kg_jac_add(ws, g2, p, t2, 1.f, r2); kg_jac_add(ws, g1, p, t2, -1.f, r2);
             float vn = 0, v1 = 0, v2 = 0;
             for (int j = 0; j < KG_NV; j++) { float v = ws.qvel[j]; vn += rn[j] * v; v1 += r1[j] * v; v2 += r2[j] * v; }
-            float mu = ws.st_mu[s], dist = ws.st_dist[s], r = dist - m.margin;
+            float mu = m.pair_mu[s < 32 ? (s >> 2) : 8 + (s - 32)], dist = ws.st_dist[s], r = dist - m.margin;   // staging slot -> pair lane
             float tran = (g1 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g1]) + (g2 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g2]);
             float imp = kg_impedance(m, r);
             float R = fmaxf((1.f - imp) / imp * (tran + mu * mu * tran), 1e-15f);
             float Rpy = fmaxf(2.f * mu * mu / m.impratio * R, 1e-15f);
             float Dv = 1.f / Rpy, kr = K * imp * r;
             ws.gmu[l] = mu;
-            for (int k = 0; k < 4; k++) ws.gD[l][k] = Dv;
+            ws.gD[l] = Dv;
             ws.garef[l][0] = -Bd * (vn + mu * v1) - kr; ws.garef[l][1] = -Bd * (vn - mu * v1) - kr;
             ws.garef[l][2] = -Bd * (vn + mu * v2) - kr; ws.garef[l][3] = -Bd * (vn - mu * v2) - kr;
         }
@@ -756,7 +802,7 @@ KG_DEV int kg_group_rows(const KgWS &ws, int g, const float *bd, float *jar) {
 KG_DEV int kg_nbase(const KgWS &ws) { return 9 + 3 * (ws.ngroup - 9); }
 
 // base-row products  out[b] = J_b . x   (lane per base row)
-KG_DEV void kg_base_dots(KgWS &ws, const float *x, float *out, int kg_lane) {
+KG_NOINL void kg_base_dots(KgWS &ws, const float *x, float *out, int kg_lane) {
     KG_PHASE(l) {
         int nb = kg_nbase(ws);
         for (int b = l; b < nb; b += 32) {
@@ -770,13 +816,90 @@ KG_DEV void kg_base_dots(KgWS &ws, const float *x, float *out, int kg_lane) {
     KG_SYNC();
 }
 
+// x <- (M + diag_add I)^-1 x in closed form.  M is block diagonal {hand 9x9, object 6x6}; the hand block is
+// [mu I3, C; C^T, blockdiag(A_1,A_2,A_3)] (slides couple to each finger's 2x2 hinge block, fingers do not couple to
+// each other), the object block is [m' I3, T; T^T, Io'].  Both are eliminated by 3x3 Schur complements: lanes 0..2
+// own a finger, lane 3 the object.  (The reference engine does a generic sparse L^T D L here.)
+KG_DEV void kg_inv3_sym(const float *S, float *Si) {   // inverse of a symmetric 3x3 given as xx,yy,zz,xy,xz,yz
+    float c0 = S[1] * S[2] - S[5] * S[5], c1 = S[4] * S[5] - S[3] * S[2], c2 = S[3] * S[5] - S[4] * S[1];
+    float det = S[0] * c0 + S[3] * c1 + S[4] * c2, id = 1.0f / det;
+    Si[0] = c0 * id; Si[3] = c1 * id; Si[4] = c2 * id;
+    Si[1] = (S[0] * S[2] - S[4] * S[4]) * id; Si[5] = (S[3] * S[4] - S[0] * S[5]) * id;
+    Si[2] = (S[0] * S[1] - S[3] * S[3]) * id;
+}
+KG_NOINL void kg_minv(KgWS &ws, float diag_add, float *x, int kg_lane) {
+    KG_PHASE(l) {
+        if (l < 3) {
+            int h1 = 3 + 2 * l, h2 = 4 + 2 * l;
+            float a11 = ws.M[h1 * KG_MS + h1] + diag_add, a12 = ws.M[h1 * KG_MS + h2], a22 = ws.M[h2 * KG_MS + h2] + diag_add;
+            float id = 1.0f / (a11 * a22 - a12 * a12);
+            float i11 = a22 * id, i12 = -a12 * id, i22 = a11 * id;
+            float f1 = x[h1], f2 = x[h2];
+            float y1 = i11 * f1 + i12 * f2, y2 = i12 * f1 + i22 * f2;   // A^-1 f_h
+            float g[3][2], S[6], r[3];
+            for (int i = 0; i < 3; i++) {
+                float c1 = ws.M[i * KG_MS + h1], c2 = ws.M[i * KG_MS + h2];
+                g[i][0] = c1 * i11 + c2 * i12; g[i][1] = c1 * i12 + c2 * i22;   // G = C A^-1
+                r[i] = c1 * y1 + c2 * y2;
+            }
+            const int ii[6] = {0, 1, 2, 0, 0, 1}, jj[6] = {0, 1, 2, 1, 2, 2};
+            for (int e = 0; e < 6; e++) S[e] = g[ii[e]][0] * ws.M[jj[e] * KG_MS + h1] + g[ii[e]][1] * ws.M[jj[e] * KG_MS + h2];
+            for (int e = 0; e < 6; e++) ws.mv_S[l][e] = S[e];
+            for (int i = 0; i < 3; i++) ws.mv_r[l][i] = r[i];
+            ws.mv_y[l][0] = y1; ws.mv_y[l][1] = y2;
+            ws.mv_i[l][0] = i11; ws.mv_i[l][1] = i12; ws.mv_i[l][2] = i22;
+        } else if (l == 3) {
+            // object: x_t = (f_t - T x_r)/m',  (Io' - T^T T / m') x_r = f_r - T^T f_t / m'
+            float mp = ws.M[9 * KG_MS + 9] + diag_add, im = 1.0f / mp;
+            float T[9], S[6], rhs[3];
+            for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) T[3 * j + i] = ws.M[(9 + j) * KG_MS + 12 + i];
+            const int ii[6] = {0, 1, 2, 0, 0, 1}, jj[6] = {0, 1, 2, 1, 2, 2};
+            for (int e = 0; e < 6; e++) {
+                float tt = T[ii[e]] * T[jj[e]] + T[3 + ii[e]] * T[3 + jj[e]] + T[6 + ii[e]] * T[6 + jj[e]];
+                S[e] = ws.M[(12 + ii[e]) * KG_MS + 12 + jj[e]] + (ii[e] == jj[e] ? diag_add : 0.f) - tt * im;
+            }
+            float ft[3] = {x[9], x[10], x[11]};
+            for (int i = 0; i < 3; i++) rhs[i] = x[12 + i] - (T[i] * ft[0] + T[3 + i] * ft[1] + T[6 + i] * ft[2]) * im;
+            float Si[6];
+            kg_inv3_sym(S, Si);
+            float xr[3] = {Si[0] * rhs[0] + Si[3] * rhs[1] + Si[4] * rhs[2], Si[3] * rhs[0] + Si[1] * rhs[1] + Si[5] * rhs[2],
+                           Si[4] * rhs[0] + Si[5] * rhs[1] + Si[2] * rhs[2]};
+            for (int j = 0; j < 3; j++) x[9 + j] = (ft[j] - (T[3 * j] * xr[0] + T[3 * j + 1] * xr[1] + T[3 * j + 2] * xr[2])) * im;
+            for (int i = 0; i < 3; i++) x[12 + i] = xr[i];
+        }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        if (l < 3) {
+            // every finger lane redundantly solves the 3x3 slide system, then back-substitutes its own hinges
+            float mu = ws.M[0] + diag_add;
+            float S[6], rhs[3], Si[6];
+            for (int e = 0; e < 6; e++) S[e] = (e < 3 ? mu : 0.f) - ws.mv_S[0][e] - ws.mv_S[1][e] - ws.mv_S[2][e];
+            for (int i = 0; i < 3; i++) rhs[i] = x[i] - ws.mv_r[0][i] - ws.mv_r[1][i] - ws.mv_r[2][i];
+            kg_inv3_sym(S, Si);
+            float xs[3] = {Si[0] * rhs[0] + Si[3] * rhs[1] + Si[4] * rhs[2], Si[3] * rhs[0] + Si[1] * rhs[1] + Si[5] * rhs[2],
+                           Si[4] * rhs[0] + Si[5] * rhs[1] + Si[2] * rhs[2]};
+            int h1 = 3 + 2 * l, h2 = 4 + 2 * l;
+            float t1 = 0.f, t2 = 0.f;   // C^T xs
+            for (int i = 0; i < 3; i++) { t1 += ws.M[i * KG_MS + h1] * xs[i]; t2 += ws.M[i * KG_MS + h2] * xs[i]; }
+            ws.mv_y[l][0] -= ws.mv_i[l][0] * t1 + ws.mv_i[l][1] * t2;
+            ws.mv_y[l][1] -= ws.mv_i[l][1] * t1 + ws.mv_i[l][2] * t2;
+            if (l == 0) { ws.mv_xs[0] = xs[0]; ws.mv_xs[1] = xs[1]; ws.mv_xs[2] = xs[2]; }
+        }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        if (l < 3) { x[l] = ws.mv_xs[l]; x[3 + 2 * l] = ws.mv_y[l][0]; x[4 + 2 * l] = ws.mv_y[l][1]; }
+    }
+    KG_SYNC();
+}
+
 KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
     const float tol = 1e-8f;
     // ---- unconstrained acceleration
     KG_PHASE(l) { if (l < KG_NV) ws.qas[l] = ws.fs[l]; }
     KG_SYNC();
-    kg_cholesky(ws.M, ws.L, 0.f, kg_lane);
-    kg_cholsolve(ws.L, ws.qas, kg_lane);
+    kg_minv(ws, 0.f, ws.qas, kg_lane);
     // ---- warm start: the cheaper of qacc_warmstart and qacc_smooth
     kg_base_dots(ws, ws.qwarm, ws.bdot, kg_lane);
     kg_base_dots(ws, ws.qas, ws.bdir, kg_lane);
@@ -790,9 +913,9 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
         }
         float jar[4];
         int n = kg_group_rows(ws, l, ws.bdot, jar);
-        for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) cw += 0.5f * ws.gD[l][k] * jar[k] * jar[k];
+        for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) cw += 0.5f * ws.gD[l] * jar[k] * jar[k];
         n = kg_group_rows(ws, l, ws.bdir, jar);
-        for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) cs += 0.5f * ws.gD[l][k] * jar[k] * jar[k];
+        for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) cs += 0.5f * ws.gD[l] * jar[k] * jar[k];
         ws.red[l] = cw; ws.red2[l] = cs;
     }
     KG_SYNC();
@@ -804,25 +927,24 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
             if (use_smooth) ws.Mdq[l] = 0.f;
         }
         if (use_smooth) { int nb = kg_nbase(ws); for (int b = l; b < nb; b += 32) ws.bdot[b] = ws.bdir[b]; }
-        if (l == 0) { ws.s_cost = 3.0e38f; ws.s_done = 0; ws.s_iter = 0; }
+        if (l == 0) { ws.s_cost = 3.0e38f; ws.s_done = 0; ws.s_iter = 0; ws.s_exact = 0; }
     }
     KG_SYNC();
     const float scale = m.shape[ws.shape].scale;
     for (int iter = 0; iter <= KG_NEWTON_MAXIT; iter++) {
-        // ---- (a) rows at the current point: cost, weights, Hessian coefficients
+        // ---- (a) rows at the current point: cost and the weights w = D * jar of the active rows
         KG_PHASE(l) {
             float c = 0.f;
             if (l < KG_NV) c = 0.5f * ws.Mdq[l] * (ws.qacc[l] - ws.qas[l]);
             float jar[4], w[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
             int n = kg_group_rows(ws, l, ws.bdot, jar);
-            for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) { a[k] = ws.gD[l][k]; w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
+            for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) { a[k] = ws.gD[l]; w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
             if (n == 1) { ws.bw[l] = w[0]; ws.garef[l][1] = a[0]; }
             else if (n == 4) {
                 int b = 9 + 3 * (l - 9);
                 float mu = ws.gmu[l];
                 ws.bw[b] = w[0] + w[1] + w[2] + w[3]; ws.bw[b + 1] = mu * (w[0] - w[1]); ws.bw[b + 2] = mu * (w[2] - w[3]);
             } else if (l < 9) ws.bw[l] = 0.f;
-            // Hessian coefficients of the group are recomputed in (b) from the same activity test
             ws.red[l] = c;
         }
         KG_SYNC();
@@ -830,10 +952,11 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
             float cost = kg_total(ws.red, l);
             if (l == 0) {
                 // MuJoCo's test is scale*improvement < 1e-8; in fp32 the cost itself only carries ~2^-23 relative
-                // precision, so an "improvement" below that noise floor is treated as converged as well
+                // precision, so an "improvement" below that noise floor is treated as converged as well.  s_exact: the
+                // previous Newton step was a full step on an unchanged active set, i.e. the exact minimiser.
                 float improvement = scale * (ws.s_cost - cost);
                 if (iter > 0 && improvement < tol + 2.4e-7f * scale * fabsf(cost)) ws.s_done = 1;
-                if (iter == KG_NEWTON_MAXIT) ws.s_done = 1;
+                if (ws.s_exact || iter == KG_NEWTON_MAXIT) ws.s_done = 1;
                 ws.s_cost = cost;
             }
         }
@@ -841,9 +964,10 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
         if (ws.s_done) break;
         // ---- (b) gradient and Hessian (lane = dof / row of H)
         KG_PHASE(l) {
-            float gsq = 0.f;
+            float gsq = 0.f, gab = 0.f;
             if (l < KG_NV) {
                 float gr = ws.Mdq[l];
+                gab = fabsf(gr);
                 float h[KG_NV];
 #pragma unroll
                 for (int j = 0; j < KG_NV; j++) h[j] = ws.M[l * KG_MS + j];
@@ -853,7 +977,8 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
                     if (tp < 3) {
                         const float *row = ws.J + g * KG_JS;
                         float ji = row[l];
-                        gr += ji * ws.bw[g];
+                        float t = ji * ws.bw[g];
+                        gr += t; gab += fabsf(t);
                         float u = ji * ws.garef[g][1];   // D * active stored by (a)
                         if (u != 0.f) {
 #pragma unroll
@@ -863,10 +988,11 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
                         int b = 9 + 3 * (g - 9);
                         const float *rn = ws.J + b * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
                         float jn = rn[l], j1 = r1[l], j2 = r2[l];
-                        gr += jn * ws.bw[b] + j1 * ws.bw[b + 1] + j2 * ws.bw[b + 2];
+                        float t0 = jn * ws.bw[b], t1 = j1 * ws.bw[b + 1], t2 = j2 * ws.bw[b + 2];
+                        gr += t0 + t1 + t2; gab += fabsf(t0) + fabsf(t1) + fabsf(t2);
                         float jar[4], a[4];
                         kg_group_rows(ws, g, ws.bdot, jar);
-                        for (int k = 0; k < 4; k++) a[k] = jar[k] < 0.f ? ws.gD[g][k] : 0.f;
+                        for (int k = 0; k < 4; k++) a[k] = jar[k] < 0.f ? ws.gD[g] : 0.f;
                         float mu = ws.gmu[g];
                         float A = a[0] + a[1] + a[2] + a[3], B1 = mu * (a[0] - a[1]), C1 = mu * mu * (a[0] + a[1]);
                         float B2 = mu * (a[2] - a[3]), C2 = mu * mu * (a[2] + a[3]);
@@ -882,12 +1008,13 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
 #pragma unroll
                 for (int j = 0; j < KG_NV; j++) ws.L[l * KG_MS + j] = h[j];
             }
-            ws.red[l] = gsq;
+            ws.red[l] = gsq; ws.red2[l] = gab * gab;
         }
         KG_SYNC();
         KG_PHASE(l) {
-            float gn = kg_total(ws.red, l);
-            if (l == 0 && scale * sqrtf(gn) < tol) ws.s_done = 1;
+            float gn = kg_total(ws.red, l), ga = kg_total(ws.red2, l);
+            // gradient test: MuJoCo's absolute 1e-8, or the fp32 rounding floor of the sum that formed the gradient
+            if (l == 0 && (scale * sqrtf(gn) < tol || gn < 1.4e-13f * ga)) ws.s_done = 1;
             if (l < KG_NV) ws.dir[l] = -ws.grad[l];
         }
         KG_SYNC();
@@ -913,13 +1040,17 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
             if (l == 0) { ws.s_glo = p1; ws.s_ghi = p2; }   // Gauss part of phi'(0), phi''
         }
         KG_SYNC();
-        // ---- (d) exact line search: root of the piecewise-linear phi'(alpha), safeguarded Newton
+        // ---- (d) exact line search: root of the piecewise-linear phi'(alpha).  dir is the exact Newton direction of
+        // the current quadratic piece, so the first candidate is alpha = 1; if no row changes activity on [0,1] that is
+        // the exact minimiser (phi'(1) = 0 up to rounding) and the solve is finished.
         {
-            float alpha = 0.f, lo = 0.f, hi = -1.f, g0abs = 0.f, best_alpha = 0.f;
+            float alpha = 1.f, lo = 0.f, hi = -1.f, g0abs = 0.f, best_alpha = 1.f;
+            int exact = 0;
             const float gp1 = ws.s_glo, gp2 = ws.s_ghi;
             for (int ls = 0; ls < KG_LS_MAXIT; ls++) {
                 KG_PHASE(l) {
-                    float d1 = 0.f, d2 = 0.f, jar[4], jv[4];
+                    float d1 = 0.f, d2 = 0.f, d0 = 0.f, jar[4], jv[4];
+                    int nchg = 0;
                     int n = kg_group_rows(ws, l, ws.bdot, jar);
                     if (n == 1) jv[0] = ws.bdir[l];
                     else if (n == 4) {
@@ -927,26 +1058,40 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
                         float mu = ws.gmu[l], nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
                         jv[0] = nn + t1; jv[1] = nn - t1; jv[2] = nn + t2; jv[3] = nn - t2;
                     }
+                    const bool eq = ws.gtype[l] == 1;
                     for (int k = 0; k < n; k++) {
                         float x = jar[k] + alpha * jv[k];
-                        if (ws.gtype[l] == 1 || x < 0.f) { float dj = ws.gD[l][k] * jv[k]; d1 += dj * x; d2 += dj * jv[k]; }
+                        float dj = ws.gD[l] * jv[k];
+                        bool act0 = eq || jar[k] < 0.f, act = eq || x < 0.f;
+                        if (act) { d1 += dj * x; d2 += dj * jv[k]; }
+                        if (act0) d0 += dj * jar[k];
+                        nchg += (act != act0);
                     }
                     ws.red[l] = d1; ws.red2[l] = d2;
+                    if (ls == 0) { ws.cnt[l] = nchg; ws.mv_red3[l] = d0; }
                 }
                 KG_SYNC();
-                float gA = 0.f, hA = 0.f;
                 KG_PHASE(l) {
                     float d1 = kg_total(ws.red, l), d2 = kg_total(ws.red2, l);
+                    if (ls == 0) {
+                        float d0 = kg_total(ws.mv_red3, l);
+                        int chg = 0;
+                        for (int k = 0; k < 32; k++) chg += ws.cnt[k];
+                        if (l == 0) { ws.s_flag = (float)chg; ws.s_cost2 = d0; }
+                    }
                     if (l == 0) { ws.s_lo = d1; ws.s_hi = d2; }
                 }
                 KG_SYNC();
-                gA = gp1 + alpha * gp2 + ws.s_lo; hA = gp2 + ws.s_hi;
-                if (ls == 0) { g0abs = fabsf(gA); if (gA >= 0.f) { best_alpha = 0.f; break; } }
+                float gA = gp1 + alpha * gp2 + ws.s_lo, hA = gp2 + ws.s_hi;
+                if (ls == 0) {
+                    g0abs = fabsf(gp1 + ws.s_cost2);              // |phi'(0)|
+                    if (ws.s_flag == 0.f) { exact = 1; best_alpha = 1.f; break; }
+                }
                 best_alpha = alpha;
                 if (fabsf(gA) <= 1e-6f * g0abs) break;
                 if (gA < 0.f) lo = alpha; else hi = alpha;
                 float nxt = alpha - gA / hA;
-                if (!(nxt > lo) || (hi > 0.f && !(nxt < hi))) nxt = hi > 0.f ? 0.5f * (lo + hi) : 2.f * alpha + 1.f;
+                if (!(nxt > lo) || (hi > 0.f && !(nxt < hi))) nxt = hi > 0.f ? 0.5f * (lo + hi) : 2.f * alpha;
                 if (fabsf(nxt - alpha) <= 1e-7f * fmaxf(1.f, fabsf(alpha))) { best_alpha = nxt; break; }
                 alpha = nxt;
                 best_alpha = alpha;
@@ -956,7 +1101,7 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
                 if (l < KG_NV) { ws.qacc[l] += al * ws.dir[l]; ws.Mdq[l] += al * ws.Md[l]; }
                 int nb = kg_nbase(ws);
                 for (int b = l; b < nb; b += 32) ws.bdot[b] += al * ws.bdir[b];
-                if (l == 0) { ws.s_iter = iter + 1; }
+                if (l == 0) { ws.s_iter = iter + 1; ws.s_exact = exact; }
             }
             KG_SYNC();
         }
@@ -981,8 +1126,7 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
 // ------------------------------------------------------------------------------------------------ P9 Euler
 KG_DEV void kg_euler(const KgModel &m, KgWS &ws, int kg_lane) {
     const float h = m.timestep;
-    kg_cholesky(ws.M, ws.L, h * m.damping, kg_lane);
-    kg_cholsolve(ws.L, ws.ftot, kg_lane);
+    kg_minv(ws, h * m.damping, ws.ftot, kg_lane);     // implicit joint damping: (M + h B) a = f
     KG_PHASE(l) {
         if (l < KG_NV) {
             float v = ws.qvel[l] + h * ws.ftot[l];
@@ -1014,14 +1158,32 @@ KG_DEV void kg_euler(const KgModel &m, KgWS &ws, int kg_lane) {
     KG_SYNC();
 }
 
+#if defined(KG_PROF) && defined(__CUDA_ARCH__)
+#define KG_TIC() long long kg_t0_ = clock64()
+#define KG_TOC(i) do { long long t_ = clock64(); if (kg_lane == 0) ws.prof[i] += t_ - kg_t0_; kg_t0_ = t_; } while (0)
+#else
+#define KG_TIC() ((void)0)
+#define KG_TOC(i) ((void)0)
+#endif
 // one mj_step: forward (positions -> constraints -> solve) + integrate
 KG_DEV void kg_substep(const KgModel &m, KgWS &ws, int kg_lane) {
+    KG_STAGE();
+    KG_TIC();
     kg_kinematics(m, ws, kg_lane);
     kg_dynamics(m, ws, kg_lane);
+    KG_TOC(0);
+    KG_STAGE();
     kg_collision(m, ws, kg_lane);
+    KG_TOC(1);
+    KG_STAGE();
     kg_make_rows(m, ws, kg_lane);
+    KG_TOC(2);
+    KG_STAGE();
     kg_solve(m, ws, kg_lane);
+    KG_TOC(3);
+    KG_STAGE();
     kg_euler(m, ws, kg_lane);
+    KG_TOC(4);
 }
 
 // ------------------------------------------------------------------------------------------------ P8 rangefinder rays
@@ -1108,7 +1270,7 @@ KG_DEV float kg_ray_mesh(const KgModel &m, int mesh, const float *gpos, const fl
     }
     return best;
 }
-KG_DEV void kg_site_pose(const KgModel &m, const KgWS &ws, int i, float *p, float *z) {
+KG_NOINL void kg_site_pose(const KgModel &m, const KgWS &ws, int i, float *p, float *z) {
     int sb = m.site_body[i];
     float R[9], org[3];
     if (sb == 0) { for (int c = 0; c < 9; c++) R[c] = ws.Rh[c]; kg_copy(org, ws.hp); }
@@ -1143,7 +1305,7 @@ KG_DEV void kg_rays(const KgModel &m, KgWS &ws, int kg_lane) {
                 float x = kg_ray_mesh(m, kg_mesh_of_geom(ws, g), ws.gpos[g], ws.gmat[g], size, p, v);
                 if (x >= 0.f && (best < 0.f || x < best)) best = x;
             }
-            ws.range[l] = best;
+            KG_RANGE(ws)[l] = best;
         }
     }
     KG_SYNC();
@@ -1174,7 +1336,7 @@ KG_DEV void kg_obs(const KgModel &m, KgWS &ws, int kg_lane, float *reward, int *
         kg_multmv(w, T, off); kg_add(wrist, ws.gpos[1], w);
         kg_mulmv(tt, T, wrist);
         const float *obj = ws.gpos[8];
-        float *o = ws.obs;
+        float *o = KG_WSOBS(ws);
         const int fgeom[6] = {2, 4, 6, 3, 5, 7};
         if (l < 6) {
             float r[3];
@@ -1205,13 +1367,13 @@ KG_DEV void kg_obs(const KgModel &m, KgWS &ws, int kg_lane, float *reward, int *
             kg_sub(df, p, obj);
             o[36 + l - 8] = sqrtf(kg_dot(df, df));
         }
-        if (l < KG_NSITE) { float r = ws.range[l]; o[50 + l] = (r == -1.f) ? 6.f : r; }
+        if (l < KG_NSITE) { float r = KG_RANGE(ws)[l]; o[50 + l] = (r == -1.f) ? 6.f : r; }
     }
     KG_SYNC();
     // experimental_sensor (O8), reward (R1)
     KG_PHASE(l) {
         if (l == 0) {
-            float *o = ws.obs;
+            float *o = KG_WSOBS(ws);
             const float *fl = o;
             float s1[3], s2[3];
             kg_sub(s1, fl, fl + 6); kg_sub(s2, fl, fl + 3);
@@ -1337,6 +1499,7 @@ struct KgEnvArrays {
     float *obs;                   // [82][N] last observation (input of the expert controller)
     float *last_action;           // [4][N] action applied by the last step (given or expert)
     int *stats;                   // [4] mpr pairs, newton iterations, contact overflows, substeps
+    long long *prof;              // [8] KG_PROF builds only
     int N, max_steps;
 };
 
@@ -1346,6 +1509,9 @@ KG_DEV void kg_load_env(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
         if (l < 16) ws.qpos[l] = A.qpos[l * N + env];
         if (l < 15) { ws.qvel[l] = A.qvel[l * N + env]; ws.qwarm[l] = A.qwarm[l * N + env]; }
         if (l == 31) { ws.stat_mpr = 0; ws.stat_newton = 0; ws.stat_overflow = 0; ws.qvel[15] = 0.f; ws.qwarm[15] = 0.f; }
+#ifdef KG_PROF
+        if (l < 8) ws.prof[l] = 0;
+#endif
     }
     KG_SYNC();
     float hq[4] = {A.hand_quat[env], A.hand_quat[A.N + env], A.hand_quat[2 * A.N + env], A.hand_quat[3 * A.N + env]};
@@ -1368,7 +1534,7 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
     float act[4] = {0, 0, 0, 0};
     if (action_in) { for (int c = 0; c < 4; c++) act[c] = action_in[c * A.N + env]; }
     else {
-        KG_PHASE(l) { for (int i = l; i < KG_NOBS; i += 32) ws.obs[i] = A.obs[i * A.N + env]; }
+        KG_PHASE(l) { for (int i = l; i < KG_NOBS; i += 32) KG_WSOBS(ws)[i] = A.obs[i * A.N + env]; }
         KG_SYNC();
         KG_PHASE(l) {
             if (l == 0) {
@@ -1378,7 +1544,7 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
                 e.prev_fx[0] = A.ex_f[2 * N + env]; e.prev_fx[1] = A.ex_f[3 * N + env]; e.prev_fx[2] = A.ex_f[4 * N + env];
                 e.have_prev = A.ex_i[env]; e.num_good = A.ex_i[N + env]; e.total_steps = A.ex_i[2 * N + env];
                 float a4[4];
-                kg_expert_action(e, ws.obs, expert_mode, a4);
+                kg_expert_action(e, KG_WSOBS(ws), expert_mode, a4);
                 A.ex_f[2 * N + env] = e.prev_fx[0]; A.ex_f[3 * N + env] = e.prev_fx[1]; A.ex_f[4 * N + env] = e.prev_fx[2];
                 A.ex_i[env] = e.have_prev; A.ex_i[N + env] = e.num_good; A.ex_i[2 * N + env] = e.total_steps;
                 for (int c = 0; c < 4; c++) ws.red[c] = a4[c];
@@ -1390,13 +1556,16 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
     }
     kg_ctrl_from_action(ws, act, kg_lane);
     for (int s = 0; s < nsub; s++) kg_substep(m, ws, kg_lane);
+    KG_TIC();
     kg_rays(m, ws, kg_lane);
+    KG_TOC(5);
     float rew = 0.f; int dn = 0;
     kg_obs(m, ws, kg_lane, &rew, &dn);
+    KG_TOC(6);
     kg_store_env(ws, A, env, kg_lane);
     KG_PHASE(l) {
         const int N = A.N;
-        for (int i = l; i < KG_NOBS; i += 32) { float v = ws.obs[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
+        for (int i = l; i < KG_NOBS; i += 32) { float v = KG_WSOBS(ws)[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
         if (l == 0) {
             // reward/done were produced by lane 0 of kg_obs; TimeLimit (gym_kinova_gripper/__init__.py:3-7, MAIN:164)
             int el = A.elapsed[env] + 1;
@@ -1407,6 +1576,9 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
             for (int c = 0; c < 4; c++) { A.last_action[c * N + env] = act[c]; if (action_out) action_out[c * N + env] = act[c]; }
 #if defined(__CUDA_ARCH__)
             if (A.stats) { atomicAdd(A.stats, ws.stat_mpr); atomicAdd(A.stats + 1, ws.stat_newton); atomicAdd(A.stats + 2, ws.stat_overflow); atomicAdd(A.stats + 3, nsub); }
+#ifdef KG_PROF
+            if (A.prof) for (int i = 0; i < 8; i++) atomicAdd((unsigned long long *)A.prof + i, (unsigned long long)ws.prof[i]);
+#endif
 #else
             if (A.stats) { A.stats[0] += ws.stat_mpr; A.stats[1] += ws.stat_newton; A.stats[2] += ws.stat_overflow; A.stats[3] += nsub; }
 #endif
@@ -1462,11 +1634,11 @@ KG_DEV void kg_env_reset(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int e
     kg_store_env(ws, A, env, kg_lane);
     KG_PHASE(l) {
         const int N = A.N;
-        for (int i = l; i < KG_NOBS; i += 32) { float v = ws.obs[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
+        for (int i = l; i < KG_NOBS; i += 32) { float v = KG_WSOBS(ws)[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
         if (l < 4) A.hand_quat[l * N + env] = hq[l];
         if (l == 0) {
             A.shape[env] = shape; A.elapsed[env] = 0;
-            A.ex_f[env] = ws.obs[21]; A.ex_f[N + env] = ws.obs[81];
+            A.ex_f[env] = KG_WSOBS(ws)[21]; A.ex_f[N + env] = KG_WSOBS(ws)[81];
             A.ex_f[2 * N + env] = 0.f; A.ex_f[3 * N + env] = 0.f; A.ex_f[4 * N + env] = 0.f;
             A.ex_i[env] = 0; A.ex_i[N + env] = 0; A.ex_i[2 * N + env] = 0;
         }

@@ -94,6 +94,7 @@ void kgo_env_reset(const KgoModel *m, KgoEnv *e, int shape, const double hand_eu
 /* action: 4 values [wrist, f1, f2, f3].  returns done (incl. TimeLimit). info3 = finger,grasp,lift */
 int kgo_env_step(const KgoModel *m, KgoEnv *e, const double action[4], double obs[KGO_NOBS],
                  double *reward, double info3[3]);
+void kgo_set_rays_every_substep(int on);
 void kgo_get_obs(const KgoModel *m, const KgoState *s, const KgoData *d, int global_rep, double *obs /*82 or 74*/);
 void kgo_ctrl_from_action(const KgoData *d, const double action[4], double ctrl[KGO_NU]);
 /* expert controller (EXP:610-671): mode 0 naive, 1 position-dependent, 2 combined.

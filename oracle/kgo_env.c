@@ -160,10 +160,15 @@ void kgo_env_reset(const KgoModel *m, KgoEnv *e, int shape, const double hand_eu
     e->have_prev = 0; e->num_good_grasps = 0; e->total_steps = 0;
 }
 
+static int g_rays_every_substep = 0;
+/* 1 = compute the 17 rangefinders in every substep, as mj_step does (only the last values are ever read, so results
+ * are identical); used by the CPU-baseline timing so that the oracle carries the reference's cost structure */
+void kgo_set_rays_every_substep(int on) { g_rays_every_substep = on; }
+
 int kgo_env_step(const KgoModel *m, KgoEnv *e, const double action[4], double obs[KGO_NOBS], double *reward, double info3[3]) {
     double ctrl[KGO_NU];
     kgo_ctrl_from_action(&e->d, action, ctrl);
-    for (int k = 0; k < 15; k++) kgo_step(m, &e->st, ctrl, k == 14 ? KGO_RAYS : 0, &e->d);
+    for (int k = 0; k < 15; k++) kgo_step(m, &e->st, ctrl, (k == 14 || g_rays_every_substep) ? KGO_RAYS : 0, &e->d);
     kgo_get_obs(m, &e->st, &e->d, 0, obs);
     /* _get_reward, ENV:661-666 on global obs[23] = object geom z */
     double z = e->d.geom_xpos[24 + 2];

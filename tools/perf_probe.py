@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Kernel-time probe for build variants: python tools/perf_probe.py <lib.so> [envs] [steps].
+Times kg_step_kernel with the library's own CUDA events (kg_last_step_ms) on the configs[1] workload."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from kinovagrasping_b200 import _lib
+from kinovagrasping_b200.handle import Handle
+
+lib = _lib.bind(C.CDLL(os.path.abspath(sys.argv[1])))
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 12
+variant = int(os.environ.get("KG_VARIANT", "1"))
+h = Handle(n, lib=lib)
+shape = (np.arange(n) % 2).astype(np.int32)
+import torch
+sh = torch.from_numpy(shape).cuda()
+done = torch.zeros(n, dtype=torch.int32, device="cuda")
+h.reset_sampled(0, sh.data_ptr(), 0, variant, 0, 1234, 0)
+ms = []
+for t in range(steps):
+    h.step(0, 2, 0, 0, done.data_ptr())
+    ms.append(h.last_step_ms())
+    h.reset_sampled(done.data_ptr(), 0, 0, variant, 0, 1234, 0)
+h.sync()
+st = h.stats()
+ms = np.array(ms)
+print(f"{os.path.basename(sys.argv[1]):28s} envs {n} kernel ms: median {np.median(ms[3:]):.3f} min {ms[3:].min():.3f} max {ms[3:].max():.3f} "
+      f"-> {n * 15 / np.median(ms[3:]) * 1e3:.3e} substeps/s | mpr/sub {st['mpr_pairs'] / st['substeps']:.2f} newton/sub {st['newton_iters'] / st['substeps']:.2f} ovf {st['contact_overflow']}")
+prof = (C.c_longlong * 8)()
+lib.kg_get_prof(h.h, prof)
+tot = sum(prof)
+if tot:
+    names = ["kin+dyn", "collision", "rows", "solve", "euler", "rays", "obs", "-"]
+    print("   stage share: " + "  ".join(f"{nm} {100.0 * c / tot:.1f}%" for nm, c in zip(names, prof) if c) + f" | cycles/substep/env {tot / st['substeps']:.0f}")
