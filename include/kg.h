@@ -87,9 +87,15 @@ int kg_get_last_action_host(kg_handle h, float *action_host);
  * overflowed the per-env contact capacity, [3] substeps executed. */
 int kg_get_stats(kg_handle h, long long stats_host[4]);
 
-/* Profiling builds (-DKG_PROF): SM cycles summed over envs per stage since the last call:
- * [0] kinematics+dynamics [1] collision [2] constraint rows [3] solver [4] Euler [5] rays [6] obs; zeros otherwise. */
-int kg_get_prof(kg_handle h, long long cycles_host[8]);
+/* Profiling builds (-DKG_PROF) only; zeros otherwise.  32 slots since the last call, summed over envs.
+ * SM cycles: [0] kinematics+dynamics [1] barrier wait before collision [2] collision (broadphase, plane, separating-axis
+ * re-test, MPR) [3] contact compaction [4] wait before rows [5] constraint rows [6] wait before solve [7] solver
+ * set-up (M^-1, warm start) [8] cost phase [9] gradient+Hessian [10] Cholesky factor+solve [11] directional products
+ * [12] line search [13] solver epilogue [14] wait before Euler [15] Euler [16] rays [17] obs [18] wait before kinematics
+ * [19] store/load.  Counters: [20] support calls [21] hill-climb moves [22] MPR calls [23] MPR loop iterations
+ * [24] separating-axis re-tests [25] of which still separated [26] plane supports [27] line-search evaluations. */
+#define KG_NPROF 32
+int kg_get_prof(kg_handle h, long long slots_host[KG_NPROF]);
 
 /* Test hook: one mj_forward of env `env` with the given ctrl[9]; dumps intermediates to host memory.
  * out layout (floats): M[225] bias[15] fsmooth[15] qacc_smooth[15] qacc[15] ftotal[15] ncon[1]

@@ -24,6 +24,7 @@
 #include "kg_model.h"
 #include <math.h>
 #include <float.h>
+#include <stddef.h>
 
 #if defined(__CUDA_ARCH__)
 #define KG_DEV __device__ __forceinline__
@@ -70,11 +71,22 @@ struct kg_float4 { float x, y, z, w; };
 #define KG_NEWTON_MAXIT 20             // iteration cap; the loop exits early on the (fp32-aware) 1e-8 tests
 #endif
 #define KG_LS_MAXIT 12
+#define KG_NPROF 32
+
+// Profiling builds (-DKG_PROF): KG_PROBE(i) charges the cycles since the previous probe of this warp to slot i,
+// KG_COUNT(i, n) adds n to counter slot i (any lane).  Slots: kg_get_prof in include/kg.h.
+#if defined(KG_PROF) && defined(__CUDA_ARCH__)
+#define KG_PROBE(i) do { long long t_ = clock64(); if (kg_lane == 0) { ws.prof[i] += t_ - ws.prof_t0; ws.prof_t0 = t_; } } while (0)
+#define KG_COUNT(i, n) atomicAdd((unsigned long long *)&ws.prof[i], (unsigned long long)(n))
+#else
+#define KG_PROBE(i) ((void)0)
+#define KG_COUNT(i, n) ((void)0)
+#endif
 
 // obs / rangefinder staging aliases the constraint Jacobian storage (J is dead outside the substep loop)
 #define KG_WSOBS(ws) ((ws).J)
 #define KG_RANGE(ws) ((ws).J + 96)
-struct KgWS {
+struct alignas(16) KgWS {
     // ---- state
     float qpos[16], qvel[16], qwarm[16], ctrl[12], sens_q[12];
     // ---- per-episode constants
@@ -109,9 +121,11 @@ struct KgWS {
     // ---- statistics
     int stat_mpr, stat_newton, stat_overflow, stat_pad;
 #ifdef KG_PROF
-    long long prof[8];                 // cycles per stage (kin+dyn, collision, rows, solve, euler, rays, obs)
+    long long prof[KG_NPROF], prof_t0;  // see KG_PROBE / kg_get_prof
 #endif
 };
+
+static_assert(offsetof(KgWS, M) % 16 == 0 && offsetof(KgWS, L) % 16 == 0 && sizeof(KgWS) % 16 == 0, "128-bit row access needs 16-byte aligned matrices");
 
 // ------------------------------------------------------------------------------------------------ small math
 KG_DEV float kg_dot(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -329,37 +343,80 @@ KG_DEV void kg_dynamics(const KgModel &m, KgWS &ws, int kg_lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ dense 15x15 Cholesky
-// A (stride KG_MS) -> lower factor in Lm.  Lanes own rows.
-KG_NOINL void kg_cholesky(const float *A, float *Lm, float diag_add, int kg_lane) {
+// x <- (A)^-1 x for the SPD Newton Hessian A (rows of stride KG_MS in shared memory, written by the lanes that own
+// them); on return A holds the lower factor.  GPU: every lane keeps its row in registers and the right-looking
+// factorisation, the forward and the backward substitution exchange pivots / columns with warp shuffles
+// (about 400 warp instructions, no serial lane-0 section).  The host emulation runs the same arithmetic in the same order.
+KG_DEV void kg_chol_factor_solve(float *A, float *x, int kg_lane) {
+#if defined(__CUDA_ARCH__)
+    const unsigned FULL = 0xffffffffu;
+    const int l = kg_lane, r = l < KG_NV ? l : KG_NV - 1;
+    float a[16], invd[KG_NV];
+    {
+        const float4 *row = reinterpret_cast<const float4 *>(A + r * KG_MS);
+        float4 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
+        a[0] = q0.x; a[1] = q0.y; a[2] = q0.z; a[3] = q0.w; a[4] = q1.x; a[5] = q1.y; a[6] = q1.z; a[7] = q1.w;
+        a[8] = q2.x; a[9] = q2.y; a[10] = q2.z; a[11] = q2.w; a[12] = q3.x; a[13] = q3.y; a[14] = q3.z; a[15] = 0.f;
+    }
+    float xi = x[r];
+#pragma unroll
     for (int j = 0; j < KG_NV; j++) {
-        KG_PHASE(l) {
-            if (l == j) {
-                float s = A[j * KG_MS + j] + diag_add;
-                for (int k = 0; k < j; k++) s -= Lm[j * KG_MS + k] * Lm[j * KG_MS + k];
-                Lm[j * KG_MS + j] = sqrtf(fmaxf(s, 1e-20f));
-            }
-        }
-        KG_SYNC();
-        KG_PHASE(l) {
-            if (l > j && l < KG_NV) {
-                float t = A[l * KG_MS + j];
-                for (int k = 0; k < j; k++) t -= Lm[l * KG_MS + k] * Lm[j * KG_MS + k];
-                Lm[l * KG_MS + j] = t / Lm[j * KG_MS + j];
-            }
-        }
-        KG_SYNC();
-    }
-}
-// x <- (L L^T)^-1 x, executed by lane 0 (latency-bound either way at n = 15)
-KG_NOINL void kg_cholsolve(const float *Lm, float *x, int kg_lane) {
-    KG_PHASE(l) {
-        if (l == 0) {
-            float y[KG_NV];
-            for (int i = 0; i < KG_NV; i++) { float t = x[i]; for (int k = 0; k < i; k++) t -= Lm[i * KG_MS + k] * y[k]; y[i] = t / Lm[i * KG_MS + i]; }
-            for (int i = KG_NV - 1; i >= 0; i--) { float t = y[i]; for (int k = i + 1; k < KG_NV; k++) t -= Lm[k * KG_MS + i] * y[k]; y[i] = t / Lm[i * KG_MS + i]; x[i] = y[i]; }
+        float djj = __shfl_sync(FULL, a[j], j);
+        float d = sqrtf(fmaxf(djj, 1e-20f)), inv = 1.0f / d;
+        invd[j] = inv;
+        float lj = (l == j) ? d : a[j] * inv;      // L[l][j] for l >= j (rows above j hold don't-care values)
+        a[j] = lj;
+#pragma unroll
+        for (int k = j + 1; k < KG_NV; k++) {
+            float lkj = __shfl_sync(FULL, lj, k);
+            a[k] = fmaf(-lj, lkj, a[k]);
         }
     }
-    KG_SYNC();
+    // forward substitution L y = x
+#pragma unroll
+    for (int k = 0; k < KG_NV; k++) {
+        float t = __shfl_sync(FULL, xi, k) * invd[k];
+        xi = (l == k) ? t : (l > k ? fmaf(-a[k], t, xi) : xi);
+    }
+    // the backward pass needs column l of L: transpose through shared memory
+    __syncwarp();
+    if (l < KG_NV) {
+        float4 *row = reinterpret_cast<float4 *>(A + l * KG_MS);
+        row[0] = make_float4(a[0], a[1], a[2], a[3]); row[1] = make_float4(a[4], a[5], a[6], a[7]);
+        row[2] = make_float4(a[8], a[9], a[10], a[11]); row[3] = make_float4(a[12], a[13], a[14], 0.f);
+    }
+    __syncwarp();
+    float c[KG_NV];
+#pragma unroll
+    for (int k = 0; k < KG_NV; k++) c[k] = A[k * KG_MS + r];
+#pragma unroll
+    for (int k = KG_NV - 1; k >= 0; k--) {
+        float t = __shfl_sync(FULL, xi, k) * invd[k];
+        xi = (l == k) ? t : (l < k ? fmaf(-c[k], t, xi) : xi);
+    }
+    if (l < KG_NV) x[l] = xi;
+    __syncwarp();
+#else
+    (void)kg_lane;
+    float invd[KG_NV];
+    for (int j = 0; j < KG_NV; j++) {
+        float d = sqrtf(fmaxf(A[j * KG_MS + j], 1e-20f)), inv = 1.0f / d;
+        invd[j] = inv;
+        A[j * KG_MS + j] = d;
+        for (int l = j + 1; l < KG_NV; l++) A[l * KG_MS + j] *= inv;
+        for (int l = j + 1; l < KG_NV; l++) for (int k = j + 1; k <= l; k++) A[l * KG_MS + k] -= A[l * KG_MS + j] * A[k * KG_MS + j];
+    }
+    for (int k = 0; k < KG_NV; k++) {
+        float t = x[k] * invd[k];
+        x[k] = t;
+        for (int l = k + 1; l < KG_NV; l++) x[l] -= A[l * KG_MS + k] * t;
+    }
+    for (int k = KG_NV - 1; k >= 0; k--) {
+        float t = x[k] * invd[k];
+        x[k] = t;
+        for (int l = 0; l < k; l++) x[l] -= A[k * KG_MS + l] * t;
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ P5 hull support (hill climbing)
@@ -388,7 +445,9 @@ KG_DEV void kg_support(const KgModel &m, const KgWS &ws, int g, int mesh, int &c
         }
         if (nxt == c) break;
         c = nxt;
+        KG_COUNT(21, 1);
     }
+    KG_COUNT(20, 1);
     cur = c;
     float lv[3] = {bx, by, bz}, wv[3];
     kg_mulmv(wv, R, lv);
@@ -470,8 +529,10 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgWS &ws, int g1, int mesh1, int g2, 
     for (int c = 0; c < 3; c++) dir[c] = -p[0].v[c];
     kg_normalize(dir);
     int state = 0, it = 0;
+    KG_COUNT(22, 1);
     for (int guard = 0; guard < 400; guard++) {
         KgSupp s;
+        KG_COUNT(23, 1);
         {
             float nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
             kg_support(m, ws, g1, mesh1, cur1, dir, org, hmargin, s.v1);
@@ -610,6 +671,7 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
                     int cur = ws.cv2[l];
                     if (cur >= m.mesh[mesh2].nvert) cur = 0;
                     kg_support(m, ws, g2, mesh2, cur, nd, zero, 0.f, w);
+                    KG_COUNT(26, 1);
                     ws.cv2[l] = (unsigned short)cur;
                     if (w[2] <= margin) {
                         const float thresh = 0.3f * rb2;
@@ -657,6 +719,7 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
                         kg_support(m, ws, g1, mesh1, c1, n0, ws.gpos[g1], 0.5f * margin, s1);
                         kg_support(m, ws, g2, mesh2, c2, nn, ws.gpos[g1], 0.5f * margin, s2);
                         separated = (kg_dot(s1, n0) - kg_dot(s2, n0)) < 0.f;
+                        KG_COUNT(24, 1); KG_COUNT(25, separated ? 1 : 0);
                     }
                     if (!separated) {
                         hit = kg_mpr(m, ws, g1, mesh1, g2, mesh2, 0.5f * margin, c1, c2, &depth, nrm, pos, &sepf);
@@ -680,6 +743,7 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
         ws.cnt[l] = n;
     }
     KG_SYNC();
+    KG_PROBE(2);
     // compaction: contact groups 9.. reference staging slots
     KG_PHASE(l) {
         int off = 0, total = 0;
@@ -931,6 +995,7 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
     }
     KG_SYNC();
     const float scale = m.shape[ws.shape].scale;
+    KG_PROBE(7);
     for (int iter = 0; iter <= KG_NEWTON_MAXIT; iter++) {
         // ---- (a) rows at the current point: cost and the weights w = D * jar of the active rows
         KG_PHASE(l) {
@@ -961,6 +1026,7 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
             }
         }
         KG_SYNC();
+        KG_PROBE(8);
         if (ws.s_done) break;
         // ---- (b) gradient and Hessian (lane = dof / row of H)
         KG_PHASE(l) {
@@ -1018,9 +1084,10 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
             if (l < KG_NV) ws.dir[l] = -ws.grad[l];
         }
         KG_SYNC();
+        KG_PROBE(9);
         if (ws.s_done) break;
-        kg_cholesky(ws.L, ws.L, 0.f, kg_lane);
-        kg_cholsolve(ws.L, ws.dir, kg_lane);
+        kg_chol_factor_solve(ws.L, ws.dir, kg_lane);
+        KG_PROBE(10);
         // ---- (c) directional products
         kg_base_dots(ws, ws.dir, ws.bdir, kg_lane);
         KG_PHASE(l) {
@@ -1040,6 +1107,7 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
             if (l == 0) { ws.s_glo = p1; ws.s_ghi = p2; }   // Gauss part of phi'(0), phi''
         }
         KG_SYNC();
+        KG_PROBE(11);
         // ---- (d) exact line search: root of the piecewise-linear phi'(alpha).  dir is the exact Newton direction of
         // the current quadratic piece, so the first candidate is alpha = 1; if no row changes activity on [0,1] that is
         // the exact minimiser (phi'(1) = 0 up to rounding) and the solve is finished.
@@ -1048,6 +1116,7 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
             int exact = 0;
             const float gp1 = ws.s_glo, gp2 = ws.s_ghi;
             for (int ls = 0; ls < KG_LS_MAXIT; ls++) {
+                if (kg_lane == 0) KG_COUNT(27, 1);
                 KG_PHASE(l) {
                     float d1 = 0.f, d2 = 0.f, d0 = 0.f, jar[4], jv[4];
                     int nchg = 0;
@@ -1104,6 +1173,7 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
                 if (l == 0) { ws.s_iter = iter + 1; ws.s_exact = exact; }
             }
             KG_SYNC();
+            KG_PROBE(12);
         }
     }
     // ---- total force, warm start for the next substep
@@ -1158,32 +1228,29 @@ KG_DEV void kg_euler(const KgModel &m, KgWS &ws, int kg_lane) {
     KG_SYNC();
 }
 
-#if defined(KG_PROF) && defined(__CUDA_ARCH__)
-#define KG_TIC() long long kg_t0_ = clock64()
-#define KG_TOC(i) do { long long t_ = clock64(); if (kg_lane == 0) ws.prof[i] += t_ - kg_t0_; kg_t0_ = t_; } while (0)
-#else
-#define KG_TIC() ((void)0)
-#define KG_TOC(i) ((void)0)
-#endif
 // one mj_step: forward (positions -> constraints -> solve) + integrate
 KG_DEV void kg_substep(const KgModel &m, KgWS &ws, int kg_lane) {
     KG_STAGE();
-    KG_TIC();
+    KG_PROBE(18);
     kg_kinematics(m, ws, kg_lane);
     kg_dynamics(m, ws, kg_lane);
-    KG_TOC(0);
+    KG_PROBE(0);
     KG_STAGE();
+    KG_PROBE(1);
     kg_collision(m, ws, kg_lane);
-    KG_TOC(1);
+    KG_PROBE(3);
     KG_STAGE();
+    KG_PROBE(4);
     kg_make_rows(m, ws, kg_lane);
-    KG_TOC(2);
+    KG_PROBE(5);
     KG_STAGE();
+    KG_PROBE(6);
     kg_solve(m, ws, kg_lane);
-    KG_TOC(3);
+    KG_PROBE(13);
     KG_STAGE();
+    KG_PROBE(14);
     kg_euler(m, ws, kg_lane);
-    KG_TOC(4);
+    KG_PROBE(15);
 }
 
 // ------------------------------------------------------------------------------------------------ P8 rangefinder rays
@@ -1499,7 +1566,7 @@ struct KgEnvArrays {
     float *obs;                   // [82][N] last observation (input of the expert controller)
     float *last_action;           // [4][N] action applied by the last step (given or expert)
     int *stats;                   // [4] mpr pairs, newton iterations, contact overflows, substeps
-    long long *prof;              // [8] KG_PROF builds only
+    long long *prof;              // [KG_NPROF] KG_PROF builds only
     int N, max_steps;
 };
 
@@ -1510,7 +1577,10 @@ KG_DEV void kg_load_env(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
         if (l < 15) { ws.qvel[l] = A.qvel[l * N + env]; ws.qwarm[l] = A.qwarm[l * N + env]; }
         if (l == 31) { ws.stat_mpr = 0; ws.stat_newton = 0; ws.stat_overflow = 0; ws.qvel[15] = 0.f; ws.qwarm[15] = 0.f; }
 #ifdef KG_PROF
-        if (l < 8) ws.prof[l] = 0;
+        if (l < KG_NPROF) ws.prof[l] = 0;
+#if defined(__CUDA_ARCH__)
+        if (l == 0) ws.prof_t0 = clock64();
+#endif
 #endif
     }
     KG_SYNC();
@@ -1556,12 +1626,12 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
     }
     kg_ctrl_from_action(ws, act, kg_lane);
     for (int s = 0; s < nsub; s++) kg_substep(m, ws, kg_lane);
-    KG_TIC();
+    KG_PROBE(19);
     kg_rays(m, ws, kg_lane);
-    KG_TOC(5);
+    KG_PROBE(16);
     float rew = 0.f; int dn = 0;
     kg_obs(m, ws, kg_lane, &rew, &dn);
-    KG_TOC(6);
+    KG_PROBE(17);
     kg_store_env(ws, A, env, kg_lane);
     KG_PHASE(l) {
         const int N = A.N;
@@ -1577,7 +1647,7 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
 #if defined(__CUDA_ARCH__)
             if (A.stats) { atomicAdd(A.stats, ws.stat_mpr); atomicAdd(A.stats + 1, ws.stat_newton); atomicAdd(A.stats + 2, ws.stat_overflow); atomicAdd(A.stats + 3, nsub); }
 #ifdef KG_PROF
-            if (A.prof) for (int i = 0; i < 8; i++) atomicAdd((unsigned long long *)A.prof + i, (unsigned long long)ws.prof[i]);
+            if (A.prof) for (int i = 0; i < KG_NPROF; i++) atomicAdd((unsigned long long *)A.prof + i, (unsigned long long)ws.prof[i]);
 #endif
 #else
             if (A.stats) { A.stats[0] += ws.stat_mpr; A.stats[1] += ws.stat_newton; A.stats[2] += ws.stat_overflow; A.stats[3] += nsub; }

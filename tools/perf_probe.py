@@ -32,9 +32,14 @@ st = h.stats()
 ms = np.array(ms)
 print(f"{os.path.basename(sys.argv[1]):28s} envs {n} kernel ms: median {np.median(ms[3:]):.3f} min {ms[3:].min():.3f} max {ms[3:].max():.3f} "
       f"-> {n * 15 / np.median(ms[3:]) * 1e3:.3e} substeps/s | mpr/sub {st['mpr_pairs'] / st['substeps']:.2f} newton/sub {st['newton_iters'] / st['substeps']:.2f} ovf {st['contact_overflow']}")
-prof = (C.c_longlong * 8)()
+prof = (C.c_longlong * 32)()
 lib.kg_get_prof(h.h, prof)
-tot = sum(prof)
+prof = list(prof)
+tot = sum(prof[:20])
 if tot:
-    names = ["kin+dyn", "collision", "rows", "solve", "euler", "rays", "obs", "-"]
-    print("   stage share: " + "  ".join(f"{nm} {100.0 * c / tot:.1f}%" for nm, c in zip(names, prof) if c) + f" | cycles/substep/env {tot / st['substeps']:.0f}")
+    names = ["kin+dyn", "w>coll", "collision", "compact", "w>rows", "rows", "w>solve", "sol.setup", "sol.cost", "sol.hess", "sol.chol", "sol.dirs",
+             "sol.ls", "sol.epi", "w>euler", "euler", "rays", "obs", "w>kin", "ldst"]
+    print("   cycles: " + "  ".join(f"{nm} {100.0 * c / tot:.1f}%" for nm, c in zip(names, prof) if c) + f" | cycles/substep/env {tot / st['substeps']:.0f}")
+    ss = float(st["substeps"])
+    cn = ["support", "climb", "mpr", "mpr_iter", "sepchk", "sep_ok", "plane_sup", "ls_eval"]
+    print("   per substep: " + "  ".join(f"{nm} {prof[20 + i] / ss:.2f}" for i, nm in enumerate(cn)))
