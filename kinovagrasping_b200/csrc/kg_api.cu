@@ -15,7 +15,10 @@
 #ifndef KG_EMU
 #include <cuda_runtime.h>
 #ifndef KG_WARPS
-#define KG_WARPS 8
+#define KG_WARPS 16         // environments (= warps) per CTA; one CTA per SM: 16 workspaces + the finger hulls fill its shared memory
+#endif
+#ifndef KG_MINBLOCKS
+#define KG_MINBLOCKS 1      // CTAs per SM the register allocation must leave room for (512 threads x 128 registers = the whole file)
 #endif
 __constant__ KgModel c_model;
 #endif
@@ -36,6 +39,7 @@ struct kg_handle_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 #endif
     float last_ms = 0.f;
+    int fhull_bytes = 0;       // shared-memory copy of the finger hulls appended to each CTA's workspaces
 #ifdef KG_EMU
     KgHostTables tables;
 #endif
@@ -95,21 +99,15 @@ KG_DEV KgSample kg_sample_pose(const KgModel &m, unsigned long long seed, int en
 }
 
 // one mj_forward with a dump of the intermediates (test hook behind kg_forward_debug)
-KG_DEV void kg_debug_run(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *ctrl, float *out, int kg_lane) {
+KG_DEV void kg_debug_run(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *ctrl, float *out, int kg_lane, const KgCta &cta) {
     kg_load_env(m, ws, A, env, kg_lane);
     KG_PHASE(l) { if (l < 9) ws.ctrl[l] = ctrl[l]; }
     KG_SYNC();
     kg_kinematics(m, ws, kg_lane);
     kg_dynamics(m, ws, kg_lane);
-    kg_collision(m, ws, kg_lane);
+    kg_collision(m, ws, kg_lane, cta, 0);
     kg_make_rows(m, ws, kg_lane);
-    kg_solve(m, ws, kg_lane);
-    KG_PHASE(l) {
-        for (int i = l; i < 225; i += 32) out[i] = ws.M[(i / 15) * KG_MS + (i % 15)];
-        if (l < 15) {
-            out[225 + l] = ws.bias[l]; out[240 + l] = ws.fs[l]; out[255 + l] = ws.qas[l];
-            out[270 + l] = ws.qacc[l]; out[285 + l] = ws.ftot[l];
-        }
+    KG_PHASE(l) {      // the contact staging shares storage with the solver scratch: dump it before the solve
         if (l == 0) out[300] = (float)ws.ncon_total;
         if (l < KG_MAXCON) {
             float *o = out + 301 + 8 * l;
@@ -119,6 +117,15 @@ KG_DEV void kg_debug_run(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int e
                 o[4] = ws.st_n[s][0]; o[5] = ws.st_n[s][1]; o[6] = ws.st_n[s][2]; o[7] = ws.gmu[9 + l] + 10.f * ws.st_g1[s] + 100.f * ws.st_g2[s];
             } else for (int c = 0; c < 8; c++) o[c] = 0.f;
         }
+    }
+    KG_SYNC();
+    kg_solve(m, ws, kg_lane);
+    KG_PHASE(l) {
+        for (int i = l; i < 225; i += 32) out[i] = ws.M[(i / 15) * KG_MS + (i % 15)];
+        if (l < 15) {
+            out[225 + l] = ws.bias[l]; out[240 + l] = ws.fs[l]; out[255 + l] = ws.qas[l];
+            out[270 + l] = ws.qacc[l]; out[285 + l] = ws.ftot[l];
+        }
         for (int i = l; i < 27; i += 32) out[485 + i] = ws.gpos[i / 3][i % 3];
         for (int i = l; i < 81; i += 32) out[512 + i] = ws.gmat[i / 9][i % 9];
     }
@@ -127,13 +134,31 @@ KG_DEV void kg_debug_run(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int e
 
 // ------------------------------------------------------------------------------------------------ kernels / emu loops
 #ifndef KG_EMU
-__global__ void __launch_bounds__(KG_WARPS * 32) kg_step_kernel(KgEnvArrays A, const float *action, int mode, int nsub, float *obs, float *reward, int *done, float *act_out) {
+// The finger hulls (proximal + distal: the meshes every narrowphase scan touches) are staged once per CTA behind the
+// per-warp workspaces; returns the shared-memory table.
+__device__ __forceinline__ const float *kg_cta_finger_hulls(unsigned char *dst) {
+    const int n4 = c_model.hnpad[1] + c_model.hnpad[2];
+    const float4 *src = reinterpret_cast<const float4 *>(c_model.hull_pad) + c_model.hpad0[1];
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = __ldg(src + i);
+    __syncthreads();
+    return reinterpret_cast<const float *>(dst);
+}
+__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_step_kernel(KgEnvArrays A, const float *action, int mode, int nsub, float *obs, float *reward, int *done, float *act_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * KG_WARPS + warp;
+    unsigned char *tail = smem + KG_WARPS * sizeof(KgWS);
+    KgCta cta;
+    cta.ws_base = reinterpret_cast<KgWS *>(smem); cta.warp = warp;
+    cta.q = reinterpret_cast<int *>(tail); cta.queue = reinterpret_cast<unsigned short *>(tail + 16);
+    if (threadIdx.x < 4) cta.q[threadIdx.x] = 0;
+    const float *fh = kg_cta_finger_hulls(tail + KG_CTA_QBYTES);
     if (env >= A.N) return;
     KgWS &ws = *(reinterpret_cast<KgWS *>(smem) + warp);
-    kg_env_step(c_model, ws, A, env, action, mode, nsub, obs, reward, done, act_out, lane);
+    if (lane == 0) ws.fhull = fh;
+    __syncwarp();
+    kg_env_step(c_model, ws, A, env, action, mode, nsub, obs, reward, done, act_out, lane, cta);
 }
 __global__ void __launch_bounds__(KG_WARPS * 32) kg_reset_kernel(KgEnvArrays A, const int *mask, const int *shape, const float *euler, const float *objp,
                                                                  int sampled, int orient, int variant, int test_table, unsigned long long seed, int *ep_count, int env_offset, float *obs) {
@@ -158,26 +183,36 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_reset_kernel(KgEnvArrays A, 
 __global__ void kg_debug_kernel(KgEnvArrays A, int env, const float *ctrl, float *out) {
     extern __shared__ __align__(16) unsigned char smem[];
     KgWS &ws = *reinterpret_cast<KgWS *>(smem);
-    kg_debug_run(c_model, ws, A, env, ctrl, out, threadIdx.x & 31);
+    unsigned char *tail = smem + sizeof(KgWS);
+    KgCta cta;
+    cta.ws_base = &ws; cta.warp = 0;
+    cta.q = reinterpret_cast<int *>(tail); cta.queue = reinterpret_cast<unsigned short *>(tail + 16);
+    if (threadIdx.x < 4) cta.q[threadIdx.x] = 0;
+    const float *fh = kg_cta_finger_hulls(tail + KG_CTA_QBYTES);
+    if (threadIdx.x == 0) ws.fhull = fh;
+    __syncwarp();
+    kg_debug_run(c_model, ws, A, env, ctrl, out, threadIdx.x & 31, cta);
 }
 #else
 static KgWS g_ws;
+static KgCta g_cta = {&g_ws, 0, nullptr, nullptr};
 #endif
 
 static size_t ws_bytes() { return sizeof(KgWS); }
+#define KG_FHULL_BYTES ((size_t)h->fhull_bytes + KG_CTA_QBYTES)
 #ifndef KG_EMU
-static_assert(2 * (KG_WARPS * sizeof(KgWS) + 1024) <= 227 * 1024 || KG_WARPS != 8, "KgWS too large for two 8-warp CTAs per SM");
+static_assert(KG_WARPS * sizeof(KgWS) + 16 * 1024 <= 227 * 1024, "KG_WARPS workspaces + finger hulls + task queue must fit one SM's shared memory");
 #endif
 
 static int launch_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
 #ifdef KG_EMU
-    for (int env = 0; env < h->n; env++) kg_env_step(h->model, g_ws, h->A, env, action, mode, h->frame_skip, obs, reward, done, act_out, 0);
+    for (int env = 0; env < h->n; env++) kg_env_step(h->model, g_ws, h->A, env, action, mode, h->frame_skip, obs, reward, done, act_out, 0, g_cta);
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)h->stream;
     int blocks = (h->n + KG_WARPS - 1) / KG_WARPS;
     cudaEventRecord(h->ev0, st);
-    kg_step_kernel<<<blocks, KG_WARPS * 32, KG_WARPS * ws_bytes(), st>>>(h->A, action, mode, h->frame_skip, obs, reward, done, act_out);
+    kg_step_kernel<<<blocks, KG_WARPS * 32, KG_WARPS * ws_bytes() + KG_FHULL_BYTES, st>>>(h->A, action, mode, h->frame_skip, obs, reward, done, act_out);
     cudaEventRecord(h->ev1, st);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -225,19 +260,23 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     std::string e = kg_load_model(blob, nbytes, &h->model, &t);
     if (!e.empty()) { h->err = "model card: " + e; return KG_EMODEL; }
     KgModel &m = h->model;
+    h->fhull_bytes = 16 * (m.hnpad[1] + m.hnpad[2]);
+    if (m.hpad0[2] != m.hpad0[1] + m.hnpad[1]) { h->err = "model card: finger hulls must be contiguous"; return KG_EMODEL; }
+    for (int k = 3; k < KG_NMESH; k++) if (m.hnpad[k] > KG_MAXOBJVERT) { h->err = "model card: object hull too large"; return KG_EMODEL; }
 #ifdef KG_EMU
-    m.hull_vert = t.hull_vert.data(); m.adj_start = t.adj_start.data(); m.adj = t.adj.data(); m.tri = t.tri.data();
+    m.hull_vert = t.hull_vert.data(); m.adj_start = t.adj_start.data(); m.adj = t.adj.data(); m.adj8 = t.adj8.data(); m.hull_pad = t.hull_pad.data(); m.tri = t.tri.data();
     m.bvh_lo = t.bvh_lo.data(); m.bvh_hi = t.bvh_hi.data(); m.bvh_meta = t.bvh_meta.data();
     m.pose_train = t.pose_train.data(); m.pose_test = t.pose_test.data();
+    g_ws.fhull = m.hull_pad + 4 * (size_t)m.hpad0[1];     // host emulation: no staging copy
 #else
 #define UP(field, vec) do { void *p_; TRY(be_alloc(h, &p_, (vec).size() * sizeof((vec)[0]))); CUDA_TRY(h, cudaMemcpy(p_, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice)); m.field = (decltype(m.field))p_; } while (0)
-    UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(tri, t.tri);
+    UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(adj8, t.adj8); UP(hull_pad, t.hull_pad); UP(tri, t.tri);
     UP(bvh_lo, t.bvh_lo); UP(bvh_hi, t.bvh_hi); UP(bvh_meta, t.bvh_meta); UP(pose_train, t.pose_train); UP(pose_test, t.pose_test);
 #undef UP
     CUDA_TRY(h, cudaMemcpyToSymbol(c_model, &m, sizeof(KgModel)));
-    CUDA_TRY(h, cudaFuncSetAttribute(kg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes() + KG_FHULL_BYTES)));
     CUDA_TRY(h, cudaFuncSetAttribute(kg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
-    CUDA_TRY(h, cudaFuncSetAttribute(kg_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_bytes()));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ws_bytes() + KG_FHULL_BYTES)));
     CUDA_TRY(h, cudaEventCreate(&h->ev0)); CUDA_TRY(h, cudaEventCreate(&h->ev1));
 #endif
     const size_t N = (size_t)n_envs;
@@ -365,9 +404,9 @@ int kg_forward_debug(kg_handle h, int env, const float *ctrl, float *out) {
     if (!h || env < 0 || env >= h->n || !ctrl || !out) return KG_EINVAL;
     TRY(be_h2d(h, h->d_ctrl, ctrl, 9 * 4));
 #ifdef KG_EMU
-    kg_debug_run(h->model, g_ws, h->A, env, h->d_ctrl, h->d_debug, 0);
+    kg_debug_run(h->model, g_ws, h->A, env, h->d_ctrl, h->d_debug, 0, g_cta);
 #else
-    kg_debug_kernel<<<1, 32, ws_bytes(), (cudaStream_t)h->stream>>>(h->A, env, h->d_ctrl, h->d_debug);
+    kg_debug_kernel<<<1, 32, ws_bytes() + KG_FHULL_BYTES, (cudaStream_t)h->stream>>>(h->A, env, h->d_ctrl, h->d_debug);
     CUDA_TRY(h, cudaGetLastError());
 #endif
     TRY(be_d2h(h, out, h->d_debug, KG_DEBUG_FLOATS * 4));

@@ -25,6 +25,8 @@
 #include <math.h>
 #include <float.h>
 #include <stddef.h>
+#include <string.h>
+#include <stdio.h>
 
 #if defined(__CUDA_ARCH__)
 #define KG_DEV __device__ __forceinline__
@@ -32,16 +34,17 @@
 #define KG_PHASE(l) for (int l = kg_lane, kg_once_ = 0; kg_once_ < 1; ++kg_once_)
 #define KG_SYNC() __syncwarp()
 #define KG_LDG4(p) __ldg((const float4 *)(p))
+#define KG_LDGU4(p) __ldg((const uint4 *)(p))
+#define KG_F2U(x) __float_as_uint(x)
 // Block-wide rendezvous between pipeline stages.  Functionally unnecessary (warps never share data); it keeps the
 // 8 warps of a CTA inside the same ~10-20 KB code region so that they share instruction-cache lines (the whole
 // substep is ~100 KB of SASS, far beyond the 32 KB L1.5 I-cache; ncu showed stall_no_instruction dominating).
-#ifdef KG_STAGE_SYNC
-#define KG_STAGE() __syncthreads()
-#else
-#define KG_STAGE() ((void)0)
+#ifndef KG_STAGE_MASK
+#define KG_STAGE_MASK 0x1f   // bit i: rendezvous before stage i (0 kinematics, 1 collision, 2 rows, 3 solve, 4 Euler)
 #endif
+#define KG_STAGE(i) do { if ((KG_STAGE_MASK >> (i)) & 1) __syncthreads(); } while (0)
 #else
-#define KG_STAGE() ((void)0)
+#define KG_STAGE(i) ((void)0)
 #if defined(__CUDACC__)
 #define KG_DEV __host__ __device__ inline
 #define KG_NOINL __host__ __device__
@@ -55,7 +58,10 @@ static int kg_emu_lane_order = 0;
 #define KG_PHASE(l) for (int kg_i_ = 0, l = kg_emu_lane_order ? 31 : 0; kg_i_ < 32; ++kg_i_, l += kg_emu_lane_order ? -1 : 1)
 #define KG_SYNC() ((void)0)
 struct kg_float4 { float x, y, z, w; };
+struct kg_uint4 { unsigned x, y, z, w; };
 #define KG_LDG4(p) (*(const kg_float4 *)(p))
+#define KG_LDGU4(p) (*(const kg_uint4 *)(p))
+static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u; }
 #endif
 
 #define KG_NV 15
@@ -83,9 +89,12 @@ struct kg_float4 { float x, y, z, w; };
 #define KG_COUNT(i, n) ((void)0)
 #endif
 
-// obs / rangefinder staging aliases the constraint Jacobian storage (J is dead outside the substep loop)
+// obs / rangefinder staging aliases the constraint Jacobian storage (J is dead outside the substep loop); so does the
+// per-env copy of the object's hull vertices during the collision stage (J is rebuilt right after it)
 #define KG_WSOBS(ws) ((ws).J)
 #define KG_RANGE(ws) ((ws).J + 96)
+#define KG_OBJHULL(ws) ((ws).J)
+#define KG_MAXOBJVERT 160     // padded to a multiple of 32
 struct alignas(16) KgWS {
     // ---- state
     float qpos[16], qvel[16], qwarm[16], ctrl[12], sens_q[12];
@@ -97,12 +106,15 @@ struct alignas(16) KgWS {
     float gpos[9][3], gmat[9][9];
     float oR[9];
     // ---- dynamics
-    float M[KG_NV * KG_MS], L[KG_NV * KG_MS];
+    float M[KG_NV * KG_MS];
+    // the Newton-solver scratch and the contact staging of the collision stage are never live together
+    union {
+        struct { float L[KG_NV * KG_MS], bdot[KG_NBASE + 2], bdir[KG_NBASE + 2], bw[KG_NBASE + 2]; };
+        struct { float st_dist[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3]; unsigned char st_g1[KG_NSTAGE], st_g2[KG_NSTAGE]; };
+    };
     float bias[16], fs[16], qas[16], qacc[16], Mdq[16], grad[16], dir[16], Md[16], ftot[16];
     float sbias[3][3];
-    // ---- contact staging
-    float st_dist[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3];
-    unsigned char st_g1[KG_NSTAGE], st_g2[KG_NSTAGE];
+    // ---- collision bookkeeping
     int cnt[32];
     unsigned short cv1[32], cv2[32];   // warm-start hull vertices per pair lane
     float sep[32][3];                  // cached separating axis per hull-pair lane (valid while sepok[l] != 0)
@@ -110,8 +122,8 @@ struct alignas(16) KgWS {
     // ---- constraint groups: slot g<3 tendon, 3..8 limits, 9.. contacts
     int gtype[32], gslot[32], ngroup, ncon_total;
     float gmu[32], garef[32][4], gD[32];
-    float J[KG_NBASE * KG_JS];
-    float bdot[KG_NBASE + 2], bdir[KG_NBASE + 2], bw[KG_NBASE + 2];
+    alignas(16) float J[KG_NBASE * KG_JS];
+    const float *fhull;                // finger hull vertices (proximal then distal, xyzw): the CTA's shared-memory copy
     float red[32], red2[32];
     // ---- solver scalars (written by lane 0, read by all after a sync)
     float s_alpha, s_cost, s_flag, s_lo, s_hi, s_glo, s_ghi, s_cost2;
@@ -125,7 +137,8 @@ struct alignas(16) KgWS {
 #endif
 };
 
-static_assert(offsetof(KgWS, M) % 16 == 0 && offsetof(KgWS, L) % 16 == 0 && sizeof(KgWS) % 16 == 0, "128-bit row access needs 16-byte aligned matrices");
+static_assert(offsetof(KgWS, M) % 16 == 0 && offsetof(KgWS, L) % 16 == 0 && offsetof(KgWS, J) % 16 == 0 && sizeof(KgWS) % 16 == 0, "128-bit access needs 16-byte aligned members");
+static_assert(KG_MAXOBJVERT * 4 <= KG_NBASE * KG_JS, "object hull copy must fit into J");
 
 // ------------------------------------------------------------------------------------------------ small math
 KG_DEV float kg_dot(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -137,6 +150,18 @@ KG_DEV void kg_sub(float *r, const float *a, const float *b) { r[0] = a[0] - b[0
 KG_DEV void kg_add(float *r, const float *a, const float *b) { r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; }
 KG_DEV void kg_addscl(float *r, const float *a, const float *b, float s) { r[0] = a[0] + s * b[0]; r[1] = a[1] + s * b[1]; r[2] = a[2] + s * b[2]; }
 KG_DEV void kg_copy(float *r, const float *a) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
+// direction-only normalisation for the MPR search directions (the result steers support queries; rsqrt's 2 ulp is
+// far below the 1e-6 portal tolerance).  Output normals and frames keep the exact kg_normalize below.
+KG_DEV void kg_normalize_dir(float *a) {
+    float n2 = kg_dot(a, a);
+    if (n2 < 1e-38f) { a[0] = 1; a[1] = 0; a[2] = 0; return; }
+#if defined(__CUDA_ARCH__)
+    float inv = rsqrtf(n2);
+#else
+    float inv = 1.0f / sqrtf(n2);
+#endif
+    a[0] *= inv; a[1] *= inv; a[2] *= inv;
+}
 KG_DEV float kg_normalize(float *a) {
     float n = sqrtf(kg_dot(a, a));
     if (n < 1e-30f) { a[0] = 1; a[1] = 0; a[2] = 0; return n; }
@@ -362,7 +387,11 @@ KG_DEV void kg_chol_factor_solve(float *A, float *x, int kg_lane) {
 #pragma unroll
     for (int j = 0; j < KG_NV; j++) {
         float djj = __shfl_sync(FULL, a[j], j);
+#ifndef KG_CHOL_EXACT
+        float inv = rsqrtf(fmaxf(djj, 1e-20f)), d = djj * inv;   // the factor only shapes the Newton direction; 2 ulp is plenty
+#else
         float d = sqrtf(fmaxf(djj, 1e-20f)), inv = 1.0f / d;
+#endif
         invd[j] = inv;
         float lj = (l == j) ? d : a[j] * inv;      // L[l][j] for l >= j (rows above j hold don't-care values)
         a[j] = lj;
@@ -426,8 +455,7 @@ KG_DEV void kg_chol_factor_solve(float *A, float *x, int kg_lane) {
 KG_DEV void kg_support(const KgModel &m, const KgWS &ws, int g, int mesh, int &cur, const float *dir, const float *origin, float margin, float *out) {
     const KgMesh &mi = m.mesh[mesh];
     const float *vert = m.hull_vert + 4 * (size_t)mi.vert0;
-    const int *adjs = m.adj_start + mi.vert0;
-    const unsigned short *adj = m.adj;
+    const unsigned short *adj8 = m.adj8;
     const float *R = ws.gmat[g];
     float ld[3];
     kg_multmv(ld, R, dir);
@@ -435,13 +463,23 @@ KG_DEV void kg_support(const KgModel &m, const KgWS &ws, int g, int mesh, int &c
     auto v = KG_LDG4(vert + 4 * c);
     float best = v.x * ld[0] + v.y * ld[1] + v.z * ld[2];
     float bx = v.x, by = v.y, bz = v.z;
+    unsigned info = KG_F2U(v.w);
     for (int guard = 0; guard < 1024; guard++) {
-        int a0 = adjs[c], a1 = adjs[c + 1], nxt = c;
-        for (int a = a0; a < a1; a++) {
-            int nb = adj[a];
-            auto w = KG_LDG4(vert + 4 * nb);
-            float d = w.x * ld[0] + w.y * ld[1] + w.z * ld[2];
-            if (d > best) { best = d; nxt = nb; bx = w.x; by = w.y; bz = w.z; }
+        // one hill-climbing move: the 8 neighbours of a chunk are fetched with independent 128-bit loads, so a move costs
+        // two dependent memory latencies (ids, vertices) whatever the degree; ties keep the first neighbour in list order
+        const int ch0 = (int)(info & 0xffffffu), nch = (int)(info >> 24);
+        int nxt = c;
+        for (int k = 0; k < nch; k++) {
+            auto q = KG_LDGU4(adj8 + 8 * (size_t)(ch0 + k));
+            const unsigned id[8] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16, q.z & 0xffffu, q.z >> 16, q.w & 0xffffu, q.w >> 16};
+            decltype(v) w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = KG_LDG4(vert + 4 * id[i]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float d = w[i].x * ld[0] + w[i].y * ld[1] + w[i].z * ld[2];
+                if (d > best) { best = d; nxt = (int)id[i]; bx = w[i].x; by = w[i].y; bz = w[i].z; info = KG_F2U(w[i].w); }
+            }
         }
         if (nxt == c) break;
         c = nxt;
@@ -450,6 +488,55 @@ KG_DEV void kg_support(const KgModel &m, const KgWS &ws, int g, int mesh, int &c
     KG_COUNT(20, 1);
     cur = c;
     float lv[3] = {bx, by, bz}, wv[3];
+    kg_mulmv(wv, R, lv);
+    for (int k = 0; k < 3; k++) out[k] = wv[k] + (ws.gpos[g][k] - origin[k]) + margin * dir[k];
+}
+
+// Warp-cooperative support of geom g's hull along the (warp-uniform) direction dir, inflated by `margin`, relative to
+// `origin`.  The 32 lanes scan the whole vertex table with independent 128-bit loads (no hill-climbing chain).  The
+// tables are padded to a multiple of 32 vertices with copies of vertex 0, so the scan is branch-free; each lane tracks
+// only (best dot, index), the arg-max is reduced with redux.sync on an order-preserving integer key and, among equal
+// maxima, the lowest vertex index wins (a pad entry can therefore never be returned); the winning vertex is then
+// fetched once.  Every lane returns the same result.  The host emulation scans the vertices in index order (same tie rule).
+KG_DEV const float *kg_hull_table(const KgModel &m, const KgWS &ws, int mesh) {
+    // object -> this env's shared-memory copy, fingers -> the CTA's shared-memory copy, palm -> global memory
+    return mesh >= 3 ? KG_OBJHULL(ws) : (mesh == 0 ? m.hull_pad : ws.fhull + (mesh == 2 ? 4 * m.hnpad[1] : 0));
+}
+KG_DEV void kg_support_coop(const KgModel &m, const KgWS &ws, int g, int mesh, const float *dir, const float *origin, float margin,
+                            float *out, int *vidx, int kg_lane) {
+    const float *vert = kg_hull_table(m, ws, mesh);
+    const float *R = ws.gmat[g];
+    float ld[3];
+    kg_multmv(ld, R, dir);
+    float best = -FLT_MAX;
+    int bi = 0;
+#if defined(__CUDA_ARCH__)
+    const int npad = m.hnpad[mesh];
+    const float4 *v4 = reinterpret_cast<const float4 *>(vert);
+#pragma unroll 4
+    for (int i = kg_lane; i < npad; i += 32) {
+        float4 v = v4[i];
+        float d = v.x * ld[0] + v.y * ld[1] + v.z * ld[2];
+        if (d > best) { best = d; bi = i; }
+    }
+    unsigned u = __float_as_uint(best);
+    unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    unsigned mx = __reduce_max_sync(0xffffffffu, key);
+    bi = __reduce_min_sync(0xffffffffu, key == mx ? bi : 0x7fffffff);
+    float4 w = v4[bi];
+    float lv[3] = {w.x, w.y, w.z};
+#else
+    (void)kg_lane;
+    const int nv = m.mesh[mesh].nvert;
+    for (int i = 0; i < nv; i++) {
+        const float *v = vert + 4 * i;
+        float d = v[0] * ld[0] + v[1] * ld[1] + v[2] * ld[2];
+        if (d > best) { best = d; bi = i; }
+    }
+    float lv[3] = {vert[4 * bi], vert[4 * bi + 1], vert[4 * bi + 2]};
+#endif
+    *vidx = bi;
+    float wv[3];
     kg_mulmv(wv, R, lv);
     for (int k = 0; k < 3; k++) out[k] = wv[k] + (ws.gpos[g][k] - origin[k]) + margin * dir[k];
 }
@@ -471,7 +558,7 @@ KG_DEV void kg_portal_dir(const KgSupp *p, float *dir) {
     float a[3], b[3];
     kg_sub(a, p[2].v, p[1].v); kg_sub(b, p[3].v, p[1].v);
     kg_cross(dir, a, b);
-    kg_normalize(dir);
+    kg_normalize_dir(dir);
 }
 KG_DEV bool kg_reach_tol(const KgSupp *p, const KgSupp &v4, const float *dir) {
     float dv4 = kg_dot(v4.v, dir);
@@ -512,13 +599,18 @@ KG_DEV float kg_tri_dist2(const float *x0, const float *Bv, const float *C, floa
     dv = kg_seg_dist2(Bv, C, w2); if (dv < dist) { dist = dv; kg_copy(w, w2); }
     return dist;
 }
+#if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
+static long kg_emu_mpr_iters = 0;
+#endif
 // ccdMPRPenetration on the margin-inflated hulls of geoms g1, g2; coordinates are relative to geom g1's centre.
+// WARP-UNIFORM: all 32 lanes call it with the same arguments, run the same scalar portal algebra and share the two
+// cooperative support scans of every iteration; all lanes return the same result.
 // Written as ONE loop around ONE support evaluation (state machine over libccd's discoverPortal / refinePortal /
 // findPenetr) so that the hill-climbing support code exists once in the instruction stream.
 // On a "no overlap" exit that PROVES separation (support of A-B along dir is negative) *sep_found is set and dir is
 // returned in nrm: the caller re-tests that axis first in the next substep (two supports instead of a full MPR).
 KG_DEV bool kg_mpr(const KgModel &m, const KgWS &ws, int g1, int mesh1, int g2, int mesh2, float hmargin, int &cur1, int &cur2,
-                   float *depth, float *nrm, float *pos, int *sep_found) {
+                   float *depth, float *nrm, float *pos, int *sep_found, int kg_lane) {
     *sep_found = 0;
     KgSupp p[4];
     float dir[3], va[3], vb[3], dot;
@@ -527,16 +619,19 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgWS &ws, int g1, int mesh1, int g2, 
     kg_sub(p[0].v, ws.gpos[g1], ws.gpos[g2]);
     if (kg_iszero(p[0].v[0]) && kg_iszero(p[0].v[1]) && kg_iszero(p[0].v[2])) p[0].v[0] += KG_CCD_EPS * 10;
     for (int c = 0; c < 3; c++) dir[c] = -p[0].v[c];
-    kg_normalize(dir);
+    kg_normalize_dir(dir);
     int state = 0, it = 0;
-    KG_COUNT(22, 1);
+    if (kg_lane == 0) KG_COUNT(22, 1);
     for (int guard = 0; guard < 400; guard++) {
         KgSupp s;
-        KG_COUNT(23, 1);
+        if (kg_lane == 0) KG_COUNT(23, 1);
+#if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
+        kg_emu_mpr_iters++;
+#endif
         {
             float nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
-            kg_support(m, ws, g1, mesh1, cur1, dir, org, hmargin, s.v1);
-            kg_support(m, ws, g2, mesh2, cur2, nd, org, hmargin, v2);
+            kg_support_coop(m, ws, g1, mesh1, dir, org, hmargin, s.v1, &cur1, kg_lane);
+            kg_support_coop(m, ws, g2, mesh2, nd, org, hmargin, v2, &cur2, kg_lane);
             kg_sub(s.v, s.v1, v2);
         }
         bool check_portal = false;
@@ -552,14 +647,14 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgWS &ws, int g1, int mesh1, int g2, 
                 for (int c = 0; c < 3; c++) pos[c] = p[1].v1[c] - 0.5f * p[1].v[c];
                 return true;
             }
-            kg_normalize(dir);
+            kg_normalize_dir(dir);
             state = 1;
         } else if (state == 1) {
             p[2] = s;
             dot = kg_dot(s.v, dir);
             if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; kg_copy(nrm, dir); } return false; }
             kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
-            kg_cross(dir, va, vb); kg_normalize(dir);
+            kg_cross(dir, va, vb); kg_normalize_dir(dir);
             if (kg_dot(dir, p[0].v) > 0) { KgSupp t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
             state = 2;
         } else if (state == 2) {
@@ -575,7 +670,7 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgWS &ws, int g1, int mesh1, int g2, 
             }
             if (cont) {
                 kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
-                kg_cross(dir, va, vb); kg_normalize(dir);
+                kg_cross(dir, va, vb); kg_normalize_dir(dir);
             } else { state = 3; check_portal = true; }
         } else if (state == 3) {
             dot = kg_dot(s.v, dir);
@@ -645,16 +740,71 @@ KG_DEV void kg_pair_of_lane(int l, int &g1, int &g2) {
     else if (l < 14) { g1 = 8; g2 = l - 6; }
     else if (l == 14) { g1 = 8; g2 = 1; }
     else {
-        const unsigned char t1[15] = {1, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3, 4, 4, 5, 5};
-        const unsigned char t2[15] = {3, 5, 7, 4, 5, 4, 5, 6, 7, 6, 7, 6, 7, 6, 7};
-        g1 = t1[l - 15]; g2 = t2[l - 15];
+        // nibble k of T1 / T2 = geom1 / geom2 of dynamic pair k: (1,3)(1,5)(1,7)(2,4)(2,5)(3,4)(3,5)(2,6)(2,7)(3,6)(3,7)(4,6)(4,7)(5,6)(5,7)
+        const unsigned long long T1 = 0x554433223322111ull, T2 = 0x767676765454753ull;
+        const int sh = 4 * (l - 15);
+        g1 = (int)((T1 >> sh) & 15); g2 = (int)((T2 >> sh) & 15);
     }
 }
 KG_DEV int kg_mesh_of_geom(const KgWS &ws, int g) { return g == 8 ? 3 + ws.shape : (g == 1 ? 0 : ((g & 1) ? 2 : 1)); }
 KG_DEV float kg_rbound(const KgModel &m, const KgWS &ws, int g) { return g == 8 ? m.shape[ws.shape].rbound : (g == 1 ? m.hand_rbound[0] : ((g & 1) ? m.hand_rbound[2] : m.hand_rbound[1])); }
 
-KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
+// One narrowphase task: full MPR of pair lane lp of the environment whose workspace is wo (warp-uniform; wo may belong
+// to another warp of the CTA, which is parked at the stage barrier meanwhile).  Lane 0 files the result.
+KG_DEV void kg_mpr_task(const KgModel &m, KgWS &wo, int lp, int kg_lane) {
+    int g1, g2;
+    kg_pair_of_lane(lp, g1, g2);
+    const int mesh1 = kg_mesh_of_geom(wo, g1), mesh2 = kg_mesh_of_geom(wo, g2);
+    const float margin = m.margin;
+    int c1 = 0, c2 = 0, sepf = 0;
+    float depth = 0.f, nrm[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
+#if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
+    long it0_ = kg_emu_mpr_iters;
+#endif
+#if defined(KG_PROF) && defined(__CUDA_ARCH__)
+    long long tm0_ = clock64();
+#endif
+    bool hit = kg_mpr(m, wo, g1, mesh1, g2, mesh2, 0.5f * margin, c1, c2, &depth, nrm, pos, &sepf, kg_lane);
+#if defined(KG_PROF) && defined(__CUDA_ARCH__)
+    if (kg_lane == 0) atomicAdd((unsigned long long *)&wo.prof[28], (unsigned long long)(clock64() - tm0_));
+#endif
+#if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
+    fprintf(stderr, "MPR %d %d %ld %d %d\n", g1, g2, kg_emu_mpr_iters - it0_, (int)hit, sepf);
+#endif
+    KG_SYNC();
     KG_PHASE(l) {
+        if (l == 0) {
+            wo.sepok[lp] = sepf;
+            if (sepf) { wo.sep[lp][0] = nrm[0]; wo.sep[lp][1] = nrm[1]; wo.sep[lp][2] = nrm[2]; }
+            wo.cv1[lp] = (unsigned short)c1; wo.cv2[lp] = (unsigned short)c2;
+            if (hit && depth > 0.f) {
+                int sl = 32 + (lp - 8);
+                wo.st_dist[sl] = margin - depth;
+                kg_add(wo.st_pos[sl], pos, wo.gpos[g1]);
+                kg_copy(wo.st_n[sl], nrm);
+                wo.st_g1[sl] = (unsigned char)g1; wo.st_g2[sl] = (unsigned char)g2;
+                wo.cnt[lp] = 1;
+            }
+        }
+    }
+    KG_SYNC();
+}
+
+// CTA context of a warp: the workspaces of all the CTA's environments and the shared narrowphase task queue
+struct KgCta { KgWS *ws_base; int warp; int *q; unsigned short *queue; };
+#define KG_CTA_QBYTES 512   // int q[4] + unsigned short queue[8 warps x 22 pairs], rounded up
+
+KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane, const KgCta &cta, int sub) {
+    KG_PHASE(l) {
+        {   // this env's object hull -> shared memory (J is dead until the rows are rebuilt)
+            const float *src = m.hull_pad + 4 * (size_t)m.hpad0[3 + ws.shape];
+            const int npad = m.hnpad[3 + ws.shape];
+            float *dst = KG_OBJHULL(ws);
+            for (int i = l; i < npad; i += 32) {
+                auto v = KG_LDG4(src + 4 * i);
+                dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+            }
+        }
         int n = 0;
         float tried = 0.f;
         if (l < 30) {
@@ -710,9 +860,7 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
                     int c1 = ws.cv1[l], c2 = ws.cv2[l];
                     if (c1 >= m.mesh[mesh1].nvert) c1 = 0;
                     if (c2 >= m.mesh[mesh2].nvert) c2 = 0;
-                    float depth, nrm[3], pos[3];
-                    bool hit = false, separated = false;
-                    int sepf = 0;
+                    bool separated = false;
                     if (ws.sepok[l]) {
                         // the axis that separated the inflated hulls in the previous substep: still separating?
                         float n0[3] = {ws.sep[l][0], ws.sep[l][1], ws.sep[l][2]}, nn[3] = {-n0[0], -n0[1], -n0[2]}, s1[3], s2[3];
@@ -721,21 +869,8 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
                         separated = (kg_dot(s1, n0) - kg_dot(s2, n0)) < 0.f;
                         KG_COUNT(24, 1); KG_COUNT(25, separated ? 1 : 0);
                     }
-                    if (!separated) {
-                        hit = kg_mpr(m, ws, g1, mesh1, g2, mesh2, 0.5f * margin, c1, c2, &depth, nrm, pos, &sepf);
-                        tried = 1.f;
-                        ws.sepok[l] = sepf;
-                        if (sepf) { ws.sep[l][0] = nrm[0]; ws.sep[l][1] = nrm[1]; ws.sep[l][2] = nrm[2]; }
-                    }
+                    if (!separated) tried = 1.f;       // full MPR below, warp-cooperatively
                     ws.cv1[l] = (unsigned short)c1; ws.cv2[l] = (unsigned short)c2;
-                    if (hit && depth > 0.f) {
-                        int s = 32 + (l - 8);
-                        ws.st_dist[s] = margin - depth;
-                        kg_add(ws.st_pos[s], pos, ws.gpos[g1]);
-                        kg_copy(ws.st_n[s], nrm);
-                        ws.st_g1[s] = (unsigned char)g1; ws.st_g2[s] = (unsigned char)g2;
-                        n = 1;
-                    }
                 } else ws.sepok[l] = 0;
             }
         }
@@ -744,6 +879,35 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane) {
     }
     KG_SYNC();
     KG_PROBE(2);
+    // narrowphase proper: every pair that needs a full MPR is one task, run by all 32 lanes of a warp (uniform control
+    // flow).  On the GPU the tasks of the CTA's environments go through one shared queue and are pulled by whichever
+    // warp is free, so an environment in a six-contact grasp does not hold up the stage while its neighbours idle.
+#if defined(__CUDA_ARCH__)
+    {
+        int *qn = cta.q + 2 * (sub & 1);                           // [0] tasks queued, [1] next task to hand out
+        if (cta.warp == 0 && kg_lane == 0) { int *qo = cta.q + 2 * ((sub + 1) & 1); qo[0] = 0; qo[1] = 0; }
+        if (kg_lane >= 8 && kg_lane < 30 && ws.red2[kg_lane] != 0.f) cta.queue[atomicAdd(qn, 1)] = (unsigned short)((cta.warp << 8) | kg_lane);
+        __syncthreads();
+        const int ntask = qn[0];
+        for (;;) {
+            int t = 0;
+            if (kg_lane == 0) t = atomicAdd(qn + 1, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= ntask) break;
+            const int task = cta.queue[t], lp = task & 0xff;
+            KgWS &wo = cta.ws_base[task >> 8];
+            kg_mpr_task(m, wo, lp, kg_lane);
+        }
+        __syncthreads();
+    }
+#else
+    (void)cta; (void)sub;
+    for (int lp = 8; lp < 30; lp++) {
+        if (ws.red2[lp] == 0.f) continue;
+        kg_mpr_task(m, ws, lp, kg_lane);
+    }
+#endif
+    KG_PROBE(3);
     // compaction: contact groups 9.. reference staging slots
     KG_PHASE(l) {
         int off = 0, total = 0;
@@ -1229,25 +1393,25 @@ KG_DEV void kg_euler(const KgModel &m, KgWS &ws, int kg_lane) {
 }
 
 // one mj_step: forward (positions -> constraints -> solve) + integrate
-KG_DEV void kg_substep(const KgModel &m, KgWS &ws, int kg_lane) {
-    KG_STAGE();
+KG_DEV void kg_substep(const KgModel &m, KgWS &ws, int kg_lane, const KgCta &cta, int sub) {
+    KG_STAGE(0);
     KG_PROBE(18);
     kg_kinematics(m, ws, kg_lane);
     kg_dynamics(m, ws, kg_lane);
     KG_PROBE(0);
-    KG_STAGE();
+    KG_STAGE(1);
     KG_PROBE(1);
-    kg_collision(m, ws, kg_lane);
+    kg_collision(m, ws, kg_lane, cta, sub);
     KG_PROBE(3);
-    KG_STAGE();
+    KG_STAGE(2);
     KG_PROBE(4);
     kg_make_rows(m, ws, kg_lane);
     KG_PROBE(5);
-    KG_STAGE();
+    KG_STAGE(3);
     KG_PROBE(6);
     kg_solve(m, ws, kg_lane);
     KG_PROBE(13);
-    KG_STAGE();
+    KG_STAGE(4);
     KG_PROBE(14);
     kg_euler(m, ws, kg_lane);
     KG_PROBE(15);
@@ -1599,7 +1763,7 @@ KG_DEV void kg_store_env(KgWS &ws, const KgEnvArrays &A, int env, int kg_lane) {
 // One RL step of one env: [expert action] -> ctrl -> nsub x mj_step -> rays -> obs/reward/done (+TimeLimit).
 // action_in == nullptr selects the on-device expert (mode 0 naive, 1 position-dependent, 2 combined).
 KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *action_in, int expert_mode,
-                        int nsub, float *obs_out, float *reward_out, int *done_out, float *action_out, int kg_lane) {
+                        int nsub, float *obs_out, float *reward_out, int *done_out, float *action_out, int kg_lane, const KgCta &cta) {
     kg_load_env(m, ws, A, env, kg_lane);
     float act[4] = {0, 0, 0, 0};
     if (action_in) { for (int c = 0; c < 4; c++) act[c] = action_in[c * A.N + env]; }
@@ -1625,7 +1789,7 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
         KG_SYNC();
     }
     kg_ctrl_from_action(ws, act, kg_lane);
-    for (int s = 0; s < nsub; s++) kg_substep(m, ws, kg_lane);
+    for (int s = 0; s < nsub; s++) kg_substep(m, ws, kg_lane, cta, s);
     KG_PROBE(19);
     kg_rays(m, ws, kg_lane);
     KG_PROBE(16);

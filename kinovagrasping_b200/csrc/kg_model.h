@@ -47,7 +47,10 @@ struct KgModel {
     KgShape shape[KG_NSHAPE];
     KgMesh mesh[KG_NMESH];
     // big read-only tables (device pointers on the GPU, host pointers in the emulation build)
-    const float *hull_vert;        // xyzw per vertex (w unused): 128-bit loads
+    const float *hull_vert;        // xyzw per vertex, 128-bit loads; w = bits of (first adj8 chunk | n chunks << 24)
+    const float *hull_pad;         // the same vertices, every mesh padded to a multiple of 32 with copies of its vertex 0 (branch-free scans)
+    int hpad0[KG_NMESH], hnpad[KG_NMESH];
+    const unsigned short *adj8;    // neighbour lists in 16-byte chunks of 8 mesh-local vertex ids, padded with the vertex itself
     const int *adj_start;
     const unsigned short *adj;
     const float *tri;              // 9 floats per triangle, BVH leaf order
@@ -59,9 +62,9 @@ struct KgModel {
 
 // ---------------------------------------------------------------------------------- host loader
 struct KgHostTables {
-    std::vector<float> hull_vert, tri, bvh_lo, bvh_hi, pose_train, pose_test;
+    std::vector<float> hull_vert, hull_pad, tri, bvh_lo, bvh_hi, pose_train, pose_test;
     std::vector<int> adj_start, bvh_meta;
-    std::vector<unsigned short> adj;
+    std::vector<unsigned short> adj, adj8;
 };
 
 namespace kgdetail {
@@ -201,6 +204,27 @@ inline std::string kg_load_model(const void *blob_, size_t nbytes, KgModel *m, K
     for (size_t i = 0; i < hv->count / 3; i++) for (int c = 0; c < 3; c++) t->hull_vert[4 * i + c] = (float)hvd[3 * i + c];
     ip = I("hull_adj_start", &n); KG_NEED(ip); t->adj_start.assign(ip, ip + n);
     ip = I("hull_adj", &n); KG_NEED(ip); t->adj.resize(n); for (size_t i = 0; i < n; i++) t->adj[i] = (unsigned short)ip[i];
+    // chunked neighbour lists: one 128-bit load brings 8 neighbour ids, whose vertices are then fetched in parallel
+    for (int k = 0; k < KG_NMESH; k++) {
+        const KgMesh &mk = m->mesh[k];
+        for (int v = 0; v < mk.nvert; v++) {
+            int a0 = t->adj_start[mk.vert0 + v], a1 = t->adj_start[mk.vert0 + v + 1];
+            uint32_t first = (uint32_t)(t->adj8.size() / 8), nch = (uint32_t)((a1 - a0 + 7) / 8);
+            for (uint32_t i = 0; i < nch * 8; i++) t->adj8.push_back(a0 + (int)i < a1 ? t->adj[a0 + i] : (unsigned short)v);
+            uint32_t info = first | (nch << 24);
+            std::memcpy(&t->hull_vert[4 * (size_t)(mk.vert0 + v) + 3], &info, 4);
+        }
+    }
+    for (int k = 0; k < KG_NMESH; k++) {
+        const KgMesh &mk = m->mesh[k];
+        m->hpad0[k] = (int)(t->hull_pad.size() / 4);
+        m->hnpad[k] = (mk.nvert + 31) / 32 * 32;
+        for (int v = 0; v < m->hnpad[k]; v++) {
+            const float *src = &t->hull_vert[4 * (size_t)(mk.vert0 + (v < mk.nvert ? v : 0))];
+            for (int c = 0; c < 3; c++) t->hull_pad.push_back(src[c]);
+            t->hull_pad.push_back(0.f);
+        }
+    }
     const float *fp;
     fp = F("tri_vert", &n); KG_NEED(fp); t->tri.assign(fp, fp + n);
     fp = F("bvh_lo", &n); KG_NEED(fp); t->bvh_lo.assign(n / 3 * 4, 0.f); for (size_t i = 0; i < n / 3; i++) for (int c = 0; c < 3; c++) t->bvh_lo[4 * i + c] = fp[3 * i + c];

@@ -42,4 +42,4 @@ if tot:
     print("   cycles: " + "  ".join(f"{nm} {100.0 * c / tot:.1f}%" for nm, c in zip(names, prof) if c) + f" | cycles/substep/env {tot / st['substeps']:.0f}")
     ss = float(st["substeps"])
     cn = ["support", "climb", "mpr", "mpr_iter", "sepchk", "sep_ok", "plane_sup", "ls_eval"]
-    print("   per substep: " + "  ".join(f"{nm} {prof[20 + i] / ss:.2f}" for i, nm in enumerate(cn)))
+    print("   per substep: " + "  ".join(f"{nm} {prof[20 + i] / ss:.2f}" for i, nm in enumerate(cn)) + f" | cycles per MPR iteration {prof[28] / max(1, prof[23]):.0f}")
