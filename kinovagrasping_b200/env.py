@@ -54,7 +54,11 @@ class VecKinovaGripperEnv:
     def __init__(self, n_envs, device=0, frame_skip=15, max_episode_steps=30, lib=None, use_torch=True):
         self.n = int(n_envs)
         self.card = ModelCard()
-        self.h = Handle(self.n, device=device, lib=lib)
+        self.env_offset = 0                           # global id of env 0 (multi-GPU shards, shard.make_sharded_env)
+        host = isinstance(device, str) and device == "cpu"   # tests only: the host-emulation library takes host pointers
+        if host and lib is None:
+            raise ValueError("device='cpu' needs the test-only emulation library; the package has no CPU path")
+        self.h = Handle(self.n, device=0 if host else device, lib=lib)
         self.h.set_frame_skip(frame_skip)
         self.h.set_max_episode_steps(max_episode_steps)
         self._max_episode_steps = max_episode_steps
@@ -62,7 +66,7 @@ class VecKinovaGripperEnv:
         if use_torch:
             import torch
             self.torch = torch
-            self.device = torch.device("cuda", device)
+            self.device = torch.device("cpu") if host else torch.device("cuda", device)
             f32 = dict(dtype=torch.float32, device=self.device)
             self.obs_soa = torch.zeros((82, self.n), **f32)
             self.reward = torch.zeros(self.n, **f32)
@@ -70,13 +74,14 @@ class VecKinovaGripperEnv:
             self.action_soa = torch.zeros((4, self.n), **f32)
             self.action_out = torch.zeros((4, self.n), **f32)
             self.shape_ids = torch.zeros(self.n, dtype=torch.int32, device=self.device)
-            self.h.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+            if not host:
+                self.h.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.shape_ids_host = np.zeros(self.n, dtype=np.int32)
 
     # ---- reset
     def set_shapes(self, shape_keys):
         """env i -> shape_keys[i mod len] (the Latin-square order of SURVEY 8d config 2/3)."""
-        ids = np.array([SHAPES.index(shape_keys[i % len(shape_keys)]) for i in range(self.n)], dtype=np.int32)
+        ids = np.array([SHAPES.index(shape_keys[(self.env_offset + i) % len(shape_keys)]) for i in range(self.n)], dtype=np.int32)
         self.shape_ids_host = ids
         if self.use_torch:
             self.shape_ids.copy_(self.torch.from_numpy(ids))

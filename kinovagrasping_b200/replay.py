@@ -1,0 +1,313 @@
+"""GPU-resident episode replay with n-step window sampling: the reference's `ReplayBuffer_Queue`
+(utils.py:9-460) restated as one preallocated ring of episodes in device memory.
+
+Reference semantics kept (each cited where it is implemented):
+  * episode-structured FIFO: `add` appends to the episode in progress, a `done` transition closes it and the oldest
+    episode is evicted once `replay_ep_num >= max_episode` (utils.py:34-79); `replace` rewrites the last stored
+    reward/done of the episode in progress and closes it, evicting at `>` (utils.py:309-343);
+  * `add_episode` start/finish bookkeeping of `episodes` / `timesteps_count` (utils.py:81-101);
+  * `sample_batch_nstep(batch_size)`: `batch_size` EPISODES drawn uniformly from [0, replay_ep_num-1), and from each
+    `ceiling = len - n` windows of n consecutive steps (`ceiling-1` random starts in [0, ceiling) plus the last window),
+    so the result has sum(ceiling) rows (utils.py:240-306).  The draws use `np.random` in the reference's own call
+    order, so a seeded reference run and a seeded run of this class return identical batches (tests/test_learner.py).
+What changes: storage is `[episode][t][dim]` fp32 tensors on the device (no Python lists, no per-sample H2D), windows
+are gathered by one index_select per field, and the vectorised environment feeds it with `add_batch` (one scatter per
+step for all N environments).  `sample_windows` is the fixed-shape, all-on-device sampler used under CUDA graphs."""
+import numpy as np
+import torch
+
+
+class ReplayBuffer_Queue:
+    def __init__(self, state_dim, action_dim, max_episode=10000, n_steps=5, max_episode_len=32, device=None, n_envs=0):
+        self.state_dim, self.action_dim = int(state_dim), int(action_dim)
+        self.max_episode = int(max_episode)
+        self.n_steps = int(n_steps)
+        self.device = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.T = int(max_episode_len)
+        self.cap = self.max_episode + 2            # complete episodes + the one in progress + one spare row
+        self.size = 0                              # transitions ever added (utils.py:12)
+        self.episodes_count = 0                    # episodes ever closed
+        self.replay_ep_num = 0                     # complete episodes currently held
+        self.episodes = []
+        self.timesteps_count = 0
+        self.orientation_indexes = []
+        self.head = 0                              # physical row of logical episode 0
+        self.lengths = np.zeros(self.cap, dtype=np.int64)   # host mirror of the per-row lengths
+        self._alloc(self.T)
+        # staging for the vectorised feeder (episodes in progress, one per environment)
+        self.n_envs = int(n_envs)
+        if self.n_envs:
+            f = dict(dtype=torch.float32, device=self.device)
+            self.st_state = torch.zeros((self.n_envs, self.T, self.state_dim), **f)
+            self.st_action = torch.zeros((self.n_envs, self.T, self.action_dim), **f)
+            self.st_next = torch.zeros((self.n_envs, self.T, self.state_dim), **f)
+            self.st_reward = torch.zeros((self.n_envs, self.T), **f)
+            self.st_notdone = torch.zeros((self.n_envs, self.T), **f)
+            self.st_len = torch.zeros(self.n_envs, dtype=torch.long, device=self.device)
+            self._env_ids = torch.arange(self.n_envs, device=self.device)
+        self.len_dev = torch.zeros(self.cap, dtype=torch.long, device=self.device)
+        self._host_len_dirty = False
+
+    # ------------------------------------------------------------------ storage
+    def _alloc(self, T):
+        f = dict(dtype=torch.float32, device=self.device)
+        new = [torch.zeros((self.cap, T, self.state_dim), **f), torch.zeros((self.cap, T, self.action_dim), **f),
+               torch.zeros((self.cap, T, self.state_dim), **f), torch.zeros((self.cap, T), **f), torch.zeros((self.cap, T), **f)]
+        if hasattr(self, "state"):
+            for old, nw in zip((self.state, self.action, self.next_state, self.reward, self.not_done), new):
+                nw[:, :old.shape[1]] = old
+        self.state, self.action, self.next_state, self.reward, self.not_done = new
+        self.T = T
+
+    def _row(self, logical):
+        return (self.head + logical) % self.cap
+
+    def _t(self, x, dim):
+        return torch.as_tensor(np.asarray(x, dtype=np.float32).reshape(dim), dtype=torch.float32).to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ reference single-transition API
+    def add(self, state, action, next_state, reward, done):
+        """utils.py:34-60."""
+        row = self._row(self.replay_ep_num)
+        t = int(self.lengths[row])
+        if t >= self.T:
+            self._alloc(2 * self.T)
+        self.state[row, t] = self._t(state, self.state_dim)
+        self.action[row, t] = self._t(action, self.action_dim)
+        self.next_state[row, t] = self._t(next_state, self.state_dim)
+        self.reward[row, t] = float(reward)
+        self.not_done[row, t] = 1.0 - float(done)
+        self.lengths[row] = t + 1
+        self.len_dev[row] = t + 1
+        self.size += 1
+        self.timesteps_count += 1
+        if done:
+            self.episodes_count += 1
+            self.replay_ep_num += 1
+            self._open_row()
+            if self.replay_ep_num >= self.max_episode:
+                self.remove_episode()
+
+    def _open_row(self):
+        row = self._row(self.replay_ep_num)
+        self.lengths[row] = 0
+        self.len_dev[row] = 0
+
+    def remove_episode(self, idx=0):
+        """utils.py:62-79 (FIFO: only the oldest episode can be dropped from a ring)."""
+        if idx != 0:
+            raise ValueError("the device ring evicts in FIFO order only")
+        self.head = (self.head + 1) % self.cap
+        if self.episodes:
+            self.episodes.pop(0)
+        if len(self.orientation_indexes) > 0:
+            self.orientation_indexes.pop(0)
+        self.replay_ep_num -= 1
+
+    def add_episode(self, start):
+        """utils.py:81-101."""
+        if start:
+            if self.replay_ep_num == 0:
+                self.episodes.append([self.timesteps_count])
+            else:
+                self.episodes[-1].append(self.timesteps_count)
+        else:
+            if self.replay_ep_num == 0:
+                self.episodes.append(self.timesteps_count)
+                self.episodes.append([])
+                self.timesteps_count = 0
+            else:
+                self.episodes[-1].append(self.timesteps_count)
+                self.episodes.append([])
+                self.timesteps_count = 0
+
+    def add_orientation_idx_to_replay(self, idx):
+        self.orientation_indexes.append(idx)
+
+    def replace(self, reward, done):
+        """utils.py:309-343: lifted-and-done rewrites the last stored step of the episode in progress."""
+        if not done:
+            print("Can only replace last time step of the latest episode")
+            raise ValueError
+        row = self._row(self.replay_ep_num)
+        idx = int(self.lengths[row]) - 1
+        old_reward = float(self.reward[row, idx])
+        self.reward[row, idx] = float(reward)
+        self.not_done[row, idx] = 1.0 - float(done)
+        self.episodes_count += 1
+        self.replay_ep_num += 1
+        self._open_row()
+        if self.replay_ep_num > self.max_episode:
+            self.remove_episode()
+        return old_reward
+
+    def episode_length(self, logical):
+        if self._host_len_dirty:                   # the vectorised feeder only updates the device copy
+            self.lengths[:] = self.len_dev.cpu().numpy()
+            self._host_len_dirty = False
+        return int(self.lengths[self._row(logical)])
+
+    def episode(self, logical):
+        """(state, action, next_state, reward, not_done) views of one stored episode."""
+        row, n = self._row(logical), self.episode_length(logical)
+        return self.state[row, :n], self.action[row, :n], self.next_state[row, :n], self.reward[row, :n], self.not_done[row, :n]
+
+    # ------------------------------------------------------------------ sampling
+    def _gather(self, rows, starts):
+        rows = torch.as_tensor(np.asarray(rows, dtype=np.int64), device=self.device)
+        starts = torch.as_tensor(np.asarray(starts, dtype=np.int64), device=self.device)
+        return self._gather_dev(rows, starts)
+
+    def _gather_dev(self, rows, starts):
+        t = starts[:, None] + torch.arange(self.n_steps, device=self.device)[None, :]
+        flat = (rows[:, None] * self.T + t).reshape(-1)
+        W = rows.shape[0]
+
+        def g(x):
+            return x.reshape(self.cap * self.T, *x.shape[2:]).index_select(0, flat).reshape(W, self.n_steps, *x.shape[2:])
+        return g(self.state), g(self.action), g(self.next_state), g(self.reward), g(self.not_done)
+
+    def sample_batch_nstep(self, batch_size, num_ts_from_ep=5):
+        """utils.py:240-306, same np.random call order: one randint(replay_ep_num-1, size=batch_size), then per
+        episode (ceiling-1) x randint(ceiling)."""
+        if batch_size < 1:
+            e = torch.zeros(0, device=self.device)
+            return e, e, e, e, e
+        episode_idx_arr = np.random.randint(self.replay_ep_num - 1, size=batch_size)
+        rows, starts = [], []
+        for idx in episode_idx_arr:
+            episode_len = self.episode_length(int(idx))
+            ceiling = episode_len - self.n_steps
+            if ceiling < 1:
+                raise ValueError(f"episode {idx} has {episode_len} steps: too short for {self.n_steps}-step windows "
+                                 "(callers drop such episodes, main_DDPGfD.py:470-471)")
+            for _ in range(ceiling - 1):
+                starts.append(np.random.randint(ceiling)); rows.append(self._row(int(idx)))
+            starts.append(ceiling); rows.append(self._row(int(idx)))
+        return self._gather(rows, starts)
+
+    def sample_windows(self, n_windows, generator=None):
+        """Fixed-shape device sampler with the same per-window distribution as sample_batch_nstep: an episode is drawn with
+        probability proportional to its window count `ceiling` (the reference emits `ceiling` rows per drawn episode),
+        then the window is the last one with probability 1/ceiling and uniform over [0, ceiling) otherwise.
+        No host synchronisation: usable inside a captured CUDA graph."""
+        n_valid = self.replay_ep_num - 1
+        logical = torch.arange(self.cap, device=self.device)
+        rows_all = (self.head + logical) % self.cap
+        ceil_all = (self.len_dev[rows_all] - self.n_steps).clamp(min=0).float()
+        ceil_all = torch.where(logical < n_valid, ceil_all, torch.zeros_like(ceil_all))
+        pick = torch.multinomial(ceil_all, n_windows, replacement=True, generator=generator)
+        rows = rows_all[pick]
+        ceiling = ceil_all[pick]
+        u = torch.rand(n_windows, 2, device=self.device, generator=generator)
+        last = u[:, 0] * ceiling < 1.0
+        starts = torch.where(last, ceiling, torch.floor(u[:, 1] * ceiling)).long()
+        return self._gather_dev(rows, starts)
+
+    # ------------------------------------------------------------------ vectorised feeder
+    def add_batch(self, state, action, next_state, reward, done, record=None, replace=None):
+        """One step of all N environments (tensors on the device, env-major [N, dim]).
+        record[i]  : store this transition (default all).  The rollout loops do not store the lifting steps
+                     (expert_data.py:794, main_DDPGfD.py:451-456).
+        replace[i] : lifted-and-done: rewrite the last stored reward with `reward[i]` and close the episode
+                     (utils.py:309-343).
+        A stored `done` transition closes the episode as in `add`.  Closed episodes with len - n_steps <= 1 are dropped
+        (main_DDPGfD.py:470-471); the others are committed to the ring in env order, evicting the oldest when full.
+        Returns the number of episodes committed."""
+        N = self.n_envs
+        dev = self.device
+        done = done.to(dev).bool()
+        record = torch.ones(N, dtype=torch.bool, device=dev) if record is None else record.to(dev).bool()
+        replace = torch.zeros(N, dtype=torch.bool, device=dev) if replace is None else replace.to(dev).bool()
+        t = self.st_len.clamp(max=self.T - 1)
+        ids = self._env_ids[record]
+        if ids.numel():
+            tt = t[record]
+            self.st_state[ids, tt] = state[record]
+            self.st_action[ids, tt] = action[record]
+            self.st_next[ids, tt] = next_state[record]
+            self.st_reward[ids, tt] = reward[record].float()
+            self.st_notdone[ids, tt] = 1.0 - done[record].float()
+            self.st_len[ids] = tt + 1
+        rep = replace & (self.st_len > 0)
+        if bool(rep.any()):
+            ids = self._env_ids[rep]
+            last = self.st_len[rep] - 1
+            self.st_reward[ids, last] = reward[rep].float()
+            self.st_notdone[ids, last] = 0.0
+        closing = (record & done) | rep
+        n_close = int(closing.sum())
+        if n_close == 0:
+            return 0
+        ids = self._env_ids[closing]
+        lens = self.st_len[ids]
+        keep = (lens - self.n_steps) > 1
+        ids, lens = ids[keep], lens[keep]
+        k = int(ids.numel())
+        self.size += int(self.st_len[closing].sum())
+        if k:
+            if k > self.max_episode:
+                ids, lens, k = ids[-self.max_episode:], lens[-self.max_episode:], self.max_episode
+            evict = max(0, self.replay_ep_num + k - (self.max_episode - 1))
+            if evict:
+                self.head = (self.head + evict) % self.cap
+                self.replay_ep_num -= evict
+            rows = (self.head + self.replay_ep_num + torch.arange(k, device=dev)) % self.cap
+            self.state[rows] = self.st_state[ids]
+            self.action[rows] = self.st_action[ids]
+            self.next_state[rows] = self.st_next[ids]
+            self.reward[rows] = self.st_reward[ids]
+            self.not_done[rows] = self.st_notdone[ids]
+            self.len_dev[rows] = lens
+            self._host_len_dirty = True
+            self.replay_ep_num += k
+            self.episodes_count += k
+            self._open_row()
+        self.st_len[self._env_ids[closing]] = 0
+        return k
+
+    def abandon(self, mask):
+        """Forget the staged (unfinished) episodes of the masked environments (time-limit without a stored done)."""
+        self.st_len[mask.to(self.device).bool()] = 0
+
+    # ------------------------------------------------------------------ persistence (utils.py:345-460 layout)
+    def save_replay_buffer(self, save_filepath):
+        """Eight np.save files with the reference's names; episodes as object arrays of per-episode lists."""
+        import os
+        os.makedirs(save_filepath, exist_ok=True)
+        n = self.replay_ep_num
+
+        def obj(field):
+            a = np.empty(n + 1, dtype=object)
+            for i in range(n):
+                row, ln = self._row(i), self.episode_length(i)
+                a[i] = [np.asarray(v) for v in field[row, :ln].cpu().numpy()]
+            a[n] = []
+            return a
+        np.save(os.path.join(save_filepath, "state"), obj(self.state), allow_pickle=True)
+        np.save(os.path.join(save_filepath, "action"), obj(self.action), allow_pickle=True)
+        np.save(os.path.join(save_filepath, "next_state"), obj(self.next_state), allow_pickle=True)
+        np.save(os.path.join(save_filepath, "reward"), obj(self.reward), allow_pickle=True)
+        np.save(os.path.join(save_filepath, "not_done"), obj(self.not_done), allow_pickle=True)
+        np.save(os.path.join(save_filepath, "episodes"), np.array(self.episodes, dtype=object), allow_pickle=True)
+        np.save(os.path.join(save_filepath, "episodes_info"), np.array([self.max_episode, self.size, self.episodes_count, self.replay_ep_num]), allow_pickle=True)
+        np.save(os.path.join(save_filepath, "orientation_indexes"), np.array(self.orientation_indexes, dtype=object), allow_pickle=True)
+        return save_filepath
+
+    def store_saved_data_into_replay(self, filepath):
+        """Load episodes written by save_replay_buffer (ours or the reference's) and append them."""
+        import os
+        st = np.load(os.path.join(filepath, "state.npy"), allow_pickle=True)
+        ac = np.load(os.path.join(filepath, "action.npy"), allow_pickle=True)
+        ns = np.load(os.path.join(filepath, "next_state.npy"), allow_pickle=True)
+        rw = np.load(os.path.join(filepath, "reward.npy"), allow_pickle=True)
+        nd = np.load(os.path.join(filepath, "not_done.npy"), allow_pickle=True)
+        for e in range(len(st)):
+            if len(st[e]) == 0:
+                continue
+            self.add_episode(1)
+            for t in range(len(st[e])):
+                self.add(st[e][t], ac[e][t], ns[e][t], rw[e][t], 1.0 - float(nd[e][t]) if t == len(st[e]) - 1 else 0.0)
+            if float(nd[e][-1]) != 0.0:          # an episode saved without a stored done: close it explicitly
+                self.replace(float(rw[e][-1]), True)
+            self.add_episode(0)
