@@ -23,6 +23,18 @@ FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 SUBSTEPS = 15
 
 
+def ncu_traffic(n_envs):
+    """DRAM bytes per kg_step_kernel launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json),
+    only if it was taken at this env count; else None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if int(d.get("envs", -1)) == int(n_envs):
+            return d["dram_bytes_read"] + d["dram_bytes_write"]
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -115,7 +127,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_core, chunk = 32, 1
+    per_core, chunk = 128, 1
     # every "step" = one RL step over cores*per_core envs
     import multiprocessing as mp
     from oracle import kgo
@@ -248,9 +260,11 @@ def run_ours(args):
                            "parallelism": "env-sharded x%d, no data-path collective" % world},
                 "e2e": {"value": e2e_value, "unit": "physics substeps/s", "h2d_bytes_per_step": 16 * n + 4 * n, "d2h_bytes_per_step": (82 + 2) * 4 * n},
                 "gpu_launches": 2 * args.steps,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(n),
                              "peak_source": peak_src, "kernel": "kg_step_kernel", "kernel_ms": kernel_ms,
-                             "note": "state I/O is not the limiter (SURVEY 8d): the path is FP32-issue/latency bound, see fp32"},
+                             "algorithmic_bytes_per_launch": alg_bytes,
+                             "note": "state I/O is not the limiter (SURVEY 8d): the path is FP32-issue/latency bound, see fp32; "
+                                     "traffic above the algorithmic bytes is the first touch of the model tables (hulls, BVH, pose rows)"},
                 "fp32": {"achieved_tflops": fp32_achieved, "peak_tflops": FP32_PEAK_TFLOPS, "frac": fp32_achieved / FP32_PEAK_TFLOPS,
                          "basis": "3.3e5 algorithmic flop per substep (SURVEY 8d) / computed FP32 peak 148x128x2x1.965 GHz"},
                 "stats_per_substep": {"mpr_pairs": stats["mpr_pairs"] / max(1, stats["substeps"]), "newton_iters": stats["newton_iters"] / max(1, stats["substeps"]),
@@ -275,8 +289,8 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--variant", default="B", choices=["A", "B"])
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-envs", type=int, default=4)
-    ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--cpu-envs", type=int, default=16, help="cpu_baseline sample: env streams per host core")
+    ap.add_argument("--cpu-steps", type=int, default=900, help="cpu_baseline sample: RL steps per env stream (~15 s of CPU work)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1353,6 +1353,9 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
             ws.qwarm[l] = ws.qacc[l];
         }
         if (l == 0) ws.stat_newton += ws.s_iter;
+#if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
+        if (l == 0) fprintf(stderr, "NEWTON %d %d\n", ws.s_iter, ws.ngroup - 9);
+#endif
     }
     KG_SYNC();
 }
