@@ -66,9 +66,10 @@ static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u
 
 #define KG_NV 15
 #define KG_MS 16                       // row stride of 15x15 matrices
-#define KG_MAXCON 23                   // contact groups per env (overflow is counted and dropped)
+#define KG_MAXCON 19                   // contact groups per env (overflow is counted and dropped)
 #define KG_NBASE (9 + 3 * KG_MAXCON)   // 3 tendon rows, 6 limit rows, 3 frame rows per contact
-#define KG_JS 17                       // row stride of J (odd: conflict-free column access)
+#define KG_JS 20                       // row stride of J: rows are 16-byte aligned (128-bit row loads; the eight rows a
+                                       // quarter-warp reads together fall into disjoint bank groups: 20 b mod 32 = 0,20,8,28,16,4,24,12)
 #define KG_NSTAGE 54                   // contact staging slots: 8 plane lanes x 4 + 22 hull lanes
 #define KG_NOBS 82
 #define KG_MPR_TOL 1e-6f
@@ -191,6 +192,18 @@ KG_DEV void kg_quat2mat(float *M, const float *q) {
     M[0] = w * w + x * x - y * y - z * z; M[1] = 2 * (x * y - w * z); M[2] = 2 * (x * z + w * y);
     M[3] = 2 * (x * y + w * z); M[4] = w * w - x * x + y * y - z * z; M[5] = 2 * (y * z - w * x);
     M[6] = 2 * (x * z - w * y); M[7] = 2 * (y * z + w * x); M[8] = w * w - x * x - y * y + z * z;
+}
+
+// 16 consecutive floats from a 16-byte aligned shared-memory address with four 128-bit loads
+KG_DEV void kg_ld16(const float *p, float *v) {
+#if defined(__CUDA_ARCH__)
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    float4 a = q[0], b = q[1], c = q[2], d = q[3];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y; v[14] = d.z; v[15] = d.w;
+#else
+    for (int i = 0; i < 16; i++) v[i] = p[i];
+#endif
 }
 
 // warp total of ws.red[] (every lane wrote its partial in the previous phase)
@@ -377,13 +390,10 @@ KG_DEV void kg_chol_factor_solve(float *A, float *x, int kg_lane) {
     const unsigned FULL = 0xffffffffu;
     const int l = kg_lane, r = l < KG_NV ? l : KG_NV - 1;
     float a[16], invd[KG_NV];
-    {
-        const float4 *row = reinterpret_cast<const float4 *>(A + r * KG_MS);
-        float4 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
-        a[0] = q0.x; a[1] = q0.y; a[2] = q0.z; a[3] = q0.w; a[4] = q1.x; a[5] = q1.y; a[6] = q1.z; a[7] = q1.w;
-        a[8] = q2.x; a[9] = q2.y; a[10] = q2.z; a[11] = q2.w; a[12] = q3.x; a[13] = q3.y; a[14] = q3.z; a[15] = 0.f;
-    }
-    float xi = x[r];
+    // lanes 0..14 hold the rows of A, lane 15 holds the right-hand side as a 16th row: the right-looking updates then
+    // perform the forward substitution L y = x on it for free (y_j appears in lane 15 when column j is scaled)
+    kg_ld16(l == KG_NV ? x : A + r * KG_MS, a);
+    float xi = 0.f;
 #pragma unroll
     for (int j = 0; j < KG_NV; j++) {
         float djj = __shfl_sync(FULL, a[j], j);
@@ -395,17 +405,13 @@ KG_DEV void kg_chol_factor_solve(float *A, float *x, int kg_lane) {
         invd[j] = inv;
         float lj = (l == j) ? d : a[j] * inv;      // L[l][j] for l >= j (rows above j hold don't-care values)
         a[j] = lj;
+        float yj = __shfl_sync(FULL, lj, KG_NV);
+        if (l == j) xi = yj;
 #pragma unroll
         for (int k = j + 1; k < KG_NV; k++) {
             float lkj = __shfl_sync(FULL, lj, k);
             a[k] = fmaf(-lj, lkj, a[k]);
         }
-    }
-    // forward substitution L y = x
-#pragma unroll
-    for (int k = 0; k < KG_NV; k++) {
-        float t = __shfl_sync(FULL, xi, k) * invd[k];
-        xi = (l == k) ? t : (l > k ? fmaf(-a[k], t, xi) : xi);
     }
     // the backward pass needs column l of L: transpose through shared memory
     __syncwarp();
@@ -1033,11 +1039,14 @@ KG_DEV int kg_nbase(const KgWS &ws) { return 9 + 3 * (ws.ngroup - 9); }
 KG_NOINL void kg_base_dots(KgWS &ws, const float *x, float *out, int kg_lane) {
     KG_PHASE(l) {
         int nb = kg_nbase(ws);
+        float xv[16];
+        kg_ld16(x, xv);
         for (int b = l; b < nb; b += 32) {
-            const float *row = ws.J + b * KG_JS;
+            float row[16];
+            kg_ld16(ws.J + b * KG_JS, row);
             float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < KG_NV; j++) s += row[j] * x[j];
+            for (int j = 0; j < KG_NV; j++) s += row[j] * xv[j];
             out[b] = s;
         }
     }
@@ -1205,12 +1214,14 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
                     int tp = ws.gtype[g];
                     if (tp == 0) continue;
                     if (tp < 3) {
-                        const float *row = ws.J + g * KG_JS;
-                        float ji = row[l];
+                        const float *rowp = ws.J + g * KG_JS;
+                        float ji = rowp[l];
                         float t = ji * ws.bw[g];
                         gr += t; gab += fabsf(t);
                         float u = ji * ws.garef[g][1];   // D * active stored by (a)
-                        if (u != 0.f) {
+                        if (ws.garef[g][1] != 0.f) {     // warp-uniform: skip inactive limit rows
+                            float row[16];
+                            kg_ld16(rowp, row);
 #pragma unroll
                             for (int j = 0; j < KG_NV; j++) h[j] += u * row[j];
                         }
@@ -1228,8 +1239,10 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
                         float B2 = mu * (a[2] - a[3]), C2 = mu * mu * (a[2] + a[3]);
                         if (A != 0.f) {
                             float u = A * jn + B1 * j1 + B2 * j2, v1 = B1 * jn + C1 * j1, v2 = B2 * jn + C2 * j2;
+                            float vn[16], w1[16], w2[16];
+                            kg_ld16(rn, vn); kg_ld16(r1, w1); kg_ld16(r2, w2);
 #pragma unroll
-                            for (int j = 0; j < KG_NV; j++) h[j] += u * rn[j] + v1 * r1[j] + v2 * r2[j];
+                            for (int j = 0; j < KG_NV; j++) h[j] += u * vn[j] + v1 * w1[j] + v2 * w2[j];
                         }
                     }
                 }
@@ -1475,8 +1488,7 @@ KG_DEV float kg_ray_mesh(const KgModel &m, int mesh, const float *gpos, const fl
     kg_normalize(b1);
     const KgMesh &mi = m.mesh[mesh];
     const float *tv = m.tri + 9 * (size_t)mi.tri0;
-    const float *lo = m.bvh_lo + 4 * (size_t)mi.bvh0, *hi = m.bvh_hi + 4 * (size_t)mi.bvh0;
-    const int *meta = m.bvh_meta + 2 * (size_t)mi.bvh0;
+    const float *node = m.bvh_node + 8 * (size_t)mi.bvh0;    // 32-byte nodes: (lo.xyz, first|left), (hi.xyz, count)
     float inv[3];
     for (int c = 0; c < 3; c++) inv[c] = fabsf(lv[c]) > 1e-30f ? 1.0f / lv[c] : (lv[c] >= 0 ? 1e30f : -1e30f);
     float best = -1.f;
@@ -1484,7 +1496,7 @@ KG_DEV float kg_ray_mesh(const KgModel &m, int mesh, const float *gpos, const fl
     stack[sp++] = 0;
     while (sp) {
         int n = stack[--sp];
-        auto nlo = KG_LDG4(lo + 4 * n); auto nhi = KG_LDG4(hi + 4 * n);
+        auto nlo = KG_LDG4(node + 8 * n); auto nhi = KG_LDG4(node + 8 * n + 4);
         float l3[3] = {nlo.x, nlo.y, nlo.z}, h3[3] = {nhi.x, nhi.y, nhi.z};
         float t0 = 0.f, t1 = best < 0.f ? 1e30f : best;
         bool hit = true;
@@ -1495,7 +1507,7 @@ KG_DEV float kg_ray_mesh(const KgModel &m, int mesh, const float *gpos, const fl
         }
         if (t0 > t1 * (1.f + 1e-5f) + 1e-7f) hit = false;
         if (!hit) continue;
-        int first = meta[2 * n], cnt = meta[2 * n + 1];
+        int first = (int)KG_F2U(nlo.w), cnt = (int)KG_F2U(nhi.w);
         if (cnt == 0) { if (sp < 46) { stack[sp++] = first; stack[sp++] = first + 1; } }
         else for (int i = 0; i < cnt; i++) {
             float x = kg_ray_tri(tv + 9 * (size_t)(first + i), lp, lv, b0, b1);

@@ -54,16 +54,15 @@ struct KgModel {
     const int *adj_start;
     const unsigned short *adj;
     const float *tri;              // 9 floats per triangle, BVH leaf order
-    const float *bvh_lo, *bvh_hi;  // xyz + pad per node
-    const int *bvh_meta;           // (left|first, count) per node
+    const float *bvh_node;         // 8 floats per node: lo.xyz, bits(left child | first triangle), hi.xyz, bits(triangle count; 0 = inner)
     const float *pose_train, *pose_test;  // [shape][orient][row][9]
     int pose_rows_train, pose_rows_test;
 };
 
 // ---------------------------------------------------------------------------------- host loader
 struct KgHostTables {
-    std::vector<float> hull_vert, hull_pad, tri, bvh_lo, bvh_hi, pose_train, pose_test;
-    std::vector<int> adj_start, bvh_meta;
+    std::vector<float> hull_vert, hull_pad, tri, bvh_node, pose_train, pose_test;
+    std::vector<int> adj_start;
     std::vector<unsigned short> adj, adj8;
 };
 
@@ -227,9 +226,20 @@ inline std::string kg_load_model(const void *blob_, size_t nbytes, KgModel *m, K
     }
     const float *fp;
     fp = F("tri_vert", &n); KG_NEED(fp); t->tri.assign(fp, fp + n);
-    fp = F("bvh_lo", &n); KG_NEED(fp); t->bvh_lo.assign(n / 3 * 4, 0.f); for (size_t i = 0; i < n / 3; i++) for (int c = 0; c < 3; c++) t->bvh_lo[4 * i + c] = fp[3 * i + c];
-    fp = F("bvh_hi", &n); KG_NEED(fp); t->bvh_hi.assign(n / 3 * 4, 0.f); for (size_t i = 0; i < n / 3; i++) for (int c = 0; c < 3; c++) t->bvh_hi[4 * i + c] = fp[3 * i + c];
-    ip = I("bvh_meta", &n); KG_NEED(ip); t->bvh_meta.assign(ip, ip + n);
+    {
+        size_t nlo = 0, nhi = 0, nmeta = 0;
+        const float *lo = F("bvh_lo", &nlo), *hi = F("bvh_hi", &nhi);
+        const int *meta = I("bvh_meta", &nmeta);
+        KG_NEED(lo); KG_NEED(hi); KG_NEED(meta);
+        size_t nn = nlo / 3;
+        if (nhi != nlo || nmeta != 2 * nn) return "bvh sections disagree";
+        t->bvh_node.assign(8 * nn, 0.f);
+        for (size_t i = 0; i < nn; i++) {
+            for (int c = 0; c < 3; c++) { t->bvh_node[8 * i + c] = lo[3 * i + c]; t->bvh_node[8 * i + 4 + c] = hi[3 * i + c]; }
+            std::memcpy(&t->bvh_node[8 * i + 3], &meta[2 * i], 4);
+            std::memcpy(&t->bvh_node[8 * i + 7], &meta[2 * i + 1], 4);
+        }
+    }
     fp = F("pose_train", &n); KG_NEED(fp); t->pose_train.assign(fp, fp + n); m->pose_rows_train = (int)(n / (KG_NSHAPE * 3 * 9));
     fp = F("pose_test", &n); KG_NEED(fp); t->pose_test.assign(fp, fp + n); m->pose_rows_test = (int)(n / (KG_NSHAPE * 3 * 9));
 #undef KG_NEED
