@@ -259,7 +259,7 @@ def run_ours(args):
                            "l2": "flushed between timed steps by a 256 MiB write (excluded from the timed spans); state is 2.4 MB per 4096 envs",
                            "parallelism": "env-sharded x%d, no data-path collective" % world},
                 "e2e": {"value": e2e_value, "unit": "physics substeps/s", "h2d_bytes_per_step": 16 * n + 4 * n, "d2h_bytes_per_step": (82 + 2) * 4 * n},
-                "gpu_launches": 2 * args.steps,
+                "gpu_launches": 3 * args.steps,   # kg_schedule_kernel + kg_step_kernel + kg_reset_kernel per step
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(n),
                              "peak_source": peak_src, "kernel": "kg_step_kernel", "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_launch": alg_bytes,

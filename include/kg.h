@@ -80,6 +80,10 @@ int kg_set_frame_skip(kg_handle h, int frame_skip);        /* KinovaGripper_Env(
 /* Multi-GPU sharding: this handle owns global envs [offset, offset+n).  Only the pose sampler's counter-based RNG
  * looks at it, so that a run's draws do not depend on how many GPUs the envs are spread over. */
 int kg_set_env_offset(kg_handle h, int offset);
+/* Launch schedule of kg_step (no effect on results): 1 (default) = warp slots are filled in order of decreasing cost of
+ * each env's previous step, so that the environments sharing a CTA's stage barriers carry similar contact loads;
+ * 0 = env i runs in slot i. */
+int kg_set_schedule(kg_handle h, int mode);
 /* The action the last kg_step applied (the caller's, or the on-device expert's: get_action, expert_data.py:610). float[4][n]. */
 int kg_get_last_action_host(kg_handle h, float *action_host);
 

@@ -30,6 +30,8 @@ struct kg_handle_s {
     KgModel model;            // host copy; table pointers are device pointers (or host pointers under KG_EMU)
     KgEnvArrays A;
     int *ep_count = nullptr;  // [n] episodes started per env (RNG counter)
+    int *perm = nullptr;      // [n] launch schedule of kg_step_kernel: warp slot -> env, heaviest envs first
+    int schedule = 1;         // 0 = slot i runs env i; 1 = slots sorted by the load of each env's last step
     std::vector<void *> allocs;
     // scratch for the *_host entry points
     float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_euler = nullptr, *d_objp = nullptr, *d_q = nullptr;
@@ -144,10 +146,33 @@ __device__ __forceinline__ const float *kg_cta_finger_hulls(unsigned char *dst) 
     __syncthreads();
     return reinterpret_cast<const float *>(dst);
 }
-__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_step_kernel(KgEnvArrays A, const float *action, int mode, int nsub, float *obs, float *reward, int *done, float *act_out) {
+// Launch schedule.  The environments of one CTA rendezvous before every pipeline stage, so a CTA runs at the pace of its
+// slowest environment (ncu: 37 % of all warp samples were barrier waits with envs placed by index).  The cost of an env's
+// step is dominated by its contact state (MPR pairs, Newton iterations) and changes slowly from one RL step to the next,
+// so the warp slots are filled in order of decreasing cost of the previous step: CTAs become homogeneous, and the
+// heaviest CTAs start first so that the light ones fill the tail of the grid.  One CTA counting sort (256 keys).
+#define KG_SCHED_KEYS 256
+__global__ void __launch_bounds__(1024) kg_schedule_kernel(const int *load, int *perm, int n) {
+    __shared__ int hist[KG_SCHED_KEYS], base[KG_SCHED_KEYS];
+    for (int i = threadIdx.x; i < KG_SCHED_KEYS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(max(load[i], 0), KG_SCHED_KEYS - 1)], 1);
+    __syncthreads();
+    if (threadIdx.x < 32) {      // exclusive prefix over the keys in DESCENDING order, 8 keys per lane
+        int s[8], tot = 0;
+        for (int k = 0; k < 8; k++) { s[k] = tot; tot += hist[KG_SCHED_KEYS - 1 - (8 * threadIdx.x + k)]; }
+        int inc = tot;
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += v; }
+        for (int k = 0; k < 8; k++) base[KG_SCHED_KEYS - 1 - (8 * threadIdx.x + k)] = inc - tot + s[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&base[min(max(load[i], 0), KG_SCHED_KEYS - 1)], 1)] = i;
+}
+__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_step_kernel(KgEnvArrays A, const int *perm, const float *action, int mode, int nsub, float *obs, float *reward, int *done, float *act_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * KG_WARPS + warp;
+    const int slot = blockIdx.x * KG_WARPS + warp;
+    const int env = slot < A.N ? (perm ? perm[slot] : slot) : A.N;
     unsigned char *tail = smem + KG_WARPS * sizeof(KgWS);
     KgCta cta;
     cta.ws_base = reinterpret_cast<KgWS *>(smem); cta.warp = warp;
@@ -212,7 +237,8 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
     cudaStream_t st = (cudaStream_t)h->stream;
     int blocks = (h->n + KG_WARPS - 1) / KG_WARPS;
     cudaEventRecord(h->ev0, st);
-    kg_step_kernel<<<blocks, KG_WARPS * 32, KG_WARPS * ws_bytes() + KG_FHULL_BYTES, st>>>(h->A, action, mode, h->frame_skip, obs, reward, done, act_out);
+    if (h->schedule) kg_schedule_kernel<<<1, 1024, 0, st>>>(h->A.load, h->perm, h->n);
+    kg_step_kernel<<<blocks, KG_WARPS * 32, KG_WARPS * ws_bytes() + KG_FHULL_BYTES, st>>>(h->A, h->schedule ? h->perm : nullptr, action, mode, h->frame_skip, obs, reward, done, act_out);
     cudaEventRecord(h->ev1, st);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -286,6 +312,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     TRY(be_alloc(h, (void **)&A.hand_quat, 4 * N * 4)); TRY(be_alloc(h, (void **)&A.shape, N * 4)); TRY(be_alloc(h, (void **)&A.elapsed, N * 4));
     TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
     TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
+    TRY(be_alloc(h, (void **)&A.load, N * 4)); TRY(be_alloc(h, (void **)&h->perm, N * 4));
     TRY(be_alloc(h, (void **)&h->d_action, 4 * N * 4)); TRY(be_alloc(h, (void **)&h->d_obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&h->d_reward, N * 4));
     TRY(be_alloc(h, (void **)&h->d_done, N * 4)); TRY(be_alloc(h, (void **)&h->d_mask, N * 4)); TRY(be_alloc(h, (void **)&h->d_shape, N * 4));
     TRY(be_alloc(h, (void **)&h->d_euler, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_objp, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_q, 31 * N * 4));
@@ -319,6 +346,7 @@ int kg_set_stream(kg_handle h, void *stream) { if (!h) return KG_EINVAL; h->stre
 int kg_sync(kg_handle h) { if (!h) return KG_EINVAL; return be_sync(h); }
 int kg_set_max_episode_steps(kg_handle h, int steps) { if (!h || steps <= 0) return KG_EINVAL; h->A.max_steps = steps; return KG_OK; }
 int kg_set_frame_skip(kg_handle h, int fs) { if (!h || fs <= 0) return KG_EINVAL; h->frame_skip = fs; return KG_OK; }
+int kg_set_schedule(kg_handle h, int mode) { if (!h || mode < 0 || mode > 1) return KG_EINVAL; h->schedule = mode; return KG_OK; }
 int kg_set_env_offset(kg_handle h, int offset) { if (!h || offset < 0) return KG_EINVAL; h->env_offset = offset; return KG_OK; }
 int kg_get_last_action_host(kg_handle h, float *act) {
     if (!h || !act) return KG_EINVAL;

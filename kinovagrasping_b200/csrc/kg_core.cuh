@@ -1745,6 +1745,7 @@ struct KgEnvArrays {
     float *obs;                   // [82][N] last observation (input of the expert controller)
     float *last_action;           // [4][N] action applied by the last step (given or expert)
     int *stats;                   // [4] mpr pairs, newton iterations, contact overflows, substeps
+    int *load;                    // [N] cost of each env's last RL step (Newton iterations + 2 x MPR pairs): key of the launch schedule
     long long *prof;              // [KG_NPROF] KG_PROF builds only
     int N, max_steps;
 };
@@ -1822,6 +1823,7 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
             int d = dn || (el >= A.max_steps);
             if (reward_out) reward_out[env] = rew;
             if (done_out) done_out[env] = d;
+            if (A.load) A.load[env] = d ? 0 : ws.stat_newton + 2 * ws.stat_mpr;   // a finished episode restarts contact-free
             for (int c = 0; c < 4; c++) { A.last_action[c * N + env] = act[c]; if (action_out) action_out[c * N + env] = act[c]; }
 #if defined(__CUDA_ARCH__)
             if (A.stats) { atomicAdd(A.stats, ws.stat_mpr); atomicAdd(A.stats + 1, ws.stat_newton); atomicAdd(A.stats + 2, ws.stat_overflow); atomicAdd(A.stats + 3, nsub); }

@@ -78,6 +78,9 @@ class Handle:
     def set_env_offset(self, off):
         self._chk(self.lib.kg_set_env_offset(self.h, int(off)), "kg_set_env_offset")
 
+    def set_schedule(self, mode):
+        self._chk(self.lib.kg_set_schedule(self.h, int(mode)), "kg_set_schedule")
+
     def last_action_host(self):
         a = np.zeros((4, self.n), dtype=np.float32)
         self._chk(self.lib.kg_get_last_action_host(self.h, _np_ptr(a)), "kg_get_last_action_host")

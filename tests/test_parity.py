@@ -267,3 +267,28 @@ def test_expert_modes_and_rollout_success_parity(backend, oracle, card):
         assert abs(int(succ_k.sum()) - int(succ_o.sum())) <= slack, (succ_k.sum(), succ_o.sum())
         assert succ_o.sum() > 0.3 * n                             # the side grasp does lift (sanity band, expert_plots/*.npy)
         assert h.stats()["contact_overflow"] == 0
+
+
+@pytest.mark.gpu
+def test_launch_schedule_does_not_change_results(card):
+    """The load-sorted warp-slot -> env schedule (kg_set_schedule) is a placement decision only: 12 expert RL steps with
+    auto-reset give bit-identical observations, rewards, dones and states with the schedule on and off."""
+    from kinovagrasping_b200 import _lib
+    lib = _lib.load()
+    n = 600                                           # not a multiple of the CTA's 16 slots
+    shape, euler, objp = _poses(card, n, 11, orient_idx=(2,), shapes=(0, 1, 4, 8))
+    runs = []
+    for mode in (0, 1):
+        h = Handle(n, lib=lib)
+        h.set_schedule(mode)
+        h.reset_host(shape, euler, objp)
+        trace = []
+        for _ in range(12):
+            obs, rew, done = h.step_host(None, 2)
+            trace.append((obs.copy(), rew.copy(), done.copy()))
+        trace.append(h.get_state_host())
+        runs.append(trace)
+        h.close()
+    for a, b in zip(*runs):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)

@@ -17,6 +17,8 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 12
 variant = int(os.environ.get("KG_VARIANT", "1"))
 h = Handle(n, lib=lib)
+sched = int(os.environ.get("KG_SCHEDULE", "1"))
+h.set_schedule(sched)
 shape = (np.arange(n) % 2).astype(np.int32)
 import torch
 sh = torch.from_numpy(shape).cuda()
@@ -30,7 +32,7 @@ for t in range(steps):
 h.sync()
 st = h.stats()
 ms = np.array(ms)
-print(f"{os.path.basename(sys.argv[1]):28s} envs {n} kernel ms: median {np.median(ms[3:]):.3f} min {ms[3:].min():.3f} max {ms[3:].max():.3f} "
+print(f"{os.path.basename(sys.argv[1]):28s} sched {sched} envs {n} kernel ms: median {np.median(ms[3:]):.3f} min {ms[3:].min():.3f} max {ms[3:].max():.3f} "
       f"-> {n * 15 / np.median(ms[3:]) * 1e3:.3e} substeps/s | mpr/sub {st['mpr_pairs'] / st['substeps']:.2f} newton/sub {st['newton_iters'] / st['substeps']:.2f} ovf {st['contact_overflow']}")
 prof = (C.c_longlong * 32)()
 lib.kg_get_prof(h.h, prof)
