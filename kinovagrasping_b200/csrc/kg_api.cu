@@ -32,6 +32,10 @@ struct kg_handle_s {
     int *ep_count = nullptr;  // [n] episodes started per env (RNG counter)
     int *perm = nullptr;      // [n] launch schedule of kg_step_kernel: warp slot -> env, heaviest envs first
     int schedule = 1;         // 0 = slot i runs env i; 1 = slots sorted by the load of each env's last step
+    unsigned char *carry = nullptr;   // [n][KG_CARRY_BYTES] per-env carry records between the kernels of one RL step
+    unsigned *tasks = nullptr;        // [n * 22] narrowphase task list of the current substep: (env << 8) | pair lane
+    int *q = nullptr;                 // two {queued, next} pairs: the per-env kernels fill one while the other is being reset
+    int qsel = 0;
     std::vector<void *> allocs;
     // scratch for the *_host entry points
     float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_euler = nullptr, *d_objp = nullptr, *d_q = nullptr;
@@ -41,7 +45,8 @@ struct kg_handle_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 #endif
     float last_ms = 0.f;
-    int fhull_bytes = 0;       // shared-memory copy of the finger hulls appended to each CTA's workspaces
+    int fhull_bytes = 0;       // shared-memory copy of the finger hulls in every narrowphase CTA
+    int mpr_grid = 1;          // persistent narrowphase grid: resident CTAs per SM x SMs
 #ifdef KG_EMU
     KgHostTables tables;
 #endif
@@ -100,14 +105,18 @@ KG_DEV KgSample kg_sample_pose(const KgModel &m, unsigned long long seed, int en
     return s;
 }
 
-// one mj_forward with a dump of the intermediates (test hook behind kg_forward_debug)
-KG_DEV void kg_debug_run(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *ctrl, float *out, int kg_lane, const KgCta &cta) {
+// one mj_forward with a dump of the intermediates (test hook behind kg_forward_debug), in the same three pieces as
+// a production substep: begin (kinematics + lane collision) -> narrowphase tasks -> end (rows, solve)
+KG_DEV unsigned kg_debug_begin(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *ctrl, int kg_lane) {
     kg_load_env(m, ws, A, env, kg_lane);
     KG_PHASE(l) { if (l < 9) ws.ctrl[l] = ctrl[l]; }
     KG_SYNC();
     kg_kinematics(m, ws, kg_lane);
+    return kg_collision_lane(m, ws, kg_lane);
+}
+KG_DEV void kg_debug_end(const KgModel &m, KgWS &ws, float *out, int kg_lane) {
     kg_dynamics(m, ws, kg_lane);
-    kg_collision(m, ws, kg_lane, cta, 0);
+    kg_compaction(m, ws, kg_lane);
     kg_make_rows(m, ws, kg_lane);
     KG_PHASE(l) {      // the contact staging shares storage with the solver scratch: dump it before the solve
         if (l == 0) out[300] = (float)ws.ncon_total;
@@ -136,21 +145,10 @@ KG_DEV void kg_debug_run(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int e
 
 // ------------------------------------------------------------------------------------------------ kernels / emu loops
 #ifndef KG_EMU
-// The finger hulls (proximal + distal: the meshes every narrowphase scan touches) are staged once per CTA behind the
-// per-warp workspaces; returns the shared-memory table.
-__device__ __forceinline__ const float *kg_cta_finger_hulls(unsigned char *dst) {
-    const int n4 = c_model.hnpad[1] + c_model.hnpad[2];
-    const float4 *src = reinterpret_cast<const float4 *>(c_model.hull_pad) + c_model.hpad0[1];
-    float4 *d4 = reinterpret_cast<float4 *>(dst);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = __ldg(src + i);
-    __syncthreads();
-    return reinterpret_cast<const float *>(dst);
-}
-// Launch schedule.  The environments of one CTA rendezvous before every pipeline stage, so a CTA runs at the pace of its
-// slowest environment (ncu: 37 % of all warp samples were barrier waits with envs placed by index).  The cost of an env's
-// step is dominated by its contact state (MPR pairs, Newton iterations) and changes slowly from one RL step to the next,
-// so the warp slots are filled in order of decreasing cost of the previous step: CTAs become homogeneous, and the
-// heaviest CTAs start first so that the light ones fill the tail of the grid.  One CTA counting sort (256 keys).
+// Launch schedule.  Environments that share a CTA share its instruction stream (and, in builds with stage rendezvous,
+// its pace); the cost of an env's step is dominated by its contact state (MPR pairs, Newton iterations) and changes
+// slowly from one RL step to the next, so the warp slots are filled in order of decreasing cost of the previous step:
+// the heaviest warps start first and the light ones fill the tail of the grid.  One CTA counting sort (256 keys).
 #define KG_SCHED_KEYS 256
 __global__ void __launch_bounds__(1024) kg_schedule_kernel(const int *load, int *perm, int n) {
     __shared__ int hist[KG_SCHED_KEYS], base[KG_SCHED_KEYS];
@@ -168,23 +166,91 @@ __global__ void __launch_bounds__(1024) kg_schedule_kernel(const int *load, int 
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&base[min(max(load[i], 0), KG_SCHED_KEYS - 1)], 1)] = i;
 }
-__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_step_kernel(KgEnvArrays A, const int *perm, const float *action, int mode, int nsub, float *obs, float *reward, int *done, float *act_out) {
+
+// ---- per-env kernels: one warp per environment, KG_WARPS environments per CTA, one KgWS per warp in shared memory
+#define KG_ENV_OF_WARP() \
+    extern __shared__ __align__(16) unsigned char smem[]; \
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; \
+    const int slot = blockIdx.x * KG_WARPS + warp; \
+    if (slot >= A.N) return; \
+    const int env = perm ? perm[slot] : slot; \
+    KgWS &ws = *(reinterpret_cast<KgWS *>(smem) + warp)
+
+// first kernel of an RL step: action / on-device expert, kinematics and lane-parallel collision of substep 0
+__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_begin_kernel(KgEnvArrays A, const int *perm, const float *action, int mode,
+                                                                               unsigned char *carry, int *q, unsigned *tasks) {
+    KG_ENV_OF_WARP();
+    const unsigned mask = kg_step_begin(c_model, ws, A, env, action, mode, lane);
+    kg_carry_store(ws, carry + (size_t)env * KG_CARRY_BYTES, lane);
+    kg_emit_tasks(mask, env, q, tasks, lane);
+    kg_prof_flush(ws, A, lane);
+}
+// one per substep: finish substep s (dynamics, rows, Newton solve, Euler) and, unless it is the last one, start
+// substep s+1 (kinematics, lane-parallel collision, narrowphase tasks); the last one ends the RL step (rays, obs, reward)
+template <bool LAST>
+__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_kernel(KgEnvArrays A, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
+                                                                             int nsub, float *obs, float *reward, int *done, float *act_out) {
+    KG_ENV_OF_WARP();
+    unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
+    kg_carry_load(ws, rec, lane);
+    kg_substep_finish(c_model, ws, lane);
+    if (LAST) kg_step_end(c_model, ws, A, env, nsub, obs, reward, done, act_out, lane);
+    else {
+        const unsigned mask = kg_substep_start(c_model, ws, lane);
+        kg_carry_store(ws, rec, lane);
+        kg_emit_tasks(mask, env, q, tasks, lane);
+    }
+    kg_prof_flush(ws, A, lane);
+}
+// ---- narrowphase kernel: persistent warps pull (env, pair) tasks from the global list; every task is one full MPR run
+// by all 32 lanes.  The finger hulls (the meshes every scan touches) are staged once per CTA, the object hull per warp.
+#ifndef KG_MPR_WARPS
+#define KG_MPR_WARPS 8
+#endif
+#ifndef KG_MPR_MINBLOCKS
+#define KG_MPR_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_kernel(unsigned char *carry, int *q, int *q_other, const unsigned *tasks, long long *prof) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * KG_WARPS + warp;
-    const int env = slot < A.N ? (perm ? perm[slot] : slot) : A.N;
-    unsigned char *tail = smem + KG_WARPS * sizeof(KgWS);
-    KgCta cta;
-    cta.ws_base = reinterpret_cast<KgWS *>(smem); cta.warp = warp;
-    cta.q = reinterpret_cast<int *>(tail); cta.queue = reinterpret_cast<unsigned short *>(tail + 16);
-    if (threadIdx.x < 4) cta.q[threadIdx.x] = 0;
-    const float *fh = kg_cta_finger_hulls(tail + KG_CTA_QBYTES);
-    if (env >= A.N) return;
-    KgWS &ws = *(reinterpret_cast<KgWS *>(smem) + warp);
-    if (lane == 0) ws.fhull = fh;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { q_other[0] = 0; q_other[1] = 0; }   // the list the next per-env kernel fills
+    const int ntask = q[0];
+    if (ntask == 0) return;
+    KgMprWS &mw = *(reinterpret_cast<KgMprWS *>(smem) + warp);
+    float4 *fh = reinterpret_cast<float4 *>(smem + KG_MPR_WARPS * sizeof(KgMprWS));
+    {
+        const int n4 = c_model.hnpad[1] + c_model.hnpad[2];
+        const float4 *src = reinterpret_cast<const float4 *>(c_model.hull_pad) + c_model.hpad0[1];
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) fh[i] = __ldg(src + i);
+    }
+    if (lane == 0) { mw.fhull = reinterpret_cast<const float *>(fh); mw.hull_shape = -1; }
+#ifdef KG_PROF
+    if (lane < KG_NPROF) mw.prof[lane] = 0;
+#endif
+    __syncthreads();
+#ifdef KG_PROF
+    long long t0 = clock64(), nt = 0;
+#endif
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(q + 1, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntask) break;
+        const unsigned task = tasks[t];
+        kg_mpr_task(c_model, mw, carry + (size_t)(task >> 8) * KG_CARRY_BYTES, (int)(task & 0xff), lane);
+#ifdef KG_PROF
+        nt++;
+#endif
+    }
+#ifdef KG_PROF
     __syncwarp();
-    kg_env_step(c_model, ws, A, env, action, mode, nsub, obs, reward, done, act_out, lane, cta);
+    if (prof) {
+        if (lane >= 20 && lane < 28) atomicAdd((unsigned long long *)prof + lane, (unsigned long long)mw.prof[lane]);
+        if (lane == 0) { atomicAdd((unsigned long long *)prof + 28, (unsigned long long)(clock64() - t0)); atomicAdd((unsigned long long *)prof + 29, (unsigned long long)nt); }
+    }
+#endif
 }
+
 __global__ void __launch_bounds__(KG_WARPS * 32) kg_reset_kernel(KgEnvArrays A, const int *mask, const int *shape, const float *euler, const float *objp,
                                                                  int sampled, int orient, int variant, int test_table, unsigned long long seed, int *ep_count, int env_offset, float *obs) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -205,40 +271,84 @@ __global__ void __launch_bounds__(KG_WARPS * 32) kg_reset_kernel(KgEnvArrays A, 
     if (lane == 0) ep_count[env] += 1;
     kg_env_reset(c_model, ws, A, env, sh, e, p, obs, lane);
 }
-__global__ void kg_debug_kernel(KgEnvArrays A, int env, const float *ctrl, float *out) {
+__global__ void kg_debug_begin_kernel(KgEnvArrays A, int env, const float *ctrl, unsigned char *carry, int *q, unsigned *tasks) {
     extern __shared__ __align__(16) unsigned char smem[];
     KgWS &ws = *reinterpret_cast<KgWS *>(smem);
-    unsigned char *tail = smem + sizeof(KgWS);
-    KgCta cta;
-    cta.ws_base = &ws; cta.warp = 0;
-    cta.q = reinterpret_cast<int *>(tail); cta.queue = reinterpret_cast<unsigned short *>(tail + 16);
-    if (threadIdx.x < 4) cta.q[threadIdx.x] = 0;
-    const float *fh = kg_cta_finger_hulls(tail + KG_CTA_QBYTES);
-    if (threadIdx.x == 0) ws.fhull = fh;
-    __syncwarp();
-    kg_debug_run(c_model, ws, A, env, ctrl, out, threadIdx.x & 31, cta);
+    const int lane = threadIdx.x & 31;
+    const unsigned mask = kg_debug_begin(c_model, ws, A, env, ctrl, lane);
+    kg_carry_store(ws, carry + (size_t)env * KG_CARRY_BYTES, lane);
+    kg_emit_tasks(mask, env, q, tasks, lane);
+}
+__global__ void kg_debug_end_kernel(int env, const unsigned char *carry, float *out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    KgWS &ws = *reinterpret_cast<KgWS *>(smem);
+    const int lane = threadIdx.x & 31;
+    kg_carry_load(ws, carry + (size_t)env * KG_CARRY_BYTES, lane);
+    kg_debug_end(c_model, ws, out, lane);
 }
 #else
 static KgWS g_ws;
-static KgCta g_cta = {&g_ws, 0, nullptr, nullptr};
+static KgMprWS g_mw;
 #endif
 
 static size_t ws_bytes() { return sizeof(KgWS); }
-#define KG_FHULL_BYTES ((size_t)h->fhull_bytes + KG_CTA_QBYTES)
 #ifndef KG_EMU
-static_assert(KG_WARPS * sizeof(KgWS) + 16 * 1024 <= 227 * 1024, "KG_WARPS workspaces + finger hulls + task queue must fit one SM's shared memory");
+static_assert(KG_WARPS * sizeof(KgWS) <= 227 * 1024, "KG_WARPS workspaces must fit one SM's shared memory");
+#define KG_MPR_SMEM(h) (KG_MPR_WARPS * sizeof(KgMprWS) + (size_t)(h)->fhull_bytes)
 #endif
 
-static int launch_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
 #ifdef KG_EMU
-    for (int env = 0; env < h->n; env++) kg_env_step(h->model, g_ws, h->A, env, action, mode, h->frame_skip, obs, reward, done, act_out, 0, g_cta);
+// host emulation of the narrowphase kernel: the tasks of list `sel` in order, then the list resets
+static void emu_run_tasks(kg_handle h, int sel) {
+    int *q = h->q + 2 * sel;
+    for (int t = 0; t < q[0]; t++) {
+        const unsigned task = h->tasks[t];
+        kg_mpr_task(h->model, g_mw, h->carry + (size_t)(task >> 8) * KG_CARRY_BYTES, (int)(task & 0xff), 0);
+    }
+    q[0] = 0; q[1] = 0;
+}
+#endif
+
+// One RL step = a wavefront of kernels on the handle's stream:
+//   [schedule] begin | nsub x ( narrowphase tasks | per-env substep kernel )     (2 nsub + 1 launches of our kernels)
+static int launch_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
+    const int nsub = h->frame_skip;
+#ifdef KG_EMU
+    for (int env = 0; env < h->n; env++) {
+        unsigned mask = kg_step_begin(h->model, g_ws, h->A, env, action, mode, 0);
+        kg_carry_store(g_ws, h->carry + (size_t)env * KG_CARRY_BYTES, 0);
+        kg_emit_tasks(mask, env, h->q + 2 * h->qsel, h->tasks, 0);
+    }
+    for (int s = 0; s < nsub; s++) {
+        emu_run_tasks(h, h->qsel);
+        h->qsel ^= 1;
+        for (int env = 0; env < h->n; env++) {
+            unsigned char *rec = h->carry + (size_t)env * KG_CARRY_BYTES;
+            kg_carry_load(g_ws, rec, 0);
+            kg_substep_finish(h->model, g_ws, 0);
+            if (s == nsub - 1) kg_step_end(h->model, g_ws, h->A, env, nsub, obs, reward, done, act_out, 0);
+            else {
+                unsigned mask = kg_substep_start(h->model, g_ws, 0);
+                kg_carry_store(g_ws, rec, 0);
+                kg_emit_tasks(mask, env, h->q + 2 * h->qsel, h->tasks, 0);
+            }
+        }
+    }
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)h->stream;
-    int blocks = (h->n + KG_WARPS - 1) / KG_WARPS;
+    const int blocks = (h->n + KG_WARPS - 1) / KG_WARPS;
+    const size_t smem = KG_WARPS * ws_bytes();
+    const int *perm = h->schedule ? h->perm : nullptr;
     cudaEventRecord(h->ev0, st);
     if (h->schedule) kg_schedule_kernel<<<1, 1024, 0, st>>>(h->A.load, h->perm, h->n);
-    kg_step_kernel<<<blocks, KG_WARPS * 32, KG_WARPS * ws_bytes() + KG_FHULL_BYTES, st>>>(h->A, h->schedule ? h->perm : nullptr, action, mode, h->frame_skip, obs, reward, done, act_out);
+    kg_begin_kernel<<<blocks, KG_WARPS * 32, smem, st>>>(h->A, perm, action, mode, h->carry, h->q + 2 * h->qsel, h->tasks);
+    for (int s = 0; s < nsub; s++) {
+        kg_mpr_kernel<<<h->mpr_grid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), st>>>(h->carry, h->q + 2 * h->qsel, h->q + 2 * (h->qsel ^ 1), h->tasks, h->A.prof);
+        h->qsel ^= 1;
+        if (s == nsub - 1) kg_sub_kernel<true><<<blocks, KG_WARPS * 32, smem, st>>>(h->A, perm, h->carry, h->q + 2 * h->qsel, h->tasks, nsub, obs, reward, done, act_out);
+        else kg_sub_kernel<false><<<blocks, KG_WARPS * 32, smem, st>>>(h->A, perm, h->carry, h->q + 2 * h->qsel, h->tasks, nsub, obs, reward, done, act_out);
+    }
     cudaEventRecord(h->ev1, st);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -293,16 +403,27 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     m.hull_vert = t.hull_vert.data(); m.adj_start = t.adj_start.data(); m.adj = t.adj.data(); m.adj8 = t.adj8.data(); m.hull_pad = t.hull_pad.data(); m.tri = t.tri.data();
     m.bvh_node = t.bvh_node.data();
     m.pose_train = t.pose_train.data(); m.pose_test = t.pose_test.data();
-    g_ws.fhull = m.hull_pad + 4 * (size_t)m.hpad0[1];     // host emulation: no staging copy
+    g_mw.fhull = m.hull_pad + 4 * (size_t)m.hpad0[1];     // host emulation: no staging copy
+    g_mw.hull_shape = -1;
 #else
 #define UP(field, vec) do { void *p_; TRY(be_alloc(h, &p_, (vec).size() * sizeof((vec)[0]))); CUDA_TRY(h, cudaMemcpy(p_, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice)); m.field = (decltype(m.field))p_; } while (0)
     UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(adj8, t.adj8); UP(hull_pad, t.hull_pad); UP(tri, t.tri);
     UP(bvh_node, t.bvh_node); UP(pose_train, t.pose_train); UP(pose_test, t.pose_test);
 #undef UP
     CUDA_TRY(h, cudaMemcpyToSymbol(c_model, &m, sizeof(KgModel)));
-    CUDA_TRY(h, cudaFuncSetAttribute(kg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes() + KG_FHULL_BYTES)));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
     CUDA_TRY(h, cudaFuncSetAttribute(kg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
-    CUDA_TRY(h, cudaFuncSetAttribute(kg_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ws_bytes() + KG_FHULL_BYTES)));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_mpr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_MPR_SMEM(h)));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_debug_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_bytes()));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_debug_end_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_bytes()));
+    {
+        int per_sm = 0, sms = 0;
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kg_mpr_kernel, KG_MPR_WARPS * 32, KG_MPR_SMEM(h)));
+        CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        h->mpr_grid = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    }
     CUDA_TRY(h, cudaEventCreate(&h->ev0)); CUDA_TRY(h, cudaEventCreate(&h->ev1));
 #endif
     const size_t N = (size_t)n_envs;
@@ -313,6 +434,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
     TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
     TRY(be_alloc(h, (void **)&A.load, N * 4)); TRY(be_alloc(h, (void **)&h->perm, N * 4));
+    TRY(be_alloc(h, (void **)&h->carry, N * KG_CARRY_BYTES)); TRY(be_alloc(h, (void **)&h->tasks, N * 22 * 4)); TRY(be_alloc(h, (void **)&h->q, 4 * 4));
     TRY(be_alloc(h, (void **)&h->d_action, 4 * N * 4)); TRY(be_alloc(h, (void **)&h->d_obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&h->d_reward, N * 4));
     TRY(be_alloc(h, (void **)&h->d_done, N * 4)); TRY(be_alloc(h, (void **)&h->d_mask, N * 4)); TRY(be_alloc(h, (void **)&h->d_shape, N * 4));
     TRY(be_alloc(h, (void **)&h->d_euler, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_objp, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_q, 31 * N * 4));
@@ -431,11 +553,27 @@ int kg_get_prof(kg_handle h, long long out[KG_NPROF]) {
 int kg_forward_debug(kg_handle h, int env, const float *ctrl, float *out) {
     if (!h || env < 0 || env >= h->n || !ctrl || !out) return KG_EINVAL;
     TRY(be_h2d(h, h->d_ctrl, ctrl, 9 * 4));
+    unsigned char *rec = h->carry + (size_t)env * KG_CARRY_BYTES;
 #ifdef KG_EMU
-    kg_debug_run(h->model, g_ws, h->A, env, h->d_ctrl, h->d_debug, 0, g_cta);
+    {
+        unsigned mask = kg_debug_begin(h->model, g_ws, h->A, env, h->d_ctrl, 0);
+        kg_carry_store(g_ws, rec, 0);
+        kg_emit_tasks(mask, env, h->q + 2 * h->qsel, h->tasks, 0);
+        emu_run_tasks(h, h->qsel);
+        h->qsel ^= 1;
+        kg_carry_load(g_ws, rec, 0);
+        kg_debug_end(h->model, g_ws, h->d_debug, 0);
+    }
 #else
-    kg_debug_kernel<<<1, 32, ws_bytes() + KG_FHULL_BYTES, (cudaStream_t)h->stream>>>(h->A, env, h->d_ctrl, h->d_debug);
-    CUDA_TRY(h, cudaGetLastError());
+    {
+        cudaStream_t st = (cudaStream_t)h->stream;
+        (void)rec;
+        kg_debug_begin_kernel<<<1, 32, ws_bytes(), st>>>(h->A, env, h->d_ctrl, h->carry, h->q + 2 * h->qsel, h->tasks);
+        kg_mpr_kernel<<<h->mpr_grid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), st>>>(h->carry, h->q + 2 * h->qsel, h->q + 2 * (h->qsel ^ 1), h->tasks, nullptr);
+        h->qsel ^= 1;
+        kg_debug_end_kernel<<<1, 32, ws_bytes(), st>>>(env, h->carry, h->d_debug);
+        CUDA_TRY(h, cudaGetLastError());
+    }
 #endif
     TRY(be_d2h(h, out, h->d_debug, KG_DEBUG_FLOATS * 4));
     return be_sync(h);

@@ -90,56 +90,81 @@ static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u
 #define KG_COUNT(i, n) ((void)0)
 #endif
 
-// obs / rangefinder staging aliases the constraint Jacobian storage (J is dead outside the substep loop); so does the
-// per-env copy of the object's hull vertices during the collision stage (J is rebuilt right after it)
+// obs staging aliases the constraint Jacobian storage (J is dead once the last substep's solve is over)
 #define KG_WSOBS(ws) ((ws).J)
-#define KG_RANGE(ws) ((ws).J + 96)
-#define KG_OBJHULL(ws) ((ws).J)
+#define KG_RANGE(ws) ((ws).range)
 #define KG_MAXOBJVERT 160     // padded to a multiple of 32
+// Per-environment workspace in shared memory.  An RL step is a WAVEFRONT of kernels (kg_api.cu): the per-env kernels
+// keep one KgWS per warp; between kernels the CARRY part of it lives in global memory (one KgCarry record per env,
+// env-major so that a warp moves it with coalesced 128-bit accesses).  Carry = everything a later kernel of the same
+// RL step reads: state, episode constants, the kinematics of the current substep, collision caches, staged contacts.
 struct alignas(16) KgWS {
+    // ======================================================================== carry section A (contiguous)
     // ---- state
     float qpos[16], qvel[16], qwarm[16], ctrl[12], sens_q[12];
     // ---- per-episode constants
     float Rh[9], B[3][9], fo[3][3], sax[3][3];
-    int shape, pad_;
+    int shape, ntask;
     // ---- kinematics
     float hp[3], p1[3][3], p2[3][3], c1[3][3], c2[3][3];
     float gpos[9][3], gmat[9][9];
     float oR[9];
+    // ---- collision bookkeeping
+    int cnt[32];
+    unsigned short cv1[32], cv2[32];   // warm-start hull vertices per pair lane
+    float sep[32][3];                  // cached separating axis per hull-pair lane (valid while sepok[l] != 0)
+    int sepok[32];
+    float range[20];                   // rangefinder readings (KG_NSITE used)
+    // ---- statistics
+    int stat_mpr, stat_newton, stat_overflow, stat_pad;
+    // ======================================================================== end of carry section A
     // ---- dynamics
-    float M[KG_NV * KG_MS];
-    // the Newton-solver scratch and the contact staging of the collision stage are never live together
+    alignas(16) float M[KG_NV * KG_MS];
+    // the Newton-solver scratch and the contact staging of the collision stage are never live together; the staging
+    // (carry section B) is what the narrowphase kernel fills in global memory
     union {
         struct { float L[KG_NV * KG_MS], bdot[KG_NBASE + 2], bdir[KG_NBASE + 2], bw[KG_NBASE + 2]; };
         struct { float st_dist[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3]; unsigned char st_g1[KG_NSTAGE], st_g2[KG_NSTAGE]; };
     };
     float bias[16], fs[16], qas[16], qacc[16], Mdq[16], grad[16], dir[16], Md[16], ftot[16];
     float sbias[3][3];
-    // ---- collision bookkeeping
-    int cnt[32];
-    unsigned short cv1[32], cv2[32];   // warm-start hull vertices per pair lane
-    float sep[32][3];                  // cached separating axis per hull-pair lane (valid while sepok[l] != 0)
-    int sepok[32];
     // ---- constraint groups: slot g<3 tendon, 3..8 limits, 9.. contacts
     int gtype[32], gslot[32], ngroup, ncon_total;
     float gmu[32], garef[32][4], gD[32];
     alignas(16) float J[KG_NBASE * KG_JS];
-    const float *fhull;                // finger hull vertices (proximal then distal, xyzw): the CTA's shared-memory copy
     float red[32], red2[32];
     // ---- solver scalars (written by lane 0, read by all after a sync)
     float s_alpha, s_cost, s_flag, s_lo, s_hi, s_glo, s_ghi, s_cost2;
     int s_iter, s_done, s_exact;
     // ---- closed-form M^-1 scratch (per finger lane)
     float mv_S[3][6], mv_r[3][3], mv_y[3][2], mv_i[3][3], mv_xs[4], mv_red3[32];
-    // ---- statistics
-    int stat_mpr, stat_newton, stat_overflow, stat_pad;
 #ifdef KG_PROF
     long long prof[KG_NPROF], prof_t0;  // see KG_PROBE / kg_get_prof
 #endif
 };
+#define KG_CARRY_A_BYTES (offsetof(KgWS, M))
+#define KG_CARRY_B_OFF   (offsetof(KgWS, st_dist))
+#define KG_CARRY_B_BYTES ((sizeof(float) * 7 * KG_NSTAGE + 2 * KG_NSTAGE + 15) / 16 * 16)
+#define KG_CARRY_BYTES   ((KG_CARRY_A_BYTES + KG_CARRY_B_BYTES + 127) / 128 * 128)
+// offsets of the fields the narrowphase kernel touches inside a carry record
+#define KG_COFF(field)   (offsetof(KgWS, field))
+#define KG_COFF_B(field) (KG_CARRY_A_BYTES + offsetof(KgWS, field) - KG_CARRY_B_OFF)
 
 static_assert(offsetof(KgWS, M) % 16 == 0 && offsetof(KgWS, L) % 16 == 0 && offsetof(KgWS, J) % 16 == 0 && sizeof(KgWS) % 16 == 0, "128-bit access needs 16-byte aligned members");
-static_assert(KG_MAXOBJVERT * 4 <= KG_NBASE * KG_JS, "object hull copy must fit into J");
+static_assert(KG_NOBS * 4 <= KG_NBASE * KG_JS * 4, "obs staging must fit into J");
+static_assert(KG_CARRY_B_OFF % 16 == 0 && offsetof(KgWS, st_g2) + KG_NSTAGE - KG_CARRY_B_OFF <= KG_CARRY_B_BYTES, "carry section B");
+static_assert(KG_CARRY_B_BYTES <= sizeof(float) * (KG_NV * KG_MS + 3 * (KG_NBASE + 2)), "carry section B must stay inside the union");
+
+// Workspace of the narrowphase (MPR) kernel: the geom frames of one env, the object's hull, the finger hulls of the CTA.
+struct alignas(16) KgMprWS {
+    float gpos[9][3], gmat[9][9];
+    alignas(16) float objhull[KG_MAXOBJVERT * 4];
+    const float *fhull;
+    int shape, hull_shape;
+#ifdef KG_PROF
+    long long prof[KG_NPROF];
+#endif
+};
 
 // ------------------------------------------------------------------------------------------------ small math
 KG_DEV float kg_dot(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -504,11 +529,11 @@ KG_DEV void kg_support(const KgModel &m, const KgWS &ws, int g, int mesh, int &c
 // only (best dot, index), the arg-max is reduced with redux.sync on an order-preserving integer key and, among equal
 // maxima, the lowest vertex index wins (a pad entry can therefore never be returned); the winning vertex is then
 // fetched once.  Every lane returns the same result.  The host emulation scans the vertices in index order (same tie rule).
-KG_DEV const float *kg_hull_table(const KgModel &m, const KgWS &ws, int mesh) {
-    // object -> this env's shared-memory copy, fingers -> the CTA's shared-memory copy, palm -> global memory
-    return mesh >= 3 ? KG_OBJHULL(ws) : (mesh == 0 ? m.hull_pad : ws.fhull + (mesh == 2 ? 4 * m.hnpad[1] : 0));
+KG_DEV const float *kg_hull_table(const KgModel &m, const KgMprWS &ws, int mesh) {
+    // object -> this warp's shared-memory copy, fingers -> the CTA's shared-memory copy, palm -> global memory
+    return mesh >= 3 ? ws.objhull : (mesh == 0 ? m.hull_pad : ws.fhull + (mesh == 2 ? 4 * m.hnpad[1] : 0));
 }
-KG_DEV void kg_support_coop(const KgModel &m, const KgWS &ws, int g, int mesh, const float *dir, const float *origin, float margin,
+KG_DEV void kg_support_coop(const KgModel &m, const KgMprWS &ws, int g, int mesh, const float *dir, const float *origin, float margin,
                             float *out, int *vidx, int kg_lane) {
     const float *vert = kg_hull_table(m, ws, mesh);
     const float *R = ws.gmat[g];
@@ -615,7 +640,7 @@ static long kg_emu_mpr_iters = 0;
 // findPenetr) so that the hill-climbing support code exists once in the instruction stream.
 // On a "no overlap" exit that PROVES separation (support of A-B along dir is negative) *sep_found is set and dir is
 // returned in nrm: the caller re-tests that axis first in the next substep (two supports instead of a full MPR).
-KG_DEV bool kg_mpr(const KgModel &m, const KgWS &ws, int g1, int mesh1, int g2, int mesh2, float hmargin, int &cur1, int &cur2,
+KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g2, int mesh2, float hmargin, int &cur1, int &cur2,
                    float *depth, float *nrm, float *pos, int *sep_found, int kg_lane) {
     *sep_found = 0;
     KgSupp p[4];
@@ -752,65 +777,71 @@ KG_DEV void kg_pair_of_lane(int l, int &g1, int &g2) {
         g1 = (int)((T1 >> sh) & 15); g2 = (int)((T2 >> sh) & 15);
     }
 }
-KG_DEV int kg_mesh_of_geom(const KgWS &ws, int g) { return g == 8 ? 3 + ws.shape : (g == 1 ? 0 : ((g & 1) ? 2 : 1)); }
+KG_DEV int kg_mesh_of_geom_s(int shape, int g) { return g == 8 ? 3 + shape : (g == 1 ? 0 : ((g & 1) ? 2 : 1)); }
+KG_DEV int kg_mesh_of_geom(const KgWS &ws, int g) { return kg_mesh_of_geom_s(ws.shape, g); }
 KG_DEV float kg_rbound(const KgModel &m, const KgWS &ws, int g) { return g == 8 ? m.shape[ws.shape].rbound : (g == 1 ? m.hand_rbound[0] : ((g & 1) ? m.hand_rbound[2] : m.hand_rbound[1])); }
 
-// One narrowphase task: full MPR of pair lane lp of the environment whose workspace is wo (warp-uniform; wo may belong
-// to another warp of the CTA, which is parked at the stage barrier meanwhile).  Lane 0 files the result.
-KG_DEV void kg_mpr_task(const KgModel &m, KgWS &wo, int lp, int kg_lane) {
+// One narrowphase task: full MPR of pair lane lp of env `env` (warp-uniform: all 32 lanes run the portal algebra and
+// share the cooperative support scans).  The geom frames come from the env's carry record, the result is filed there
+// by lane 0: separating axis / warm-start vertices, and on a hit the contact in staging slot 32 + (lp - 8).
+KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int lp, int kg_lane) {
+    KG_PHASE(l) {
+        const float *src = reinterpret_cast<const float *>(carry + KG_COFF(gpos));
+        float *dst = &mw.gpos[0][0];
+        for (int i = l; i < 27 + 81; i += 32) dst[i] = src[i];
+        if (l == 0) mw.shape = *reinterpret_cast<const int *>(carry + KG_COFF(shape));
+    }
+    KG_SYNC();
+    if (mw.shape != mw.hull_shape) {      // this warp's object-hull copy holds another shape
+        KG_SYNC();
+        KG_PHASE(l) {
+            const float *src = m.hull_pad + 4 * (size_t)m.hpad0[3 + mw.shape];
+            const int npad = m.hnpad[3 + mw.shape];
+            for (int i = l; i < npad; i += 32) {
+                auto v = KG_LDG4(src + 4 * i);
+                mw.objhull[4 * i] = v.x; mw.objhull[4 * i + 1] = v.y; mw.objhull[4 * i + 2] = v.z; mw.objhull[4 * i + 3] = v.w;
+            }
+        }
+        KG_SYNC();
+        KG_PHASE(l) { if (l == 0) mw.hull_shape = mw.shape; }
+        KG_SYNC();
+    }
     int g1, g2;
     kg_pair_of_lane(lp, g1, g2);
-    const int mesh1 = kg_mesh_of_geom(wo, g1), mesh2 = kg_mesh_of_geom(wo, g2);
+    const int mesh1 = kg_mesh_of_geom_s(mw.shape, g1), mesh2 = kg_mesh_of_geom_s(mw.shape, g2);
     const float margin = m.margin;
     int c1 = 0, c2 = 0, sepf = 0;
     float depth = 0.f, nrm[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
 #if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
     long it0_ = kg_emu_mpr_iters;
 #endif
-#if defined(KG_PROF) && defined(__CUDA_ARCH__)
-    long long tm0_ = clock64();
-#endif
-    bool hit = kg_mpr(m, wo, g1, mesh1, g2, mesh2, 0.5f * margin, c1, c2, &depth, nrm, pos, &sepf, kg_lane);
-#if defined(KG_PROF) && defined(__CUDA_ARCH__)
-    if (kg_lane == 0) atomicAdd((unsigned long long *)&wo.prof[28], (unsigned long long)(clock64() - tm0_));
-#endif
+    bool hit = kg_mpr(m, mw, g1, mesh1, g2, mesh2, 0.5f * margin, c1, c2, &depth, nrm, pos, &sepf, kg_lane);
 #if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
     fprintf(stderr, "MPR %d %d %ld %d %d\n", g1, g2, kg_emu_mpr_iters - it0_, (int)hit, sepf);
 #endif
-    KG_SYNC();
     KG_PHASE(l) {
         if (l == 0) {
-            wo.sepok[lp] = sepf;
-            if (sepf) { wo.sep[lp][0] = nrm[0]; wo.sep[lp][1] = nrm[1]; wo.sep[lp][2] = nrm[2]; }
-            wo.cv1[lp] = (unsigned short)c1; wo.cv2[lp] = (unsigned short)c2;
+            reinterpret_cast<int *>(carry + KG_COFF(sepok))[lp] = sepf;
+            if (sepf) { float *sp = reinterpret_cast<float *>(carry + KG_COFF(sep)) + 3 * lp; sp[0] = nrm[0]; sp[1] = nrm[1]; sp[2] = nrm[2]; }
+            reinterpret_cast<unsigned short *>(carry + KG_COFF(cv1))[lp] = (unsigned short)c1;
+            reinterpret_cast<unsigned short *>(carry + KG_COFF(cv2))[lp] = (unsigned short)c2;
             if (hit && depth > 0.f) {
-                int sl = 32 + (lp - 8);
-                wo.st_dist[sl] = margin - depth;
-                kg_add(wo.st_pos[sl], pos, wo.gpos[g1]);
-                kg_copy(wo.st_n[sl], nrm);
-                wo.st_g1[sl] = (unsigned char)g1; wo.st_g2[sl] = (unsigned char)g2;
-                wo.cnt[lp] = 1;
+                const int sl = 32 + (lp - 8);
+                reinterpret_cast<float *>(carry + KG_COFF_B(st_dist))[sl] = margin - depth;
+                float *sp = reinterpret_cast<float *>(carry + KG_COFF_B(st_pos)) + 3 * sl, *sn = reinterpret_cast<float *>(carry + KG_COFF_B(st_n)) + 3 * sl;
+                for (int c = 0; c < 3; c++) { sp[c] = pos[c] + mw.gpos[g1][c]; sn[c] = nrm[c]; }
+                (carry + KG_COFF_B(st_g1))[sl] = (unsigned char)g1; (carry + KG_COFF_B(st_g2))[sl] = (unsigned char)g2;
+                reinterpret_cast<int *>(carry + KG_COFF(cnt))[lp] = 1;
             }
         }
     }
     KG_SYNC();
 }
 
-// CTA context of a warp: the workspaces of all the CTA's environments and the shared narrowphase task queue
-struct KgCta { KgWS *ws_base; int warp; int *q; unsigned short *queue; };
-#define KG_CTA_QBYTES 512   // int q[4] + unsigned short queue[8 warps x 22 pairs], rounded up
-
-KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane, const KgCta &cta, int sub) {
+// Lane-parallel part of the collision stage: broadphase, plane contacts, re-test of the cached separating axes.
+// Returns (every lane) the mask of the pair lanes 8..29 that need a full MPR; those become narrowphase tasks.
+KG_DEV unsigned kg_collision_lane(const KgModel &m, KgWS &ws, int kg_lane) {
     KG_PHASE(l) {
-        {   // this env's object hull -> shared memory (J is dead until the rows are rebuilt)
-            const float *src = m.hull_pad + 4 * (size_t)m.hpad0[3 + ws.shape];
-            const int npad = m.hnpad[3 + ws.shape];
-            float *dst = KG_OBJHULL(ws);
-            for (int i = l; i < npad; i += 32) {
-                auto v = KG_LDG4(src + 4 * i);
-                dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
-            }
-        }
         int n = 0;
         float tried = 0.f;
         if (l < 30) {
@@ -875,7 +906,7 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane, const KgCta &c
                         separated = (kg_dot(s1, n0) - kg_dot(s2, n0)) < 0.f;
                         KG_COUNT(24, 1); KG_COUNT(25, separated ? 1 : 0);
                     }
-                    if (!separated) tried = 1.f;       // full MPR below, warp-cooperatively
+                    if (!separated) tried = 1.f;       // full MPR: a narrowphase task
                     ws.cv1[l] = (unsigned short)c1; ws.cv2[l] = (unsigned short)c2;
                 } else ws.sepok[l] = 0;
             }
@@ -884,37 +915,27 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane, const KgCta &c
         ws.cnt[l] = n;
     }
     KG_SYNC();
-    KG_PROBE(2);
-    // narrowphase proper: every pair that needs a full MPR is one task, run by all 32 lanes of a warp (uniform control
-    // flow).  On the GPU the tasks of the CTA's environments go through one shared queue and are pulled by whichever
-    // warp is free, so an environment in a six-contact grasp does not hold up the stage while its neighbours idle.
+    unsigned mask = 0;
 #if defined(__CUDA_ARCH__)
-    {
-        int *qn = cta.q + 2 * (sub & 1);                           // [0] tasks queued, [1] next task to hand out
-        if (cta.warp == 0 && kg_lane == 0) { int *qo = cta.q + 2 * ((sub + 1) & 1); qo[0] = 0; qo[1] = 0; }
-        if (kg_lane >= 8 && kg_lane < 30 && ws.red2[kg_lane] != 0.f) cta.queue[atomicAdd(qn, 1)] = (unsigned short)((cta.warp << 8) | kg_lane);
-        __syncthreads();
-        const int ntask = qn[0];
-        for (;;) {
-            int t = 0;
-            if (kg_lane == 0) t = atomicAdd(qn + 1, 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= ntask) break;
-            const int task = cta.queue[t], lp = task & 0xff;
-            KgWS &wo = cta.ws_base[task >> 8];
-            kg_mpr_task(m, wo, lp, kg_lane);
-        }
-        __syncthreads();
-    }
+    mask = __ballot_sync(0xffffffffu, ws.red2[kg_lane] != 0.f);
 #else
-    (void)cta; (void)sub;
-    for (int lp = 8; lp < 30; lp++) {
-        if (ws.red2[lp] == 0.f) continue;
-        kg_mpr_task(m, ws, lp, kg_lane);
-    }
+    (void)kg_lane;
+    for (int k = 0; k < 32; k++) if (ws.red2[k] != 0.f) mask |= 1u << k;
 #endif
-    KG_PROBE(3);
-    // compaction: contact groups 9.. reference staging slots
+    KG_PHASE(l) {
+        if (l == 0) {
+            int nt = 0;
+            for (unsigned mm = mask; mm; mm &= mm - 1) nt++;
+            ws.ntask = nt; ws.stat_mpr += nt;
+        }
+    }
+    KG_SYNC();
+    return mask;
+}
+
+// Contact compaction (after the narrowphase kernel has filed its hits): contact groups 9.. reference staging slots
+KG_DEV void kg_compaction(const KgModel &m, KgWS &ws, int kg_lane) {
+    (void)m;
     KG_PHASE(l) {
         int off = 0, total = 0;
         for (int k = 0; k < 32; k++) { int c = ws.cnt[k]; if (k < l) off += c; total += c; }
@@ -932,8 +953,6 @@ KG_DEV void kg_collision(const KgModel &m, KgWS &ws, int kg_lane, const KgCta &c
     }
     KG_SYNC();
     KG_PHASE(l) {
-        float nm = kg_total(ws.red2, l);
-        if (l == 0) ws.stat_mpr += (int)(nm + 0.5f);
         if (l >= 9 && l >= ws.ngroup) ws.gtype[l] = 0;
     }
     KG_SYNC();
@@ -1408,31 +1427,6 @@ KG_DEV void kg_euler(const KgModel &m, KgWS &ws, int kg_lane) {
     KG_SYNC();
 }
 
-// one mj_step: forward (positions -> constraints -> solve) + integrate
-KG_DEV void kg_substep(const KgModel &m, KgWS &ws, int kg_lane, const KgCta &cta, int sub) {
-    KG_STAGE(0);
-    KG_PROBE(18);
-    kg_kinematics(m, ws, kg_lane);
-    kg_dynamics(m, ws, kg_lane);
-    KG_PROBE(0);
-    KG_STAGE(1);
-    KG_PROBE(1);
-    kg_collision(m, ws, kg_lane, cta, sub);
-    KG_PROBE(3);
-    KG_STAGE(2);
-    KG_PROBE(4);
-    kg_make_rows(m, ws, kg_lane);
-    KG_PROBE(5);
-    KG_STAGE(3);
-    KG_PROBE(6);
-    kg_solve(m, ws, kg_lane);
-    KG_PROBE(13);
-    KG_STAGE(4);
-    KG_PROBE(14);
-    kg_euler(m, ws, kg_lane);
-    KG_PROBE(15);
-}
-
 // ------------------------------------------------------------------------------------------------ P8 rangefinder rays
 // mj_ray restated (see oracle/kgo_rays.c for the literal version): own-body geoms excluded, plane hit
 // from the front only, meshes culled by the geom_size box, then nearest raw-triangle hit via the BVH.
@@ -1755,7 +1749,7 @@ KG_DEV void kg_load_env(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
         const int N = A.N;
         if (l < 16) ws.qpos[l] = A.qpos[l * N + env];
         if (l < 15) { ws.qvel[l] = A.qvel[l * N + env]; ws.qwarm[l] = A.qwarm[l * N + env]; }
-        if (l == 31) { ws.stat_mpr = 0; ws.stat_newton = 0; ws.stat_overflow = 0; ws.qvel[15] = 0.f; ws.qwarm[15] = 0.f; }
+        if (l == 31) { ws.stat_mpr = 0; ws.stat_newton = 0; ws.stat_overflow = 0; ws.stat_pad = 0; ws.ntask = 0; ws.qvel[15] = 0.f; ws.qwarm[15] = 0.f; }
 #ifdef KG_PROF
         if (l < KG_NPROF) ws.prof[l] = 0;
 #if defined(__CUDA_ARCH__)
@@ -1776,10 +1770,65 @@ KG_DEV void kg_store_env(KgWS &ws, const KgEnvArrays &A, int env, int kg_lane) {
     KG_SYNC();
 }
 
-// One RL step of one env: [expert action] -> ctrl -> nsub x mj_step -> rays -> obs/reward/done (+TimeLimit).
+// ---- carry records: the part of KgWS that travels through global memory between the kernels of one RL step
+KG_DEV void kg_copy16(void *dst, const void *src, int bytes, int kg_lane) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (int i = kg_lane; i < bytes / 16; i += 32) d4[i] = s4[i];
+#else
+    (void)kg_lane;
+    memcpy(dst, src, (size_t)bytes);
+#endif
+}
+KG_DEV void kg_carry_store(const KgWS &ws, unsigned char *carry, int kg_lane) {
+    KG_SYNC();
+    kg_copy16(carry, &ws, (int)KG_CARRY_A_BYTES, kg_lane);
+    kg_copy16(carry + KG_CARRY_A_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CARRY_B_OFF, (int)KG_CARRY_B_BYTES, kg_lane);
+    KG_SYNC();
+}
+KG_DEV void kg_carry_load(KgWS &ws, const unsigned char *carry, int kg_lane) {
+    kg_copy16(&ws, carry, (int)KG_CARRY_A_BYTES, kg_lane);
+    kg_copy16(reinterpret_cast<unsigned char *>(&ws) + KG_CARRY_B_OFF, carry + KG_CARRY_A_BYTES, (int)KG_CARRY_B_BYTES, kg_lane);
+    KG_SYNC();
+#ifdef KG_PROF
+    KG_PHASE(l) {
+        if (l < KG_NPROF) ws.prof[l] = 0;
+#if defined(__CUDA_ARCH__)
+        if (l == 0) ws.prof_t0 = clock64();
+#endif
+    }
+    KG_SYNC();
+#endif
+}
+KG_DEV void kg_prof_flush(KgWS &ws, const KgEnvArrays &A, int kg_lane) {
+#if defined(KG_PROF) && defined(__CUDA_ARCH__)
+    __syncwarp();
+    if (A.prof && kg_lane < KG_NPROF) atomicAdd((unsigned long long *)A.prof + kg_lane, (unsigned long long)ws.prof[kg_lane]);
+#else
+    (void)ws; (void)A; (void)kg_lane;
+#endif
+}
+
+// The narrowphase tasks of this env (pair lanes in `mask`) go to the global task list: (env << 8) | pair lane.
+// q[0] = tasks queued.  One atomic per warp.
+KG_DEV void kg_emit_tasks(unsigned mask, int env, int *q, unsigned *tasks, int kg_lane) {
+    if (mask == 0) return;
+#if defined(__CUDA_ARCH__)
+    int base = 0;
+    if (kg_lane == 0) base = atomicAdd(q, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((mask >> kg_lane) & 1) tasks[base + __popc(mask & ((1u << kg_lane) - 1))] = ((unsigned)env << 8) | (unsigned)kg_lane;
+#else
+    (void)kg_lane;
+    for (int k = 0; k < 32; k++) if ((mask >> k) & 1) tasks[q[0]++] = ((unsigned)env << 8) | (unsigned)k;
+#endif
+}
+
+// First kernel of an RL step for one env: [expert action] -> ctrl -> kinematics + lane-parallel collision of substep 0.
 // action_in == nullptr selects the on-device expert (mode 0 naive, 1 position-dependent, 2 combined).
-KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *action_in, int expert_mode,
-                        int nsub, float *obs_out, float *reward_out, int *done_out, float *action_out, int kg_lane, const KgCta &cta) {
+// Returns the narrowphase task mask; the caller stores the carry record and emits the tasks.
+KG_DEV unsigned kg_step_begin(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *action_in, int expert_mode, int kg_lane) {
     kg_load_env(m, ws, A, env, kg_lane);
     float act[4] = {0, 0, 0, 0};
     if (action_in) { for (int c = 0; c < 4; c++) act[c] = action_in[c * A.N + env]; }
@@ -1804,8 +1853,54 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
         for (int c = 0; c < 4; c++) act[c] = ws.red[c];
         KG_SYNC();
     }
+    KG_PHASE(l) { if (l < 4) A.last_action[l * A.N + env] = act[l]; }
+    KG_SYNC();
     kg_ctrl_from_action(ws, act, kg_lane);
-    for (int s = 0; s < nsub; s++) kg_substep(m, ws, kg_lane, cta, s);
+    KG_PROBE(19);
+    kg_kinematics(m, ws, kg_lane);
+    KG_PROBE(0);
+    unsigned mask = kg_collision_lane(m, ws, kg_lane);
+    KG_PROBE(2);
+    return mask;
+}
+
+// Second half of one mj_step (the narrowphase kernel has filed the hull contacts of this substep into the carry):
+// dynamics, constraint rows, Newton solve, Euler.  The workspace holds the carry of this env.
+KG_DEV void kg_substep_finish(const KgModel &m, KgWS &ws, int kg_lane) {
+    KG_STAGE(0);
+    KG_PROBE(18);
+    kg_dynamics(m, ws, kg_lane);
+    KG_PROBE(0);
+    kg_compaction(m, ws, kg_lane);
+    KG_PROBE(3);
+    KG_STAGE(2);
+    KG_PROBE(4);
+    kg_make_rows(m, ws, kg_lane);
+    KG_PROBE(5);
+    KG_STAGE(3);
+    KG_PROBE(6);
+    kg_solve(m, ws, kg_lane);
+    KG_PROBE(13);
+    KG_STAGE(4);
+    KG_PROBE(14);
+    kg_euler(m, ws, kg_lane);
+    KG_PROBE(15);
+}
+// First half of the next mj_step: kinematics of the new state + lane-parallel collision; returns the task mask.
+KG_DEV unsigned kg_substep_start(const KgModel &m, KgWS &ws, int kg_lane) {
+    kg_kinematics(m, ws, kg_lane);
+    KG_PROBE(0);
+    KG_STAGE(1);
+    KG_PROBE(1);
+    unsigned mask = kg_collision_lane(m, ws, kg_lane);
+    KG_PROBE(2);
+    return mask;
+}
+
+// Last kernel of an RL step for one env (after the last substep's finish): rays -> obs/reward/done (+TimeLimit),
+// state and outputs back to the struct-of-arrays.
+KG_DEV void kg_step_end(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, int nsub,
+                        float *obs_out, float *reward_out, int *done_out, float *action_out, int kg_lane) {
     KG_PROBE(19);
     kg_rays(m, ws, kg_lane);
     KG_PROBE(16);
@@ -1824,12 +1919,9 @@ KG_DEV void kg_env_step(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
             if (reward_out) reward_out[env] = rew;
             if (done_out) done_out[env] = d;
             if (A.load) A.load[env] = d ? 0 : ws.stat_newton + 2 * ws.stat_mpr;   // a finished episode restarts contact-free
-            for (int c = 0; c < 4; c++) { A.last_action[c * N + env] = act[c]; if (action_out) action_out[c * N + env] = act[c]; }
+            if (action_out) for (int c = 0; c < 4; c++) action_out[c * N + env] = A.last_action[c * N + env];
 #if defined(__CUDA_ARCH__)
             if (A.stats) { atomicAdd(A.stats, ws.stat_mpr); atomicAdd(A.stats + 1, ws.stat_newton); atomicAdd(A.stats + 2, ws.stat_overflow); atomicAdd(A.stats + 3, nsub); }
-#ifdef KG_PROF
-            if (A.prof) for (int i = 0; i < KG_NPROF; i++) atomicAdd((unsigned long long *)A.prof + i, (unsigned long long)ws.prof[i]);
-#endif
 #else
             if (A.stats) { A.stats[0] += ws.stat_mpr; A.stats[1] += ws.stat_newton; A.stats[2] += ws.stat_overflow; A.stats[3] += nsub; }
 #endif

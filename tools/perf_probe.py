@@ -39,9 +39,10 @@ lib.kg_get_prof(h.h, prof)
 prof = list(prof)
 tot = sum(prof[:20])
 if tot:
-    names = ["kin+dyn", "w>coll", "collision", "compact", "w>rows", "rows", "w>solve", "sol.setup", "sol.cost", "sol.hess", "sol.chol", "sol.dirs",
-             "sol.ls", "sol.epi", "w>euler", "euler", "rays", "obs", "w>kin", "ldst"]
-    print("   cycles: " + "  ".join(f"{nm} {100.0 * c / tot:.1f}%" for nm, c in zip(names, prof) if c) + f" | cycles/substep/env {tot / st['substeps']:.0f}")
+    names = ["kin/dyn", "w>coll", "coll.lane", "compact", "w>rows", "rows", "w>solve", "sol.setup", "sol.cost", "sol.hess", "sol.chol", "sol.dirs",
+             "sol.ls", "sol.epi", "w>euler", "euler", "rays", "obs", "load+w>dyn", "begin"]
+    print("   per-env kernels, warp cycles: " + "  ".join(f"{nm} {100.0 * c / tot:.1f}%" for nm, c in zip(names, prof) if c) + f" | cycles/substep/env {tot / st['substeps']:.0f}"
+          f" | narrowphase kernel: {prof[28] / st['substeps']:.0f} warp cycles/substep/env, {prof[29] / st['substeps']:.2f} tasks")
     ss = float(st["substeps"])
     cn = ["support", "climb", "mpr", "mpr_iter", "sepchk", "sep_ok", "plane_sup", "ls_eval"]
     print("   per substep: " + "  ".join(f"{nm} {prof[20 + i] / ss:.2f}" for i, nm in enumerate(cn)) + f" | cycles per MPR iteration {prof[28] / max(1, prof[23]):.0f}")
