@@ -66,9 +66,13 @@ static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u
 
 #define KG_NV 15
 #define KG_MS 16                       // row stride of 15x15 matrices
+#ifndef KG_MAXCON
 #define KG_MAXCON 19                   // contact groups per env (overflow is counted and dropped)
+#endif
 #define KG_NBASE (9 + 3 * KG_MAXCON)   // 3 tendon rows, 6 limit rows, 3 frame rows per contact
-#define KG_JS 20                       // row stride of J: rows are 16-byte aligned (128-bit row loads; the eight rows a
+#ifndef KG_JS
+#define KG_JS 20
+#endif                                 // row stride of J: rows are 16-byte aligned (128-bit row loads; the eight rows a
                                        // quarter-warp reads together fall into disjoint bank groups: 20 b mod 32 = 0,20,8,28,16,4,24,12)
 #define KG_NSTAGE 54                   // contact staging slots: 8 plane lanes x 4 + 22 hull lanes
 #define KG_NOBS 82
@@ -124,9 +128,9 @@ struct alignas(16) KgWS {
     // (carry section B) is what the narrowphase kernel fills in global memory
     union {
         struct { float L[KG_NV * KG_MS], bdot[KG_NBASE + 2], bdir[KG_NBASE + 2], bw[KG_NBASE + 2]; };
-        struct { float st_dist[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3]; unsigned char st_g1[KG_NSTAGE], st_g2[KG_NSTAGE]; };
+        struct { float st_dist[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3]; unsigned char st_g1[KG_NSTAGE], st_g2[KG_NSTAGE], st_pad[16]; };
     };
-    float bias[16], fs[16], qas[16], qacc[16], Mdq[16], grad[16], dir[16], Md[16], ftot[16];
+    alignas(16) float bias[16], fs[16], qas[16], qacc[16], Mdq[16], grad[16], dir[16], Md[16], ftot[16];
     float sbias[3][3];
     // ---- constraint groups: slot g<3 tendon, 3..8 limits, 9.. contacts
     int gtype[32], gslot[32], ngroup, ncon_total;
@@ -153,7 +157,7 @@ struct alignas(16) KgWS {
 static_assert(offsetof(KgWS, M) % 16 == 0 && offsetof(KgWS, L) % 16 == 0 && offsetof(KgWS, J) % 16 == 0 && sizeof(KgWS) % 16 == 0, "128-bit access needs 16-byte aligned members");
 static_assert(KG_NOBS * 4 <= KG_NBASE * KG_JS * 4, "obs staging must fit into J");
 static_assert(KG_CARRY_B_OFF % 16 == 0 && offsetof(KgWS, st_g2) + KG_NSTAGE - KG_CARRY_B_OFF <= KG_CARRY_B_BYTES, "carry section B");
-static_assert(KG_CARRY_B_BYTES <= sizeof(float) * (KG_NV * KG_MS + 3 * (KG_NBASE + 2)), "carry section B must stay inside the union");
+static_assert(KG_CARRY_B_BYTES <= sizeof(float) * 7 * KG_NSTAGE + 2 * KG_NSTAGE + 16, "carry section B must stay inside the union (st_pad absorbs the 16-byte round-up)");
 
 // Workspace of the narrowphase (MPR) kernel: the geom frames of one env, the object's hull, the finger hulls of the CTA.
 struct alignas(16) KgMprWS {
