@@ -84,6 +84,11 @@ int kg_set_env_offset(kg_handle h, int offset);
  * each env's previous step, so that the environments sharing a CTA's stage barriers carry similar contact loads;
  * 0 = env i runs in slot i. */
 int kg_set_schedule(kg_handle h, int mode);
+/* Workspace mode of kg_step (no effect on results beyond fp32 rounding): 0 (default) = automatic -- split mode (light
+ * per-env workspaces, more resident warps; substeps with more contacts than a light workspace holds run in the heavy
+ * lane of the same launch) unless the last RL step the host has a count for had more than a third of the envs above the
+ * light limit, then full mode; 1 = always split; 2 = always full (every env through the full workspace). */
+int kg_set_mode(kg_handle h, int mode);
 /* The action the last kg_step applied (the caller's, or the on-device expert's: get_action, expert_data.py:610). float[4][n]. */
 int kg_get_last_action_host(kg_handle h, float *action_host);
 

@@ -6,6 +6,9 @@
 //        of the warp phases, used to debug the algorithm against the oracle without a GPU; the package
 //        never loads it and has no CPU fallback).
 #include "../../include/kg.h"
+#if !defined(KG_EMU) && !defined(KG_MPR_SMEM_HULLS) && !defined(KG_MPR_L1)
+#define KG_MPR_L1      // narrowphase kernel reads the hull tables through the read-only L1 path (no shared-memory staging: +2 % measured)
+#endif
 #include "kg_core.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +23,14 @@
 #ifndef KG_MINBLOCKS
 #define KG_MINBLOCKS 1      // CTAs per SM the register allocation must leave room for (512 threads x 128 registers = the whole file)
 #endif
+#ifndef KG_LWARPS
+#define KG_LWARPS 8         // light workspace: warps per CTA ...
+#endif
+#ifndef KG_LMINBLOCKS
+#define KG_LMINBLOCKS 3     // ... and CTAs per SM (24 warps x 80 registers)
+#endif
+#define KG_SPLIT (KG_MAXCON_LIGHT < KG_MAXCON)
+#define KG_LSMEM (KG_LWARPS * sizeof(KgWSLight))
 __constant__ KgModel c_model;
 #endif
 
@@ -36,6 +47,10 @@ struct kg_handle_s {
     unsigned *tasks = nullptr;        // [n * 22] narrowphase task list of the current substep: (env << 8) | pair lane
     int *q = nullptr;                 // two {queued, next} pairs: the per-env kernels fill one while the other is being reset
     int qsel = 0;
+    int *heavy_count = nullptr;       // device: envs whose last substep of the current RL step exceeded the light workspace
+    int *heavy_host = nullptr;        // pinned host copy of the previous step's count (read without synchronising)
+    int heavy_ctas = 1;               // heavy-lane CTAs at the front of every split-mode substep grid
+    int full_mode = 0, mode_auto = 1; // 1 = every env through the full workspace; chosen per step from heavy_host unless pinned
     std::vector<void *> allocs;
     // scratch for the *_host entry points
     float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_euler = nullptr, *d_objp = nullptr, *d_q = nullptr;
@@ -167,19 +182,27 @@ __global__ void __launch_bounds__(1024) kg_schedule_kernel(const int *load, int 
     for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&base[min(max(load[i], 0), KG_SCHED_KEYS - 1)], 1)] = i;
 }
 
-// ---- per-env kernels: one warp per environment, KG_WARPS environments per CTA, one KgWS per warp in shared memory
-#define KG_ENV_OF_WARP() \
+// ---- per-env kernels: one warp per environment, one workspace per warp in shared memory.
+// SPLIT mode (the default): every kernel runs the LIGHT workspace (KG_MAXCON_LIGHT contact groups, KG_LWARPS warps per
+// CTA, KG_LMINBLOCKS CTAs per SM -> 24 resident warps per SM instead of 16).  A substep whose contact count exceeds the
+// light workspace's rows is skipped by its light warp and run, in the SAME launch, by a HEAVY LANE: the first
+// `nheavy_ctas` CTAs of the grid hold full workspaces (as many as fit their shared memory), scan the contact counts of
+// all envs and run the substeps the light warps skip.  Both sides apply the same test to the same carry record, so
+// every env is run exactly once; the heavy lane overlaps the light CTAs instead of trailing them.
+// FULL mode: every env through the full workspace (16 warps per CTA, one CTA per SM) -- chosen by the host when the
+// last RL step it has a count for had more than a third of the envs above the light limit (contact-heavy shapes).
+#define KG_ENV_OF_WARP(WS, WARPS, BLOCK) \
     extern __shared__ __align__(16) unsigned char smem[]; \
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; \
-    const int slot = blockIdx.x * KG_WARPS + warp; \
+    const int slot = (BLOCK) * (WARPS) + warp; \
     if (slot >= A.N) return; \
     const int env = perm ? perm[slot] : slot; \
-    KgWS &ws = *(reinterpret_cast<KgWS *>(smem) + warp)
+    WS &ws = *(reinterpret_cast<WS *>(smem) + warp)
 
 // first kernel of an RL step: action / on-device expert, kinematics and lane-parallel collision of substep 0
-__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_begin_kernel(KgEnvArrays A, const int *perm, const float *action, int mode,
-                                                                               unsigned char *carry, int *q, unsigned *tasks) {
-    KG_ENV_OF_WARP();
+__global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_begin_kernel(KgEnvArrays A, const int *perm, const float *action, int mode,
+                                                                                 unsigned char *carry, int *q, unsigned *tasks) {
+    KG_ENV_OF_WARP(KgWSLight, KG_LWARPS, blockIdx.x);
     const unsigned mask = kg_step_begin(c_model, ws, A, env, action, mode, lane);
     kg_carry_store(ws, carry + (size_t)env * KG_CARRY_BYTES, lane);
     kg_emit_tasks(mask, env, q, tasks, lane);
@@ -187,12 +210,9 @@ __global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_begin_kernel(K
 }
 // one per substep: finish substep s (dynamics, rows, Newton solve, Euler) and, unless it is the last one, start
 // substep s+1 (kinematics, lane-parallel collision, narrowphase tasks); the last one ends the RL step (rays, obs, reward)
-template <bool LAST>
-__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_kernel(KgEnvArrays A, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
-                                                                             int nsub, float *obs, float *reward, int *done, float *act_out) {
-    KG_ENV_OF_WARP();
-    unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
-    kg_carry_load(ws, rec, lane);
+template <class WS, bool LAST>
+__device__ __forceinline__ void kg_sub_body(WS &ws, const KgEnvArrays &A, int env, unsigned char *rec, int *q, unsigned *tasks,
+                                            int nsub, float *obs, float *reward, int *done, float *act_out, int lane) {
     kg_substep_finish(c_model, ws, lane);
     if (LAST) kg_step_end(c_model, ws, A, env, nsub, obs, reward, done, act_out, lane);
     else {
@@ -201,6 +221,63 @@ __global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_kernel(KgE
         kg_emit_tasks(mask, env, q, tasks, lane);
     }
     kg_prof_flush(ws, A, lane);
+}
+// contacts of the substep a carry record is about to finish = the per-pair counts the collision stage and the
+// narrowphase tasks filed (one word per lane, summed over the warp)
+__device__ __forceinline__ int kg_warp_sum(int v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#define KG_HEAVY_WARPS ((int)(KG_LSMEM / sizeof(KgWSNoSync)))     // full workspaces that fit a light CTA's shared memory
+template <bool LAST>
+__global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(KgEnvArrays A, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
+                                                                               int nheavy_ctas, int *heavy_count, int nsub, float *obs, float *reward, int *done, float *act_out) {
+    if ((int)blockIdx.x < nheavy_ctas) {
+        // ---- heavy lane: persistent warps with full workspaces (no stage rendezvous: they loop independently)
+        extern __shared__ __align__(16) unsigned char smem[];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (warp >= KG_HEAVY_WARPS) return;
+        KgWSNoSync &ws = *(reinterpret_cast<KgWSNoSync *>(smem) + warp);
+        const int W = nheavy_ctas * KG_HEAVY_WARPS;
+        int nh = 0;
+        for (int e0 = blockIdx.x * KG_HEAVY_WARPS + warp; e0 < A.N; e0 += 4 * W) {
+            int c[4];      // four independent count loads in flight
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int env = e0 + k * W;
+                c[k] = env < A.N ? reinterpret_cast<const int *>(carry + (size_t)env * KG_CARRY_BYTES + KG_COFF(cnt))[lane] : 0;
+            }
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                if (kg_warp_sum(c[k]) <= KG_MAXCON_LIGHT) continue;
+                const int env = e0 + k * W;
+                unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
+                kg_carry_load(ws, rec, lane);
+                kg_sub_body<KgWSNoSync, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
+                __syncwarp();
+                nh++;
+            }
+        }
+        if (LAST && nh && lane == 0) atomicAdd(heavy_count, nh);      // what the host picks the mode of later steps from
+        return;
+    }
+    KG_ENV_OF_WARP(KgWSLight, KG_LWARPS, blockIdx.x - nheavy_ctas);
+    unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
+    kg_carry_load(ws, rec, lane);
+    if (nheavy_ctas > 0 && kg_warp_sum(ws.cnt[lane]) > KG_MAXCON_LIGHT) return;      // the heavy lane runs this one
+    kg_sub_body<KgWSLight, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
+}
+template <bool LAST>
+__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_full_kernel(KgEnvArrays A, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
+                                                                                  int *heavy_count, int nsub, float *obs, float *reward, int *done, float *act_out) {
+    KG_ENV_OF_WARP(KgWS, KG_WARPS, blockIdx.x);
+    unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
+    kg_carry_load(ws, rec, lane);
+    if (LAST) {
+        const int total = kg_warp_sum(ws.cnt[lane]);
+        if ((slot & 15) == 0 && total > KG_MAXCON_LIGHT && lane == 0) atomicAdd(heavy_count, 16);     // 1-in-16 sample of the same count
+    }
+    kg_sub_body<KgWS, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
 }
 // ---- narrowphase kernel: persistent warps pull (env, pair) tasks from the global list; every task is one full MPR run
 // by all 32 lanes.  The finger hulls (the meshes every scan touches) are staged once per CTA, the object hull per warp.
@@ -217,6 +294,7 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
     const int ntask = q[0];
     if (ntask == 0) return;
     KgMprWS &mw = *(reinterpret_cast<KgMprWS *>(smem) + warp);
+#ifndef KG_MPR_L1
     float4 *fh = reinterpret_cast<float4 *>(smem + KG_MPR_WARPS * sizeof(KgMprWS));
     {
         const int n4 = c_model.hnpad[1] + c_model.hnpad[2];
@@ -224,13 +302,20 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
         for (int i = threadIdx.x; i < n4; i += blockDim.x) fh[i] = __ldg(src + i);
     }
     if (lane == 0) { mw.fhull = reinterpret_cast<const float *>(fh); mw.hull_shape = -1; }
+#endif
 #ifdef KG_PROF
     if (lane < KG_NPROF) mw.prof[lane] = 0;
 #endif
+#ifndef KG_MPR_L1
     __syncthreads();
+#else
+    __syncwarp();
+#endif
 #ifdef KG_PROF
     long long t0 = clock64(), nt = 0;
 #endif
+    // dynamic task list: no look-ahead on purpose -- a warp that reserved its next task while still inside a long MPR
+    // would hold that task back from the idle warps (measured: 10 % slower at 4096 envs)
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(q + 1, 1);
@@ -251,14 +336,14 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
 #endif
 }
 
-__global__ void __launch_bounds__(KG_WARPS * 32) kg_reset_kernel(KgEnvArrays A, const int *mask, const int *shape, const float *euler, const float *objp,
+__global__ void __launch_bounds__(KG_LWARPS * 32) kg_reset_kernel(KgEnvArrays A, const int *mask, const int *shape, const float *euler, const float *objp,
                                                                  int sampled, int orient, int variant, int test_table, unsigned long long seed, int *ep_count, int env_offset, float *obs) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * KG_WARPS + warp;
+    const int env = blockIdx.x * KG_LWARPS + warp;
     if (env >= A.N) return;
     if (mask && mask[env] == 0) return;
-    KgWS &ws = *(reinterpret_cast<KgWS *>(smem) + warp);
+    KgWSLight &ws = *(reinterpret_cast<KgWSLight *>(smem) + warp);
     int sh = shape ? shape[env] : A.shape[env];
     float e[3], p[3];
     if (sampled) {
@@ -294,7 +379,12 @@ static KgMprWS g_mw;
 static size_t ws_bytes() { return sizeof(KgWS); }
 #ifndef KG_EMU
 static_assert(KG_WARPS * sizeof(KgWS) <= 227 * 1024, "KG_WARPS workspaces must fit one SM's shared memory");
+static_assert(KG_LMINBLOCKS * (KG_LWARPS * sizeof(KgWSLight) + 1024) <= 228 * 1024, "KG_LMINBLOCKS light CTAs must fit one SM's shared memory");
+#ifdef KG_MPR_L1
+#define KG_MPR_SMEM(h) (KG_MPR_WARPS * sizeof(KgMprWS))
+#else
 #define KG_MPR_SMEM(h) (KG_MPR_WARPS * sizeof(KgMprWS) + (size_t)(h)->fhull_bytes)
+#endif
 #endif
 
 #ifdef KG_EMU
@@ -337,17 +427,34 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)h->stream;
-    const int blocks = (h->n + KG_WARPS - 1) / KG_WARPS;
-    const size_t smem = KG_WARPS * ws_bytes();
+    const int blocks = (h->n + KG_LWARPS - 1) / KG_LWARPS;
+    const size_t smem = KG_LSMEM, hsmem = KG_WARPS * ws_bytes();
     const int *perm = h->schedule ? h->perm : nullptr;
+    const int fblocks = (h->n + KG_WARPS - 1) / KG_WARPS;
+    // mode of this step, from the newest count of above-the-light-limit envs the host has (never waits for the device)
+    if (KG_SPLIT && h->heavy_host) {
+        const float frac = (float)*(volatile int *)h->heavy_host / (float)h->n;
+        if (h->mode_auto) { if (!h->full_mode && frac > 0.33f) h->full_mode = 1; else if (h->full_mode && frac < 0.20f) h->full_mode = 0; }
+    }
+    const bool full = !KG_SPLIT || h->full_mode;
+    const int nhc = KG_SPLIT ? h->heavy_ctas : 0;
+    cudaMemcpyAsync(h->heavy_host, h->heavy_count, sizeof(int), cudaMemcpyDeviceToHost, st);      // last step's count -> pinned host word
+    cudaMemsetAsync(h->heavy_count, 0, sizeof(int), st);
     cudaEventRecord(h->ev0, st);
     if (h->schedule) kg_schedule_kernel<<<1, 1024, 0, st>>>(h->A.load, h->perm, h->n);
-    kg_begin_kernel<<<blocks, KG_WARPS * 32, smem, st>>>(h->A, perm, action, mode, h->carry, h->q + 2 * h->qsel, h->tasks);
+    kg_begin_kernel<<<blocks, KG_LWARPS * 32, smem, st>>>(h->A, perm, action, mode, h->carry, h->q + 2 * h->qsel, h->tasks);
     for (int s = 0; s < nsub; s++) {
         kg_mpr_kernel<<<h->mpr_grid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), st>>>(h->carry, h->q + 2 * h->qsel, h->q + 2 * (h->qsel ^ 1), h->tasks, h->A.prof);
         h->qsel ^= 1;
-        if (s == nsub - 1) kg_sub_kernel<true><<<blocks, KG_WARPS * 32, smem, st>>>(h->A, perm, h->carry, h->q + 2 * h->qsel, h->tasks, nsub, obs, reward, done, act_out);
-        else kg_sub_kernel<false><<<blocks, KG_WARPS * 32, smem, st>>>(h->A, perm, h->carry, h->q + 2 * h->qsel, h->tasks, nsub, obs, reward, done, act_out);
+        int *qn = h->q + 2 * h->qsel;
+        const bool last = s == nsub - 1;
+        if (full) {
+            if (last) kg_sub_full_kernel<true><<<fblocks, KG_WARPS * 32, hsmem, st>>>(h->A, perm, h->carry, qn, h->tasks, h->heavy_count, nsub, obs, reward, done, act_out);
+            else kg_sub_full_kernel<false><<<fblocks, KG_WARPS * 32, hsmem, st>>>(h->A, perm, h->carry, qn, h->tasks, h->heavy_count, nsub, obs, reward, done, act_out);
+        } else {
+            if (last) kg_sub_kernel<true><<<blocks + nhc, KG_LWARPS * 32, smem, st>>>(h->A, perm, h->carry, qn, h->tasks, nhc, h->heavy_count, nsub, obs, reward, done, act_out);
+            else kg_sub_kernel<false><<<blocks + nhc, KG_LWARPS * 32, smem, st>>>(h->A, perm, h->carry, qn, h->tasks, nhc, h->heavy_count, nsub, obs, reward, done, act_out);
+        }
     }
     cudaEventRecord(h->ev1, st);
     CUDA_TRY(h, cudaGetLastError());
@@ -371,8 +478,8 @@ static int launch_reset(kg_handle h, const int *mask, const int *shape, const fl
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)h->stream;
-    int blocks = (h->n + KG_WARPS - 1) / KG_WARPS;
-    kg_reset_kernel<<<blocks, KG_WARPS * 32, KG_WARPS * ws_bytes(), st>>>(h->A, mask, shape, euler, objp, sampled, orient, variant, test_table, seed, h->ep_count, h->env_offset, obs);
+    int blocks = (h->n + KG_LWARPS - 1) / KG_LWARPS;
+    kg_reset_kernel<<<blocks, KG_LWARPS * 32, KG_LSMEM, st>>>(h->A, mask, shape, euler, objp, sampled, orient, variant, test_table, seed, h->ep_count, h->env_offset, obs);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 #endif
@@ -411,10 +518,12 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     UP(bvh_node, t.bvh_node); UP(pose_train, t.pose_train); UP(pose_test, t.pose_test);
 #undef UP
     CUDA_TRY(h, cudaMemcpyToSymbol(c_model, &m, sizeof(KgModel)));
-    CUDA_TRY(h, cudaFuncSetAttribute(kg_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
-    CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
-    CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
-    CUDA_TRY(h, cudaFuncSetAttribute(kg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_LSMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_LSMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_LSMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_LSMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
+    CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KG_WARPS * ws_bytes())));
     CUDA_TRY(h, cudaFuncSetAttribute(kg_mpr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_MPR_SMEM(h)));
     CUDA_TRY(h, cudaFuncSetAttribute(kg_debug_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_bytes()));
     CUDA_TRY(h, cudaFuncSetAttribute(kg_debug_end_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_bytes()));
@@ -423,6 +532,10 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kg_mpr_kernel, KG_MPR_WARPS * 32, KG_MPR_SMEM(h)));
         CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         h->mpr_grid = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+        const int hb = (n_envs + KG_HEAVY_WARPS - 1) / KG_HEAVY_WARPS;
+        h->heavy_ctas = hb < sms ? hb : (sms > 0 ? sms : 1);
+        CUDA_TRY(h, cudaHostAlloc((void **)&h->heavy_host, sizeof(int), cudaHostAllocDefault));
+        *h->heavy_host = 0;
     }
     CUDA_TRY(h, cudaEventCreate(&h->ev0)); CUDA_TRY(h, cudaEventCreate(&h->ev1));
 #endif
@@ -435,6 +548,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
     TRY(be_alloc(h, (void **)&A.load, N * 4)); TRY(be_alloc(h, (void **)&h->perm, N * 4));
     TRY(be_alloc(h, (void **)&h->carry, N * KG_CARRY_BYTES)); TRY(be_alloc(h, (void **)&h->tasks, N * 22 * 4)); TRY(be_alloc(h, (void **)&h->q, 4 * 4));
+    TRY(be_alloc(h, (void **)&h->heavy_count, 4));
     TRY(be_alloc(h, (void **)&h->d_action, 4 * N * 4)); TRY(be_alloc(h, (void **)&h->d_obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&h->d_reward, N * 4));
     TRY(be_alloc(h, (void **)&h->d_done, N * 4)); TRY(be_alloc(h, (void **)&h->d_mask, N * 4)); TRY(be_alloc(h, (void **)&h->d_shape, N * 4));
     TRY(be_alloc(h, (void **)&h->d_euler, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_objp, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_q, 31 * N * 4));
@@ -458,6 +572,7 @@ int kg_destroy(kg_handle h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->heavy_host) cudaFreeHost(h->heavy_host);
 #endif
     delete h;
     return KG_OK;
@@ -467,6 +582,11 @@ int kg_num_envs(kg_handle h) { return h ? h->n : KG_EINVAL; }
 int kg_set_stream(kg_handle h, void *stream) { if (!h) return KG_EINVAL; h->stream = stream; return KG_OK; }
 int kg_sync(kg_handle h) { if (!h) return KG_EINVAL; return be_sync(h); }
 int kg_set_max_episode_steps(kg_handle h, int steps) { if (!h || steps <= 0) return KG_EINVAL; h->A.max_steps = steps; return KG_OK; }
+int kg_set_mode(kg_handle h, int mode) {
+    if (!h || mode < 0 || mode > 2) return KG_EINVAL;
+    h->mode_auto = mode == 0; h->full_mode = mode == 2;
+    return KG_OK;
+}
 int kg_set_frame_skip(kg_handle h, int fs) { if (!h || fs <= 0) return KG_EINVAL; h->frame_skip = fs; return KG_OK; }
 int kg_set_schedule(kg_handle h, int mode) { if (!h || mode < 0 || mode > 1) return KG_EINVAL; h->schedule = mode; return KG_OK; }
 int kg_set_env_offset(kg_handle h, int offset) { if (!h || offset < 0) return KG_EINVAL; h->env_offset = offset; return KG_OK; }

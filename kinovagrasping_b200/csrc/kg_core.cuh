@@ -39,10 +39,7 @@
 // Block-wide rendezvous between pipeline stages.  Functionally unnecessary (warps never share data); it keeps the
 // 8 warps of a CTA inside the same ~10-20 KB code region so that they share instruction-cache lines (the whole
 // substep is ~100 KB of SASS, far beyond the 32 KB L1.5 I-cache; ncu showed stall_no_instruction dominating).
-#ifndef KG_STAGE_MASK
-#define KG_STAGE_MASK 0x1f   // bit i: rendezvous before stage i (0 kinematics, 1 collision, 2 rows, 3 solve, 4 Euler)
-#endif
-#define KG_STAGE(i) do { if ((KG_STAGE_MASK >> (i)) & 1) __syncthreads(); } while (0)
+#define KG_STAGE(i) do { if ((WS::STAGE_MASK >> (i)) & 1) __syncthreads(); } while (0)
 #else
 #define KG_STAGE(i) ((void)0)
 #if defined(__CUDACC__)
@@ -64,12 +61,17 @@ struct kg_uint4 { unsigned x, y, z, w; };
 static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u; }
 #endif
 
+#ifndef KG_STAGE_MASK
+#define KG_STAGE_MASK 0x1f   // bit i: rendezvous before stage i (0 kinematics, 1 collision, 2 rows, 3 solve, 4 Euler)
+#endif
 #define KG_NV 15
 #define KG_MS 16                       // row stride of 15x15 matrices
 #ifndef KG_MAXCON
-#define KG_MAXCON 19                   // contact groups per env (overflow is counted and dropped)
+#define KG_MAXCON 19                   // contact groups per env in the full workspace (overflow is counted and dropped)
 #endif
-#define KG_NBASE (9 + 3 * KG_MAXCON)   // 3 tendon rows, 6 limit rows, 3 frame rows per contact
+#ifndef KG_MAXCON_LIGHT
+#define KG_MAXCON_LIGHT 8              // ... in the light workspace: envs with more contacts go to the full-workspace kernel
+#endif
 #ifndef KG_JS
 #define KG_JS 20
 #endif                                 // row stride of J: rows are 16-byte aligned (128-bit row loads; the eight rows a
@@ -102,7 +104,11 @@ static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u
 // keep one KgWS per warp; between kernels the CARRY part of it lives in global memory (one KgCarry record per env,
 // env-major so that a warp moves it with coalesced 128-bit accesses).  Carry = everything a later kernel of the same
 // RL step reads: state, episode constants, the kinematics of the current substep, collision caches, staged contacts.
-struct alignas(16) KgWS {
+template <int MAXCON_, int STAGE_MASK_>
+struct alignas(16) KgWST {
+    static constexpr int MAXCON = MAXCON_;               // contact groups this workspace has rows for
+    static constexpr int NBASE = 9 + 3 * MAXCON_;        // 3 tendon rows, 6 limit rows, 3 frame rows per contact
+    static constexpr int STAGE_MASK = STAGE_MASK_;       // CTA-wide rendezvous before the stages in this mask (KG_STAGE)
     // ======================================================================== carry section A (contiguous)
     // ---- state
     float qpos[16], qvel[16], qwarm[16], ctrl[12], sens_q[12];
@@ -127,7 +133,7 @@ struct alignas(16) KgWS {
     // the Newton-solver scratch and the contact staging of the collision stage are never live together; the staging
     // (carry section B) is what the narrowphase kernel fills in global memory
     union {
-        struct { float L[KG_NV * KG_MS], bdot[KG_NBASE + 2], bdir[KG_NBASE + 2], bw[KG_NBASE + 2]; };
+        struct { float L[KG_NV * KG_MS], bdot[NBASE + 2], bdir[NBASE + 2], bw[NBASE + 2]; };
         struct { float st_dist[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3]; unsigned char st_g1[KG_NSTAGE], st_g2[KG_NSTAGE], st_pad[16]; };
     };
     alignas(16) float bias[16], fs[16], qas[16], qacc[16], Mdq[16], grad[16], dir[16], Md[16], ftot[16];
@@ -135,7 +141,7 @@ struct alignas(16) KgWS {
     // ---- constraint groups: slot g<3 tendon, 3..8 limits, 9.. contacts
     int gtype[32], gslot[32], ngroup, ncon_total;
     float gmu[32], garef[32][4], gD[32];
-    alignas(16) float J[KG_NBASE * KG_JS];
+    alignas(16) float J[NBASE * KG_JS];
     float red[32], red2[32];
     // ---- solver scalars (written by lane 0, read by all after a sync)
     float s_alpha, s_cost, s_flag, s_lo, s_hi, s_glo, s_ghi, s_cost2;
@@ -146,6 +152,12 @@ struct alignas(16) KgWS {
     long long prof[KG_NPROF], prof_t0;  // see KG_PROBE / kg_get_prof
 #endif
 };
+// Two instances: the FULL workspace (KG_MAXCON contact groups; the host emulation and the debug entry points use only
+// this one) and the LIGHT one the product kernels run first: fewer Jacobian rows -> more warps per SM.  The carry
+// sections do not depend on the row count, so a record written through one workspace loads into the other.
+typedef KgWST<KG_MAXCON, KG_STAGE_MASK> KgWS;
+typedef KgWST<KG_MAXCON_LIGHT, KG_STAGE_MASK> KgWSLight;
+typedef KgWST<KG_MAXCON, 0> KgWSNoSync;      // full workspace without stage rendezvous (warps loop independently)
 #define KG_CARRY_A_BYTES (offsetof(KgWS, M))
 #define KG_CARRY_B_OFF   (offsetof(KgWS, st_dist))
 #define KG_CARRY_B_BYTES ((sizeof(float) * 7 * KG_NSTAGE + 2 * KG_NSTAGE + 15) / 16 * 16)
@@ -155,14 +167,19 @@ struct alignas(16) KgWS {
 #define KG_COFF_B(field) (KG_CARRY_A_BYTES + offsetof(KgWS, field) - KG_CARRY_B_OFF)
 
 static_assert(offsetof(KgWS, M) % 16 == 0 && offsetof(KgWS, L) % 16 == 0 && offsetof(KgWS, J) % 16 == 0 && sizeof(KgWS) % 16 == 0, "128-bit access needs 16-byte aligned members");
-static_assert(KG_NOBS * 4 <= KG_NBASE * KG_JS * 4, "obs staging must fit into J");
+static_assert(KG_NOBS * 4 <= KgWSLight::NBASE * KG_JS * 4, "obs staging must fit into J");
 static_assert(KG_CARRY_B_OFF % 16 == 0 && offsetof(KgWS, st_g2) + KG_NSTAGE - KG_CARRY_B_OFF <= KG_CARRY_B_BYTES, "carry section B");
 static_assert(KG_CARRY_B_BYTES <= sizeof(float) * 7 * KG_NSTAGE + 2 * KG_NSTAGE + 16, "carry section B must stay inside the union (st_pad absorbs the 16-byte round-up)");
+static_assert(offsetof(KgWSLight, M) == offsetof(KgWS, M) && offsetof(KgWSLight, st_dist) == offsetof(KgWS, st_dist) && offsetof(KgWSLight, st_g2) == offsetof(KgWS, st_g2),
+              "carry sections must sit at the same offsets in both workspaces");
+static_assert(offsetof(KgWSLight, J) % 16 == 0 && sizeof(KgWSLight) % 16 == 0, "128-bit access needs 16-byte aligned members");
 
 // Workspace of the narrowphase (MPR) kernel: the geom frames of one env, the object's hull, the finger hulls of the CTA.
 struct alignas(16) KgMprWS {
     float gpos[9][3], gmat[9][9];
+#ifndef KG_MPR_L1
     alignas(16) float objhull[KG_MAXOBJVERT * 4];
+#endif
     const float *fhull;
     int shape, hull_shape;
 #ifdef KG_PROF
@@ -254,7 +271,7 @@ KG_DEV float kg_total(const float *red, int l) {
 
 // ------------------------------------------------------------------------------------------------ episode constants
 // hand_quat is what the reference writes into the XML at every reset (ENV:851-881); here it is data.
-KG_DEV void kg_episode_constants(const KgModel &m, KgWS &ws, const float *hand_quat, int shape, int kg_lane) {
+template <class WS> KG_DEV void kg_episode_constants(const KgModel &m, WS &ws, const float *hand_quat, int shape, int kg_lane) {
     KG_PHASE(l) {
         if (l == 0) {
             kg_quat2mat(ws.Rh, hand_quat);
@@ -275,7 +292,7 @@ KG_DEV void kg_episode_constants(const KgModel &m, KgWS &ws, const float *hand_q
 }
 
 // ------------------------------------------------------------------------------------------------ P1 kinematics
-KG_DEV void kg_kinematics(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV void kg_kinematics(const KgModel &m, WS &ws, int kg_lane) {
     KG_PHASE(l) {
         float hp[3];
         for (int c = 0; c < 3; c++) hp[c] = m.l7_pos[c] + ws.sax[0][c] * ws.qpos[0] + ws.sax[1][c] * ws.qpos[1] + ws.sax[2][c] * ws.qpos[2];
@@ -325,7 +342,7 @@ KG_DEV void kg_kinematics(const KgModel &m, KgWS &ws, int kg_lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ P2 + P3: M, bias, smooth force
-KG_DEV void kg_dynamics(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV void kg_dynamics(const KgModel &m, WS &ws, int kg_lane) {
     KG_PHASE(l) {
         for (int i = l; i < KG_NV * KG_MS; i += 32) ws.M[i] = 0.f;
     }
@@ -487,7 +504,7 @@ KG_DEV void kg_chol_factor_solve(float *A, float *x, int kg_lane) {
 // Support point of geom g's convex hull, inflated by `margin`, along the unit world direction dir, expressed relative
 // to `origin`.  The geom frame comes from the workspace (shared memory), the vertices from the read-only hull table;
 // `cur` is the warm-start vertex (kept per pair across calls and substeps).
-KG_DEV void kg_support(const KgModel &m, const KgWS &ws, int g, int mesh, int &cur, const float *dir, const float *origin, float margin, float *out) {
+template <class WS> KG_DEV void kg_support(const KgModel &m, const WS &ws, int g, int mesh, int &cur, const float *dir, const float *origin, float margin, float *out) {
     const KgMesh &mi = m.mesh[mesh];
     const float *vert = m.hull_vert + 4 * (size_t)mi.vert0;
     const unsigned short *adj8 = m.adj8;
@@ -535,7 +552,12 @@ KG_DEV void kg_support(const KgModel &m, const KgWS &ws, int g, int mesh, int &c
 // fetched once.  Every lane returns the same result.  The host emulation scans the vertices in index order (same tie rule).
 KG_DEV const float *kg_hull_table(const KgModel &m, const KgMprWS &ws, int mesh) {
     // object -> this warp's shared-memory copy, fingers -> the CTA's shared-memory copy, palm -> global memory
+#ifdef KG_MPR_L1
+    (void)ws;
+    return m.hull_pad + 4 * (size_t)m.hpad0[mesh];     // every table through the read-only L1 path (KG_MPR_L1)
+#else
     return mesh >= 3 ? ws.objhull : (mesh == 0 ? m.hull_pad : ws.fhull + (mesh == 2 ? 4 * m.hnpad[1] : 0));
+#endif
 }
 KG_DEV void kg_support_coop(const KgModel &m, const KgMprWS &ws, int g, int mesh, const float *dir, const float *origin, float margin,
                             float *out, int *vidx, int kg_lane) {
@@ -550,7 +572,11 @@ KG_DEV void kg_support_coop(const KgModel &m, const KgMprWS &ws, int g, int mesh
     const float4 *v4 = reinterpret_cast<const float4 *>(vert);
 #pragma unroll 4
     for (int i = kg_lane; i < npad; i += 32) {
+#ifdef KG_MPR_L1
+        float4 v = __ldg(v4 + i);
+#else
         float4 v = v4[i];
+#endif
         float d = v.x * ld[0] + v.y * ld[1] + v.z * ld[2];
         if (d > best) { best = d; bi = i; }
     }
@@ -558,7 +584,11 @@ KG_DEV void kg_support_coop(const KgModel &m, const KgMprWS &ws, int g, int mesh
     unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
     unsigned mx = __reduce_max_sync(0xffffffffu, key);
     bi = __reduce_min_sync(0xffffffffu, key == mx ? bi : 0x7fffffff);
+#ifdef KG_MPR_L1
+    float4 w = __ldg(v4 + bi);
+#else
     float4 w = v4[bi];
+#endif
     float lv[3] = {w.x, w.y, w.z};
 #else
     (void)kg_lane;
@@ -782,8 +812,8 @@ KG_DEV void kg_pair_of_lane(int l, int &g1, int &g2) {
     }
 }
 KG_DEV int kg_mesh_of_geom_s(int shape, int g) { return g == 8 ? 3 + shape : (g == 1 ? 0 : ((g & 1) ? 2 : 1)); }
-KG_DEV int kg_mesh_of_geom(const KgWS &ws, int g) { return kg_mesh_of_geom_s(ws.shape, g); }
-KG_DEV float kg_rbound(const KgModel &m, const KgWS &ws, int g) { return g == 8 ? m.shape[ws.shape].rbound : (g == 1 ? m.hand_rbound[0] : ((g & 1) ? m.hand_rbound[2] : m.hand_rbound[1])); }
+template <class WS> KG_DEV int kg_mesh_of_geom(const WS &ws, int g) { return kg_mesh_of_geom_s(ws.shape, g); }
+template <class WS> KG_DEV float kg_rbound(const KgModel &m, const WS &ws, int g) { return g == 8 ? m.shape[ws.shape].rbound : (g == 1 ? m.hand_rbound[0] : ((g & 1) ? m.hand_rbound[2] : m.hand_rbound[1])); }
 
 // One narrowphase task: full MPR of pair lane lp of env `env` (warp-uniform: all 32 lanes run the portal algebra and
 // share the cooperative support scans).  The geom frames come from the env's carry record, the result is filed there
@@ -796,6 +826,7 @@ KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int
         if (l == 0) mw.shape = *reinterpret_cast<const int *>(carry + KG_COFF(shape));
     }
     KG_SYNC();
+#ifndef KG_MPR_L1
     if (mw.shape != mw.hull_shape) {      // this warp's object-hull copy holds another shape
         KG_SYNC();
         KG_PHASE(l) {
@@ -810,6 +841,7 @@ KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int
         KG_PHASE(l) { if (l == 0) mw.hull_shape = mw.shape; }
         KG_SYNC();
     }
+#endif
     int g1, g2;
     kg_pair_of_lane(lp, g1, g2);
     const int mesh1 = kg_mesh_of_geom_s(mw.shape, g1), mesh2 = kg_mesh_of_geom_s(mw.shape, g2);
@@ -844,7 +876,7 @@ KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int
 
 // Lane-parallel part of the collision stage: broadphase, plane contacts, re-test of the cached separating axes.
 // Returns (every lane) the mask of the pair lanes 8..29 that need a full MPR; those become narrowphase tasks.
-KG_DEV unsigned kg_collision_lane(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV unsigned kg_collision_lane(const KgModel &m, WS &ws, int kg_lane) {
     KG_PHASE(l) {
         int n = 0;
         float tried = 0.f;
@@ -938,7 +970,7 @@ KG_DEV unsigned kg_collision_lane(const KgModel &m, KgWS &ws, int kg_lane) {
 }
 
 // Contact compaction (after the narrowphase kernel has filed its hits): contact groups 9.. reference staging slots
-KG_DEV void kg_compaction(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV void kg_compaction(const KgModel &m, WS &ws, int kg_lane) {
     (void)m;
     KG_PHASE(l) {
         int off = 0, total = 0;
@@ -950,9 +982,9 @@ KG_DEV void kg_compaction(const KgModel &m, KgWS &ws, int kg_lane) {
         }
         if (l == 0) {
             ws.ncon_total = total;
-            int nc = total > KG_MAXCON ? KG_MAXCON : total;
+            int nc = total > WS::MAXCON ? WS::MAXCON : total;
             ws.ngroup = 9 + nc;
-            if (total > KG_MAXCON) ws.stat_overflow += 1;
+            if (total > WS::MAXCON) ws.stat_overflow += 1;
         }
     }
     KG_SYNC();
@@ -970,7 +1002,7 @@ KG_DEV float kg_impedance(const KgModel &m, float r) {
     return m.dmin + y * (m.dmax - m.dmin);
 }
 // translational Jacobian row of the point p on the body carrying geom g, projected on f, ADDED with sign sg
-KG_NOINL void kg_jac_add(const KgWS &ws, int g, const float *p, const float *f, float sg, float *row) {
+template <class WS> KG_NOINL void kg_jac_add(const WS &ws, int g, const float *p, const float *f, float sg, float *row) {
     if (g == 0) return;
     if (g == 8) {
         float r[3], t[3];
@@ -989,7 +1021,7 @@ KG_NOINL void kg_jac_add(const KgWS &ws, int g, const float *p, const float *f, 
     if (g & 1) { kg_sub(r, p, ws.p2[k]); kg_cross(t, a, r); row[4 + 2 * k] += sg * kg_dot(f, t); }
 }
 
-KG_DEV void kg_make_rows(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV void kg_make_rows(const KgModel &m, WS &ws, int kg_lane) {
     KG_PHASE(l) {
         const float K = m.solK, Bd = m.solB;
         if (l < 3) {
@@ -1046,7 +1078,7 @@ KG_DEV void kg_make_rows(const KgModel &m, KgWS &ws, int kg_lane) {
 // ------------------------------------------------------------------------------------------------ P7 Newton solver
 // Scalar rows of group g at the point described by base-row products bd[]:
 //   tendon/limit: jar = bd[g] - aref ;  contact c: jar_k = bd[n] +- mu bd[t] - aref_k
-KG_DEV int kg_group_rows(const KgWS &ws, int g, const float *bd, float *jar) {
+template <class WS> KG_DEV int kg_group_rows(const WS &ws, int g, const float *bd, float *jar) {
     int tp = ws.gtype[g];
     if (tp == 0) return 0;
     if (tp < 3) { jar[0] = bd[g] - ws.garef[g][0]; return 1; }
@@ -1056,10 +1088,10 @@ KG_DEV int kg_group_rows(const KgWS &ws, int g, const float *bd, float *jar) {
     jar[2] = n + t2 - ws.garef[g][2]; jar[3] = n - t2 - ws.garef[g][3];
     return 4;
 }
-KG_DEV int kg_nbase(const KgWS &ws) { return 9 + 3 * (ws.ngroup - 9); }
+template <class WS> KG_DEV int kg_nbase(const WS &ws) { return 9 + 3 * (ws.ngroup - 9); }
 
 // base-row products  out[b] = J_b . x   (lane per base row)
-KG_NOINL void kg_base_dots(KgWS &ws, const float *x, float *out, int kg_lane) {
+template <class WS> KG_NOINL void kg_base_dots(WS &ws, const float *x, float *out, int kg_lane) {
     KG_PHASE(l) {
         int nb = kg_nbase(ws);
         float xv[16];
@@ -1087,7 +1119,7 @@ KG_DEV void kg_inv3_sym(const float *S, float *Si) {   // inverse of a symmetric
     Si[1] = (S[0] * S[2] - S[4] * S[4]) * id; Si[5] = (S[3] * S[4] - S[0] * S[5]) * id;
     Si[2] = (S[0] * S[1] - S[3] * S[3]) * id;
 }
-KG_NOINL void kg_minv(KgWS &ws, float diag_add, float *x, int kg_lane) {
+template <class WS> KG_NOINL void kg_minv(WS &ws, float diag_add, float *x, int kg_lane) {
     KG_PHASE(l) {
         if (l < 3) {
             int h1 = 3 + 2 * l, h2 = 4 + 2 * l;
@@ -1154,7 +1186,7 @@ KG_NOINL void kg_minv(KgWS &ws, float diag_add, float *x, int kg_lane) {
     KG_SYNC();
 }
 
-KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) {
     const float tol = 1e-8f;
     // ---- unconstrained acceleration
     KG_PHASE(l) { if (l < KG_NV) ws.qas[l] = ws.fs[l]; }
@@ -1397,7 +1429,7 @@ KG_DEV void kg_solve(const KgModel &m, KgWS &ws, int kg_lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ P9 Euler
-KG_DEV void kg_euler(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV void kg_euler(const KgModel &m, WS &ws, int kg_lane) {
     const float h = m.timestep;
     kg_minv(ws, h * m.damping, ws.ftot, kg_lane);     // implicit joint damping: (M + h B) a = f
     KG_PHASE(l) {
@@ -1514,7 +1546,7 @@ KG_DEV float kg_ray_mesh(const KgModel &m, int mesh, const float *gpos, const fl
     }
     return best;
 }
-KG_NOINL void kg_site_pose(const KgModel &m, const KgWS &ws, int i, float *p, float *z) {
+template <class WS> KG_NOINL void kg_site_pose(const KgModel &m, const WS &ws, int i, float *p, float *z) {
     int sb = m.site_body[i];
     float R[9], org[3];
     if (sb == 0) { for (int c = 0; c < 9; c++) R[c] = ws.Rh[c]; kg_copy(org, ws.hp); }
@@ -1531,7 +1563,7 @@ KG_NOINL void kg_site_pose(const KgModel &m, const KgWS &ws, int i, float *p, fl
     kg_mulmv(t, R, m.site_pos + 3 * i); kg_add(p, org, t);
     kg_mulmv(z, R, m.site_z + 3 * i);
 }
-KG_DEV void kg_rays(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV void kg_rays(const KgModel &m, WS &ws, int kg_lane) {
     KG_PHASE(l) {
         if (l < KG_NSITE) {
             float p[3], v[3];
@@ -1570,7 +1602,7 @@ KG_DEV float kg_dotprod20(const float *hand, const float *p) {
 }
 KG_DEV float kg_tri_area(const float *a, const float *b) { float c[3]; kg_cross(c, a, b); return 0.5f * sqrtf(kg_dot(c, c)); }
 
-KG_DEV void kg_obs(const KgModel &m, KgWS &ws, int kg_lane, float *reward, int *done) {
+template <class WS> KG_DEV void kg_obs(const KgModel &m, WS &ws, int kg_lane, float *reward, int *done) {
     // hand frame (O1): T = (R_palm C)^T, wrist = p_palm + T^T [-0.009, 0.048, 0]
     KG_PHASE(l) {
         const float *Rp = ws.gmat[1];
@@ -1662,7 +1694,7 @@ KG_DEV void kg_obs(const KgModel &m, KgWS &ws, int kg_lane, float *reward, int *
 }
 
 // ------------------------------------------------------------------------------------------------ S1: ctrl from the 4-d action (ENV:1501-1534)
-KG_DEV void kg_ctrl_from_action(KgWS &ws, const float *action, int kg_lane) {
+template <class WS> KG_DEV void kg_ctrl_from_action(WS &ws, const float *action, int kg_lane) {
     KG_PHASE(l) {
         if (l == 0) {
             const float *Rp = ws.gmat[1];
@@ -1748,7 +1780,7 @@ struct KgEnvArrays {
     int N, max_steps;
 };
 
-KG_DEV void kg_load_env(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, int kg_lane) {
+template <class WS> KG_DEV void kg_load_env(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, int kg_lane) {
     KG_PHASE(l) {
         const int N = A.N;
         if (l < 16) ws.qpos[l] = A.qpos[l * N + env];
@@ -1765,7 +1797,7 @@ KG_DEV void kg_load_env(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
     float hq[4] = {A.hand_quat[env], A.hand_quat[A.N + env], A.hand_quat[2 * A.N + env], A.hand_quat[3 * A.N + env]};
     kg_episode_constants(m, ws, hq, A.shape[env], kg_lane);
 }
-KG_DEV void kg_store_env(KgWS &ws, const KgEnvArrays &A, int env, int kg_lane) {
+template <class WS> KG_DEV void kg_store_env(WS &ws, const KgEnvArrays &A, int env, int kg_lane) {
     KG_PHASE(l) {
         const int N = A.N;
         if (l < 16) A.qpos[l * N + env] = ws.qpos[l];
@@ -1785,13 +1817,13 @@ KG_DEV void kg_copy16(void *dst, const void *src, int bytes, int kg_lane) {
     memcpy(dst, src, (size_t)bytes);
 #endif
 }
-KG_DEV void kg_carry_store(const KgWS &ws, unsigned char *carry, int kg_lane) {
+template <class WS> KG_DEV void kg_carry_store(const WS &ws, unsigned char *carry, int kg_lane) {
     KG_SYNC();
     kg_copy16(carry, &ws, (int)KG_CARRY_A_BYTES, kg_lane);
     kg_copy16(carry + KG_CARRY_A_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CARRY_B_OFF, (int)KG_CARRY_B_BYTES, kg_lane);
     KG_SYNC();
 }
-KG_DEV void kg_carry_load(KgWS &ws, const unsigned char *carry, int kg_lane) {
+template <class WS> KG_DEV void kg_carry_load(WS &ws, const unsigned char *carry, int kg_lane) {
     kg_copy16(&ws, carry, (int)KG_CARRY_A_BYTES, kg_lane);
     kg_copy16(reinterpret_cast<unsigned char *>(&ws) + KG_CARRY_B_OFF, carry + KG_CARRY_A_BYTES, (int)KG_CARRY_B_BYTES, kg_lane);
     KG_SYNC();
@@ -1805,7 +1837,7 @@ KG_DEV void kg_carry_load(KgWS &ws, const unsigned char *carry, int kg_lane) {
     KG_SYNC();
 #endif
 }
-KG_DEV void kg_prof_flush(KgWS &ws, const KgEnvArrays &A, int kg_lane) {
+template <class WS> KG_DEV void kg_prof_flush(WS &ws, const KgEnvArrays &A, int kg_lane) {
 #if defined(KG_PROF) && defined(__CUDA_ARCH__)
     __syncwarp();
     if (A.prof && kg_lane < KG_NPROF) atomicAdd((unsigned long long *)A.prof + kg_lane, (unsigned long long)ws.prof[kg_lane]);
@@ -1832,7 +1864,7 @@ KG_DEV void kg_emit_tasks(unsigned mask, int env, int *q, unsigned *tasks, int k
 // First kernel of an RL step for one env: [expert action] -> ctrl -> kinematics + lane-parallel collision of substep 0.
 // action_in == nullptr selects the on-device expert (mode 0 naive, 1 position-dependent, 2 combined).
 // Returns the narrowphase task mask; the caller stores the carry record and emits the tasks.
-KG_DEV unsigned kg_step_begin(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, const float *action_in, int expert_mode, int kg_lane) {
+template <class WS> KG_DEV unsigned kg_step_begin(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, const float *action_in, int expert_mode, int kg_lane) {
     kg_load_env(m, ws, A, env, kg_lane);
     float act[4] = {0, 0, 0, 0};
     if (action_in) { for (int c = 0; c < 4; c++) act[c] = action_in[c * A.N + env]; }
@@ -1870,7 +1902,7 @@ KG_DEV unsigned kg_step_begin(const KgModel &m, KgWS &ws, const KgEnvArrays &A, 
 
 // Second half of one mj_step (the narrowphase kernel has filed the hull contacts of this substep into the carry):
 // dynamics, constraint rows, Newton solve, Euler.  The workspace holds the carry of this env.
-KG_DEV void kg_substep_finish(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV void kg_substep_finish(const KgModel &m, WS &ws, int kg_lane) {
     KG_STAGE(0);
     KG_PROBE(18);
     kg_dynamics(m, ws, kg_lane);
@@ -1891,7 +1923,7 @@ KG_DEV void kg_substep_finish(const KgModel &m, KgWS &ws, int kg_lane) {
     KG_PROBE(15);
 }
 // First half of the next mj_step: kinematics of the new state + lane-parallel collision; returns the task mask.
-KG_DEV unsigned kg_substep_start(const KgModel &m, KgWS &ws, int kg_lane) {
+template <class WS> KG_DEV unsigned kg_substep_start(const KgModel &m, WS &ws, int kg_lane) {
     kg_kinematics(m, ws, kg_lane);
     KG_PROBE(0);
     KG_STAGE(1);
@@ -1903,7 +1935,7 @@ KG_DEV unsigned kg_substep_start(const KgModel &m, KgWS &ws, int kg_lane) {
 
 // Last kernel of an RL step for one env (after the last substep's finish): rays -> obs/reward/done (+TimeLimit),
 // state and outputs back to the struct-of-arrays.
-KG_DEV void kg_step_end(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, int nsub,
+template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, int nsub,
                         float *obs_out, float *reward_out, int *done_out, float *action_out, int kg_lane) {
     KG_PROBE(19);
     kg_rays(m, ws, kg_lane);
@@ -1937,7 +1969,7 @@ KG_DEV void kg_step_end(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int en
 // reset of one env (ENV:1310-1410 without the file system): hand euler -> quaternion, hand joints 0, object at
 // obj_pos with identity orientation, velocities and warm start 0, forward kinematics + rays + first obs,
 // centroid fix-up (ENV:1382-1389), expert-controller episode state (EXP:367-379, 724-727).
-KG_DEV void kg_env_reset(const KgModel &m, KgWS &ws, const KgEnvArrays &A, int env, int shape, const float *euler, const float *objp,
+template <class WS> KG_DEV void kg_env_reset(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, int shape, const float *euler, const float *objp,
                          float *obs_out, int kg_lane) {
     float hq[4] = {1, 0, 0, 0};
     for (int i = 0; i < 3; i++) {   // MuJoCo eulerseq "xyz": q = qx qy qz

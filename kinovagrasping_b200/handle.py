@@ -81,6 +81,10 @@ class Handle:
     def set_schedule(self, mode):
         self._chk(self.lib.kg_set_schedule(self.h, int(mode)), "kg_set_schedule")
 
+    def set_mode(self, mode):
+        """0 automatic, 1 always split (light workspaces + heavy lane), 2 always full workspaces."""
+        self._chk(self.lib.kg_set_mode(self.h, int(mode)), "kg_set_mode")
+
     def last_action_host(self):
         a = np.zeros((4, self.n), dtype=np.float32)
         self._chk(self.lib.kg_get_last_action_host(self.h, _np_ptr(a)), "kg_get_last_action_host")

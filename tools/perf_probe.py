@@ -19,6 +19,8 @@ variant = int(os.environ.get("KG_VARIANT", "1"))
 h = Handle(n, lib=lib)
 sched = int(os.environ.get("KG_SCHEDULE", "1"))
 h.set_schedule(sched)
+mode = int(os.environ.get("KG_MODE", "0"))
+h.set_mode(mode)
 shape = (np.arange(n) % 2).astype(np.int32)
 import torch
 sh = torch.from_numpy(shape).cuda()
@@ -32,11 +34,13 @@ for t in range(steps):
 h.sync()
 st = h.stats()
 ms = np.array(ms)
-print(f"{os.path.basename(sys.argv[1]):28s} sched {sched} envs {n} kernel ms: median {np.median(ms[3:]):.3f} min {ms[3:].min():.3f} max {ms[3:].max():.3f} "
-      f"-> {n * 15 / np.median(ms[3:]) * 1e3:.3e} substeps/s | mpr/sub {st['mpr_pairs'] / st['substeps']:.2f} newton/sub {st['newton_iters'] / st['substeps']:.2f} ovf {st['contact_overflow']}")
 prof = (C.c_longlong * 32)()
 lib.kg_get_prof(h.h, prof)
 prof = list(prof)
+print(f"{os.path.basename(sys.argv[1]):28s} sched {sched} envs {n} kernel ms: mean {ms[3:].mean():.3f} median {np.median(ms[3:]):.3f} min {ms[3:].min():.3f} max {ms[3:].max():.3f} "
+      f"-> {n * 15 / ms[3:].mean() * 1e3:.3e} substeps/s | mpr/sub {st['mpr_pairs'] / st['substeps']:.2f} newton/sub {st['newton_iters'] / st['substeps']:.2f} ovf {st['contact_overflow']}"
+      f" mode {mode}")
+if os.environ.get("KG_SERIES"): print("   ms per step:", " ".join(f"{x:.2f}" for x in ms))
 tot = sum(prof[:20])
 if tot:
     names = ["kin/dyn", "w>coll", "coll.lane", "compact", "w>rows", "rows", "w>solve", "sol.setup", "sol.cost", "sol.hess", "sol.chol", "sol.dirs",
