@@ -546,6 +546,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     TRY(be_alloc(h, (void **)&A.hand_quat, 4 * N * 4)); TRY(be_alloc(h, (void **)&A.shape, N * 4)); TRY(be_alloc(h, (void **)&A.elapsed, N * 4));
     TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
     TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
+    TRY(be_alloc(h, (void **)&A.ccache, N * KG_CCACHE_BYTES));
     TRY(be_alloc(h, (void **)&A.load, N * 4)); TRY(be_alloc(h, (void **)&h->perm, N * 4));
     TRY(be_alloc(h, (void **)&h->carry, N * KG_CARRY_BYTES)); TRY(be_alloc(h, (void **)&h->tasks, N * 22 * 4)); TRY(be_alloc(h, (void **)&h->q, 4 * 4));
     TRY(be_alloc(h, (void **)&h->heavy_count, 4));

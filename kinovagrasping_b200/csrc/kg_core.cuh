@@ -158,6 +158,10 @@ struct alignas(16) KgWST {
 typedef KgWST<KG_MAXCON, KG_STAGE_MASK> KgWS;
 typedef KgWST<KG_MAXCON_LIGHT, KG_STAGE_MASK> KgWSLight;
 typedef KgWST<KG_MAXCON, 0> KgWSNoSync;      // full workspace without stage rendezvous (warps loop independently)
+// the collision caches: contiguous in the workspace, kept per env across RL steps (a cached axis is only ever RE-TESTED,
+// a cached vertex is only a starting point, so stale entries after kg_set_state cost time, not correctness)
+#define KG_CCACHE_OFF   (offsetof(KgWS, cv1))
+#define KG_CCACHE_BYTES (offsetof(KgWS, sepok) + sizeof(int) * 32 - offsetof(KgWS, cv1))
 #define KG_CARRY_A_BYTES (offsetof(KgWS, M))
 #define KG_CARRY_B_OFF   (offsetof(KgWS, st_dist))
 #define KG_CARRY_B_BYTES ((sizeof(float) * 7 * KG_NSTAGE + 2 * KG_NSTAGE + 15) / 16 * 16)
@@ -172,6 +176,7 @@ static_assert(KG_CARRY_B_OFF % 16 == 0 && offsetof(KgWS, st_g2) + KG_NSTAGE - KG
 static_assert(KG_CARRY_B_BYTES <= sizeof(float) * 7 * KG_NSTAGE + 2 * KG_NSTAGE + 16, "carry section B must stay inside the union (st_pad absorbs the 16-byte round-up)");
 static_assert(offsetof(KgWSLight, M) == offsetof(KgWS, M) && offsetof(KgWSLight, st_dist) == offsetof(KgWS, st_dist) && offsetof(KgWSLight, st_g2) == offsetof(KgWS, st_g2),
               "carry sections must sit at the same offsets in both workspaces");
+static_assert(KG_CCACHE_OFF % 16 == 0 && KG_CCACHE_BYTES % 16 == 0 && KG_CCACHE_BYTES == 640, "collision cache block");
 static_assert(offsetof(KgWSLight, J) % 16 == 0 && sizeof(KgWSLight) % 16 == 0, "128-bit access needs 16-byte aligned members");
 
 // Workspace of the narrowphase (MPR) kernel: the geom frames of one env, the object's hull, the finger hulls of the CTA.
@@ -1504,11 +1509,15 @@ KG_DEV float kg_ray_tri(const float *t, const float *p, const float *v, const fl
     float x = -kg_dot(e2, nrm) / den;
     return x >= 0.f ? x : -1.f;
 }
-KG_DEV float kg_ray_mesh(const KgModel &m, int mesh, const float *gpos, const float *gmat, const float *size, const float *pnt, const float *vec) {
-    float dp[3], lp[3], lv[3];
+// ray (pnt, vec) in the frame of a mesh geom
+KG_DEV void kg_ray_local(const float *gpos, const float *gmat, const float *pnt, const float *vec, float *lp, float *lv) {
+    float dp[3];
     kg_sub(dp, pnt, gpos);
     kg_multmv(lp, gmat, dp); kg_multmv(lv, gmat, vec);
-    if (kg_ray_box(size, lp, lv) < 0.f) return -1.f;
+}
+// nearest raw-triangle hit of the local ray (lp, lv) with a mesh, through its BVH; -1 = none.  The caller has already
+// culled the ray against the geom_size box.
+KG_DEV float kg_ray_mesh_bvh(const KgModel &m, int mesh, const float *lp, const float *lv) {
     float b0[3], b1[3];
     if (fabsf(lv[0]) < fabsf(lv[1]) && fabsf(lv[0]) < fabsf(lv[2])) { b0[0] = 0; b0[1] = lv[2]; b0[2] = -lv[1]; }
     else if (fabsf(lv[1]) < fabsf(lv[2])) { b0[0] = -lv[2]; b0[1] = 0; b0[2] = lv[0]; }
@@ -1563,25 +1572,75 @@ template <class WS> KG_NOINL void kg_site_pose(const KgModel &m, const WS &ws, i
     kg_mulmv(t, R, m.site_pos + 3 * i); kg_add(p, org, t);
     kg_mulmv(z, R, m.site_z + 3 * i);
 }
+// The 17 rangefinders against the 8 mesh geoms are 136 (site, geom) pairs.  Phase 1: a lane per site (pose, floor hit);
+// phase 2: the pairs strided over all 32 lanes, box cull, survivors appended to a hit list; phase 3: the survivors
+// strided over all 32 lanes, BVH traversal, nearest hit per site by an integer min on the (non-negative) distances.
+// Scratch lives in J (dead between the last solve and the obs staging).
+#if defined(__CUDA_ARCH__)
+#define KG_ATOMIC_INC(p) atomicAdd((p), 1)
+#define KG_ATOMIC_MIN_U(p, v) atomicMin((p), (v))
+#else
+static inline int KG_ATOMIC_INC(int *p) { return (*p)++; }
+static inline void KG_ATOMIC_MIN_U(unsigned *p, unsigned v) { if (v < *p) *p = v; }
+#endif
+#define KG_RAY_NONE 0x7f800000u     // +inf: no hit yet
 template <class WS> KG_DEV void kg_rays(const KgModel &m, WS &ws, int kg_lane) {
+    float *site = ws.J;                                                   // [KG_NSITE][6] origin, direction
+    int *hits = reinterpret_cast<int *>(ws.J + 6 * KG_NSITE + 2);         // [<= 8 KG_NSITE] surviving pair ids
+    unsigned *rmin = reinterpret_cast<unsigned *>(KG_RANGE(ws));
+    static_assert((6 * KG_NSITE + 2 + 8 * KG_NSITE) * 4 <= KgWSLight::NBASE * KG_JS * 4, "ray scratch must fit into J");
     KG_PHASE(l) {
         if (l < KG_NSITE) {
             float p[3], v[3];
             kg_site_pose(m, ws, l, p, v);
-            int sb = m.site_body[l];
-            int own = sb == 0 ? 1 : (sb <= 3 ? 2 * sb : 2 * (sb - 3) + 1);
+            for (int c = 0; c < 3; c++) { site[6 * l + c] = p[c]; site[6 * l + 3 + c] = v[c]; }
             float best = -1.f;
             if (v[2] < -1e-15f) {
                 float x = -p[2] / v[2];
                 if (x >= 0.f && fabsf(p[0] + x * v[0]) <= 2.f && fabsf(p[1] + x * v[1]) <= 2.f) best = x;
             }
-            for (int g = 1; g < 9; g++) {
-                if (g == own) continue;
-                const float *size = g == 8 ? m.shape[ws.shape].size : (g == 1 ? m.hand_size : ((g & 1) ? m.hand_size + 6 : m.hand_size + 3));
-                float x = kg_ray_mesh(m, kg_mesh_of_geom(ws, g), ws.gpos[g], ws.gmat[g], size, p, v);
-                if (x >= 0.f && (best < 0.f || x < best)) best = x;
+            rmin[l] = best < 0.f ? KG_RAY_NONE : KG_F2U(fabsf(best));
+        }
+        if (l == 0) ws.s_iter = 0;
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        for (int pr = l; pr < 8 * KG_NSITE; pr += 32) {
+            const int i = pr >> 3, g = 1 + (pr & 7);
+            const int sb = m.site_body[i];
+            const int own = sb == 0 ? 1 : (sb <= 3 ? 2 * sb : 2 * (sb - 3) + 1);
+            if (g == own) continue;
+            const float *size = g == 8 ? m.shape[ws.shape].size : (g == 1 ? m.hand_size : ((g & 1) ? m.hand_size + 6 : m.hand_size + 3));
+            float lp[3], lv[3];
+            kg_ray_local(ws.gpos[g], ws.gmat[g], site + 6 * i, site + 6 * i + 3, lp, lv);
+            if (kg_ray_box(size, lp, lv) < 0.f) continue;
+            hits[KG_ATOMIC_INC(&ws.s_iter)] = pr;
+        }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        const int n = ws.s_iter;
+        for (int k = l; k < n; k += 32) {
+            const int pr = hits[k], i = pr >> 3, g = 1 + (pr & 7);
+            float lp[3], lv[3];
+            kg_ray_local(ws.gpos[g], ws.gmat[g], site + 6 * i, site + 6 * i + 3, lp, lv);
+            const float x = kg_ray_mesh_bvh(m, kg_mesh_of_geom(ws, g), lp, lv);
+            if (x >= 0.f) KG_ATOMIC_MIN_U(&rmin[i], KG_F2U(fabsf(x)));
+        }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        if (l < KG_NSITE) {
+            const unsigned u = rmin[l];
+            float r = -1.f;
+            if (u != KG_RAY_NONE) {
+#if defined(__CUDA_ARCH__)
+                r = __uint_as_float(u);
+#else
+                memcpy(&r, &u, 4);
+#endif
             }
-            KG_RANGE(ws)[l] = best;
+            KG_RANGE(ws)[l] = r;
         }
     }
     KG_SYNC();
@@ -1777,6 +1836,7 @@ struct KgEnvArrays {
     int *stats;                   // [4] mpr pairs, newton iterations, contact overflows, substeps
     int *load;                    // [N] cost of each env's last RL step (Newton iterations + 2 x MPR pairs): key of the launch schedule
     long long *prof;              // [KG_NPROF] KG_PROF builds only
+    unsigned char *ccache;        // [N][KG_CCACHE_BYTES] collision caches (warm-start vertices, separating axes) kept across RL steps
     int N, max_steps;
 };
 
@@ -1866,6 +1926,8 @@ KG_DEV void kg_emit_tasks(unsigned mask, int env, int *q, unsigned *tasks, int k
 // Returns the narrowphase task mask; the caller stores the carry record and emits the tasks.
 template <class WS> KG_DEV unsigned kg_step_begin(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, const float *action_in, int expert_mode, int kg_lane) {
     kg_load_env(m, ws, A, env, kg_lane);
+    kg_copy16(reinterpret_cast<unsigned char *>(&ws) + KG_CCACHE_OFF, A.ccache + (size_t)env * KG_CCACHE_BYTES, (int)KG_CCACHE_BYTES, kg_lane);
+    KG_SYNC();
     float act[4] = {0, 0, 0, 0};
     if (action_in) { for (int c = 0; c < 4; c++) act[c] = action_in[c * A.N + env]; }
     else {
@@ -1944,6 +2006,7 @@ template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEn
     kg_obs(m, ws, kg_lane, &rew, &dn);
     KG_PROBE(17);
     kg_store_env(ws, A, env, kg_lane);
+    kg_copy16(A.ccache + (size_t)env * KG_CCACHE_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CCACHE_OFF, (int)KG_CCACHE_BYTES, kg_lane);
     KG_PHASE(l) {
         const int N = A.N;
         for (int i = l; i < KG_NOBS; i += 32) { float v = KG_WSOBS(ws)[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
@@ -2011,6 +2074,7 @@ template <class WS> KG_DEV void kg_env_reset(const KgModel &m, WS &ws, const KgE
     float rew; int dn;
     kg_obs(m, ws, kg_lane, &rew, &dn);
     kg_store_env(ws, A, env, kg_lane);
+    kg_copy16(A.ccache + (size_t)env * KG_CCACHE_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CCACHE_OFF, (int)KG_CCACHE_BYTES, kg_lane);   // cleared by kg_episode_constants
     KG_PHASE(l) {
         const int N = A.N;
         for (int i = l; i < KG_NOBS; i += 32) { float v = KG_WSOBS(ws)[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
