@@ -89,6 +89,10 @@ int kg_set_schedule(kg_handle h, int mode);
  * lane of the same launch) unless the last RL step the host has a count for had more than a third of the envs above the
  * light limit, then full mode; 1 = always split; 2 = always full (every env through the full workspace). */
 int kg_set_mode(kg_handle h, int mode);
+/* Pipelining of kg_step (no effect on results): the batch is cut into `groups` (1..4) contiguous env groups whose kernel
+ * chains run on separate internal streams, forked from and joined into the handle's stream, so one group's narrowphase
+ * kernel overlaps another group's per-env kernel.  Default: 2 for batches of 512 envs or more, else 1. */
+int kg_set_pipeline(kg_handle h, int groups);
 /* The action the last kg_step applied (the caller's, or the on-device expert's: get_action, expert_data.py:610). float[4][n]. */
 int kg_get_last_action_host(kg_handle h, float *action_host);
 

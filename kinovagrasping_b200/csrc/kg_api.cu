@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#define KG_MAXGROUPS 4
 #ifndef KG_EMU
 #include <cuda_runtime.h>
 #ifndef KG_WARPS
@@ -47,6 +48,7 @@ struct kg_handle_s {
     unsigned *tasks = nullptr;        // [n * 22] narrowphase task list of the current substep: (env << 8) | pair lane
     int *q = nullptr;                 // two {queued, next} pairs: the per-env kernels fill one while the other is being reset
     int qsel = 0;
+    int ngroups = 1;                  // env groups pipelined on separate streams inside one kg_step (KG_MAXGROUPS)
     int *heavy_count = nullptr;       // device: envs whose last substep of the current RL step exceeded the light workspace
     int *heavy_host = nullptr;        // pinned host copy of the previous step's count (read without synchronising)
     int heavy_ctas = 1;               // heavy-lane CTAs at the front of every split-mode substep grid
@@ -58,8 +60,14 @@ struct kg_handle_s {
     float *d_debug = nullptr, *d_ctrl = nullptr;
 #ifndef KG_EMU
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t gstream[KG_MAXGROUPS] = {};
+    cudaEvent_t gfork = nullptr, gjoin[KG_MAXGROUPS] = {};
 #endif
     float last_ms = 0.f;
+#if !defined(KG_EMU) && defined(KG_TIMING)
+    std::vector<cudaEvent_t> tev;     // KG_TIMING builds: an event after every launch of a step (tools/perf_probe.py)
+    std::vector<int> tkind;
+#endif
     int fhull_bytes = 0;       // shared-memory copy of the finger hulls in every narrowphase CTA
     int mpr_grid = 1;          // persistent narrowphase grid: resident CTAs per SM x SMs
 #ifdef KG_EMU
@@ -191,16 +199,18 @@ __global__ void __launch_bounds__(1024) kg_schedule_kernel(const int *load, int 
 // every env is run exactly once; the heavy lane overlaps the light CTAs instead of trailing them.
 // FULL mode: every env through the full workspace (16 warps per CTA, one CTA per SM) -- chosen by the host when the
 // last RL step it has a count for had more than a third of the envs above the light limit (contact-heavy shapes).
+// A launch covers the env GROUP [base, base + cnt) (launch_step pipelines the groups of a batch on separate streams);
+// perm, when given, holds per group a permutation of 0..cnt-1 at perm[base..].
 #define KG_ENV_OF_WARP(WS, WARPS, BLOCK) \
     extern __shared__ __align__(16) unsigned char smem[]; \
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31; \
     const int slot = (BLOCK) * (WARPS) + warp; \
-    if (slot >= A.N) return; \
-    const int env = perm ? perm[slot] : slot; \
+    if (slot >= cnt) return; \
+    const int env = base + (perm ? perm[base + slot] : slot); \
     WS &ws = *(reinterpret_cast<WS *>(smem) + warp)
 
 // first kernel of an RL step: action / on-device expert, kinematics and lane-parallel collision of substep 0
-__global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_begin_kernel(KgEnvArrays A, const int *perm, const float *action, int mode,
+__global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_begin_kernel(KgEnvArrays A, int base, int cnt, const int *perm, const float *action, int mode,
                                                                                  unsigned char *carry, int *q, unsigned *tasks) {
     KG_ENV_OF_WARP(KgWSLight, KG_LWARPS, blockIdx.x);
     const unsigned mask = kg_step_begin(c_model, ws, A, env, action, mode, lane);
@@ -230,7 +240,7 @@ __device__ __forceinline__ int kg_warp_sum(int v) {
 }
 #define KG_HEAVY_WARPS ((int)(KG_LSMEM / sizeof(KgWSNoSync)))     // full workspaces that fit a light CTA's shared memory
 template <bool LAST>
-__global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(KgEnvArrays A, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
+__global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(KgEnvArrays A, int base, int cnt, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
                                                                                int nheavy_ctas, int *heavy_count, int nsub, float *obs, float *reward, int *done, float *act_out) {
     if ((int)blockIdx.x < nheavy_ctas) {
         // ---- heavy lane: persistent warps with full workspaces (no stage rendezvous: they loop independently)
@@ -240,12 +250,13 @@ __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(K
         KgWSNoSync &ws = *(reinterpret_cast<KgWSNoSync *>(smem) + warp);
         const int W = nheavy_ctas * KG_HEAVY_WARPS;
         int nh = 0;
-        for (int e0 = blockIdx.x * KG_HEAVY_WARPS + warp; e0 < A.N; e0 += 4 * W) {
+        const int end = base + cnt;
+        for (int e0 = base + blockIdx.x * KG_HEAVY_WARPS + warp; e0 < end; e0 += 4 * W) {
             int c[4];      // four independent count loads in flight
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int env = e0 + k * W;
-                c[k] = env < A.N ? reinterpret_cast<const int *>(carry + (size_t)env * KG_CARRY_BYTES + KG_COFF(cnt))[lane] : 0;
+                c[k] = env < end ? reinterpret_cast<const int *>(carry + (size_t)env * KG_CARRY_BYTES + KG_COFF(cnt))[lane] : 0;
             }
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(K
     kg_sub_body<KgWSLight, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
 }
 template <bool LAST>
-__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_full_kernel(KgEnvArrays A, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
+__global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_full_kernel(KgEnvArrays A, int base, int cnt, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
                                                                                   int *heavy_count, int nsub, float *obs, float *reward, int *done, float *act_out) {
     KG_ENV_OF_WARP(KgWS, KG_WARPS, blockIdx.x);
     unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
@@ -399,6 +410,11 @@ static void emu_run_tasks(kg_handle h, int sel) {
 }
 #endif
 
+#if !defined(KG_EMU) && defined(KG_TIMING)
+#define KG_TMARK(kind) do { if (h->tev.size() <= tix) { cudaEvent_t e_; cudaEventCreate(&e_); h->tev.push_back(e_); h->tkind.push_back(0); } h->tkind[tix] = (kind); cudaEventRecord(h->tev[tix++], st); } while (0)
+#else
+#define KG_TMARK(kind) ((void)0)
+#endif
 // One RL step = a wavefront of kernels on the handle's stream:
 //   [schedule] begin | nsub x ( narrowphase tasks | per-env substep kernel )     (2 nsub + 1 launches of our kernels)
 static int launch_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
@@ -427,35 +443,71 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)h->stream;
-    const int blocks = (h->n + KG_LWARPS - 1) / KG_LWARPS;
     const size_t smem = KG_LSMEM, hsmem = KG_WARPS * ws_bytes();
-    const int *perm = h->schedule ? h->perm : nullptr;
-    const int fblocks = (h->n + KG_WARPS - 1) / KG_WARPS;
     // mode of this step, from the newest count of above-the-light-limit envs the host has (never waits for the device)
     if (KG_SPLIT && h->heavy_host) {
         const float frac = (float)*(volatile int *)h->heavy_host / (float)h->n;
         if (h->mode_auto) { if (!h->full_mode && frac > 0.33f) h->full_mode = 1; else if (h->full_mode && frac < 0.20f) h->full_mode = 0; }
     }
     const bool full = !KG_SPLIT || h->full_mode;
-    const int nhc = KG_SPLIT ? h->heavy_ctas : 0;
     cudaMemcpyAsync(h->heavy_host, h->heavy_count, sizeof(int), cudaMemcpyDeviceToHost, st);      // last step's count -> pinned host word
     cudaMemsetAsync(h->heavy_count, 0, sizeof(int), st);
     cudaEventRecord(h->ev0, st);
-    if (h->schedule) kg_schedule_kernel<<<1, 1024, 0, st>>>(h->A.load, h->perm, h->n);
-    kg_begin_kernel<<<blocks, KG_LWARPS * 32, smem, st>>>(h->A, perm, action, mode, h->carry, h->q + 2 * h->qsel, h->tasks);
+#if defined(KG_TIMING)
+    size_t tix = 0;
+    const int G = 1;
+#else
+    const int G = h->ngroups;
+#endif
+    // The env groups of the batch are independent pipelines: group g's kernels go to its own stream, so the narrowphase
+    // kernel of one group (latency-bound, few registers) overlaps the per-env kernel of another (and the launch gaps and
+    // the tail of every kernel are covered by the other groups' work).  Fork from / join into the caller's stream.
+    cudaStream_t gs[KG_MAXGROUPS];
+    int gbase[KG_MAXGROUPS + 1];
+    for (int g = 0; g <= G; g++) gbase[g] = (int)((long long)h->n * g / G);
+    if (G > 1) {
+        cudaEventRecord(h->gfork, st);
+        for (int g = 0; g < G; g++) { gs[g] = h->gstream[g]; cudaStreamWaitEvent(gs[g], h->gfork, 0); }
+    } else gs[0] = st;
+    const int qs0 = h->qsel;
+    for (int g = 0; g < G; g++) {
+        const int base = gbase[g], cnt = gbase[g + 1] - base;
+        if (cnt <= 0) continue;
+        const int *perm = h->schedule ? h->perm : nullptr;
+        const int blocks = (cnt + KG_LWARPS - 1) / KG_LWARPS;
+        KG_TMARK(0);
+        if (h->schedule) kg_schedule_kernel<<<1, 1024, 0, gs[g]>>>(h->A.load + base, h->perm + base, cnt);
+        KG_TMARK(1);
+        kg_begin_kernel<<<blocks, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, action, mode, h->carry, h->q + 4 * g + 2 * qs0, h->tasks + (size_t)base * 22);
+        KG_TMARK(2);
+    }
     for (int s = 0; s < nsub; s++) {
-        kg_mpr_kernel<<<h->mpr_grid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), st>>>(h->carry, h->q + 2 * h->qsel, h->q + 2 * (h->qsel ^ 1), h->tasks, h->A.prof);
-        h->qsel ^= 1;
-        int *qn = h->q + 2 * h->qsel;
+        const int qa = (qs0 + s) & 1, qb = qa ^ 1;
         const bool last = s == nsub - 1;
-        if (full) {
-            if (last) kg_sub_full_kernel<true><<<fblocks, KG_WARPS * 32, hsmem, st>>>(h->A, perm, h->carry, qn, h->tasks, h->heavy_count, nsub, obs, reward, done, act_out);
-            else kg_sub_full_kernel<false><<<fblocks, KG_WARPS * 32, hsmem, st>>>(h->A, perm, h->carry, qn, h->tasks, h->heavy_count, nsub, obs, reward, done, act_out);
-        } else {
-            if (last) kg_sub_kernel<true><<<blocks + nhc, KG_LWARPS * 32, smem, st>>>(h->A, perm, h->carry, qn, h->tasks, nhc, h->heavy_count, nsub, obs, reward, done, act_out);
-            else kg_sub_kernel<false><<<blocks + nhc, KG_LWARPS * 32, smem, st>>>(h->A, perm, h->carry, qn, h->tasks, nhc, h->heavy_count, nsub, obs, reward, done, act_out);
+        for (int g = 0; g < G; g++) {
+            const int base = gbase[g], cnt = gbase[g + 1] - base;
+            if (cnt <= 0) continue;
+            const int *perm = h->schedule ? h->perm : nullptr;
+            int *q = h->q + 4 * g;
+            unsigned *tasks = h->tasks + (size_t)base * 22;
+            kg_mpr_kernel<<<h->mpr_grid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), gs[g]>>>(h->carry, q + 2 * qa, q + 2 * qb, tasks, h->A.prof);
+            KG_TMARK(3);
+            if (full) {
+                const int fblocks = (cnt + KG_WARPS - 1) / KG_WARPS;
+                if (last) kg_sub_full_kernel<true><<<fblocks, KG_WARPS * 32, hsmem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, h->heavy_count, nsub, obs, reward, done, act_out);
+                else kg_sub_full_kernel<false><<<fblocks, KG_WARPS * 32, hsmem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, h->heavy_count, nsub, obs, reward, done, act_out);
+            } else {
+                const int blocks = (cnt + KG_LWARPS - 1) / KG_LWARPS;
+                const int hb = (cnt + KG_HEAVY_WARPS - 1) / KG_HEAVY_WARPS;
+                const int nhc = hb < h->heavy_ctas ? hb : h->heavy_ctas;
+                if (last) kg_sub_kernel<true><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, nsub, obs, reward, done, act_out);
+                else kg_sub_kernel<false><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, nsub, obs, reward, done, act_out);
+            }
+            KG_TMARK(last ? 5 : 4);
         }
     }
+    h->qsel = (qs0 + nsub) & 1;
+    if (G > 1) for (int g = 0; g < G; g++) { cudaEventRecord(h->gjoin[g], gs[g]); cudaStreamWaitEvent(st, h->gjoin[g], 0); }
     cudaEventRecord(h->ev1, st);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -538,6 +590,12 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
         *h->heavy_host = 0;
     }
     CUDA_TRY(h, cudaEventCreate(&h->ev0)); CUDA_TRY(h, cudaEventCreate(&h->ev1));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->gfork, cudaEventDisableTiming));
+    for (int g = 0; g < KG_MAXGROUPS; g++) {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->gjoin[g], cudaEventDisableTiming));
+    }
+    h->ngroups = n_envs >= 512 ? 2 : 1;
 #endif
     const size_t N = (size_t)n_envs;
     KgEnvArrays &A = h->A;
@@ -548,7 +606,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
     TRY(be_alloc(h, (void **)&A.ccache, N * KG_CCACHE_BYTES));
     TRY(be_alloc(h, (void **)&A.load, N * 4)); TRY(be_alloc(h, (void **)&h->perm, N * 4));
-    TRY(be_alloc(h, (void **)&h->carry, N * KG_CARRY_BYTES)); TRY(be_alloc(h, (void **)&h->tasks, N * 22 * 4)); TRY(be_alloc(h, (void **)&h->q, 4 * 4));
+    TRY(be_alloc(h, (void **)&h->carry, N * KG_CARRY_BYTES)); TRY(be_alloc(h, (void **)&h->tasks, N * 22 * 4)); TRY(be_alloc(h, (void **)&h->q, 4 * 4 * KG_MAXGROUPS));
     TRY(be_alloc(h, (void **)&h->heavy_count, 4));
     TRY(be_alloc(h, (void **)&h->d_action, 4 * N * 4)); TRY(be_alloc(h, (void **)&h->d_obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&h->d_reward, N * 4));
     TRY(be_alloc(h, (void **)&h->d_done, N * 4)); TRY(be_alloc(h, (void **)&h->d_mask, N * 4)); TRY(be_alloc(h, (void **)&h->d_shape, N * 4));
@@ -574,6 +632,8 @@ int kg_destroy(kg_handle h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->heavy_host) cudaFreeHost(h->heavy_host);
+    if (h->gfork) cudaEventDestroy(h->gfork);
+    for (int g = 0; g < KG_MAXGROUPS; g++) { if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]); if (h->gjoin[g]) cudaEventDestroy(h->gjoin[g]); }
 #endif
     delete h;
     return KG_OK;
@@ -583,6 +643,11 @@ int kg_num_envs(kg_handle h) { return h ? h->n : KG_EINVAL; }
 int kg_set_stream(kg_handle h, void *stream) { if (!h) return KG_EINVAL; h->stream = stream; return KG_OK; }
 int kg_sync(kg_handle h) { if (!h) return KG_EINVAL; return be_sync(h); }
 int kg_set_max_episode_steps(kg_handle h, int steps) { if (!h || steps <= 0) return KG_EINVAL; h->A.max_steps = steps; return KG_OK; }
+int kg_set_pipeline(kg_handle h, int groups) {
+    if (!h || groups < 1 || groups > KG_MAXGROUPS) return KG_EINVAL;
+    h->ngroups = groups;
+    return KG_OK;
+}
 int kg_set_mode(kg_handle h, int mode) {
     if (!h || mode < 0 || mode > 2) return KG_EINVAL;
     h->mode_auto = mode == 0; h->full_mode = mode == 2;
@@ -702,6 +767,17 @@ int kg_forward_debug(kg_handle h, int env, const float *ctrl, float *out) {
 #ifdef KG_EMU
 // emulation-only: 0 = lanes of a phase run 0..31, 1 = 31..0 (tests/test_emu_race.py)
 int kg_emu_set_lane_order(int reverse) { kg_emu_lane_order = reverse ? 1 : 0; return KG_OK; }
+#endif
+#if !defined(KG_EMU) && defined(KG_TIMING)
+// KG_TIMING builds only (tools/perf_probe.py): ms of the last step by launch kind: [1] schedule [2] begin [3] narrowphase
+// [4] substep [5] last substep; each launch is timed from the event after the previous launch to the event after it.
+int kg_timing_breakdown(kg_handle h, float out[8]) {
+    if (!h || !out) return KG_EINVAL;
+    for (int i = 0; i < 8; i++) out[i] = 0.f;
+    CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+    for (size_t i = 1; i < h->tev.size(); i++) { float ms = 0.f; cudaEventElapsedTime(&ms, h->tev[i - 1], h->tev[i]); out[h->tkind[i]] += ms; }
+    return KG_OK;
+}
 #endif
 int kg_last_step_ms(kg_handle h, float *ms) {
     if (!h || !ms) return KG_EINVAL;

@@ -85,6 +85,10 @@ class Handle:
         """0 automatic, 1 always split (light workspaces + heavy lane), 2 always full workspaces."""
         self._chk(self.lib.kg_set_mode(self.h, int(mode)), "kg_set_mode")
 
+    def set_pipeline(self, groups):
+        """Number of env groups (1..4) whose kernel chains kg_step overlaps on separate internal streams."""
+        self._chk(self.lib.kg_set_pipeline(self.h, int(groups)), "kg_set_pipeline")
+
     def last_action_host(self):
         a = np.zeros((4, self.n), dtype=np.float32)
         self._chk(self.lib.kg_get_last_action_host(self.h, _np_ptr(a)), "kg_get_last_action_host")

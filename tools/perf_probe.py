@@ -21,15 +21,23 @@ sched = int(os.environ.get("KG_SCHEDULE", "1"))
 h.set_schedule(sched)
 mode = int(os.environ.get("KG_MODE", "0"))
 h.set_mode(mode)
+groups = int(os.environ.get("KG_GROUPS", "0"))
+if groups: h.set_pipeline(groups)
 shape = (np.arange(n) % 2).astype(np.int32)
 import torch
 sh = torch.from_numpy(shape).cuda()
 done = torch.zeros(n, dtype=torch.int32, device="cuda")
 h.reset_sampled(0, sh.data_ptr(), 0, variant, 0, 1234, 0)
 ms = []
+brk = []
 for t in range(steps):
     h.step(0, 2, 0, 0, done.data_ptr())
     ms.append(h.last_step_ms())
+    if hasattr(lib, "kg_timing_breakdown"):
+        b = (C.c_float * 8)()
+        lib.kg_timing_breakdown.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        lib.kg_timing_breakdown(h.h, b)
+        brk.append(list(b))
     h.reset_sampled(done.data_ptr(), 0, 0, variant, 0, 1234, 0)
 h.sync()
 st = h.stats()
@@ -39,7 +47,11 @@ lib.kg_get_prof(h.h, prof)
 prof = list(prof)
 print(f"{os.path.basename(sys.argv[1]):28s} sched {sched} envs {n} kernel ms: mean {ms[3:].mean():.3f} median {np.median(ms[3:]):.3f} min {ms[3:].min():.3f} max {ms[3:].max():.3f} "
       f"-> {n * 15 / ms[3:].mean() * 1e3:.3e} substeps/s | mpr/sub {st['mpr_pairs'] / st['substeps']:.2f} newton/sub {st['newton_iters'] / st['substeps']:.2f} ovf {st['contact_overflow']}"
-      f" mode {mode}")
+      f" mode {mode} groups {groups}")
+if brk:
+    names = ["", "schedule", "begin", "narrowphase", "substep", "last"]
+    for t in (5, 18):
+        if t < len(brk): print(f"   step {t}: total {ms[t]:.3f} ms | " + "  ".join(f"{names[k]} {brk[t][k]:.3f}" for k in range(1, 6)))
 if os.environ.get("KG_SERIES"): print("   ms per step:", " ".join(f"{x:.2f}" for x in ms))
 tot = sum(prof[:20])
 if tot:
