@@ -24,8 +24,8 @@ SUBSTEPS = 15
 
 
 def ncu_traffic(n_envs):
-    """DRAM bytes per kg_step_kernel launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json),
-    only if it was taken at this env count; else None."""
+    """DRAM bytes per launch of the dominant kernel (kg_sub_kernel<false>, one physics substep over the batch) from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json), only if it was taken at this env count; else None."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
@@ -205,7 +205,7 @@ def run_ours(args):
     total_ms = float(sum(step_ms))
     stats = env.h.stats()
     clocks = sampler.stop() if rank == 0 else None
-    # kernel-only duration of the dominant kernel (kg_step_kernel), CUDA events inside the library on the launch stream
+    # device time of the whole kernel chain of a step (CUDA events inside the library on the launch stream) ...
     kt = []
     for _ in range(5):
         flush.zero_()
@@ -213,6 +213,19 @@ def run_ours(args):
         kt.append(env.h.last_step_ms())
         env.h.reset_sampled(done_i32.data_ptr(), 0, 0, 1 if variant == "B" else 0, 0, seed, env.obs_soa.data_ptr())
     kernel_ms = float(np.median(kt))
+    # ... and of the dominant kernel alone: kg_sub_kernel<false> (one physics substep over the batch, 14 launches per RL
+    # step), CUDA events after every launch on the launching stream (kg_set_timing; groups are not pipelined while it is on),
+    # averaged over one full 30-step episode cycle of the same workload
+    env.h.set_timing(1)
+    brk = []
+    for _ in range(30):
+        flush.zero_()
+        env.step(None, "combined")
+        brk.append(env.h.timing_breakdown())
+        env.h.reset_sampled(done_i32.data_ptr(), 0, 0, 1 if variant == "B" else 0, 0, seed, env.obs_soa.data_ptr())
+    env.h.set_timing(0)
+    sub_ms = float(np.mean([b["substep"] for b in brk])) / (SUBSTEPS - 1)
+    share = {k: float(np.mean([b[k] for b in brk])) for k in ("schedule", "begin", "narrowphase", "substep", "last")}
 
     # ---- e2e: host buffers through the C ABI (kg_step_host): pinned actions in, obs/reward/done out, every step
     act_h = torch.zeros((4, n), dtype=torch.float32).pin_memory()
@@ -237,19 +250,20 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
 
     # ---- max over ranks
-    t = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms, sub_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kernel_ms = [float(x) for x in t.tolist()]
+    total_ms, e2e_ms, kernel_ms, sub_ms = [float(x) for x in t.tolist()]
+    groups = 2 if n >= 512 else 1          # kg_set_pipeline default
     envs_total = n * world
     substeps = envs_total * SUBSTEPS * args.steps
     value = substeps / (total_ms * 1e-3)
     e2e_value = substeps / (e2e_ms * 1e-3)
     if rank == 0:
         hbm_peak, peak_src = peaks()
-        alg_bytes = ALG_BYTES_PER_RL_STEP * n
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        fp32_achieved = (n * SUBSTEPS * ALG_FLOP_PER_SUBSTEP) / (kernel_ms * 1e-3) / 1e12
+        alg_bytes = ALG_BYTES_PER_RL_STEP * n // SUBSTEPS          # 40 B per env per physics substep x envs per launch
+        achieved = alg_bytes / (sub_ms * 1e-3) / 1e9
+        fp32_achieved = (n * SUBSTEPS * ALG_FLOP_PER_SUBSTEP) / (kernel_ms * 1e-3) / 1e12       # whole kernel chain of a step
         line = {"metric": "batched grasp env-steps/sec", "value": value, "unit": "physics substeps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -259,10 +273,12 @@ def run_ours(args):
                            "l2": "flushed between timed steps by a 256 MiB write (excluded from the timed spans); state is 2.4 MB per 4096 envs",
                            "parallelism": "env-sharded x%d, no data-path collective" % world},
                 "e2e": {"value": e2e_value, "unit": "physics substeps/s", "h2d_bytes_per_step": 16 * n + 4 * n, "d2h_bytes_per_step": (82 + 2) * 4 * n},
-                "gpu_launches": 3 * args.steps,   # kg_schedule_kernel + kg_step_kernel + kg_reset_kernel per step
+                # per step and env group: kg_schedule_kernel + kg_begin_kernel + 15 x (kg_mpr_kernel + kg_sub_kernel); + kg_reset_kernel
+                "gpu_launches": (groups * (2 + 2 * SUBSTEPS) + 1) * args.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(n),
-                             "peak_source": peak_src, "kernel": "kg_step_kernel", "kernel_ms": kernel_ms,
-                             "algorithmic_bytes_per_launch": alg_bytes,
+                             "peak_source": peak_src, "kernel": "kg_sub_kernel<false> (one physics substep over the batch; 14 of the 31 launches of a step)",
+                             "kernel_ms": sub_ms, "step_chain_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                             "step_ms_by_launch_kind": share,
                              "note": "state I/O is not the limiter (SURVEY 8d): the path is FP32-issue/latency bound, see fp32; "
                                      "traffic above the algorithmic bytes is the first touch of the model tables (hulls, BVH, pose rows)"},
                 "fp32": {"achieved_tflops": fp32_achieved, "peak_tflops": FP32_PEAK_TFLOPS, "frac": fp32_achieved / FP32_PEAK_TFLOPS,

@@ -93,6 +93,11 @@ int kg_set_mode(kg_handle h, int mode);
  * chains run on separate internal streams, forked from and joined into the handle's stream, so one group's narrowphase
  * kernel overlaps another group's per-env kernel.  Default: 2 for batches of 512 envs or more, else 1. */
 int kg_set_pipeline(kg_handle h, int groups);
+/* Diagnostics (bench.py's roofline): with timing on, kg_step records a CUDA event after every kernel launch (and does
+ * not pipeline groups); kg_timing_breakdown then returns the milliseconds of the last step by launch kind:
+ * [1] schedule [2] begin [3] narrowphase (all launches) [4] substep kernels except the last [5] last substep kernel. */
+int kg_set_timing(kg_handle h, int on);
+int kg_timing_breakdown(kg_handle h, float ms_by_kind[8]);
 /* The action the last kg_step applied (the caller's, or the on-device expert's: get_action, expert_data.py:610). float[4][n]. */
 int kg_get_last_action_host(kg_handle h, float *action_host);
 

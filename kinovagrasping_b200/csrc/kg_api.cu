@@ -64,8 +64,9 @@ struct kg_handle_s {
     cudaEvent_t gfork = nullptr, gjoin[KG_MAXGROUPS] = {};
 #endif
     float last_ms = 0.f;
-#if !defined(KG_EMU) && defined(KG_TIMING)
-    std::vector<cudaEvent_t> tev;     // KG_TIMING builds: an event after every launch of a step (tools/perf_probe.py)
+#if !defined(KG_EMU)
+    int timing = 0;                   // kg_set_timing: an event after every launch of a step, groups not pipelined
+    std::vector<cudaEvent_t> tev;
     std::vector<int> tkind;
 #endif
     int fhull_bytes = 0;       // shared-memory copy of the finger hulls in every narrowphase CTA
@@ -410,8 +411,8 @@ static void emu_run_tasks(kg_handle h, int sel) {
 }
 #endif
 
-#if !defined(KG_EMU) && defined(KG_TIMING)
-#define KG_TMARK(kind) do { if (h->tev.size() <= tix) { cudaEvent_t e_; cudaEventCreate(&e_); h->tev.push_back(e_); h->tkind.push_back(0); } h->tkind[tix] = (kind); cudaEventRecord(h->tev[tix++], st); } while (0)
+#if !defined(KG_EMU)
+#define KG_TMARK(kind) do { if (!h->timing) break; if (h->tev.size() <= tix) { cudaEvent_t e_; cudaEventCreate(&e_); h->tev.push_back(e_); h->tkind.push_back(0); } h->tkind[tix] = (kind); cudaEventRecord(h->tev[tix++], st); } while (0)
 #else
 #define KG_TMARK(kind) ((void)0)
 #endif
@@ -453,12 +454,8 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
     cudaMemcpyAsync(h->heavy_host, h->heavy_count, sizeof(int), cudaMemcpyDeviceToHost, st);      // last step's count -> pinned host word
     cudaMemsetAsync(h->heavy_count, 0, sizeof(int), st);
     cudaEventRecord(h->ev0, st);
-#if defined(KG_TIMING)
     size_t tix = 0;
-    const int G = 1;
-#else
-    const int G = h->ngroups;
-#endif
+    const int G = h->timing ? 1 : h->ngroups;
     // The env groups of the batch are independent pipelines: group g's kernels go to its own stream, so the narrowphase
     // kernel of one group (latency-bound, few registers) overlaps the per-env kernel of another (and the launch gaps and
     // the tail of every kernel are covered by the other groups' work).  Fork from / join into the caller's stream.
@@ -633,6 +630,7 @@ int kg_destroy(kg_handle h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->heavy_host) cudaFreeHost(h->heavy_host);
     if (h->gfork) cudaEventDestroy(h->gfork);
+    for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
     for (int g = 0; g < KG_MAXGROUPS; g++) { if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]); if (h->gjoin[g]) cudaEventDestroy(h->gjoin[g]); }
 #endif
     delete h;
@@ -768,17 +766,23 @@ int kg_forward_debug(kg_handle h, int env, const float *ctrl, float *out) {
 // emulation-only: 0 = lanes of a phase run 0..31, 1 = 31..0 (tests/test_emu_race.py)
 int kg_emu_set_lane_order(int reverse) { kg_emu_lane_order = reverse ? 1 : 0; return KG_OK; }
 #endif
-#if !defined(KG_EMU) && defined(KG_TIMING)
-// KG_TIMING builds only (tools/perf_probe.py): ms of the last step by launch kind: [1] schedule [2] begin [3] narrowphase
-// [4] substep [5] last substep; each launch is timed from the event after the previous launch to the event after it.
+int kg_set_timing(kg_handle h, int on) {
+    if (!h) return KG_EINVAL;
+#ifndef KG_EMU
+    h->timing = on ? 1 : 0;
+#endif
+    return KG_OK;
+}
 int kg_timing_breakdown(kg_handle h, float out[8]) {
     if (!h || !out) return KG_EINVAL;
     for (int i = 0; i < 8; i++) out[i] = 0.f;
+#ifndef KG_EMU
+    if (!h->timing || h->tev.empty()) return KG_OK;
     CUDA_TRY(h, cudaEventSynchronize(h->ev1));
     for (size_t i = 1; i < h->tev.size(); i++) { float ms = 0.f; cudaEventElapsedTime(&ms, h->tev[i - 1], h->tev[i]); out[h->tkind[i]] += ms; }
+#endif
     return KG_OK;
 }
-#endif
 int kg_last_step_ms(kg_handle h, float *ms) {
     if (!h || !ms) return KG_EINVAL;
 #ifdef KG_EMU

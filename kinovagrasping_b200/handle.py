@@ -89,6 +89,15 @@ class Handle:
         """Number of env groups (1..4) whose kernel chains kg_step overlaps on separate internal streams."""
         self._chk(self.lib.kg_set_pipeline(self.h, int(groups)), "kg_set_pipeline")
 
+    def set_timing(self, on):
+        self._chk(self.lib.kg_set_timing(self.h, int(on)), "kg_set_timing")
+
+    def timing_breakdown(self):
+        """ms of the last step by launch kind (timing on): schedule, begin, narrowphase, substep, last."""
+        b = (C.c_float * 8)()
+        self._chk(self.lib.kg_timing_breakdown(self.h, b), "kg_timing_breakdown")
+        return {"schedule": b[1], "begin": b[2], "narrowphase": b[3], "substep": b[4], "last": b[5]}
+
     def last_action_host(self):
         a = np.zeros((4, self.n), dtype=np.float32)
         self._chk(self.lib.kg_get_last_action_host(self.h, _np_ptr(a)), "kg_get_last_action_host")

@@ -23,6 +23,7 @@ mode = int(os.environ.get("KG_MODE", "0"))
 h.set_mode(mode)
 groups = int(os.environ.get("KG_GROUPS", "0"))
 if groups: h.set_pipeline(groups)
+if os.environ.get("KG_TIMING"): h.set_timing(1)
 shape = (np.arange(n) % 2).astype(np.int32)
 import torch
 sh = torch.from_numpy(shape).cuda()
@@ -33,11 +34,9 @@ brk = []
 for t in range(steps):
     h.step(0, 2, 0, 0, done.data_ptr())
     ms.append(h.last_step_ms())
-    if hasattr(lib, "kg_timing_breakdown"):
-        b = (C.c_float * 8)()
-        lib.kg_timing_breakdown.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
-        lib.kg_timing_breakdown(h.h, b)
-        brk.append(list(b))
+    if os.environ.get("KG_TIMING"):
+        d = h.timing_breakdown()
+        brk.append([0.0, d["schedule"], d["begin"], d["narrowphase"], d["substep"], d["last"]])
     h.reset_sampled(done.data_ptr(), 0, 0, variant, 0, 1234, 0)
 h.sync()
 st = h.stats()
