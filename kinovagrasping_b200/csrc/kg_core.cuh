@@ -67,7 +67,7 @@ static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u
 #define KG_NV 15
 #define KG_MS 16                       // row stride of 15x15 matrices
 #ifndef KG_MAXCON
-#define KG_MAXCON 19                   // contact groups per env in the full workspace (overflow is counted and dropped)
+#define KG_MAXCON 23                   // contact groups per env in the full workspace (overflow is counted and dropped)
 #endif
 #ifndef KG_MAXCON_LIGHT
 #define KG_MAXCON_LIGHT 8              // ... in the light workspace: envs with more contacts go to the full-workspace kernel

@@ -154,5 +154,5 @@ class Handle:
         ncon = int(out[300])
         con = out[301:301 + 8 * 23].reshape(23, 8)
         return {"M": out[:225].reshape(15, 15), "bias": out[225:240], "fsmooth": out[240:255], "qacc_smooth": out[255:270],
-                "qacc": out[270:285], "ftotal": out[285:300], "ncon": ncon, "con": con[:min(ncon, 19)],
+                "qacc": out[270:285], "ftotal": out[285:300], "ncon": ncon, "con": con[:min(ncon, 23)],
                 "geom_xpos": out[485:512].reshape(9, 3), "geom_xmat": out[512:593].reshape(9, 9)}

@@ -24,11 +24,13 @@ h.set_mode(mode)
 groups = int(os.environ.get("KG_GROUPS", "0"))
 if groups: h.set_pipeline(groups)
 if os.environ.get("KG_TIMING"): h.set_timing(1)
-shape = (np.arange(n) % 2).astype(np.int32)
+shape_set = [int(x) for x in os.environ.get("KG_SHAPES", "0,1").split(",")]
+orient = int(os.environ.get("KG_ORIENT", "0"))           # 0 normal, 1 rotated, 2 top, 3 random
+shape = np.array([shape_set[i % len(shape_set)] for i in range(n)], dtype=np.int32)
 import torch
 sh = torch.from_numpy(shape).cuda()
 done = torch.zeros(n, dtype=torch.int32, device="cuda")
-h.reset_sampled(0, sh.data_ptr(), 0, variant, 0, 1234, 0)
+h.reset_sampled(0, sh.data_ptr(), orient, variant, 0, 1234, 0)
 ms = []
 brk = []
 for t in range(steps):
@@ -37,7 +39,7 @@ for t in range(steps):
     if os.environ.get("KG_TIMING"):
         d = h.timing_breakdown()
         brk.append([0.0, d["schedule"], d["begin"], d["narrowphase"], d["substep"], d["last"]])
-    h.reset_sampled(done.data_ptr(), 0, 0, variant, 0, 1234, 0)
+    h.reset_sampled(done.data_ptr(), 0, orient, variant, 0, 1234, 0)
 h.sync()
 st = h.stats()
 ms = np.array(ms)
