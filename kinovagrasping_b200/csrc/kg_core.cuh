@@ -36,6 +36,8 @@
 #define KG_LDG4(p) __ldg((const float4 *)(p))
 #define KG_LDGU4(p) __ldg((const uint4 *)(p))
 #define KG_F2U(x) __float_as_uint(x)
+#define KG_DIV_RN(a, b) __fdiv_rn((a), (b))
+#define KG_SQRT_RN(x) __fsqrt_rn(x)
 // Block-wide rendezvous between pipeline stages.  Functionally unnecessary (warps never share data); it keeps the
 // 8 warps of a CTA inside the same ~10-20 KB code region so that they share instruction-cache lines (the whole
 // substep is ~100 KB of SASS, far beyond the 32 KB L1.5 I-cache; ncu showed stall_no_instruction dominating).
@@ -59,6 +61,8 @@ struct kg_uint4 { unsigned x, y, z, w; };
 #define KG_LDG4(p) (*(const kg_float4 *)(p))
 #define KG_LDGU4(p) (*(const kg_uint4 *)(p))
 static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u; }
+#define KG_DIV_RN(a, b) ((a) / (b))
+#define KG_SQRT_RN(x) sqrtf(x)
 #endif
 
 #ifndef KG_STAGE_MASK
@@ -1684,10 +1688,12 @@ template <class WS> KG_DEV void kg_obs(const KgModel &m, WS &ws, int kg_lane, fl
             for (int c = 0; c < 3; c++) o[18 + c] = r[c] - tt[c];
             kg_mulmv(r, T, obj);
             for (int c = 0; c < 3; c++) { r[c] -= tt[c]; o[21 + c] = r[c]; }
-            float n = sqrtf(kg_dot(r, r));
-            float ow[3] = {r[0] / n, r[1] / n, r[2] / n};
-            o[49] = acosf(ow[1] / sqrtf(ow[0] * ow[0] + ow[1] * ow[1]));   // z_angle
-            o[48] = acosf(ow[1] / sqrtf(ow[1] * ow[1] + ow[2] * ow[2]));   // x_angle
+            // acos is ill-conditioned at +-1 (an object straight ahead): correctly rounded division / square root here, whatever
+            // the build's -prec-div / -prec-sqrt say
+            float n = KG_SQRT_RN(kg_dot(r, r));
+            float ow[3] = {KG_DIV_RN(r[0], n), KG_DIV_RN(r[1], n), KG_DIV_RN(r[2], n)};
+            o[49] = acosf(KG_DIV_RN(ow[1], KG_SQRT_RN(ow[0] * ow[0] + ow[1] * ow[1])));   // z_angle
+            o[48] = acosf(KG_DIV_RN(ow[1], KG_SQRT_RN(ow[1] * ow[1] + ow[2] * ow[2])));   // x_angle
             o[81] = kg_dotprod20(ws.hp, obj);
             const float gw[3] = {0, 0, -1};
             kg_mulmv(r, T, gw);
