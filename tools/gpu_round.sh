@@ -16,8 +16,8 @@ done
 tail -3 gpurun_out/${tag}_pytest.log; cat gpurun_out/${tag}_smoke.log gpurun_out/${tag}_bench.json gpurun_out/${tag}_bench32k.json gpurun_out/${tag}_probe.log; tail -3 gpurun_out/${tag}_bench.err
 [ "$2" = "nocapture" ] && exit 0
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/${tag}_ncu_launch.log 2>&1
-# launch index of RL step t (perf_probe, 2 groups): 64 kernels per step + 1 reset; kg_sub_kernel<0>: 28 per step, kg_mpr_kernel: 30 per step
-bash tools/gpu_ncu2.sh ${tag}_sub_light kinovagrasping_b200/libkg_b200.so "kg_sub_kernel<0>" 145 4096 8
-bash tools/gpu_ncu2.sh ${tag}_sub_heavy kinovagrasping_b200/libkg_b200.so "kg_sub_kernel<0>" 509 4096 20
+# perf_probe, 2 groups: kg_sub_kernel (both template instances) launches 30 times per RL step, kg_mpr_kernel 30 times; step 5 is contact-free, step 18 contact-rich
+bash tools/gpu_ncu2.sh ${tag}_sub_light kinovagrasping_b200/libkg_b200.so kg_sub_kernel 154 4096 8
+bash tools/gpu_ncu2.sh ${tag}_sub_heavy kinovagrasping_b200/libkg_b200.so kg_sub_kernel 544 4096 20
 bash tools/gpu_ncu2.sh ${tag}_mpr_heavy kinovagrasping_b200/libkg_b200.so kg_mpr_kernel 545 4096 20
 ls -la gpurun_out
