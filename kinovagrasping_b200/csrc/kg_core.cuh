@@ -1890,8 +1890,23 @@ template <class WS> KG_DEV void kg_carry_store(const WS &ws, unsigned char *carr
     KG_SYNC();
 }
 template <class WS> KG_DEV void kg_carry_load(WS &ws, const unsigned char *carry, int kg_lane) {
+#if defined(__CUDA_ARCH__)
+    // global -> shared without a register round trip: every 16-byte chunk of both sections is in flight at once (LDGSTS),
+    // one wait for the whole record instead of one L2 round trip per loop iteration
+    {
+        const unsigned dstA = (unsigned)__cvta_generic_to_shared(&ws);
+        const unsigned dstB = dstA + (unsigned)KG_CARRY_B_OFF;
+        for (int i = kg_lane; i < (int)(KG_CARRY_A_BYTES / 16); i += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstA + 16u * i), "l"(carry + 16 * i) : "memory");
+        for (int i = kg_lane; i < (int)(KG_CARRY_B_BYTES / 16); i += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstB + 16u * i), "l"(carry + KG_CARRY_A_BYTES + 16 * i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+#else
     kg_copy16(&ws, carry, (int)KG_CARRY_A_BYTES, kg_lane);
     kg_copy16(reinterpret_cast<unsigned char *>(&ws) + KG_CARRY_B_OFF, carry + KG_CARRY_A_BYTES, (int)KG_CARRY_B_BYTES, kg_lane);
+#endif
     KG_SYNC();
 #ifdef KG_PROF
     KG_PHASE(l) {
