@@ -36,6 +36,7 @@
 #define KG_LDG4(p) __ldg((const float4 *)(p))
 #define KG_LDGU4(p) __ldg((const uint4 *)(p))
 #define KG_F2U(x) __float_as_uint(x)
+#define KG_LD4S(p) (*reinterpret_cast<const float4 *>(p))
 #define KG_DIV_RN(a, b) __fdiv_rn((a), (b))
 #define KG_SQRT_RN(x) __fsqrt_rn(x)
 // Block-wide rendezvous between pipeline stages.  Functionally unnecessary (warps never share data); it keeps the
@@ -61,6 +62,7 @@ struct kg_uint4 { unsigned x, y, z, w; };
 #define KG_LDG4(p) (*(const kg_float4 *)(p))
 #define KG_LDGU4(p) (*(const kg_uint4 *)(p))
 static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u; }
+#define KG_LD4S(p) (*(const kg_float4 *)(p))
 #define KG_DIV_RN(a, b) ((a) / (b))
 #define KG_SQRT_RN(x) sqrtf(x)
 #endif
@@ -185,7 +187,8 @@ static_assert(offsetof(KgWSLight, J) % 16 == 0 && sizeof(KgWSLight) % 16 == 0, "
 
 // Workspace of the narrowphase (MPR) kernel: the geom frames of one env, the object's hull, the finger hulls of the CTA.
 struct alignas(16) KgMprWS {
-    float gpos[9][3], gmat[9][9];
+    // frames of the task's two geoms, laid out for 128-bit loads: centre (x, y, z, -) and the three rows of R (x, y, z, -)
+    alignas(16) float gp[2][4], gr[2][12];
 #ifndef KG_MPR_L1
     alignas(16) float objhull[KG_MAXOBJVERT * 4];
 #endif
@@ -568,10 +571,11 @@ KG_DEV const float *kg_hull_table(const KgModel &m, const KgMprWS &ws, int mesh)
     return mesh >= 3 ? ws.objhull : (mesh == 0 ? m.hull_pad : ws.fhull + (mesh == 2 ? 4 * m.hnpad[1] : 0));
 #endif
 }
-KG_DEV void kg_support_coop(const KgModel &m, const KgMprWS &ws, int g, int mesh, const float *dir, const float *origin, float margin,
+KG_DEV void kg_support_coop(const KgModel &m, const KgMprWS &ws, int slot, int mesh, const float *dir, const float *origin, float margin,
                             float *out, int *vidx, int kg_lane) {
     const float *vert = kg_hull_table(m, ws, mesh);
-    const float *R = ws.gmat[g];
+    const auto r0 = KG_LD4S(ws.gr[slot]), r1 = KG_LD4S(ws.gr[slot] + 4), r2 = KG_LD4S(ws.gr[slot] + 8), gc = KG_LD4S(ws.gp[slot]);
+    const float R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z}, gpos[3] = {gc.x, gc.y, gc.z};
     float ld[3];
     kg_multmv(ld, R, dir);
     float best = -FLT_MAX;
@@ -612,7 +616,7 @@ KG_DEV void kg_support_coop(const KgModel &m, const KgMprWS &ws, int g, int mesh
     *vidx = bi;
     float wv[3];
     kg_mulmv(wv, R, lv);
-    for (int k = 0; k < 3; k++) out[k] = wv[k] + (ws.gpos[g][k] - origin[k]) + margin * dir[k];
+    for (int k = 0; k < 3; k++) out[k] = wv[k] + (gpos[k] - origin[k]) + margin * dir[k];
 }
 
 // ------------------------------------------------------------------------------------------------ P5 MPR (libccd's algorithm, fp32)
@@ -688,9 +692,9 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g
     *sep_found = 0;
     KgSupp p[4];
     float dir[3], va[3], vb[3], dot;
-    const float *org = ws.gpos[g1];
+    const float *org = ws.gp[0];
     p[0].v1[0] = p[0].v1[1] = p[0].v1[2] = 0.f;
-    kg_sub(p[0].v, ws.gpos[g1], ws.gpos[g2]);
+    kg_sub(p[0].v, ws.gp[0], ws.gp[1]);
     if (kg_iszero(p[0].v[0]) && kg_iszero(p[0].v[1]) && kg_iszero(p[0].v[2])) p[0].v[0] += KG_CCD_EPS * 10;
     for (int c = 0; c < 3; c++) dir[c] = -p[0].v[c];
     kg_normalize_dir(dir);
@@ -704,8 +708,8 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g
 #endif
         {
             float nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
-            kg_support_coop(m, ws, g1, mesh1, dir, org, hmargin, s.v1, &cur1, kg_lane);
-            kg_support_coop(m, ws, g2, mesh2, nd, org, hmargin, v2, &cur2, kg_lane);
+            kg_support_coop(m, ws, 0, mesh1, dir, org, hmargin, s.v1, &cur1, kg_lane);
+            kg_support_coop(m, ws, 1, mesh2, nd, org, hmargin, v2, &cur2, kg_lane);
             kg_sub(s.v, s.v1, v2);
         }
         bool check_portal = false;
@@ -828,11 +832,16 @@ template <class WS> KG_DEV float kg_rbound(const KgModel &m, const WS &ws, int g
 // share the cooperative support scans).  The geom frames come from the env's carry record, the result is filed there
 // by lane 0: separating axis / warm-start vertices, and on a hit the contact in staging slot 32 + (lp - 8).
 KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int lp, int kg_lane) {
+    int g1, g2;
+    kg_pair_of_lane(lp, g1, g2);
     KG_PHASE(l) {
-        const float *src = reinterpret_cast<const float *>(carry + KG_COFF(gpos));
-        float *dst = &mw.gpos[0][0];
-        for (int i = l; i < 27 + 81; i += 32) dst[i] = src[i];
-        if (l == 0) mw.shape = *reinterpret_cast<const int *>(carry + KG_COFF(shape));
+        // the frames of the two geoms of this pair: 2 x (3 + 9) words, one per lane
+        if (l < 24) {
+            const int which = l >= 12, j = l - 12 * which, g = which ? g2 : g1;
+            if (j < 3) mw.gp[which][j] = reinterpret_cast<const float *>(carry + KG_COFF(gpos))[3 * g + j];
+            else mw.gr[which][4 * ((j - 3) / 3) + (j - 3) % 3] = reinterpret_cast<const float *>(carry + KG_COFF(gmat))[9 * g + j - 3];
+        }
+        if (l == 31) mw.shape = *reinterpret_cast<const int *>(carry + KG_COFF(shape));
     }
     KG_SYNC();
 #ifndef KG_MPR_L1
@@ -851,8 +860,6 @@ KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int
         KG_SYNC();
     }
 #endif
-    int g1, g2;
-    kg_pair_of_lane(lp, g1, g2);
     const int mesh1 = kg_mesh_of_geom_s(mw.shape, g1), mesh2 = kg_mesh_of_geom_s(mw.shape, g2);
     const float margin = m.margin;
     int c1 = 0, c2 = 0, sepf = 0;
@@ -874,7 +881,7 @@ KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int
                 const int sl = 32 + (lp - 8);
                 reinterpret_cast<float *>(carry + KG_COFF_B(st_dist))[sl] = margin - depth;
                 float *sp = reinterpret_cast<float *>(carry + KG_COFF_B(st_pos)) + 3 * sl, *sn = reinterpret_cast<float *>(carry + KG_COFF_B(st_n)) + 3 * sl;
-                for (int c = 0; c < 3; c++) { sp[c] = pos[c] + mw.gpos[g1][c]; sn[c] = nrm[c]; }
+                for (int c = 0; c < 3; c++) { sp[c] = pos[c] + mw.gp[0][c]; sn[c] = nrm[c]; }
                 (carry + KG_COFF_B(st_g1))[sl] = (unsigned char)g1; (carry + KG_COFF_B(st_g2))[sl] = (unsigned char)g2;
                 reinterpret_cast<int *>(carry + KG_COFF(cnt))[lp] = 1;
             }
