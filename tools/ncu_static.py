@@ -5,7 +5,7 @@ txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv", "--
 src = open("kinovagrasping_b200/csrc/kg_core.cuh").read().split("\n")
 starts = []
 for i, l in enumerate(src, 1):
-    m = re.match(r"^(KG_DEV|KG_NOINL)\s+[\w\s\*&]+?\b(kg_\w+)\s*\(", l)
+    m = re.match(r"^(?:template <class WS> )?(KG_DEV|KG_NOINL)\s+[\w\s\*&]+?\b(kg_\w+)\s*\(", l)
     if m: starts.append((i, m.group(2)))
 def fn(line):
     name = "?"
