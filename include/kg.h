@@ -80,6 +80,12 @@ int kg_set_frame_skip(kg_handle h, int frame_skip);        /* KinovaGripper_Env(
 /* Multi-GPU sharding: this handle owns global envs [offset, offset+n).  Only the pose sampler's counter-based RNG
  * looks at it, so that a run's draws do not depend on how many GPUs the envs are spread over. */
 int kg_set_env_offset(kg_handle h, int offset);
+/* _get_obs(state_rep="global") (kinova_gripper_env.py:484-534): while obs74 is non-NULL every kg_step / kg_reset* also
+ * writes the 74-value global-frame observation of the envs it touches to obs74 (float[74][n]; a device pointer, a host
+ * pointer in the test-only emulation).  The 82-value local layout is what step() returns in the reference (ENV:1549). */
+int kg_set_obs_global(kg_handle h, float *obs74);
+int kg_obs_global_buffer(kg_handle h, float **buf);           /* the handle's own float[74][n] buffer, for kg_set_obs_global */
+int kg_get_obs_global_host(kg_handle h, float *obs74_host);   /* copy of the buffer currently set; KG_EINVAL if none */
 /* Launch schedule of kg_step (no effect on results): 1 (default) = warp slots are filled in order of decreasing cost of
  * each env's previous step, so that the environments sharing a CTA's stage barriers carry similar contact loads;
  * 0 = env i runs in slot i. */

@@ -36,6 +36,9 @@ SIGNATURES = {
     "kg_set_env_offset": (C.c_int, [_vp, C.c_int]),
     "kg_set_schedule": (C.c_int, [_vp, C.c_int]),
     "kg_set_mode": (C.c_int, [_vp, C.c_int]),
+    "kg_set_obs_global": (C.c_int, [_vp, _vp]),
+    "kg_obs_global_buffer": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "kg_get_obs_global_host": (C.c_int, [_vp, _vp]),
     "kg_set_pipeline": (C.c_int, [_vp, C.c_int]),
     "kg_set_timing": (C.c_int, [_vp, C.c_int]),
     "kg_timing_breakdown": (C.c_int, [_vp, C.POINTER(C.c_float)]),

@@ -58,6 +58,7 @@ struct kg_handle_s {
     float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_euler = nullptr, *d_objp = nullptr, *d_q = nullptr;
     int *d_done = nullptr, *d_mask = nullptr, *d_shape = nullptr;
     float *d_debug = nullptr, *d_ctrl = nullptr;
+    float *d_obs_global = nullptr;    // [74][n] internal buffer kg_obs_global_buffer hands out
 #ifndef KG_EMU
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t gstream[KG_MAXGROUPS] = {};
@@ -602,6 +603,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
     TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
     TRY(be_alloc(h, (void **)&A.ccache, N * KG_CCACHE_BYTES));
+    TRY(be_alloc(h, (void **)&h->d_obs_global, KG_NOBS_GLOBAL * N * 4));
     TRY(be_alloc(h, (void **)&A.load, N * 4)); TRY(be_alloc(h, (void **)&h->perm, N * 4));
     TRY(be_alloc(h, (void **)&h->carry, N * KG_CARRY_BYTES)); TRY(be_alloc(h, (void **)&h->tasks, N * 22 * 4)); TRY(be_alloc(h, (void **)&h->q, 4 * 4 * KG_MAXGROUPS));
     TRY(be_alloc(h, (void **)&h->heavy_count, 4));
@@ -641,6 +643,13 @@ int kg_num_envs(kg_handle h) { return h ? h->n : KG_EINVAL; }
 int kg_set_stream(kg_handle h, void *stream) { if (!h) return KG_EINVAL; h->stream = stream; return KG_OK; }
 int kg_sync(kg_handle h) { if (!h) return KG_EINVAL; return be_sync(h); }
 int kg_set_max_episode_steps(kg_handle h, int steps) { if (!h || steps <= 0) return KG_EINVAL; h->A.max_steps = steps; return KG_OK; }
+int kg_set_obs_global(kg_handle h, float *obs74) { if (!h) return KG_EINVAL; h->A.obs_global = obs74; return KG_OK; }
+int kg_obs_global_buffer(kg_handle h, float **buf) { if (!h || !buf) return KG_EINVAL; *buf = h->d_obs_global; return KG_OK; }
+int kg_get_obs_global_host(kg_handle h, float *obs74_host) {
+    if (!h || !obs74_host || !h->A.obs_global) return KG_EINVAL;
+    TRY(be_d2h(h, obs74_host, h->A.obs_global, (size_t)KG_NOBS_GLOBAL * h->n * 4)); TRY(be_sync(h));
+    return KG_OK;
+}
 int kg_set_pipeline(kg_handle h, int groups) {
     if (!h || groups < 1 || groups > KG_MAXGROUPS) return KG_EINVAL;
     h->ngroups = groups;

@@ -37,8 +37,6 @@
 #define KG_LDGU4(p) __ldg((const uint4 *)(p))
 #define KG_F2U(x) __float_as_uint(x)
 #define KG_LD4S(p) (*reinterpret_cast<const float4 *>(p))
-#define KG_DIV_RN(a, b) __fdiv_rn((a), (b))
-#define KG_SQRT_RN(x) __fsqrt_rn(x)
 // Block-wide rendezvous between pipeline stages.  Functionally unnecessary (warps never share data); it keeps the
 // 8 warps of a CTA inside the same ~10-20 KB code region so that they share instruction-cache lines (the whole
 // substep is ~100 KB of SASS, far beyond the 32 KB L1.5 I-cache; ncu showed stall_no_instruction dominating).
@@ -63,8 +61,6 @@ struct kg_uint4 { unsigned x, y, z, w; };
 #define KG_LDGU4(p) (*(const kg_uint4 *)(p))
 static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u; }
 #define KG_LD4S(p) (*(const kg_float4 *)(p))
-#define KG_DIV_RN(a, b) ((a) / (b))
-#define KG_SQRT_RN(x) sqrtf(x)
 #endif
 
 #ifndef KG_STAGE_MASK
@@ -1695,12 +1691,10 @@ template <class WS> KG_DEV void kg_obs(const KgModel &m, WS &ws, int kg_lane, fl
             for (int c = 0; c < 3; c++) o[18 + c] = r[c] - tt[c];
             kg_mulmv(r, T, obj);
             for (int c = 0; c < 3; c++) { r[c] -= tt[c]; o[21 + c] = r[c]; }
-            // acos is ill-conditioned at +-1 (an object straight ahead): correctly rounded division / square root here, whatever
-            // the build's -prec-div / -prec-sqrt say
-            float n = KG_SQRT_RN(kg_dot(r, r));
-            float ow[3] = {KG_DIV_RN(r[0], n), KG_DIV_RN(r[1], n), KG_DIV_RN(r[2], n)};
-            o[49] = acosf(KG_DIV_RN(ow[1], KG_SQRT_RN(ow[0] * ow[0] + ow[1] * ow[1])));   // z_angle
-            o[48] = acosf(KG_DIV_RN(ow[1], KG_SQRT_RN(ow[1] * ow[1] + ow[2] * ow[2])));   // x_angle
+            // _get_angles (ENV:569-582) computes acos(y / sqrt(x^2 + y^2)) in fp64; acos is ill-conditioned at +-1 (an object
+            // straight ahead), so fp32 evaluates the same angle as atan2(|x|, y), which is accurate to an ulp everywhere
+            o[49] = atan2f(fabsf(r[0]), r[1]);   // z_angle
+            o[48] = atan2f(fabsf(r[2]), r[1]);   // x_angle
             o[81] = kg_dotprod20(ws.hp, obj);
             const float gw[3] = {0, 0, -1};
             kg_mulmv(r, T, gw);
@@ -1760,6 +1754,30 @@ template <class WS> KG_DEV void kg_obs(const KgModel &m, WS &ws, int kg_lane, fl
             int dn = (fabsf(z - 0.2f) < 0.005f) || (z >= 0.2f);
             *reward = dn ? 50.f : 0.f;
             *done = dn;
+        }
+    }
+    KG_SYNC();
+}
+
+// _get_obs(state_rep="global") (ENV:484-534): the 74-value layout = global finger / wrist / object positions (24) followed
+// by the entries the two layouts share.  Runs right after kg_obs (the local vector is still staged in the workspace).
+#define KG_NOBS_GLOBAL 74
+template <class WS> KG_DEV void kg_obs_global_store(const WS &ws, float *out, int N, int env, int kg_lane) {
+    KG_PHASE(l) {
+        const float *o = KG_WSOBS(ws);
+        const float *Rp = ws.gmat[1];
+        // wrist = p_palm + T^T [-0.009, 0.048, 0] with T^T = Rp C, columns (-Rp col1, -Rp col2, Rp col0)
+        float wrist[3];
+        for (int c = 0; c < 3; c++) wrist[c] = ws.gpos[1][c] + (-Rp[3 * c + 1]) * -0.009f + (-Rp[3 * c + 2]) * 0.048f;
+        const int fgeom[6] = {2, 4, 6, 3, 5, 7};
+        for (int i = l; i < KG_NOBS_GLOBAL; i += 32) {
+            float v;
+            if (i < 18) v = ws.gpos[fgeom[i / 3]][i % 3];
+            else if (i < 21) v = wrist[i - 18];
+            else if (i < 24) v = ws.gpos[8][i - 21];
+            else if (i < 67) v = o[i];            // joints, size, finger-object distances, angles, rangefinders
+            else v = o[i + 8];                    // finger dot products, object dot product
+            out[i * N + env] = v;
         }
     }
     KG_SYNC();
@@ -1849,6 +1867,7 @@ struct KgEnvArrays {
     int *stats;                   // [4] mpr pairs, newton iterations, contact overflows, substeps
     int *load;                    // [N] cost of each env's last RL step (Newton iterations + 2 x MPR pairs): key of the launch schedule
     long long *prof;              // [KG_NPROF] KG_PROF builds only
+    float *obs_global;            // [74][N] or NULL: _get_obs(state_rep="global") of the same step (kg_set_obs_global)
     unsigned char *ccache;        // [N][KG_CCACHE_BYTES] collision caches (warm-start vertices, separating axes) kept across RL steps
     int N, max_steps;
 };
@@ -2032,6 +2051,7 @@ template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEn
     KG_PROBE(16);
     float rew = 0.f; int dn = 0;
     kg_obs(m, ws, kg_lane, &rew, &dn);
+    if (A.obs_global) kg_obs_global_store(ws, A.obs_global, A.N, env, kg_lane);
     KG_PROBE(17);
     kg_store_env(ws, A, env, kg_lane);
     kg_copy16(A.ccache + (size_t)env * KG_CCACHE_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CCACHE_OFF, (int)KG_CCACHE_BYTES, kg_lane);
@@ -2101,6 +2121,7 @@ template <class WS> KG_DEV void kg_env_reset(const KgModel &m, WS &ws, const KgE
     kg_rays(m, ws, kg_lane);
     float rew; int dn;
     kg_obs(m, ws, kg_lane, &rew, &dn);
+    if (A.obs_global) kg_obs_global_store(ws, A.obs_global, A.N, env, kg_lane);
     kg_store_env(ws, A, env, kg_lane);
     kg_copy16(A.ccache + (size_t)env * KG_CCACHE_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CCACHE_OFF, (int)KG_CCACHE_BYTES, kg_lane);   // cleared by kg_episode_constants
     KG_PHASE(l) {

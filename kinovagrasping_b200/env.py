@@ -286,11 +286,25 @@ class KinovaGripper_Env:
         d = bool(lift > 0)
         if self._elapsed_steps >= self._max_episode_steps:
             d = True
+        self._last_obs = obs[:, 0]
         states = [float(v) for v in obs[:, 0]]
         if self.pid:
             states = states + [states[81]]
         info = {"finger_reward": 0.0, "grasp_reward": 0.0, "lift_reward": lift}
         return states, lift, d, info
+
+    def _get_obs(self, state_rep="local"):
+        """ENV:438-534: the observation of the current state, 82 values in the wrist frame ("local") or 74 in the world
+        frame ("global"; enabled on first use, valid from the next reset / step on)."""
+        if state_rep == "local":
+            return [float(v) for v in self._last_obs]
+        if state_rep == "global":
+            if not getattr(self, "_global_on", False):
+                self.h.enable_obs_global()
+                self._global_on = True
+                raise RuntimeError("global-frame observations are produced from the next reset()/step() on")
+            return [float(v) for v in self.h.obs_global_host()[:, 0]]
+        raise ValueError(f"unknown state_rep {state_rep!r}")
 
     def _get_dot_product(self, obj_state=None):
         return float(self._last_obs[81])

@@ -85,6 +85,22 @@ class Handle:
         """0 automatic, 1 always split (light workspaces + heavy lane), 2 always full workspaces."""
         self._chk(self.lib.kg_set_mode(self.h, int(mode)), "kg_set_mode")
 
+    def set_obs_global(self, ptr):
+        """float[74][n] buffer (device pointer; 0 = off) that every step / reset also fills with the global-frame obs."""
+        self._chk(self.lib.kg_set_obs_global(self.h, C.c_void_p(ptr or 0)), "kg_set_obs_global")
+
+    def enable_obs_global(self):
+        """Route the global-frame obs of every step / reset into the handle's own buffer (read it with obs_global_host)."""
+        buf = C.c_void_p()
+        self._chk(self.lib.kg_obs_global_buffer(self.h, C.byref(buf)), "kg_obs_global_buffer")
+        self.set_obs_global(buf.value)
+        return buf.value
+
+    def obs_global_host(self):
+        out = np.zeros((74, self.n), dtype=np.float32)
+        self._chk(self.lib.kg_get_obs_global_host(self.h, _np_ptr(out)), "kg_get_obs_global_host")
+        return out
+
     def set_pipeline(self, groups):
         """Number of env groups (1..4) whose kernel chains kg_step overlaps on separate internal streams."""
         self._chk(self.lib.kg_set_pipeline(self.h, int(groups)), "kg_set_pipeline")
