@@ -69,15 +69,16 @@ def flatten_parameters(module):
 
 class DDPGfD(object):
     def __init__(self, state_dim, action_dim, max_action, n, discount=0.995, tau=0.0005, batch_size=64, device=None,
-                 process_group=None):
+                 process_group=None, capturable=False):
         self.device = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self.actor = Actor(state_dim, action_dim, max_action).to(self.device)
         self.critic = Critic(state_dim, action_dim).to(self.device)
         self._seat()
         self.actor_target = copy.deepcopy(self.actor)
         self.critic_target = copy.deepcopy(self.critic)
-        self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=1e-4)
-        self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), weight_decay=1e-4)
+        # capturable: Adam keeps its step count on the device so that an update can be captured into a CUDA graph (train.py)
+        self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=1e-4, capturable=capturable)
+        self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), weight_decay=1e-4, capturable=capturable)
         self.discount = discount
         self.tau = tau
         self.n = n

@@ -47,6 +47,18 @@ class ReplayBuffer_Queue:
             self._env_ids = torch.arange(self.n_envs, device=self.device)
         self.len_dev = torch.zeros(self.cap, dtype=torch.long, device=self.device)
         self._host_len_dirty = False
+        # device copy of (head, complete episodes - 1) for the device sampler: a captured CUDA graph replays sample_windows
+        # without running this Python, so the ring's bookkeeping has to be data, not constants (publish_meta)
+        self._meta_dev = torch.zeros(2, dtype=torch.long, device=self.device)
+        self._meta_host = (-1, -1)
+
+    def publish_meta(self):
+        """Refresh the device copy of the ring bookkeeping; call before replaying a graph that contains sample_windows."""
+        cur = (int(self.head), int(self.replay_ep_num) - 1)
+        if cur != self._meta_host:
+            self._meta_dev.copy_(torch.tensor(cur, dtype=torch.long))
+            self._meta_host = cur
+        return self._meta_dev
 
     # ------------------------------------------------------------------ storage
     def _alloc(self, T):
@@ -191,11 +203,12 @@ class ReplayBuffer_Queue:
         probability proportional to its window count `ceiling` (the reference emits `ceiling` rows per drawn episode),
         then the window is the last one with probability 1/ceiling and uniform over [0, ceiling) otherwise.
         No host synchronisation: usable inside a captured CUDA graph."""
-        n_valid = self.replay_ep_num - 1
+        capturing = self.device.type == "cuda" and torch.cuda.is_current_stream_capturing()
+        meta = self._meta_dev if capturing else self.publish_meta()
         logical = torch.arange(self.cap, device=self.device)
-        rows_all = (self.head + logical) % self.cap
+        rows_all = (meta[0] + logical) % self.cap
         ceil_all = (self.len_dev[rows_all] - self.n_steps).clamp(min=0).float()
-        ceil_all = torch.where(logical < n_valid, ceil_all, torch.zeros_like(ceil_all))
+        ceil_all = torch.where(logical < meta[1], ceil_all, torch.zeros_like(ceil_all))
         pick = torch.multinomial(ceil_all, n_windows, replacement=True, generator=generator)
         rows = rows_all[pick]
         ceiling = ceil_all[pick]

@@ -77,6 +77,51 @@ def run_episode(env, act_fn, replay=None, shapes=("CubeS",), orientation="normal
     return success, stored
 
 
+class GraphedUpdates:
+    """`network_repl_freq` (10) consecutive updates -- device-side window sampling from both buffers, the n-step update, the
+    target-network mix on the last one -- captured once into a CUDA graph and replayed: an update is ~60 small kernels and
+    was launch-bound (3.3 ms each eagerly at batch 4096).  Single process only (the all-reduce stays eager)."""
+
+    def __init__(self, policy, agent, expert, batch, expert_prob):
+        self.policy, self.agent, self.expert = policy, agent, expert
+        self.n_agent = int(batch * (1 - expert_prob))
+        self.n_expert = batch - self.n_agent
+        self.block = policy.network_repl_freq
+        self.graph = None
+        self.losses = None
+
+    def _one(self):
+        if self.n_agent:
+            a = self.agent.sample_windows(self.n_agent)
+            e = self.expert.sample_windows(self.n_expert)
+            batch = tuple(torch.cat((x, y), 0) for x, y in zip(a, e))
+        else:
+            batch = self.expert.sample_windows(self.n_expert)
+        return self.policy.train_on_batch(*batch)
+
+    def run(self, n_updates):
+        """n_updates rounded up to a multiple of the block; returns the losses of the last update (device tensors)."""
+        self.agent.publish_meta(); self.expert.publish_meta()
+        if self.graph is None:
+            assert self.policy.total_it % self.block == 0
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                    # eager warm-up block: optimizer state, cuBLAS workspaces
+                for _ in range(self.block):
+                    self._one()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                for _ in range(self.block):
+                    self.losses = self._one()
+            self.policy.total_it -= self.block               # capturing records the block, it does not run it
+            n_updates -= self.block                          # the warm-up block did run
+        for _ in range((max(n_updates, 0) + self.block - 1) // self.block):
+            self.graph.replay()
+            self.policy.total_it += self.block
+        return self.losses
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=4096, help="global number of environments")
@@ -95,6 +140,7 @@ def main():
     ap.add_argument("--max-episodes", type=int, default=40000, help="replay capacity in episodes per rank")
     ap.add_argument("--tau", type=float, default=0.0005, help="target-network mixing (DDPG:221 default)")
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true", help="run the updates eagerly (always the case under torchrun)")
     ap.add_argument("--save", default=None)
     args = ap.parse_args()
 
@@ -108,7 +154,8 @@ def main():
     env = make_sharded_env(args.envs, rank, world, local)
     shapes = tuple(args.shapes.split(","))
     max_action = 0.8                                          # action_space.high (ENV:128)
-    policy = DDPGfD(82, 4, max_action, n=5, tau=args.tau, batch_size=args.batch, device=dev)
+    graphed = world == 1 and not args.no_graph
+    policy = DDPGfD(82, 4, max_action, n=5, tau=args.tau, batch_size=args.batch, device=dev, capturable=graphed)
     gen = torch.Generator(device=dev)
     gen.manual_seed(args.seed * 1000 + rank)
     expert = ReplayBuffer_Queue(82, 4, args.max_episodes, 5, device=dev, n_envs=env.n)
@@ -133,8 +180,12 @@ def main():
 
     evaluate("untrained", 0)
     losses = None
-    for _ in range(args.pretrain_updates):                    # pre-training: demonstrations only (DDPG:227-229)
-        losses = policy.train_on_batch(*expert.sample_windows(args.batch, generator=gen))
+    if graphed and args.pretrain_updates:                     # pre-training: demonstrations only (DDPG:227-229)
+        losses = GraphedUpdates(policy, agent, expert, args.batch, 1.0).run(args.pretrain_updates)
+    else:
+        for _ in range(args.pretrain_updates):
+            losses = policy.train_on_batch(*expert.sample_windows(args.batch, generator=gen))
+    upd = GraphedUpdates(policy, agent, expert, args.batch, args.expert_prob) if graphed else None
     if args.pretrain_updates:
         log(phase="pretrain", updates=args.pretrain_updates, losses=[float(x) for x in losses])
         evaluate("pretrained", 0)
@@ -150,11 +201,14 @@ def main():
         losses = None
         tu = time.perf_counter()
         if agent.replay_ep_num > 2:
-            for _ in range(args.updates):
-                a = agent.sample_windows(n_agent, generator=gen)
-                e = expert.sample_windows(args.batch - n_agent, generator=gen)
-                s_, a_, n_, r_, d_ = (torch.cat((x, y), 0) for x, y in zip(a, e))
-                losses = policy.train_on_batch(s_, a_, n_, r_, d_)
+            if upd is not None:
+                losses = upd.run(args.updates)
+            else:
+                for _ in range(args.updates):
+                    a = agent.sample_windows(n_agent, generator=gen)
+                    e = expert.sample_windows(args.batch - n_agent, generator=gen)
+                    s_, a_, n_, r_, d_ = (torch.cat((x, y), 0) for x, y in zip(a, e))
+                    losses = policy.train_on_batch(s_, a_, n_, r_, d_)
         torch.cuda.synchronize()
         t_upd = time.perf_counter() - tu
         log(phase="train", sweep=sweep, rollout_success=count(succ), agent_episodes=agent.replay_ep_num, rollout_s=t_roll, update_s=t_upd,
