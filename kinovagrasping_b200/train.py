@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--tau", type=float, default=0.0005, help="target-network mixing (DDPG:221 default)")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true", help="run the updates eagerly (always the case under torchrun)")
+    ap.add_argument("--fp32-matmul", action="store_true", help="keep the actor/critic GEMMs in IEEE fp32 instead of TF32 tensor cores")
     ap.add_argument("--save", default=None)
     args = ap.parse_args()
 
@@ -150,6 +151,8 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if not args.fp32_matmul:
+        torch.set_float32_matmul_precision("high")            # TF32 tensor cores for the 20k x 400 x 300 GEMMs of an update
     torch.manual_seed(args.seed)                              # same initial weights on every rank
     env = make_sharded_env(args.envs, rank, world, local)
     shapes = tuple(args.shapes.split(","))
