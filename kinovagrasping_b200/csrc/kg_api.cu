@@ -25,7 +25,11 @@
 #define KG_MINBLOCKS 1      // CTAs per SM the register allocation must leave room for (512 threads x 128 registers = the whole file)
 #endif
 #ifndef KG_LWARPS
+#ifdef KG_PROF
+#define KG_LWARPS 7         // (the probe arrays of a KG_PROF build enlarge every workspace by 264 bytes)
+#else
 #define KG_LWARPS 8         // light workspace: warps per CTA ...
+#endif
 #endif
 #ifndef KG_LMINBLOCKS
 #define KG_LMINBLOCKS 3     // ... and CTAs per SM (24 warps x 80 registers)
