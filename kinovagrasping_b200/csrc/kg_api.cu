@@ -561,14 +561,14 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     if (m.hpad0[2] != m.hpad0[1] + m.hnpad[1]) { h->err = "model card: finger hulls must be contiguous"; return KG_EMODEL; }
     for (int k = 3; k < KG_NMESH; k++) if (m.hnpad[k] > KG_MAXOBJVERT) { h->err = "model card: object hull too large"; return KG_EMODEL; }
 #ifdef KG_EMU
-    m.hull_vert = t.hull_vert.data(); m.adj_start = t.adj_start.data(); m.adj = t.adj.data(); m.adj8 = t.adj8.data(); m.hull_pad = t.hull_pad.data(); m.tri = t.tri.data();
+    m.hull_vert = t.hull_vert.data(); m.adj_start = t.adj_start.data(); m.adj = t.adj.data(); m.adj8 = t.adj8.data(); m.hull_pad = t.hull_pad.data(); m.hull_oct = t.hull_oct.data(); m.tri = t.tri.data();
     m.bvh_node = t.bvh_node.data();
     m.pose_train = t.pose_train.data(); m.pose_test = t.pose_test.data();
     g_mw.fhull = m.hull_pad + 4 * (size_t)m.hpad0[1];     // host emulation: no staging copy
     g_mw.hull_shape = -1;
 #else
 #define UP(field, vec) do { void *p_; TRY(be_alloc(h, &p_, (vec).size() * sizeof((vec)[0]))); CUDA_TRY(h, cudaMemcpy(p_, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice)); m.field = (decltype(m.field))p_; } while (0)
-    UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(adj8, t.adj8); UP(hull_pad, t.hull_pad); UP(tri, t.tri);
+    UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(adj8, t.adj8); UP(hull_pad, t.hull_pad); UP(hull_oct, t.hull_oct); UP(tri, t.tri);
     UP(bvh_node, t.bvh_node); UP(pose_train, t.pose_train); UP(pose_test, t.pose_test);
 #undef UP
     CUDA_TRY(h, cudaMemcpyToSymbol(c_model, &m, sizeof(KgModel)));

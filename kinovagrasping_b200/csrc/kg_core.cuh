@@ -576,7 +576,27 @@ KG_DEV void kg_support_coop(const KgModel &m, const KgMprWS &ws, int slot, int m
     kg_multmv(ld, R, dir);
     float best = -FLT_MAX;
     int bi = 0;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(KG_MPR_L1)
+    // scan only the vertices that can be a support vertex for a direction of ld's octant (kg_model.h: exact candidate
+    // lists, 25-40 % of a finger or palm hull); an entry carries its vertex index in w
+    const int oct = (ld[0] < 0.f ? 1 : 0) | (ld[1] < 0.f ? 2 : 0) | (ld[2] < 0.f ? 4 : 0);
+    const int npad = m.octn[mesh][oct];
+    const float4 *v4 = reinterpret_cast<const float4 *>(m.hull_oct) + m.oct0[mesh][oct];
+    bi = 0x7fffffff;
+#pragma unroll 4
+    for (int i = kg_lane; i < npad; i += 32) {
+        float4 v = __ldg(v4 + i);
+        float d = v.x * ld[0] + v.y * ld[1] + v.z * ld[2];
+        if (d > best) { best = d; bi = __float_as_int(v.w); }
+    }
+    unsigned u = __float_as_uint(best);
+    unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    unsigned mx = __reduce_max_sync(0xffffffffu, key);
+    bi = __reduce_min_sync(0xffffffffu, key == mx ? bi : 0x7fffffff);
+    float4 w = __ldg(reinterpret_cast<const float4 *>(vert) + bi);
+    float lv[3] = {w.x, w.y, w.z};
+    (void)vert;
+#elif defined(__CUDA_ARCH__)
     const int npad = m.hnpad[mesh];
     const float4 *v4 = reinterpret_cast<const float4 *>(vert);
 #pragma unroll 4

@@ -50,6 +50,11 @@ struct KgModel {
     const float *hull_vert;        // xyzw per vertex, 128-bit loads; w = bits of (first adj8 chunk | n chunks << 24)
     const float *hull_pad;         // the same vertices, every mesh padded to a multiple of 32 with copies of its vertex 0 (branch-free scans)
     int hpad0[KG_NMESH], hnpad[KG_NMESH];
+    // per mesh and direction octant (bit c set = component c negative): the vertices that can be a support vertex for SOME
+    // direction of that closed octant, ascending vertex index, xyz + bits(vertex index), padded to a multiple of 32 with
+    // copies of the list's first entry.  Exact: the arg-max of a scan over the list equals the arg-max over the mesh.
+    const float *hull_oct;
+    int oct0[KG_NMESH][8], octn[KG_NMESH][8];
     const unsigned short *adj8;    // neighbour lists in 16-byte chunks of 8 mesh-local vertex ids, padded with the vertex itself
     const int *adj_start;
     const unsigned short *adj;
@@ -61,7 +66,7 @@ struct KgModel {
 
 // ---------------------------------------------------------------------------------- host loader
 struct KgHostTables {
-    std::vector<float> hull_vert, hull_pad, tri, bvh_node, pose_train, pose_test;
+    std::vector<float> hull_vert, hull_pad, hull_oct, tri, bvh_node, pose_train, pose_test;
     std::vector<int> adj_start;
     std::vector<unsigned short> adj, adj8;
 };
@@ -222,6 +227,83 @@ inline std::string kg_load_model(const void *blob_, size_t nbytes, KgModel *m, K
             const float *src = &t->hull_vert[4 * (size_t)(mk.vert0 + (v < mk.nvert ? v : 0))];
             for (int c = 0; c < 3; c++) t->hull_pad.push_back(src[c]);
             t->hull_pad.push_back(0.f);
+        }
+    }
+    // ---- octant candidate lists.  On a convex polytope vertex v maximises d.x iff d.(v - u) >= 0 for every hull
+    // neighbour u, so v is a candidate of octant o iff the cone {d : d.(v-u) >= 0 for all u, s_c d_c >= 0} is more than {0}.
+    // A non-trivial cone in R^3 contains one of the directions +-(n_i x n_j) of its constraint normals (or a normal
+    // itself), so feasibility is a finite check (in double, with a tolerance that can only ADD candidates).
+    for (int k = 0; k < KG_NMESH; k++) {
+        const KgMesh &mk = m->mesh[k];
+        std::vector<std::vector<int>> lists(8);
+        std::vector<double> nrm;
+        for (int v = 0; v < mk.nvert; v++) {
+            const float *pv = &t->hull_vert[4 * (size_t)(mk.vert0 + v)];
+            nrm.clear();
+            for (int a = t->adj_start[mk.vert0 + v]; a < t->adj_start[mk.vert0 + v + 1]; a++) {
+                const float *pu = &t->hull_vert[4 * (size_t)(mk.vert0 + t->adj[a])];
+                double e[3] = {(double)pv[0] - pu[0], (double)pv[1] - pu[1], (double)pv[2] - pu[2]};
+                double l = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+                if (l > 0) { nrm.push_back(e[0] / l); nrm.push_back(e[1] / l); nrm.push_back(e[2] / l); }
+            }
+            const size_t nedge = nrm.size() / 3;
+            for (int o = 0; o < 8; o++) {
+                nrm.resize(3 * nedge);
+                for (int c = 0; c < 3; c++) { double s3[3] = {0, 0, 0}; s3[c] = ((o >> c) & 1) ? -1.0 : 1.0; nrm.insert(nrm.end(), s3, s3 + 3); }
+                const size_t nc = nrm.size() / 3;
+                auto ok = [&](const double *d) {
+                    double l = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                    if (l < 1e-12) return false;
+                    for (size_t i = 0; i < nc; i++) if (nrm[3 * i] * d[0] + nrm[3 * i + 1] * d[1] + nrm[3 * i + 2] * d[2] < -1e-6 * l) return false;
+                    return true;
+                };
+                bool feas = false;
+                for (size_t i = 0; i < nc && !feas; i++) {
+                    const double *a = &nrm[3 * i];
+                    double na[3] = {-a[0], -a[1], -a[2]};
+                    if (ok(a) || ok(na)) { feas = true; break; }
+                    for (size_t j = i + 1; j < nc && !feas; j++) {
+                        const double *b = &nrm[3 * j];
+                        double x[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+                        double nx[3] = {-x[0], -x[1], -x[2]};
+                        if (ok(x) || ok(nx)) feas = true;
+                    }
+                }
+                if (feas || nedge == 0) lists[o].push_back(v);
+            }
+        }
+        for (int o = 0; o < 8; o++) {
+            if (lists[o].empty()) lists[o].push_back(0);
+            m->oct0[k][o] = (int)(t->hull_oct.size() / 4);
+            m->octn[k][o] = ((int)lists[o].size() + 31) / 32 * 32;
+            for (int i = 0; i < m->octn[k][o]; i++) {
+                const int v = lists[o][i < (int)lists[o].size() ? i : 0];
+                const float *src = &t->hull_vert[4 * (size_t)(mk.vert0 + v)];
+                for (int c = 0; c < 3; c++) t->hull_oct.push_back(src[c]);
+                float w; std::memcpy(&w, &v, 4); t->hull_oct.push_back(w);
+            }
+        }
+        // self-check: on a fixed set of directions the list scan must return the vertex of the exhaustive scan
+        uint32_t rs = 12345u + 977u * (uint32_t)k;
+        for (int it = 0; it < 3000; it++) {
+            float d[3];
+            for (int c = 0; c < 3; c++) { rs = rs * 1664525u + 1013904223u; d[c] = (float)((rs >> 8) & 0xffff) / 32768.f - 1.f; }
+            if (it < 27) { d[0] = (float)(it % 3 - 1); d[1] = (float)((it / 3) % 3 - 1); d[2] = (float)(it / 9 - 1); }   // axes, face and edge diagonals
+            if (d[0] == 0.f && d[1] == 0.f && d[2] == 0.f) continue;
+            const int o = (d[0] < 0) | ((d[1] < 0) << 1) | ((d[2] < 0) << 2);
+            float best = -3.4e38f, bo = -3.4e38f; int bi = 0, oi = 0;
+            for (int v = 0; v < mk.nvert; v++) {
+                const float *pv = &t->hull_vert[4 * (size_t)(mk.vert0 + v)];
+                float dv = pv[0] * d[0] + pv[1] * d[1] + pv[2] * d[2];
+                if (dv > best) { best = dv; bi = v; }
+            }
+            for (int i = 0; i < m->octn[k][o]; i++) {
+                const float *pv = &t->hull_oct[4 * (size_t)(m->oct0[k][o] + i)];
+                float dv = pv[0] * d[0] + pv[1] * d[1] + pv[2] * d[2];
+                int v; std::memcpy(&v, pv + 3, 4);
+                if (dv > bo || (dv == bo && v < oi)) { bo = dv; oi = v; }
+            }
+            if (oi != bi) return "octant support table disagrees with the exhaustive scan";
         }
     }
     const float *fp;
