@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- batched grasp env-steps/sec (BASELINE.json metric) on configs[1]:
 4096 envs per GPU, CubeS/CubeB alternating, hand_orientation "normal", on-device expert PID (combined),
-30-step episodes with auto-reset on done.  One "step" = one RL step (15 fused physics substeps + obs + reward +
-controller + auto-reset) over the whole batch.  See DESIGN.md "Measurement".
+30-step episodes with auto-reset on done.  One "step" = one RL step (15 physics substeps + obs + reward + controller +
+auto-reset: begin | 15 x (narrowphase | per-env substep) kernels per env group, then the masked reset) over the whole batch.
+See DESIGN.md "Measurement".
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E] [--variant A|B]
 """
