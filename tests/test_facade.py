@@ -1,0 +1,69 @@
+"""The single-env facade with the reference's signatures (gym_kinova_gripper KinovaGripper_Env: ENV:1310-1410 reset,
+ENV:1495-1552 step, the accessors main_DDPGfD.py / expert_data.py call) on the host emulation, against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import _emu_lib
+from kinovagrasping_b200 import env as kenv
+from kinovagrasping_b200.modelcard import SHAPES
+
+
+@pytest.fixture()
+def facade():
+    e = kenv.make("gym_kinova_gripper:kinovagripper-v0", device=0, lib=_emu_lib())
+    yield e
+    e.close()
+
+
+def test_make_rejects_other_ids_and_arm_model():
+    with pytest.raises(ValueError):
+        kenv.make("CartPole-v1", lib=_emu_lib())
+    with pytest.raises(ValueError):
+        kenv.KinovaGripper_Env(arm_or_end_effector="arm", lib=_emu_lib())
+
+
+def test_reset_and_step_signatures_match_reference(facade, oracle):
+    e = facade
+    assert e.action_space.shape == (4,) and e.action_space.high[0] == pytest.approx(0.8)
+    e.seed(3)
+    e._max_episode_steps = 30                                   # MAIN:164,384 set it on the wrapper
+    e.Generate_Latin_Square(30, "objects.csv", shape_keys=["CubeS", "CubeB", "Vase1S"])
+    state = e.reset(shape_keys=["CubeS", "CubeB", "Vase1S"], hand_orientation="random", env_name="env", mode="train")
+    assert isinstance(state, list) and len(state) == 82 and all(isinstance(v, float) for v in state)
+    assert max(abs(v) for v in state[18:21]) < 1e-6              # wrist in its own frame
+    assert e.get_orientation() in ("normal", "rotated", "top") and e.get_random_shape() in ("CubeS", "CubeB", "Vase1S")
+    assert e.get_coords_filename().endswith(e.get_random_shape() + ".txt") and "with_noise/train_coords/" + e.get_orientation() in e.get_coords_filename()
+    obj = e.get_obj_coords()
+    # the oracle from the same start: obj position + the pose row's (truncated) euler
+    shape_id = SHAPES.index(e.get_random_shape())
+    tab = e.card.pose("train")[shape_id, ["normal", "rotated", "top"].index(e.get_orientation())][1:]
+    row = tab[e.get_orientation_idx()]
+    ref_env, ref_obs = oracle.env_reset(shape_id, row[6:9].astype(np.float64), np.array(obj, dtype=np.float64))
+    assert np.abs(np.array(state) - ref_obs).max() < 1e-5
+    assert e.Tfw.shape == (4, 4) and abs(np.linalg.det(e.Tfw[:3, :3]) - 1.0) < 1e-5
+    # a 6-d action [0, 0, wrist, f1, f2, f3] is cut to its last four entries (ENV:1502-1503)
+    nxt, reward, done, info = e.step([0.0, 0.0, 0.0, 0.4, 0.4, 0.4])
+    ref_obs, r, d, _ = oracle.env_step(ref_env, np.array([0.0, 0.4, 0.4, 0.4]))
+    assert isinstance(nxt, list) and len(nxt) == 82 and isinstance(reward, float) and isinstance(done, bool)
+    assert set(info) == {"finger_reward", "grasp_reward", "lift_reward"} and info["finger_reward"] == 0.0
+    assert np.abs(np.array(nxt) - ref_obs).max() < 2e-4 and reward == r and done == d
+    assert e._get_dot_product() == pytest.approx(nxt[81])
+    assert e._get_obs() == nxt
+
+
+def test_timelimit_and_global_obs(facade):
+    e = facade
+    e._max_episode_steps = 4
+    e.reset(shape_keys=["CubeS"], hand_orientation="normal", start_pos=[0.0, 0.0])
+    with pytest.raises(RuntimeError):
+        e._get_obs("global")                                     # switched on here, filled from the next step on
+    dones = []
+    for _ in range(4):
+        obs, rew, done, info = e.step([0.0, 0.3, 0.3, 0.3])
+        dones.append(done)
+    assert dones == [False, False, False, True]                  # gym TimeLimit on the wrapper
+    g = e._get_obs("global")
+    assert len(g) == 74 and g[24:67] == obs[24:67] and g[67:74] == obs[75:82]
+    assert abs(g[23] - e.get_obj_coords()[2]) < 0.01             # the object still stands on the floor, world z
+    with pytest.raises(ValueError):
+        e._get_obs("metric")
