@@ -539,6 +539,24 @@ static int launch_reset(kg_handle h, const int *mask, const int *shape, const fl
 #endif
 }
 
+#ifndef KG_EMU
+// FP32 FMA microbenchmark (the FP32 roofline denominator is measured on the box, not taken from a data sheet):
+// 8 independent FMA chains per thread, 1024 threads per CTA, 2 CTAs per SM.
+__global__ void __launch_bounds__(1024, 2) kg_fma_peak_kernel(float *out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[0] = s;      // never true: keeps the chains alive
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -779,6 +797,33 @@ int kg_forward_debug(kg_handle h, int env, const float *ctrl, float *out) {
 // emulation-only: 0 = lanes of a phase run 0..31, 1 = 31..0 (tests/test_emu_race.py)
 int kg_emu_set_lane_order(int reverse) { kg_emu_lane_order = reverse ? 1 : 0; return KG_OK; }
 #endif
+int kg_measure_fp32_peak(kg_handle h, float *tflops) {
+    if (!h || !tflops) return KG_EINVAL;
+    *tflops = 0.f;
+#ifndef KG_EMU
+    cudaStream_t st = (cudaStream_t)h->stream;
+    int sms = 0;
+    CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const int iters = 4096, grid = 2 * sms;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(h, cudaEventCreate(&e0)); CUDA_TRY(h, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {            // first repetition warms up
+        cudaEventRecord(e0, st);
+        kg_fma_peak_kernel<<<grid, 1024, 0, st>>>(h->d_debug, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1, st);
+        CUDA_TRY(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(h, cudaGetLastError());
+    const double flop = 2.0 * 8.0 * 16.0 * (double)iters * 1024.0 * (double)grid;
+    *tflops = (float)(flop / (best * 1e-3) / 1e12);
+#endif
+    return KG_OK;
+}
 int kg_set_timing(kg_handle h, int on) {
     if (!h) return KG_EINVAL;
 #ifndef KG_EMU

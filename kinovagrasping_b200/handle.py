@@ -105,6 +105,12 @@ class Handle:
         """Number of env groups (1..4) whose kernel chains kg_step overlaps on separate internal streams."""
         self._chk(self.lib.kg_set_pipeline(self.h, int(groups)), "kg_set_pipeline")
 
+    def measure_fp32_peak(self):
+        """TFLOP/s of an FP32 FMA microbenchmark on this device (the measured FP32 roofline denominator)."""
+        v = C.c_float()
+        self._chk(self.lib.kg_measure_fp32_peak(self.h, C.byref(v)), "kg_measure_fp32_peak")
+        return float(v.value)
+
     def set_timing(self, on):
         self._chk(self.lib.kg_set_timing(self.h, int(on)), "kg_set_timing")
 
