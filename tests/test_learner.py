@@ -166,3 +166,24 @@ def test_vectorised_feeder_and_device_sampler(device):
             buf.add_batch(s, torch.zeros((N, 4), device=device), s, torch.zeros(N, device=device), d)
     assert buf.replay_ep_num == 7
     assert float(buf.episode(6)[0][0, 0]) == 2000.0 and float(buf.episode(0)[0][0, 0]) >= 1000.0
+
+
+def test_device_sampler_follows_the_ring_bookkeeping():
+    """sample_windows reads head / episode count from a device tensor (so that a captured CUDA graph keeps working as the
+    ring moves): after evictions the sampler only returns windows of episodes that are still held."""
+    from kinovagrasping_b200.replay import ReplayBuffer_Queue
+    n, T = 4, 12
+    buf = ReplayBuffer_Queue(3, 1, max_episode=6, n_steps=2, max_episode_len=T, device="cpu", n_envs=n)
+    tag = 0
+    for sweep in range(5):                                   # 20 episodes through a ring of 5 complete ones
+        for t in range(8):
+            s = torch.full((n, 3), float(tag)) + torch.arange(n)[:, None] * 0.001
+            done = torch.full((n,), t == 7)
+            buf.add_batch(s, torch.zeros(n, 1), s + 0.5, torch.zeros(n), done)
+        tag += 1
+        meta = buf.publish_meta()
+        assert int(meta[0]) == buf.head and int(meta[1]) == buf.replay_ep_num - 1
+        st = buf.sample_windows(64)[0]
+        held = {float(buf.episode(i)[0][0, 0].floor()) for i in range(buf.replay_ep_num - 1)}
+        assert set(st[:, 0, 0].floor().tolist()) <= held
+    assert buf.replay_ep_num <= 5
