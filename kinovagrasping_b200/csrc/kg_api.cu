@@ -46,7 +46,7 @@ struct kg_handle_s {
     KgModel model;            // host copy; table pointers are device pointers (or host pointers under KG_EMU)
     KgEnvArrays A;
     int *ep_count = nullptr;  // [n] episodes started per env (RNG counter)
-    int *perm = nullptr;      // [n] launch schedule of kg_step_kernel: warp slot -> env, heaviest envs first
+    int *perm = nullptr;      // [n] launch schedule of the per-env kernels: per env group, warp slot -> env (group-relative), heaviest envs first
     int schedule = 1;         // 0 = slot i runs env i; 1 = slots sorted by the load of each env's last step
     unsigned char *carry = nullptr;   // [n][KG_CARRY_BYTES] per-env carry records between the kernels of one RL step
     unsigned *tasks = nullptr;        // [n * 22] narrowphase task list of the current substep: (env << 8) | pair lane
