@@ -107,6 +107,14 @@ class VecKinovaGripperEnv:
         self.h.reset(0 if mask is None else mask.data_ptr(), self.shape_ids.data_ptr(), e.data_ptr(), p.data_ptr(), self.obs_soa.data_ptr())
         return self.obs_soa.t()
 
+    def enable_global_obs(self):
+        """Also produce _get_obs(state_rep="global") (74 values, world frame) at every reset / step; returns the [N, 74]
+        view that those calls keep up to date."""
+        t = self.torch
+        self.obs_global_soa = t.zeros((74, self.n), dtype=t.float32, device=self.device)
+        self.h.set_obs_global(self.obs_global_soa.data_ptr())
+        return self.obs_global_soa.t()
+
     # ---- step
     def step(self, actions=None, expert_mode="naive"):
         """actions: [N, 4] tensor ([wrist, f1, f2, f3]) or None for the on-device expert.

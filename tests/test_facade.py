@@ -67,3 +67,14 @@ def test_timelimit_and_global_obs(facade):
     assert abs(g[23] - e.get_obj_coords()[2]) < 0.01             # the object still stands on the floor, world z
     with pytest.raises(ValueError):
         e._get_obs("metric")
+
+
+def test_vector_env_global_obs_view():
+    import torch
+    from kinovagrasping_b200 import shard
+    env = shard.make_sharded_env(5, 0, 1, "cpu", lib=_emu_lib())
+    g = env.enable_global_obs()
+    obs = env.reset(("CubeS", "Cone1B"), "random", variant="A", seed=9)
+    assert g.shape == (5, 74) and torch.equal(g[:, 24:67], obs[:, 24:67]) and torch.equal(g[:, 67:74], obs[:, 75:82])
+    obs, rew, done, info = env.step(None, "naive")
+    assert torch.equal(g[:, 24:67], obs[:, 24:67]) and float(g[:, 23].min()) > 0.0      # object centre above the floor
