@@ -30,7 +30,9 @@ extern "C" {
 typedef struct kg_handle_s *kg_handle;
 
 /* Replaces KinovaGripper_Env.__init__ + load_model_from_path/MjSim for n_envs environments
- * (kinova_gripper_env.py:51-102, 878-879, 1002-1003).  model_blob = assets/model_card.bin. */
+ * (kinova_gripper_env.py:51-102, 878-879, 1002-1003).  model_blob = assets/model_card.bin.
+ * kg_create makes `device` the calling thread's current CUDA device; every later call on the handle expects it to be
+ * current still (one process per GPU, or cudaSetDevice before switching between handles of different devices). */
 int kg_create(int n_envs, int device, const void *model_blob, size_t nbytes, kg_handle *out);
 int kg_destroy(kg_handle h);
 const char *kg_last_error(kg_handle h);
