@@ -48,6 +48,22 @@ int kg_sync(kg_handle h);
 int kg_reset(kg_handle h, const int *mask_dev, const int *shape_dev, const float *euler_dev,
              const float *objpos_dev, float *obs_dev);
 
+/* kg_reset with the slide-joint start positions determine_hand_location (kinova_gripper_env.py:1286-1307) computes for
+ * the 'rotated' / 'top' orientations and _set_state (692-703) writes into qpos[0:3]: handpos_dev float[3][n] or NULL (zeros,
+ * what 'normal' and every freshly constructed env get). */
+int kg_reset_pose(kg_handle h, const int *mask_dev, const int *shape_dev, const float *euler_dev,
+                  const float *objpos_dev, const float *handpos_dev, float *obs_dev);
+int kg_reset_pose_host(kg_handle h, const int *mask_host, const int *shape_host, const float *euler_host,
+                       const float *objpos_host, const float *handpos_host, float *obs_host);
+/* determine_hand_location for kg_reset_sampled: 0 (default) = slides start at 0 -- what main_DDPGfD.py gets, because it
+ * builds a new env per episode (MAIN:381) and a new env's Tfw is all zeros (ENV:110); 1 = what expert_data.py gets, which
+ * reuses one env (EXP:696): the offsets are computed from the Tfw of the env's PREVIOUS episode (none for its first). */
+int kg_set_hand_location(kg_handle h, int mode);
+/* Length of the action vectors kg_step / kg_step_host take: 4 (default) = [wrist, f1, f2, f3], padded to
+ * [0, 0, wrist, f1, f2, f3] as kinova_gripper_env.py:1502-1503 does; 6 = [slide_x, slide_y, slide_z, f1, f2, f3]
+ * (action[0:3] is the slide vector of kinova_gripper_env.py:1518).  action_dev is float[dim][n]; action_out stays 4-d. */
+int kg_set_action_dim(kg_handle h, int dim);
+
 /* Replaces select_orienation + determine_obj_hand_coords + sample_initial_object_hand_pos
  * (kinova_gripper_env.py:1180-1283, 1008-1054): rows are drawn on the device from the with_noise tables.
  * shape_dev: int[n] or NULL (keep each env's current shape).  orient: 0 normal, 1 rotated, 2 top,

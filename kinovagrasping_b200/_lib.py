@@ -27,6 +27,10 @@ SIGNATURES = {
     "kg_step": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "kg_step_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "kg_reset_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "kg_reset_pose": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kg_reset_pose_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kg_set_hand_location": (C.c_int, [_vp, C.c_int]),
+    "kg_set_action_dim": (C.c_int, [_vp, C.c_int]),
     "kg_get_state": (C.c_int, [_vp, _vp, _vp]),
     "kg_set_state": (C.c_int, [_vp, _vp, _vp]),
     "kg_get_state_host": (C.c_int, [_vp, _vp, _vp]),

@@ -12,6 +12,8 @@
 #include "kg_core.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -53,13 +55,17 @@ struct kg_handle_s {
     int *q = nullptr;                 // two {queued, next} pairs: the per-env kernels fill one while the other is being reset
     int qsel = 0;
     int ngroups = 1;                  // env groups pipelined on separate streams inside one kg_step (KG_MAXGROUPS)
+    int *subseq = nullptr;            // [n] substeps finished in the current RL step: the heavy lane and the light warps CLAIM an env's
+                                      // substep s with atomicCAS(s -> s + 1) on it, so exactly one of them runs it
+    int model_ref = 0;                // this handle holds a reference on its device's shared model tables
     int *heavy_count = nullptr;       // device: envs whose last substep of the current RL step exceeded the light workspace
     int *heavy_host = nullptr;        // pinned host copy of the previous step's count (read without synchronising)
     int heavy_ctas = 1;               // heavy-lane CTAs at the front of every split-mode substep grid
+    int hand_location = 0;            // kg_set_hand_location
     int full_mode = 0, mode_auto = 1; // 1 = every env through the full workspace; chosen per step from heavy_host unless pinned
     std::vector<void *> allocs;
     // scratch for the *_host entry points
-    float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_euler = nullptr, *d_objp = nullptr, *d_q = nullptr;
+    float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_euler = nullptr, *d_objp = nullptr, *d_handp = nullptr, *d_q = nullptr;
     int *d_done = nullptr, *d_mask = nullptr, *d_shape = nullptr;
     float *d_debug = nullptr, *d_ctrl = nullptr;
     float *d_obs_global = nullptr;    // [74][n] internal buffer kg_obs_global_buffer hands out
@@ -111,7 +117,7 @@ KG_DEV unsigned long long kg_mix(unsigned long long x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
 }
-struct KgSample { int shape; float euler[3], objp[3]; };
+struct KgSample { int shape, orient; float euler[3], objp[3]; };
 // select_orienation (ENV:1180-1222) + sample_initial_object_hand_pos (ENV:1008-1054): the reference drops
 // file line 0 and draws randint(0, len(data)), i.e. file lines 1..rows-1.
 KG_DEV KgSample kg_sample_pose(const KgModel &m, unsigned long long seed, int env, int episode, int shape, int orient, int variant, int test_table) {
@@ -126,12 +132,28 @@ KG_DEV KgSample kg_sample_pose(const KgModel &m, unsigned long long seed, int en
     }
     int row = 1 + (int)(r % (unsigned long long)(rows - 1));
     KgSample s;
-    s.shape = shape;
+    s.shape = shape; s.orient = o;
     const float *p = tab + (((size_t)shape * 3 + (variant == 1 ? 0 : o)) * rows + row) * 9;
     s.objp[0] = p[0]; s.objp[1] = p[1]; s.objp[2] = p[2];
     const float *e = variant == 1 ? tab + (((size_t)shape * 3 + 2) * rows + row) * 9 : p;
     s.euler[0] = e[6]; s.euler[1] = e[7]; s.euler[2] = e[8];
     return s;
+}
+
+// determine_hand_location (ENV:1286-1307): the slide-joint start positions of the 'rotated' / 'top' orientations,
+// [-x, -y, z] of Tfw[0:3,0:3] v with v = (0.051, -0.075, 0.06) / (-0.005, -0.155, Z + 0.06), Z = 0.14 (self.obj_size stays
+// 'm', ENV:62).  The reference evaluates it BEFORE write_xml, i.e. with the Tfw its env object still holds from the
+// PREVIOUS episode (zeros for a freshly constructed env): hq_prev is that episode's hand quaternion.
+KG_DEV void kg_hand_location(const KgModel &m, const float *hq_prev, int has_prev, int orient, float *hand) {
+    hand[0] = hand[1] = hand[2] = 0.f;
+    if (orient == 0 || !has_prev) return;
+    float Rh[9], Rp[9];
+    kg_quat2mat(Rh, hq_prev);
+    kg_mulmm(Rp, Rh, m.palm_gR);
+    const float vx = orient == 2 ? -0.005f : 0.051f, vy = orient == 2 ? -0.155f : -0.075f, vz = orient == 2 ? 0.14f + 0.06f : 0.06f;
+    // rows of Tfw[0:3,0:3] = (-Rp col1, -Rp col2, Rp col0)
+    const float l0 = -(Rp[1] * vx + Rp[4] * vy + Rp[7] * vz), l1 = -(Rp[2] * vx + Rp[5] * vy + Rp[8] * vz), l2 = Rp[0] * vx + Rp[3] * vy + Rp[6] * vz;
+    hand[0] = -l0; hand[1] = -l1; hand[2] = l2;
 }
 
 // one mj_forward with a dump of the intermediates (test hook behind kg_forward_debug), in the same three pieces as
@@ -201,8 +223,11 @@ __global__ void __launch_bounds__(1024) kg_schedule_kernel(const int *load, int 
 // CTA, KG_LMINBLOCKS CTAs per SM -> 24 resident warps per SM instead of 16).  A substep whose contact count exceeds the
 // light workspace's rows is skipped by its light warp and run, in the SAME launch, by a HEAVY LANE: the first
 // `nheavy_ctas` CTAs of the grid hold full workspaces (as many as fit their shared memory), scan the contact counts of
-// all envs and run the substeps the light warps skip.  Both sides apply the same test to the same carry record, so
-// every env is run exactly once; the heavy lane overlaps the light CTAs instead of trailing them.
+// all envs and run the substeps the light warps skip.  Both sides apply the same test to the env's carry record, but that
+// record is REWRITTEN by whoever runs the env (and a heavy CTA may finish an env before its light CTA is even scheduled),
+// so the test alone cannot decide: a side that wants to run substep s of an env first claims it with
+// atomicCAS(subseq[env], s, s + 1).  The claim precedes every store to the record, so a side that saw a rewritten (or
+// torn) record finds the claim taken and skips; every env is run exactly once per launch.
 // FULL mode: every env through the full workspace (16 warps per CTA, one CTA per SM) -- chosen by the host when the
 // last RL step it has a count for had more than a third of the envs above the light limit (contact-heavy shapes).
 // A launch covers the env GROUP [base, base + cnt) (launch_step pipelines the groups of a batch on separate streams);
@@ -217,8 +242,9 @@ __global__ void __launch_bounds__(1024) kg_schedule_kernel(const int *load, int 
 
 // first kernel of an RL step: action / on-device expert, kinematics and lane-parallel collision of substep 0
 __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_begin_kernel(KgEnvArrays A, int base, int cnt, const int *perm, const float *action, int mode,
-                                                                                 unsigned char *carry, int *q, unsigned *tasks) {
+                                                                                 unsigned char *carry, int *q, unsigned *tasks, int *subseq) {
     KG_ENV_OF_WARP(KgWSLight, KG_LWARPS, blockIdx.x);
+    if (lane == 0) subseq[env] = 0;
     const unsigned mask = kg_step_begin(c_model, ws, A, env, action, mode, lane);
     kg_carry_store(ws, carry + (size_t)env * KG_CARRY_BYTES, lane);
     kg_emit_tasks(mask, env, q, tasks, lane);
@@ -244,10 +270,16 @@ __device__ __forceinline__ int kg_warp_sum(int v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// claim substep `sidx` of an env for this warp (see the SPLIT mode note above); warp-uniform result
+__device__ __forceinline__ bool kg_claim(int *seq, int sidx, int lane) {
+    int ok = 0;
+    if (lane == 0) ok = atomicCAS(seq, sidx, sidx + 1) == sidx;
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
 #define KG_HEAVY_WARPS ((int)(KG_LSMEM / sizeof(KgWSNoSync)))     // full workspaces that fit a light CTA's shared memory
 template <bool LAST>
 __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(KgEnvArrays A, int base, int cnt, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
-                                                                               int nheavy_ctas, int *heavy_count, int nsub, float *obs, float *reward, int *done, float *act_out) {
+                                                                               int nheavy_ctas, int *heavy_count, int *subseq, int sidx, int nsub, float *obs, float *reward, int *done, float *act_out) {
     if ((int)blockIdx.x < nheavy_ctas) {
         // ---- heavy lane: persistent warps with full workspaces (no stage rendezvous: they loop independently)
         extern __shared__ __align__(16) unsigned char smem[];
@@ -268,6 +300,7 @@ __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(K
             for (int k = 0; k < 4; k++) {
                 if (kg_warp_sum(c[k]) <= KG_MAXCON_LIGHT) continue;
                 const int env = e0 + k * W;
+                if (!kg_claim(subseq + env, sidx, lane)) continue;
                 unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
                 kg_carry_load(ws, rec, lane);
                 kg_sub_body<KgWSNoSync, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
@@ -281,7 +314,10 @@ __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(K
     KG_ENV_OF_WARP(KgWSLight, KG_LWARPS, blockIdx.x - nheavy_ctas);
     unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
     kg_carry_load(ws, rec, lane);
-    if (nheavy_ctas > 0 && kg_warp_sum(ws.cnt[lane]) > KG_MAXCON_LIGHT) return;      // the heavy lane runs this one
+    if (nheavy_ctas > 0) {
+        if (kg_warp_sum(ws.cnt[lane]) > KG_MAXCON_LIGHT) return;      // the heavy lane runs this one
+        if (!kg_claim(subseq + env, sidx, lane)) return;              // ... or already has (the record was rewritten)
+    }
     kg_sub_body<KgWSLight, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
 }
 template <bool LAST>
@@ -353,8 +389,8 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
 #endif
 }
 
-__global__ void __launch_bounds__(KG_LWARPS * 32) kg_reset_kernel(KgEnvArrays A, const int *mask, const int *shape, const float *euler, const float *objp,
-                                                                 int sampled, int orient, int variant, int test_table, unsigned long long seed, int *ep_count, int env_offset, float *obs) {
+__global__ void __launch_bounds__(KG_LWARPS * 32) kg_reset_kernel(KgEnvArrays A, const int *mask, const int *shape, const float *euler, const float *objp, const float *handp,
+                                                                 int sampled, int orient, int variant, int test_table, int hand_location, unsigned long long seed, int *ep_count, int env_offset, float *obs) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * KG_LWARPS + warp;
@@ -362,16 +398,20 @@ __global__ void __launch_bounds__(KG_LWARPS * 32) kg_reset_kernel(KgEnvArrays A,
     if (mask && mask[env] == 0) return;
     KgWSLight &ws = *(reinterpret_cast<KgWSLight *>(smem) + warp);
     int sh = shape ? shape[env] : A.shape[env];
-    float e[3], p[3];
+    float e[3], p[3], hp[3] = {0.f, 0.f, 0.f};
     if (sampled) {
         KgSample s = kg_sample_pose(c_model, seed, env + env_offset, ep_count[env], sh, orient, variant, test_table);
         for (int c = 0; c < 3; c++) { e[c] = s.euler[c]; p[c] = s.objp[c]; }
+        if (hand_location) {
+            const float hq[4] = {A.hand_quat[env], A.hand_quat[A.N + env], A.hand_quat[2 * A.N + env], A.hand_quat[3 * A.N + env]};
+            kg_hand_location(c_model, hq, ep_count[env] > 0, s.orient, hp);
+        }
     } else {
-        for (int c = 0; c < 3; c++) { e[c] = euler[c * A.N + env]; p[c] = objp[c * A.N + env]; }
+        for (int c = 0; c < 3; c++) { e[c] = euler[c * A.N + env]; p[c] = objp[c * A.N + env]; if (handp) hp[c] = handp[c * A.N + env]; }
     }
     __syncwarp();
     if (lane == 0) ep_count[env] += 1;
-    kg_env_reset(c_model, ws, A, env, sh, e, p, obs, lane);
+    kg_env_reset(c_model, ws, A, env, sh, e, p, hp, obs, lane);
 }
 __global__ void kg_debug_begin_kernel(KgEnvArrays A, int env, const float *ctrl, unsigned char *carry, int *q, unsigned *tasks) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -480,7 +520,7 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
         KG_TMARK(0);
         if (h->schedule) kg_schedule_kernel<<<1, 1024, 0, gs[g]>>>(h->A.load + base, h->perm + base, cnt);
         KG_TMARK(1);
-        kg_begin_kernel<<<blocks, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, action, mode, h->carry, h->q + 4 * g + 2 * qs0, h->tasks + (size_t)base * 22);
+        kg_begin_kernel<<<blocks, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, action, mode, h->carry, h->q + 4 * g + 2 * qs0, h->tasks + (size_t)base * 22, h->subseq);
         KG_TMARK(2);
     }
     for (int s = 0; s < nsub; s++) {
@@ -502,8 +542,8 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
                 const int blocks = (cnt + KG_LWARPS - 1) / KG_LWARPS;
                 const int hb = (cnt + KG_HEAVY_WARPS - 1) / KG_HEAVY_WARPS;
                 const int nhc = hb < h->heavy_ctas ? hb : h->heavy_ctas;
-                if (last) kg_sub_kernel<true><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, nsub, obs, reward, done, act_out);
-                else kg_sub_kernel<false><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, nsub, obs, reward, done, act_out);
+                if (last) kg_sub_kernel<true><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
+                else kg_sub_kernel<false><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
             }
             KG_TMARK(last ? 5 : 4);
         }
@@ -515,25 +555,30 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
     return 0;
 #endif
 }
-static int launch_reset(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, int sampled, int orient,
+static int launch_reset(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, const float *handp, int sampled, int orient,
                         int variant, int test_table, unsigned long long seed, float *obs) {
 #ifdef KG_EMU
     for (int env = 0; env < h->n; env++) {
         if (mask && mask[env] == 0) continue;
         int sh = shape ? shape[env] : h->A.shape[env];
-        float e[3], p[3];
+        float e[3], p[3], hp[3] = {0.f, 0.f, 0.f};
         if (sampled) {
             KgSample s = kg_sample_pose(h->model, seed, env + h->env_offset, h->ep_count[env], sh, orient, variant, test_table);
             for (int c = 0; c < 3; c++) { e[c] = s.euler[c]; p[c] = s.objp[c]; }
-        } else for (int c = 0; c < 3; c++) { e[c] = euler[c * h->n + env]; p[c] = objp[c * h->n + env]; }
+            if (h->hand_location) {
+                const int N = h->n;
+                const float hq[4] = {h->A.hand_quat[env], h->A.hand_quat[N + env], h->A.hand_quat[2 * N + env], h->A.hand_quat[3 * N + env]};
+                kg_hand_location(h->model, hq, h->ep_count[env] > 0, s.orient, hp);
+            }
+        } else for (int c = 0; c < 3; c++) { e[c] = euler[c * h->n + env]; p[c] = objp[c * h->n + env]; if (handp) hp[c] = handp[c * h->n + env]; }
         h->ep_count[env] += 1;
-        kg_env_reset(h->model, g_ws, h->A, env, sh, e, p, obs, 0);
+        kg_env_reset(h->model, g_ws, h->A, env, sh, e, p, hp, obs, 0);
     }
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)h->stream;
     int blocks = (h->n + KG_LWARPS - 1) / KG_LWARPS;
-    kg_reset_kernel<<<blocks, KG_LWARPS * 32, KG_LSMEM, st>>>(h->A, mask, shape, euler, objp, sampled, orient, variant, test_table, seed, h->ep_count, h->env_offset, obs);
+    kg_reset_kernel<<<blocks, KG_LWARPS * 32, KG_LSMEM, st>>>(h->A, mask, shape, euler, objp, handp, sampled, orient, variant, test_table, h->hand_location, seed, h->ep_count, h->env_offset, obs);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 #endif
@@ -557,6 +602,60 @@ __global__ void __launch_bounds__(1024, 2) kg_fma_peak_kernel(float *out, int it
 }
 #endif
 
+#ifndef KG_EMU
+// The kernels read the model through the __constant__ symbol c_model, of which there is ONE copy per device, so the
+// tables it points to are per DEVICE, not per handle: the first handle on a device uploads them, later handles share
+// them (same model card only), the last kg_destroy frees them.  (The reference's own flow needs this: eval_policy,
+// MAIN:146, builds a temporary env while the training env is alive and drops it again.)
+struct KgDevModel { int refs = 0; unsigned long long hash = 0; KgModel model; std::vector<void *> allocs; };
+static std::mutex g_model_mu;
+static std::map<int, KgDevModel> g_models;
+static unsigned long long kg_fnv1a(const void *p, size_t n) {
+    const unsigned char *b = (const unsigned char *)p;
+    unsigned long long x = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) { x ^= b[i]; x *= 1099511628211ull; }
+    return x;
+}
+static void model_free_locked(KgDevModel &dm) {
+    for (void *p : dm.allocs) cudaFree(p);
+    dm.allocs.clear(); dm.refs = 0;
+}
+static int model_acquire(kg_handle h, int device, const void *blob, size_t nbytes) {
+    std::lock_guard<std::mutex> lk(g_model_mu);
+    KgDevModel &dm = g_models[device];
+    const unsigned long long hash = kg_fnv1a(blob, nbytes);
+    if (dm.refs > 0) {
+        if (dm.hash != hash) { h->err = "model card: another model card is live on this device (one model per device at a time)"; return KG_EMODEL; }
+        h->model = dm.model; dm.refs++; h->model_ref = 1;
+        return KG_OK;
+    }
+    KgHostTables t;
+    KgModel m;
+    std::string e = kg_load_model(blob, nbytes, &m, &t);
+    if (!e.empty()) { h->err = "model card: " + e; return KG_EMODEL; }
+    cudaError_t ce = cudaSuccess;
+#define UP(field, vec) do { void *p_ = nullptr; size_t b_ = (vec).size() * sizeof((vec)[0]); \
+        if (ce == cudaSuccess) ce = cudaMalloc(&p_, b_ ? b_ : 4); \
+        if (ce == cudaSuccess) { dm.allocs.push_back(p_); ce = cudaMemcpy(p_, (vec).data(), b_, cudaMemcpyHostToDevice); } \
+        m.field = (decltype(m.field))p_; } while (0)
+    UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(adj8, t.adj8); UP(hull_pad, t.hull_pad); UP(hull_oct, t.hull_oct); UP(tri, t.tri);
+    UP(bvh_node, t.bvh_node); UP(pose_train, t.pose_train); UP(pose_test, t.pose_test);
+#undef UP
+    if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(c_model, &m, sizeof(KgModel));
+    if (ce != cudaSuccess) { h->err = std::string("model upload: ") + cudaGetErrorString(ce); model_free_locked(dm); return KG_ECUDA; }
+    dm.model = m; dm.hash = hash; dm.refs = 1;
+    h->model = m; h->model_ref = 1;
+    return KG_OK;
+}
+static void model_release(kg_handle h) {
+    if (!h->model_ref) return;
+    std::lock_guard<std::mutex> lk(g_model_mu);
+    auto it = g_models.find(h->device);
+    if (it != g_models.end() && --it->second.refs <= 0) { model_free_locked(it->second); g_models.erase(it); }
+    h->model_ref = 0;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -565,31 +664,25 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     kg_handle h = new kg_handle_s();
     *out = h;
     h->n = n_envs; h->device = device;
-    KgHostTables local;
 #ifdef KG_EMU
     KgHostTables &t = h->tables;
-#else
-    KgHostTables &t = local;
-    CUDA_TRY(h, cudaSetDevice(device));
-#endif
     std::string e = kg_load_model(blob, nbytes, &h->model, &t);
     if (!e.empty()) { h->err = "model card: " + e; return KG_EMODEL; }
     KgModel &m = h->model;
-    h->fhull_bytes = 16 * (m.hnpad[1] + m.hnpad[2]);
-    if (m.hpad0[2] != m.hpad0[1] + m.hnpad[1]) { h->err = "model card: finger hulls must be contiguous"; return KG_EMODEL; }
-    for (int k = 3; k < KG_NMESH; k++) if (m.hnpad[k] > KG_MAXOBJVERT) { h->err = "model card: object hull too large"; return KG_EMODEL; }
-#ifdef KG_EMU
     m.hull_vert = t.hull_vert.data(); m.adj_start = t.adj_start.data(); m.adj = t.adj.data(); m.adj8 = t.adj8.data(); m.hull_pad = t.hull_pad.data(); m.hull_oct = t.hull_oct.data(); m.tri = t.tri.data();
     m.bvh_node = t.bvh_node.data();
     m.pose_train = t.pose_train.data(); m.pose_test = t.pose_test.data();
     g_mw.fhull = m.hull_pad + 4 * (size_t)m.hpad0[1];     // host emulation: no staging copy
     g_mw.hull_shape = -1;
 #else
-#define UP(field, vec) do { void *p_; TRY(be_alloc(h, &p_, (vec).size() * sizeof((vec)[0]))); CUDA_TRY(h, cudaMemcpy(p_, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice)); m.field = (decltype(m.field))p_; } while (0)
-    UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(adj8, t.adj8); UP(hull_pad, t.hull_pad); UP(hull_oct, t.hull_oct); UP(tri, t.tri);
-    UP(bvh_node, t.bvh_node); UP(pose_train, t.pose_train); UP(pose_test, t.pose_test);
-#undef UP
-    CUDA_TRY(h, cudaMemcpyToSymbol(c_model, &m, sizeof(KgModel)));
+    CUDA_TRY(h, cudaSetDevice(device));
+    { int r_ = model_acquire(h, device, blob, nbytes); if (r_ != KG_OK) return r_; }
+    KgModel &m = h->model;
+#endif
+    h->fhull_bytes = 16 * (m.hnpad[1] + m.hnpad[2]);
+    if (m.hpad0[2] != m.hpad0[1] + m.hnpad[1]) { h->err = "model card: finger hulls must be contiguous"; return KG_EMODEL; }
+    for (int k = 3; k < KG_NMESH; k++) if (m.hnpad[k] > KG_MAXOBJVERT) { h->err = "model card: object hull too large"; return KG_EMODEL; }
+#ifndef KG_EMU
     CUDA_TRY(h, cudaFuncSetAttribute(kg_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_LSMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_LSMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_LSMEM));
@@ -619,17 +712,17 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
 #endif
     const size_t N = (size_t)n_envs;
     KgEnvArrays &A = h->A;
-    A.N = n_envs; A.max_steps = 30;
+    A.N = n_envs; A.max_steps = 30; A.act_dim = 4;
     TRY(be_alloc(h, (void **)&A.qpos, 16 * N * 4)); TRY(be_alloc(h, (void **)&A.qvel, 15 * N * 4)); TRY(be_alloc(h, (void **)&A.qwarm, 15 * N * 4));
     TRY(be_alloc(h, (void **)&A.hand_quat, 4 * N * 4)); TRY(be_alloc(h, (void **)&A.shape, N * 4)); TRY(be_alloc(h, (void **)&A.elapsed, N * 4));
     TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
-    TRY(be_alloc(h, (void **)&A.stats, 4 * 4)); TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
+    TRY(be_alloc(h, (void **)&A.stats, 4 * 8)); TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
     TRY(be_alloc(h, (void **)&A.ccache, N * KG_CCACHE_BYTES));
     TRY(be_alloc(h, (void **)&h->d_obs_global, KG_NOBS_GLOBAL * N * 4));
     TRY(be_alloc(h, (void **)&A.load, N * 4)); TRY(be_alloc(h, (void **)&h->perm, N * 4));
     TRY(be_alloc(h, (void **)&h->carry, N * KG_CARRY_BYTES)); TRY(be_alloc(h, (void **)&h->tasks, N * 22 * 4)); TRY(be_alloc(h, (void **)&h->q, 4 * 4 * KG_MAXGROUPS));
-    TRY(be_alloc(h, (void **)&h->heavy_count, 4));
-    TRY(be_alloc(h, (void **)&h->d_action, 4 * N * 4)); TRY(be_alloc(h, (void **)&h->d_obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&h->d_reward, N * 4));
+    TRY(be_alloc(h, (void **)&h->heavy_count, 4)); TRY(be_alloc(h, (void **)&h->subseq, N * 4));
+    TRY(be_alloc(h, (void **)&h->d_action, 6 * N * 4)); TRY(be_alloc(h, (void **)&h->d_handp, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&h->d_reward, N * 4));
     TRY(be_alloc(h, (void **)&h->d_done, N * 4)); TRY(be_alloc(h, (void **)&h->d_mask, N * 4)); TRY(be_alloc(h, (void **)&h->d_shape, N * 4));
     TRY(be_alloc(h, (void **)&h->d_euler, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_objp, 3 * N * 4)); TRY(be_alloc(h, (void **)&h->d_q, 31 * N * 4));
     TRY(be_alloc(h, (void **)&h->d_debug, KG_DEBUG_FLOATS * 4)); TRY(be_alloc(h, (void **)&h->d_ctrl, 16 * 4));
@@ -649,7 +742,9 @@ int kg_destroy(kg_handle h) {
     for (void *p : h->allocs) free(p);
 #else
     cudaSetDevice(h->device);
+    cudaDeviceSynchronize();      // nothing of this handle may still be running when its buffers go
     for (void *p : h->allocs) cudaFree(p);
+    model_release(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->heavy_host) cudaFreeHost(h->heavy_host);
@@ -691,13 +786,22 @@ int kg_get_last_action_host(kg_handle h, float *act) {
     return be_sync(h);
 }
 
-int kg_reset(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, float *obs) {
+int kg_reset_pose(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, const float *handp, float *obs) {
     if (!h || !shape || !euler || !objp) { if (h) h->err = "kg_reset: shape/euler/objpos are required"; return KG_EINVAL; }
-    return launch_reset(h, mask, shape, euler, objp, 0, 0, 0, 0, 0ull, obs);
+    return launch_reset(h, mask, shape, euler, objp, handp, 0, 0, 0, 0, 0ull, obs);
+}
+int kg_reset(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, float *obs) {
+    return kg_reset_pose(h, mask, shape, euler, objp, nullptr, obs);
+}
+int kg_set_hand_location(kg_handle h, int mode) { if (!h || mode < 0 || mode > 1) return KG_EINVAL; h->hand_location = mode; return KG_OK; }
+int kg_set_action_dim(kg_handle h, int dim) {
+    if (!h || (dim != 4 && dim != 6)) { if (h) h->err = "kg_set_action_dim: 4 or 6"; return KG_EINVAL; }
+    h->A.act_dim = dim;
+    return KG_OK;
 }
 int kg_reset_sampled(kg_handle h, const int *mask, const int *shape, int orient, int variant, int test_table, uint64_t seed, float *obs) {
     if (!h || orient < 0 || orient > 3 || variant < 0 || variant > 1) { if (h) h->err = "kg_reset_sampled: bad orient/variant"; return KG_EINVAL; }
-    return launch_reset(h, mask, shape, nullptr, nullptr, 1, orient, variant, test_table ? 1 : 0, (unsigned long long)seed, obs);
+    return launch_reset(h, mask, shape, nullptr, nullptr, nullptr, 1, orient, variant, test_table ? 1 : 0, (unsigned long long)seed, obs);
 }
 int kg_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
     if (!h || mode < 0 || mode > 2) { if (h) h->err = "kg_step: expert_mode must be 0, 1 or 2"; return KG_EINVAL; }
@@ -706,21 +810,25 @@ int kg_step(kg_handle h, const float *action, int mode, float *obs, float *rewar
 int kg_step_host(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done) {
     if (!h) return KG_EINVAL;
     const size_t N = h->n;
-    if (action) TRY(be_h2d(h, h->d_action, action, 4 * N * 4));
+    if (action) TRY(be_h2d(h, h->d_action, action, (size_t)h->A.act_dim * N * 4));
     TRY(kg_step(h, action ? h->d_action : nullptr, mode, obs ? h->d_obs : nullptr, reward ? h->d_reward : nullptr, done ? h->d_done : nullptr, nullptr));
     if (obs) TRY(be_d2h(h, obs, h->d_obs, KG_NOBS * N * 4));
     if (reward) TRY(be_d2h(h, reward, h->d_reward, N * 4));
     if (done) TRY(be_d2h(h, done, h->d_done, N * 4));
     return be_sync(h);
 }
-int kg_reset_host(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, float *obs) {
+int kg_reset_pose_host(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, const float *handp, float *obs) {
     if (!h || !shape || !euler || !objp) { if (h) h->err = "kg_reset_host: shape/euler/objpos are required"; return KG_EINVAL; }
     const size_t N = h->n;
     if (mask) TRY(be_h2d(h, h->d_mask, mask, N * 4));
     TRY(be_h2d(h, h->d_shape, shape, N * 4)); TRY(be_h2d(h, h->d_euler, euler, 3 * N * 4)); TRY(be_h2d(h, h->d_objp, objp, 3 * N * 4));
-    TRY(kg_reset(h, mask ? h->d_mask : nullptr, h->d_shape, h->d_euler, h->d_objp, obs ? h->d_obs : nullptr));
+    if (handp) TRY(be_h2d(h, h->d_handp, handp, 3 * N * 4));
+    TRY(kg_reset_pose(h, mask ? h->d_mask : nullptr, h->d_shape, h->d_euler, h->d_objp, handp ? h->d_handp : nullptr, obs ? h->d_obs : nullptr));
     if (obs) TRY(be_d2h(h, obs, h->d_obs, KG_NOBS * N * 4));
     return be_sync(h);
+}
+int kg_reset_host(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, float *obs) {
+    return kg_reset_pose_host(h, mask, shape, euler, objp, nullptr, obs);
 }
 int kg_get_state(kg_handle h, float *qpos, float *qvel) {
     if (!h) return KG_EINVAL;
@@ -752,7 +860,7 @@ int kg_set_state_host(kg_handle h, const float *qpos, const float *qvel) {
 }
 int kg_get_stats(kg_handle h, long long out[4]) {
     if (!h || !out) return KG_EINVAL;
-    int s[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+    long long s[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};       // 64-bit device counters: 32768 envs x 15 substeps wrap 2^31 in ~4.4k steps
     TRY(be_d2h(h, s, h->A.stats, sizeof s)); TRY(be_sync(h));
     TRY(be_h2d(h, h->A.stats, z, sizeof z)); TRY(be_sync(h));
     for (int i = 0; i < 4; i++) out[i] = s[i];

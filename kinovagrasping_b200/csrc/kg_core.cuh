@@ -1677,14 +1677,15 @@ template <class WS> KG_DEV void kg_rays(const KgModel &m, WS &ws, int kg_lane) {
 // Restates _get_obs('local') / _get_reward (ENV:438-534, 631-687) on the kinematics of the LAST forward
 // pass (the one-substep staleness of SURVEY 8a O-note is reproduced: this runs before nothing else
 // touches ws.gpos / ws.sens_q).
+// (u_obj . u_ctr)^20: the 20th power multiplies the relative rounding error of the cosine by 20, which in fp32 (four 2-ulp
+// divisions and two square roots) lands at 1-2e-5 -- above the 1e-5 obs tolerance.  Seven of these per RL step and env, so
+// the few dozen operations are done in fp64 (inputs are the fp32 kinematics; the result is rounded once).
 KG_DEV float kg_dotprod20(const float *hand, const float *p) {
-    float ox = fabsf(p[0] - hand[0]), oy = fabsf(p[1] - hand[1]);
-    float on = sqrtf(ox * ox + oy * oy);
-    float cx = fabsf(hand[0]), cy = fabsf(hand[1]);
-    float cn = sqrtf(cx * cx + cy * cy);
-    float d = (ox / on) * (cx / cn) + (oy / on) * (cy / cn);
-    float d2 = d * d, d4 = d2 * d2, d8 = d4 * d4, d16 = d8 * d8;
-    return d16 * d4;
+    const double ox = fabs((double)p[0] - (double)hand[0]), oy = fabs((double)p[1] - (double)hand[1]);
+    const double cx = fabs((double)hand[0]), cy = fabs((double)hand[1]);
+    const double d = (ox * cx + oy * cy) / sqrt((ox * ox + oy * oy) * (cx * cx + cy * cy));
+    const double d2 = d * d, d4 = d2 * d2, d8 = d4 * d4, d16 = d8 * d8;
+    return (float)(d16 * d4);
 }
 KG_DEV float kg_tri_area(const float *a, const float *b) { float c[3]; kg_cross(c, a, b); return 0.5f * sqrtf(kg_dot(c, c)); }
 
@@ -1803,18 +1804,22 @@ template <class WS> KG_DEV void kg_obs_global_store(const WS &ws, float *out, in
     KG_SYNC();
 }
 
-// ------------------------------------------------------------------------------------------------ S1: ctrl from the 4-d action (ENV:1501-1534)
-template <class WS> KG_DEV void kg_ctrl_from_action(WS &ws, const float *action, int kg_lane) {
+// ------------------------------------------------------------------------------------------------ S1: ctrl from the action (ENV:1501-1534)
+// a6 = [slide_x, slide_y, slide_z (wrist), f1, f2, f3]; a 4-d action [wrist, f1, f2, f3] is padded to [0, 0, wrist, f1, f2, f3]
+// by the caller exactly as ENV:1502-1503 does.  slide_vector = Tfw[0:3,0:3] a6[0:3], x and y negated (ENV:1518-1522);
+// gravity compensation = Tfw[0:3,0:3] (0, 0, 0.733*10/25), x and y negated (ENV:1511-1515).
+template <class WS> KG_DEV void kg_ctrl_from_action(WS &ws, const float *a6, int kg_lane) {
     KG_PHASE(l) {
         if (l == 0) {
             const float *Rp = ws.gmat[1];
-            // T z-column: T * (0,0,s) = s * (T[2], T[5], T[8]) with T rows = (-Rp col1, -Rp col2, Rp col0)
-            float tz[3] = {-Rp[7], -Rp[8], Rp[6]};
+            // rows of T = Tfw[0:3,0:3] are (-Rp col1, -Rp col2, Rp col0)
+            const float T[9] = {-Rp[1], -Rp[4], -Rp[7], -Rp[2], -Rp[5], -Rp[8], Rp[0], Rp[3], Rp[6]};
             const float gcomp = 0.733f * 10.f / 25.f;
-            float a0 = action[0];
-            ws.ctrl[0] = -tz[0] * a0; ws.ctrl[2] = -tz[1] * a0; ws.ctrl[4] = tz[2] * a0;
-            ws.ctrl[1] = -tz[0] * gcomp; ws.ctrl[3] = -tz[1] * gcomp; ws.ctrl[5] = tz[2] * gcomp;
-            ws.ctrl[6] = action[1]; ws.ctrl[7] = action[2]; ws.ctrl[8] = action[3];
+            float sv[3];
+            for (int r = 0; r < 3; r++) sv[r] = T[3 * r] * a6[0] + T[3 * r + 1] * a6[1] + T[3 * r + 2] * a6[2];
+            ws.ctrl[0] = -sv[0]; ws.ctrl[2] = -sv[1]; ws.ctrl[4] = sv[2];
+            ws.ctrl[1] = -T[2] * gcomp; ws.ctrl[3] = -T[5] * gcomp; ws.ctrl[5] = T[8] * gcomp;
+            ws.ctrl[6] = a6[3]; ws.ctrl[7] = a6[4]; ws.ctrl[8] = a6[5];
         }
     }
     KG_SYNC();
@@ -1884,12 +1889,13 @@ struct KgEnvArrays {
     int *ex_i;                    // [3][N] have_prev, num_good, total_steps
     float *obs;                   // [82][N] last observation (input of the expert controller)
     float *last_action;           // [4][N] action applied by the last step (given or expert)
-    int *stats;                   // [4] mpr pairs, newton iterations, contact overflows, substeps
+    unsigned long long *stats;    // [4] mpr pairs, newton iterations, contact overflows, substeps (64-bit: they run for a whole training)
     int *load;                    // [N] cost of each env's last RL step (Newton iterations + 2 x MPR pairs): key of the launch schedule
     long long *prof;              // [KG_NPROF] KG_PROF builds only
     float *obs_global;            // [74][N] or NULL: _get_obs(state_rep="global") of the same step (kg_set_obs_global)
     unsigned char *ccache;        // [N][KG_CCACHE_BYTES] collision caches (warm-start vertices, separating axes) kept across RL steps
     int N, max_steps;
+    int act_dim;                  // 4 = [wrist, f1, f2, f3], 6 = [slide_x, slide_y, slide_z, f1, f2, f3] (ENV:1502-1503)
 };
 
 template <class WS> KG_DEV void kg_load_env(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, int kg_lane) {
@@ -1995,9 +2001,13 @@ template <class WS> KG_DEV unsigned kg_step_begin(const KgModel &m, WS &ws, cons
     kg_load_env(m, ws, A, env, kg_lane);
     kg_copy16(reinterpret_cast<unsigned char *>(&ws) + KG_CCACHE_OFF, A.ccache + (size_t)env * KG_CCACHE_BYTES, (int)KG_CCACHE_BYTES, kg_lane);
     KG_SYNC();
-    float act[4] = {0, 0, 0, 0};
-    if (action_in) { for (int c = 0; c < 4; c++) act[c] = action_in[c * A.N + env]; }
-    else {
+    float act[4] = {0, 0, 0, 0}, sxy[2] = {0, 0};      // act = [wrist (slide_z), f1, f2, f3]; sxy = slide_x, slide_y of a 6-d action
+    if (action_in) {
+        if (A.act_dim == 6) {
+            sxy[0] = action_in[env]; sxy[1] = action_in[A.N + env];
+            for (int c = 0; c < 4; c++) act[c] = action_in[(c + 2) * A.N + env];
+        } else for (int c = 0; c < 4; c++) act[c] = action_in[c * A.N + env];
+    } else {
         KG_PHASE(l) { for (int i = l; i < KG_NOBS; i += 32) KG_WSOBS(ws)[i] = A.obs[i * A.N + env]; }
         KG_SYNC();
         KG_PHASE(l) {
@@ -2020,7 +2030,10 @@ template <class WS> KG_DEV unsigned kg_step_begin(const KgModel &m, WS &ws, cons
     }
     KG_PHASE(l) { if (l < 4) A.last_action[l * A.N + env] = act[l]; }
     KG_SYNC();
-    kg_ctrl_from_action(ws, act, kg_lane);
+    {
+        const float a6[6] = {sxy[0], sxy[1], act[0], act[1], act[2], act[3]};
+        kg_ctrl_from_action(ws, a6, kg_lane);
+    }
     KG_PROBE(19);
     kg_kinematics(m, ws, kg_lane);
     KG_PROBE(0);
@@ -2088,9 +2101,12 @@ template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEn
             if (A.load) A.load[env] = d ? 0 : ws.stat_newton + 2 * ws.stat_mpr;   // a finished episode restarts contact-free
             if (action_out) for (int c = 0; c < 4; c++) action_out[c * N + env] = A.last_action[c * N + env];
 #if defined(__CUDA_ARCH__)
-            if (A.stats) { atomicAdd(A.stats, ws.stat_mpr); atomicAdd(A.stats + 1, ws.stat_newton); atomicAdd(A.stats + 2, ws.stat_overflow); atomicAdd(A.stats + 3, nsub); }
+            if (A.stats) {
+                atomicAdd(A.stats, (unsigned long long)ws.stat_mpr); atomicAdd(A.stats + 1, (unsigned long long)ws.stat_newton);
+                atomicAdd(A.stats + 2, (unsigned long long)ws.stat_overflow); atomicAdd(A.stats + 3, (unsigned long long)nsub);
+            }
 #else
-            if (A.stats) { A.stats[0] += ws.stat_mpr; A.stats[1] += ws.stat_newton; A.stats[2] += ws.stat_overflow; A.stats[3] += nsub; }
+            if (A.stats) { A.stats[0] += (unsigned long long)ws.stat_mpr; A.stats[1] += (unsigned long long)ws.stat_newton; A.stats[2] += (unsigned long long)ws.stat_overflow; A.stats[3] += (unsigned long long)nsub; }
 #endif
         }
     }
@@ -2100,8 +2116,9 @@ template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEn
 // reset of one env (ENV:1310-1410 without the file system): hand euler -> quaternion, hand joints 0, object at
 // obj_pos with identity orientation, velocities and warm start 0, forward kinematics + rays + first obs,
 // centroid fix-up (ENV:1382-1389), expert-controller episode state (EXP:367-379, 724-727).
+// handp = the slide joint positions determine_hand_location (ENV:1286-1307) puts into qpos[0:3] (0 for 'normal').
 template <class WS> KG_DEV void kg_env_reset(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, int shape, const float *euler, const float *objp,
-                         float *obs_out, int kg_lane) {
+                         const float *handp, float *obs_out, int kg_lane) {
     float hq[4] = {1, 0, 0, 0};
     for (int i = 0; i < 3; i++) {   // MuJoCo eulerseq "xyz": q = qx qy qz
         float s, c;
@@ -2124,7 +2141,10 @@ template <class WS> KG_DEV void kg_env_reset(const KgModel &m, WS &ws, const KgE
     }
     KG_SYNC();
     KG_PHASE(l) {
-        if (l == 0) { ws.qpos[9] = objp[0]; ws.qpos[10] = objp[1]; ws.qpos[11] = objp[2]; ws.qpos[12] = 1.f; }
+        if (l == 0) {
+            ws.qpos[0] = handp[0]; ws.qpos[1] = handp[1]; ws.qpos[2] = handp[2];
+            ws.qpos[9] = objp[0]; ws.qpos[10] = objp[1]; ws.qpos[11] = objp[2]; ws.qpos[12] = 1.f;
+        }
     }
     KG_SYNC();
     kg_episode_constants(m, ws, hq, shape, kg_lane);

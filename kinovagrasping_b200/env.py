@@ -142,27 +142,52 @@ class _Box:
         self.shape = self.low.shape
 
 
+# The reference keeps two pieces of state in FILES that outlive an env object (MAIN:381 builds a new env per episode and
+# relies on them): the remaining Latin-square shape list in ./objects.csv / ./eval_objects.csv (ENV:961-999) and the hand
+# euler inside each shape's XML (ENV:851-877).  Unless persist_objects_csv=True, the lists live here, keyed by filename.
+_MEM_FILES = {}
+# euler of body j2s7s300_link_7 as the shipped XMLs hold it (XML:59 of each file); write_xml overwrites it
+_XML_EULER = {k: [-1.57, 0.0, -1.57] for k in SHAPES}
+_XML_EULER["CubeS"] = [-0.06, -0.16, -0.13]
+
+
+def truncate_euler(rot):
+    """write_xml (ENV:870-874): every component goes into the XML as the first 5 characters of str(value)."""
+    out = []
+    for v in rot:
+        t = str(np.float64(v))[0:5]
+        try:
+            out.append(float(t))
+        except ValueError:          # e.g. '-8.7e' -- the XML would not load in the reference either
+            raise ValueError(f"hand euler {v!r} does not survive the reference's 5-character truncation")
+    return out
+
+
 class KinovaGripper_Env:
-    """Single-env facade with the reference's signatures.  Shape / orientation / pose selection follows
-    ENV:1149-1283 (Latin-square shape list popped from the end, np.random orientation thresholds, uniformly drawn
-    pose row with the 5-character euler truncation); the objects.csv round trip is kept in memory unless
-    `persist_objects_csv=True`."""
+    """Single-env facade with the reference's signatures; also stands in for gym's TimeLimit wrapper (`.env` is self).
+    Shape / orientation / pose selection restates ENV:884-1054 and ENV:1149-1410 call for call (same np.random draws in
+    the same order, the same list/"file" bookkeeping and the same quirks -- each noted where it happens), so
+    main_DDPGfD.py / expert_data.py run unchanged on it (tests/test_callsite.py)."""
     metadata = {"render.modes": ["human"]}
 
-    def __init__(self, arm_or_end_effector="hand", frame_skip=15, device=0, lib=None, persist_objects_csv=False):
+    def __init__(self, arm_or_end_effector="hand", frame_skip=15, device=0, lib=None, persist_objects_csv=False, handle=None):
         if arm_or_end_effector != "hand":
             print("CHOOSE EITHER HAND OR ARM")      # the arm model is out of scope (SURVEY 2)
             raise ValueError
         self.card = ModelCard()
-        self.h = Handle(1, device=device, lib=lib)
+        self.h = handle if handle is not None else Handle(1, device=device, lib=lib)
         self.h.set_frame_skip(frame_skip)
+        self.h.set_action_dim(6)                    # step() pads 4-d actions itself, as ENV:1502-1503 does
         self.frame_skip = frame_skip
-        self._max_episode_steps = 100
+        self._max_episode_steps = 100               # gym registration (gym_kinova_gripper/__init__.py:3-7)
         self.h.set_max_episode_steps(10 ** 9)       # TimeLimit is applied by this wrapper (gym semantics)
         self._elapsed_steps = 0
         self.pid = False
+        self.state_rep = "local"
         self.with_grasp_reward = False
         self.Grasp_Reward = False
+        self.obj_size = "m"                         # ENV:62; never changed on the Latin-square path
+        self.filename = "/kinova_description/j2s7s300_end_effector_v1_mbox.xml"
         self.orientation = "normal"
         self.random_shape = "CubeS"
         self.orientation_idx = 0
@@ -173,57 +198,136 @@ class KinovaGripper_Env:
         self.obj_keys = []
         self.all_objects = {k: f"/kinova_description/j2s7s300_end_effector_v1_{k}.xml" for k in SHAPES}
         self.action_space = _Box([-0.8] * 4, [0.8] * 4)
-        self.Tfw = np.zeros([4, 4])
+        self.Tfw = np.zeros([4, 4])                 # ENV:110: a new env has no hand frame yet
         self.wrist_pose = np.zeros(3)
         self.persist = persist_objects_csv
         self.env = self                               # gym's TimeLimit exposes the raw env as .env
         self.np_random = np.random
+        self._shape_id = 0
+        self._euler = list(_XML_EULER["CubeS"])
+        self._last_obs = np.zeros(82, dtype=np.float32)
 
-    # ---- small accessors used by MAIN / EXP
+    # ---- small accessors used by MAIN / EXP (ENV:748-805)
     def seed(self, seed=None):
         np.random.seed(seed)
         return [seed]
+    def set_obj_coords(self, x, y, z): self.obj_coords[0] = x; self.obj_coords[1] = y; self.obj_coords[2] = z
     def get_obj_coords(self): return self.obj_coords
-    def get_orientation(self): return self.orientation
-    def get_orientation_idx(self): return self.orientation_idx
-    def get_coords_filename(self): return self.coords_filename
+    def set_random_shape(self, shape): self.random_shape = shape
     def get_random_shape(self): return self.random_shape
-    def set_with_grasp_reward(self, v): self.with_grasp_reward = v
+    def set_orientation_idx(self, idx): self.orientation_idx = idx
+    def get_orientation_idx(self): return self.orientation_idx
+    def set_obj_coord_region(self, region): self.obj_coord_region = region
+    def get_obj_coord_region(self): return self.obj_coord_region
+    def get_orientation(self): return self.orientation
+    def set_orientation(self, orientation): self.orientation = orientation
     def get_with_grasp_reward(self): return self.with_grasp_reward
+    def set_with_grasp_reward(self, with_grasp): self.with_grasp_reward = with_grasp
+    def get_coords_filename(self): return self.coords_filename
+    def set_coords_filename(self, coords_filename): self.coords_filename = coords_filename
     def get_all_objects(self): return self.all_objects
     def get_obj_keys(self): return self.obj_keys
 
-    def check_obj_file_empty(self, filename):
+    # ---- the shape-list "files" (ENV:884-893, 961-999)
+    def _file_exists(self, filename):
+        return os.path.exists(filename) if self.persist else filename in _MEM_FILES
+
+    def _file_write(self, filename, keys):
         if self.persist:
-            if not os.path.exists(filename):
-                return False
+            with open(filename, "w", newline="") as f:
+                w = csv.writer(f)
+                for key in keys:
+                    w.writerow(key)      # one character per column, as the reference writes it (ENV:961-964)
+        else:
+            _MEM_FILES[filename] = list(keys)
+
+    def _file_read(self, filename):
+        if self.persist:
+            with open(filename, newline="") as f:
+                return ["".join(row) for row in csv.reader(f)]
+        return list(_MEM_FILES[filename])
+
+    def check_obj_file_empty(self, filename):
+        """ENV:884-893: a MISSING file counts as not empty."""
+        if not self._file_exists(filename):
+            return False
+        if self.persist:
             with open(filename, "r") as f:
                 return not f.read(1)
-        return len(self.obj_keys) == 0
+        return len(_MEM_FILES[filename]) == 0
 
     def experiment(self, shape_keys):
+        """ENV:807-818: keys ACCUMULATE in self.objects over calls; a mismatch with the request is an error."""
         for key in shape_keys:
-            if key not in self.all_objects:
-                print("Invlaid shape key requested")
-                raise ValueError
-            self.objects[key] = self.all_objects[key]
+            self.objects[key] = self.all_objects[key]     # KeyError for a shape outside the set, as in the reference
         if len(shape_keys) == 0:
             print("No shape keys")
+            raise ValueError
+        elif len(shape_keys) != len(self.objects):
+            print("Invlaid shape key requested")
             raise ValueError
         return self.objects
 
     def Generate_Latin_Square(self, max_elements, filename, shape_keys, test=False):
+        """ENV:895-964: APPENDS max_elements keys to self.obj_keys, then writes the whole list to the file."""
         self.objects = self.experiment(shape_keys)
         self.obj_keys = self.obj_keys + latin_square_keys(list(self.objects.keys()), max_elements)
-        if self.persist:
-            with open(filename, "w", newline="") as f:
-                w = csv.writer(f)
-                for key in self.obj_keys:
-                    w.writerow(key)      # one character per column, as the reference writes it (ENV:961-964)
+        self._file_write(filename, self.obj_keys)
+
+    def objects_file_to_list(self, filename, num_objects, shape_keys):
+        """ENV:966-981.  Quirk kept: when the file has to be generated the keys end up in self.obj_keys TWICE (once
+        appended by Generate_Latin_Square, once more by reading the file back)."""
+        if self._file_exists(filename):
+            if self.check_obj_file_empty(filename):
+                print("Object file is empty!")
+                self.Generate_Latin_Square(num_objects, filename, shape_keys)
+        else:
+            self.Generate_Latin_Square(num_objects, filename, shape_keys)
+        for row in self._file_read(filename):
+            self.obj_keys.append(row)
+
+    def get_object(self, filename):
+        """ENV:986-1005: pop from the END, write the remaining list back."""
+        random_shape = self.obj_keys.pop()
+        self._file_write(filename, self.obj_keys)
+        return random_shape, self.objects[random_shape]
+
+    def obj_shape_generator(self, obj_params):
+        """ENV:1056-1146 for the single-geom shapes of SURVEY 2 (obj_params = [shape_name, size])."""
+        key = obj_params[0] + obj_params[1]
+        if key not in self.all_objects:
+            raise ValueError(f"object {key!r} is outside the CubeS..Vase2B set")
+        self.filename = self.all_objects[key]
+        return key
+
+    def select_object(self, env_name, shape_keys, obj_params):
+        """ENV:1149-1177."""
+        if env_name == "env":
+            obj_list_filename, num_objects = "objects.csv", 20000
+        else:
+            obj_list_filename, num_objects = "eval_objects.csv", 200
+        if len(self.objects) == 0:
+            self.objects = self.experiment(shape_keys)
+        if len(self.obj_keys) == 0:
+            self.objects_file_to_list(obj_list_filename, num_objects, shape_keys)
+        if obj_params is None:
+            random_shape, self.filename = self.get_object(obj_list_filename)
+        else:
+            random_shape = self.obj_shape_generator(obj_params)
+        return random_shape
 
     def select_orienation(self, random_shape, hand_orientation):
+        """ENV:1180-1222 (same np.random calls, including the RBowl / Lemon branches)."""
         orientation_type = 0.330
-        if hand_orientation == "random":
+        if random_shape.find("RBowl") != -1:
+            if hand_orientation == "random":
+                orientation_type = np.random.uniform(0.333, 1)
+        elif random_shape.find("Lemon") != -1:
+            if hand_orientation == "random":
+                Choice1 = np.random.uniform(0, 0.333)
+                Choice2 = np.random.uniform(0.667, 1)
+                orientation_type = np.random.choice([Choice1, Choice2])
+        elif hand_orientation == "random":
             orientation_type = np.random.rand()
         if orientation_type < 0.333:
             return "normal"
@@ -231,79 +335,138 @@ class KinovaGripper_Env:
             return "top"
         return "rotated"
 
+    def _get_obj_size(self):
+        """ENV:706-746 for a single-geom object: the mesh geom's box half sizes with the axis re-ordering heuristic."""
+        size = [float(v) for v in self.card.get("mesh_geom").reshape(17, 15)[3 + self._shape_id, 8:11]]
+        if size[2] == 0:
+            size[2] = size[1]; size[1] = size[0]
+        diffs = [abs(size[0] - size[1]), abs(size[1] - size[2]), abs(size[0] - size[2])]
+        if int(np.argmin(diffs)) != 0:
+            size[0], size[2] = size[2], size[0]
+        return [max(size[0], 0), max(size[1], 0), 0 + size[2]]
+
+    def determine_hand_location(self):
+        """ENV:1286-1307.  Evaluated BEFORE the new hand euler is written, so self.Tfw is still the previous episode's
+        (all zeros for a freshly constructed env, ENV:110): the quirk SURVEY 8a documents."""
+        if self.orientation == "normal":
+            return 0, 0, 0, 0, 0, 0
+        if self.orientation == "top":
+            Z = {"b": 0.15, "m": 0.14, "s": 0.13}[self.obj_size]
+            stuff = np.matmul(self.Tfw[0:3, 0:3], [-0.005, -0.155, Z + 0.06])
+            return -stuff[0], -stuff[1], stuff[2], 0, 0, 0
+        temp = np.matmul(self.Tfw[0:3, 0:3], np.array([0.051, -0.075, 0.06]))
+        return -temp[0], -temp[1], temp[2], 0, 0, 0
+
+    def sample_initial_object_hand_pos(self, coords_filename, with_noise=True, orient_idx=None, region=None):
+        """ENV:1008-1054 on the model card's copy of the coordinate file (file line 0 is consumed by the delimiter
+        sniffing, ENV:1012, so data[i] is file line i + 1).  Quirk kept: with a region, the index is drawn over the
+        FILTERED list but then applied to the unfiltered one (ENV:1040-1046)."""
+        mode = "test" if "/test_coords/" in coords_filename else "train"
+        tab = self.card.pose(mode)[self._shape_id, ORIENTATIONS.index(self.orientation)]
+        data = [[float(r[0]), float(r[1]), float(r[2])] + ([float(r[3]), float(r[4]), float(r[5])] if with_noise is True else [0, 0, 0]) for r in tab[1:]]
+        if orient_idx is None:
+            if region is not None:
+                all_regions = {"left": [-.09, -.03], "center": [-.03, .03], "target": [-.01, .01], "right": [.03, .09], "origin": [0, 0]}
+                if region == "origin":
+                    return 0, 0, data[0][2], 0, 0, 0, None
+                sampling_range = all_regions[region]
+                region_data = [d for d in data if sampling_range[0] <= d[0] <= sampling_range[1]]
+                orient_idx = np.random.randint(0, len(region_data))
+            else:
+                orient_idx = np.random.randint(0, len(data))
+        c = data[orient_idx]
+        return c[0], c[1], c[2], c[3], c[4], c[5], orient_idx
+
+    def write_xml(self, new_rotation):
+        """ENV:851-881 without the file system: the hand euler the shape's XML now holds (5-character truncation)."""
+        self._euler = truncate_euler(new_rotation)
+        _XML_EULER[self.random_shape] = list(self._euler)
+
+    def determine_obj_hand_coords(self, random_shape, mode, with_noise=True):
+        """ENV:1225-1283."""
+        if with_noise is not True:
+            # the no_noise directories are capitalised ('Normal/') while the path is built in lower case (ENV:1245): on a
+            # case-sensitive file system the reference fails right here
+            raise FileNotFoundError("obj_hand_coords/no_noise/<mode>_coords/" + str(self.orientation) + "/" + random_shape + ".txt")
+        if mode != "test":
+            mode = "train"
+        coords_filename = ("gym_kinova_gripper/envs/kinova_description/obj_hand_coords/with_noise/" + str(mode) + "_coords/"
+                           + str(self.orientation) + "/" + random_shape + ".txt")
+        obj_x, obj_y, obj_z, hand_x, hand_y, hand_z, orient_idx = self.sample_initial_object_hand_pos(
+            coords_filename, with_noise=with_noise, orient_idx=None, region=self.obj_coord_region)
+        self.write_xml(np.array([hand_x, hand_y, hand_z]))
+        return obj_x, obj_y, obj_z, hand_x, hand_y, hand_z, orient_idx, coords_filename
+
     # ---- reset / step with the reference's signatures
     def reset(self, shape_keys, hand_orientation, with_grasp=False, env_name="env", mode="train", start_pos=None,
               obj_params=None, qpos=None, obj_coord_region=None, with_noise=True):
+        """ENV:1310-1410."""
         self.set_with_grasp_reward(with_grasp)
-        self.obj_coord_region = obj_coord_region
-        if len(self.objects) == 0:
-            self.objects = self.experiment(shape_keys)
-        if len(self.obj_keys) == 0:
-            self.Generate_Latin_Square(20000 if env_name == "env" else 200, "objects.csv" if env_name == "env" else "eval_objects.csv", shape_keys)
-        if obj_params is None:
-            random_shape = self.obj_keys.pop()
-        else:
-            random_shape = obj_params[0] + obj_params[1]
-        self.random_shape = random_shape
-        self.orientation = self.select_orienation(random_shape, hand_orientation)
-        shape_id = SHAPES.index(random_shape)
-        tab = self.card.pose("test" if mode == "test" else "train")[shape_id, ORIENTATIONS.index(self.orientation)]
-        data = tab[1:]                               # the reference drops file line 0 (ENV:1012)
+        self.set_obj_coord_region(obj_coord_region)
+        random_shape = self.select_object(env_name, shape_keys, obj_params)
+        self.set_random_shape(random_shape)
+        self._shape_id = SHAPES.index(random_shape)
+        self._euler = list(_XML_EULER[random_shape])       # load_model_from_path of that shape's XML (ENV:1002)
+        self.set_orientation(self.select_orienation(random_shape, hand_orientation))
+        xloc, yloc, zloc, f1prox, f2prox, f3prox = self.determine_hand_location()
+        if qpos is not None:
+            raise NotImplementedError("reset(qpos=...) (ENV:349-353) is a test hook outside the hot path")
         if start_pos is None:
-            if obj_coord_region is not None and obj_coord_region != "origin":
-                rng = {"left": [-.09, -.03], "center": [-.03, .03], "target": [-.01, .01], "right": [.03, .09]}[obj_coord_region]
-                cand = np.nonzero((data[:, 0] >= rng[0]) & (data[:, 0] <= rng[1]))[0]
-                idx = int(cand[np.random.randint(0, len(cand))])
-            else:
-                idx = int(np.random.randint(0, len(data)))
-            row = data[idx]
-            obj = [float(row[0]), float(row[1]), float(row[2])]
-            euler = [float(row[6]), float(row[7]), float(row[8])] if with_noise else [0.0, 0.0, 0.0]
-            if obj_coord_region == "origin":
-                obj, euler, idx = [0.0, 0.0, float(data[0][2])], [0.0, 0.0, 0.0], None
-            self.orientation_idx = idx
-            self.coords_filename = ("gym_kinova_gripper/envs/kinova_description/obj_hand_coords/" + ("with_noise/" if with_noise else "no_noise/")
-                                    + ("test" if mode == "test" else "train") + "_coords/" + self.orientation + "/" + random_shape + ".txt")
+            obj_x, obj_y, obj_z, hand_x, hand_y, hand_z, orient_idx, coords_filename = self.determine_obj_hand_coords(random_shape, mode, with_noise=with_noise)
+            self.set_orientation_idx(orient_idx)
+            self.set_coords_filename(coords_filename)
+        elif len(start_pos) == 3:
+            obj_x, obj_y, obj_z = start_pos[0], start_pos[1], start_pos[2]
+        elif len(start_pos) == 2:
+            obj_x, obj_y = start_pos[0], start_pos[1]
+            obj_z = self._get_obj_size()[-1]
         else:
-            obj = [float(start_pos[0]), float(start_pos[1]), float(start_pos[2]) if len(start_pos) > 2 else float(self.card.get("mesh_geom").reshape(17, 15)[3 + shape_id, 10])]
-            euler = [-1.57, 0.0, -1.57] if self.orientation == "normal" else ([0.0, 0.0, 0.0] if self.orientation == "top" else [-1.2, 0.0, 0.0])
-        obs = self.h.reset_host(np.array([shape_id], dtype=np.int32), np.array(euler, dtype=np.float32).reshape(3, 1),
-                                np.array(obj, dtype=np.float32).reshape(3, 1))
-        self.obj_coords = obj
-        self._elapsed_steps = 0
+            xloc, yloc, zloc, f1prox, f2prox, f3prox = start_pos[0], start_pos[1], start_pos[2], start_pos[3], start_pos[4], start_pos[5]
+            obj_x, obj_y, obj_z = start_pos[6], start_pos[7], start_pos[8]
+        if f1prox != 0 or f2prox != 0 or f3prox != 0:
+            raise NotImplementedError("non-zero proximal start angles (9-value start_pos) are outside the hot path")
         self.Grasp_Reward = False
+        obs = self.h.reset_host(np.array([self._shape_id], dtype=np.int32), np.array(self._euler, dtype=np.float32).reshape(3, 1),
+                                np.array([obj_x, obj_y, obj_z], dtype=np.float32).reshape(3, 1),
+                                handpos=np.array([xloc, yloc, zloc], dtype=np.float32).reshape(3, 1))
+        self._elapsed_steps = 0
         self._last_obs = obs[:, 0]
-        self._update_frames(euler)
+        self.set_obj_coords(obj_x, obj_y, obj_z)
+        self._update_frames()
         states = [float(v) for v in obs[:, 0]]
         if self.pid:
-            states = states + [states[81]]
+            states = states + [states[81]]      # ENV:530-531
         return states
 
-    def _update_frames(self, euler):
+    def _update_frames(self):
         # Tfw / wrist_pose as _get_trans_mat_wrist_pose leaves them (ENV:274-288); host copy for callers that read env.Tfw
         from .hostmath import hand_frame_from_euler
-        self.Tfw, self.wrist_pose = hand_frame_from_euler(self.card, euler, self.h.get_state_host()[0][:3, 0])
+        self.Tfw, self.wrist_pose = hand_frame_from_euler(self.card, self._euler, self.h.get_state_host()[0][:3, 0])
 
     def step(self, action, graspnetwork=False):
-        action = np.asarray(action, dtype=np.float32).reshape(-1)
-        if len(action) == 6:
-            action = action[2:6]                     # [0, 0, wrist, f1, f2, f3] (ENV:1502-1503)
-        obs, rew, done = self.h.step_host(action.reshape(4, 1), 0)
+        """ENV:1495-1552 under gym's TimeLimit."""
+        action = [float(v) for v in np.asarray(action, dtype=np.float64).reshape(-1)]
+        if len(action) == 4:
+            action = [0, 0, action[0], action[1], action[2], action[3]]      # ENV:1502-1503
+        obs, rew, done = self.h.step_host(np.array(action[0:6], dtype=np.float32).reshape(6, 1), 0)
         self._elapsed_steps += 1
         lift = float(rew[0])
         d = bool(lift > 0)
         if self._elapsed_steps >= self._max_episode_steps:
             d = True
         self._last_obs = obs[:, 0]
+        self._update_frames()
         states = [float(v) for v in obs[:, 0]]
         if self.pid:
             states = states + [states[81]]
         info = {"finger_reward": 0.0, "grasp_reward": 0.0, "lift_reward": lift}
         return states, lift, d, info
 
-    def _get_obs(self, state_rep="local"):
+    def _get_obs(self, state_rep=None):
         """ENV:438-534: the observation of the current state, 82 values in the wrist frame ("local") or 74 in the world
         frame ("global"; enabled on first use, valid from the next reset / step on)."""
+        if state_rep is None:
+            state_rep = self.state_rep
         if state_rep == "local":
             return [float(v) for v in self._last_obs]
         if state_rep == "global":
@@ -314,8 +477,18 @@ class KinovaGripper_Env:
             return [float(v) for v in self.h.obs_global_host()[:, 0]]
         raise ValueError(f"unknown state_rep {state_rep!r}")
 
+    def _get_obj_pose(self):
+        """ENV:564-566: world position of the object geom (entries 21:24 of the global layout)."""
+        return np.array(self._get_obs("global")[21:24])
+
     def _get_dot_product(self, obj_state=None):
         return float(self._last_obs[81])
+
+    def render_img(self, *a, **k):
+        return None                                  # rendering is out of scope (SURVEY 2)
+
+    def render(self, *a, **k):
+        return None
 
     def close(self):
         self.h.close()

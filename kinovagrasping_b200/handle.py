@@ -55,6 +55,18 @@ class Handle:
     def reset(self, mask, shape, euler, objpos, obs):
         self._chk(self.lib.kg_reset(self.h, mask or None, shape, euler, objpos, obs or None), "kg_reset")
 
+    def reset_pose(self, mask, shape, euler, objpos, handpos, obs):
+        self._chk(self.lib.kg_reset_pose(self.h, mask or None, shape, euler, objpos, handpos or None, obs or None), "kg_reset_pose")
+
+    def set_hand_location(self, mode):
+        """0 = slides start at 0 (a new env per episode, MAIN:381); 1 = determine_hand_location with the previous episode's Tfw (EXP:696)."""
+        self._chk(self.lib.kg_set_hand_location(self.h, int(mode)), "kg_set_hand_location")
+
+    def set_action_dim(self, dim):
+        """4 = [wrist, f1, f2, f3]; 6 = [slide_x, slide_y, slide_z, f1, f2, f3] (ENV:1502-1503)."""
+        self._chk(self.lib.kg_set_action_dim(self.h, int(dim)), "kg_set_action_dim")
+        self.act_dim = int(dim)
+
     def reset_sampled(self, mask, shape, orient, variant, test_table, seed, obs):
         self._chk(self.lib.kg_reset_sampled(self.h, mask or None, shape or None, int(orient), int(variant), int(test_table),
                                             C.c_uint64(int(seed) & (2 ** 64 - 1)), obs or None), "kg_reset_sampled")
@@ -136,20 +148,21 @@ class Handle:
         return {"mpr_pairs": out[0], "newton_iters": out[1], "contact_overflow": out[2], "substeps": out[3]}
 
     # ---- host-buffer API (numpy)
-    def reset_host(self, shape, euler, objpos, mask=None):
+    def reset_host(self, shape, euler, objpos, mask=None, handpos=None):
         n = self.n
         shape = np.ascontiguousarray(shape, dtype=np.int32).reshape(n)
         euler = np.ascontiguousarray(euler, dtype=np.float32).reshape(3, n)
         objpos = np.ascontiguousarray(objpos, dtype=np.float32).reshape(3, n)
         obs = np.zeros((82, n), dtype=np.float32)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.int32).reshape(n)
-        self._chk(self.lib.kg_reset_host(self.h, None if m is None else _np_ptr(m), _np_ptr(shape), _np_ptr(euler), _np_ptr(objpos),
-                                         _np_ptr(obs)), "kg_reset_host")
+        hp = None if handpos is None else np.ascontiguousarray(handpos, dtype=np.float32).reshape(3, n)
+        self._chk(self.lib.kg_reset_pose_host(self.h, None if m is None else _np_ptr(m), _np_ptr(shape), _np_ptr(euler), _np_ptr(objpos),
+                                              None if hp is None else _np_ptr(hp), _np_ptr(obs)), "kg_reset_pose_host")
         return obs
 
     def step_host(self, action=None, expert_mode=0, obs_out=None, reward_out=None, done_out=None):
         n = self.n
-        a = None if action is None else np.ascontiguousarray(action, dtype=np.float32).reshape(4, n)
+        a = None if action is None else np.ascontiguousarray(action, dtype=np.float32).reshape(getattr(self, "act_dim", 4), n)
         obs = np.zeros((82, n), dtype=np.float32) if obs_out is None else obs_out
         rew = np.zeros(n, dtype=np.float32) if reward_out is None else reward_out
         done = np.zeros(n, dtype=np.int32) if done_out is None else done_out

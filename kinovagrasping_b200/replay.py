@@ -62,14 +62,30 @@ class ReplayBuffer_Queue:
 
     # ------------------------------------------------------------------ storage
     def _alloc(self, T):
+        """(Re)allocate the ring for episodes of up to T steps.  Growing replaces every storage AND staging tensor, so
+        anything that captured their addresses (a CUDA graph around sample_windows) is stale afterwards:
+        `storage_version` is bumped and GraphedUpdates re-captures when it changes."""
         f = dict(dtype=torch.float32, device=self.device)
-        new = [torch.zeros((self.cap, T, self.state_dim), **f), torch.zeros((self.cap, T, self.action_dim), **f),
-               torch.zeros((self.cap, T, self.state_dim), **f), torch.zeros((self.cap, T), **f), torch.zeros((self.cap, T), **f)]
-        if hasattr(self, "state"):
-            for old, nw in zip((self.state, self.action, self.next_state, self.reward, self.not_done), new):
-                nw[:, :old.shape[1]] = old
-        self.state, self.action, self.next_state, self.reward, self.not_done = new
+
+        def grown(names, lead):
+            new = [torch.zeros((lead, T, self.state_dim), **f), torch.zeros((lead, T, self.action_dim), **f),
+                   torch.zeros((lead, T, self.state_dim), **f), torch.zeros((lead, T), **f), torch.zeros((lead, T), **f)]
+            if hasattr(self, names[0]):
+                for nm, nw in zip(names, new):
+                    old = getattr(self, nm)
+                    nw[:, :old.shape[1]] = old
+            for nm, nw in zip(names, new):
+                setattr(self, nm, nw)
+        grown(("state", "action", "next_state", "reward", "not_done"), self.cap)
+        if getattr(self, "n_envs", 0) and hasattr(self, "st_state"):
+            grown(("st_state", "st_action", "st_next", "st_reward", "st_notdone"), self.n_envs)
         self.T = T
+        self.storage_version = getattr(self, "storage_version", -1) + 1
+
+    def _sync_lengths(self):
+        if self._host_len_dirty:                   # the vectorised feeder only updates the device copy
+            self.lengths[:] = self.len_dev.cpu().numpy()
+            self._host_len_dirty = False
 
     def _row(self, logical):
         return (self.head + logical) % self.cap
@@ -79,7 +95,9 @@ class ReplayBuffer_Queue:
 
     # ------------------------------------------------------------------ reference single-transition API
     def add(self, state, action, next_state, reward, done):
-        """utils.py:34-60."""
+        """utils.py:34-60.  (The reference's lists are unbounded: after remove_episode(-1) the next episode is appended to
+        the short one, so a row can outgrow max_episode_len -- the ring then grows, see _alloc.)"""
+        self._sync_lengths()
         row = self._row(self.replay_ep_num)
         t = int(self.lengths[row])
         if t >= self.T:
@@ -106,14 +124,32 @@ class ReplayBuffer_Queue:
         self.len_dev[row] = 0
 
     def remove_episode(self, idx=0):
-        """utils.py:62-79 (FIFO: only the oldest episode can be dropped from a ring)."""
-        if idx != 0:
-            raise ValueError("the device ring evicts in FIFO order only")
-        self.head = (self.head + 1) % self.cap
-        if self.episodes:
-            self.episodes.pop(0)
+        """utils.py:62-79: `list.pop(idx)` on the per-episode lists, whose entries are the replay_ep_num closed episodes
+        followed by the one in progress.  idx 0 is the FIFO eviction.  main_DDPGfD.py:470-471 calls it with -1 for an
+        episode too short to train on -- which pops the (empty) in-progress entry, so the short episode itself becomes the
+        episode in progress again and the next episode's transitions are appended to it.  Reproduced as is."""
+        self._sync_lengths()
+        n_rows = self.replay_ep_num + 1
+        i = idx + n_rows if idx < 0 else idx
+        if not 0 <= i < n_rows:
+            raise IndexError("pop index out of range")
+        if i == 0:
+            self.lengths[self._row(0)] = 0
+            self.len_dev[self._row(0)] = 0
+            self.head = (self.head + 1) % self.cap
+        else:
+            for j in range(i, n_rows - 1):          # close the gap (rare: only the ends are ever popped by the reference's callers)
+                a, b = self._row(j), self._row(j + 1)
+                for x in (self.state, self.action, self.next_state, self.reward, self.not_done):
+                    x[a] = x[b]
+                self.lengths[a] = self.lengths[b]
+            last = self._row(n_rows - 1)
+            self.lengths[last] = 0
+            self.len_dev.copy_(torch.from_numpy(self.lengths))
+        if self.episodes:                            # (only maintained by callers that use add_episode)
+            self.episodes.pop(idx)
         if len(self.orientation_indexes) > 0:
-            self.orientation_indexes.pop(0)
+            self.orientation_indexes.pop(idx)
         self.replay_ep_num -= 1
 
     def add_episode(self, start):
@@ -141,6 +177,7 @@ class ReplayBuffer_Queue:
         if not done:
             print("Can only replace last time step of the latest episode")
             raise ValueError
+        self._sync_lengths()
         row = self._row(self.replay_ep_num)
         idx = int(self.lengths[row]) - 1
         old_reward = float(self.reward[row, idx])
@@ -154,9 +191,7 @@ class ReplayBuffer_Queue:
         return old_reward
 
     def episode_length(self, logical):
-        if self._host_len_dirty:                   # the vectorised feeder only updates the device copy
-            self.lengths[:] = self.len_dev.cpu().numpy()
-            self._host_len_dirty = False
+        self._sync_lengths()
         return int(self.lengths[self._row(logical)])
 
     def episode(self, logical):
@@ -285,42 +320,107 @@ class ReplayBuffer_Queue:
 
     # ------------------------------------------------------------------ persistence (utils.py:345-460 layout)
     def save_replay_buffer(self, save_filepath):
-        """Eight np.save files with the reference's names; episodes as object arrays of per-episode lists."""
+        """utils.py:345-367: eight np.save files with the reference's names; the per-episode fields are object arrays of
+        per-episode lists, closed episodes followed by the entry of the episode in progress.  Returns the directory WITH
+        a trailing '/', as the reference does (its loader concatenates file names onto it)."""
         import os
         os.makedirs(save_filepath, exist_ok=True)
+        save_filepath += "/"
         n = self.replay_ep_num
 
         def obj(field):
             a = np.empty(n + 1, dtype=object)
-            for i in range(n):
+            for i in range(n + 1):
                 row, ln = self._row(i), self.episode_length(i)
                 a[i] = [np.asarray(v) for v in field[row, :ln].cpu().numpy()]
-            a[n] = []
             return a
-        np.save(os.path.join(save_filepath, "state"), obj(self.state), allow_pickle=True)
-        np.save(os.path.join(save_filepath, "action"), obj(self.action), allow_pickle=True)
-        np.save(os.path.join(save_filepath, "next_state"), obj(self.next_state), allow_pickle=True)
-        np.save(os.path.join(save_filepath, "reward"), obj(self.reward), allow_pickle=True)
-        np.save(os.path.join(save_filepath, "not_done"), obj(self.not_done), allow_pickle=True)
-        np.save(os.path.join(save_filepath, "episodes"), np.array(self.episodes, dtype=object), allow_pickle=True)
-        np.save(os.path.join(save_filepath, "episodes_info"), np.array([self.max_episode, self.size, self.episodes_count, self.replay_ep_num]), allow_pickle=True)
-        np.save(os.path.join(save_filepath, "orientation_indexes"), np.array(self.orientation_indexes, dtype=object), allow_pickle=True)
+
+        def ragged(lst):
+            a = np.empty(len(lst), dtype=object)
+            for i, v in enumerate(lst):
+                a[i] = v
+            return a
+        np.save(save_filepath + "state", obj(self.state), allow_pickle=True)
+        np.save(save_filepath + "action", obj(self.action), allow_pickle=True)
+        np.save(save_filepath + "next_state", obj(self.next_state), allow_pickle=True)
+        np.save(save_filepath + "reward", obj(self.reward), allow_pickle=True)
+        np.save(save_filepath + "not_done", obj(self.not_done), allow_pickle=True)
+        np.save(save_filepath + "episodes", ragged(self.episodes), allow_pickle=True)
+        np.save(save_filepath + "episodes_info", [self.max_episode, self.size, self.episodes_count, self.replay_ep_num])
+        np.save(save_filepath + "orientation_indexes", ragged(self.orientation_indexes), allow_pickle=True)
         return save_filepath
 
+    def _set_capacity(self, max_episode):
+        """Re-seat the ring for a larger max_episode (store_saved_data_into_replay adds the file's to ours)."""
+        self._sync_lengths()
+        k = self.replay_ep_num + 1
+        order = [self._row(i) for i in range(k)]
+        old = (self.state, self.action, self.next_state, self.reward, self.not_done)
+        old_len = self.lengths[order].copy()
+        self.max_episode = int(max_episode)
+        self.cap = self.max_episode + 2
+        for nm in ("state", "action", "next_state", "reward", "not_done"):
+            delattr(self, nm)
+        self.lengths = np.zeros(self.cap, dtype=np.int64)
+        self.len_dev = torch.zeros(self.cap, dtype=torch.long, device=self.device)
+        self.head = 0
+        self._alloc(self.T)
+        idx = torch.as_tensor(order, dtype=torch.long, device=self.device)
+        for o, nm in zip(old, ("state", "action", "next_state", "reward", "not_done")):
+            getattr(self, nm)[:k] = o[idx]
+        self.lengths[:k] = old_len
+        self.len_dev.copy_(torch.from_numpy(self.lengths))
+        self._meta_host = (-1, -1)
+
     def store_saved_data_into_replay(self, filepath):
-        """Load episodes written by save_replay_buffer (ours or the reference's) and append them."""
+        """utils.py:369-460 for a buffer that is still empty (the only way main_DDPGfD.py uses it, MAIN:1186): the saved
+        per-episode lists become this buffer's rows, max_episode / size / episodes_count / replay_ep_num are ADDED to, and
+        the trailing empty entry is popped with remove_episode(-1) -- which also takes 1 off replay_ep_num, so the last
+        saved episode ends up as the episode in progress (reference behaviour, kept).  Loading into a non-empty buffer
+        (the reference's list.extend path leaves an empty row in the middle of its lists and then samples it) appends the
+        saved episodes one by one instead."""
         import os
-        st = np.load(os.path.join(filepath, "state.npy"), allow_pickle=True)
-        ac = np.load(os.path.join(filepath, "action.npy"), allow_pickle=True)
-        ns = np.load(os.path.join(filepath, "next_state.npy"), allow_pickle=True)
-        rw = np.load(os.path.join(filepath, "reward.npy"), allow_pickle=True)
-        nd = np.load(os.path.join(filepath, "not_done.npy"), allow_pickle=True)
-        for e in range(len(st)):
-            if len(st[e]) == 0:
-                continue
-            self.add_episode(1)
-            for t in range(len(st[e])):
-                self.add(st[e][t], ac[e][t], ns[e][t], rw[e][t], 1.0 - float(nd[e][t]) if t == len(st[e]) - 1 else 0.0)
-            if float(nd[e][-1]) != 0.0:          # an episode saved without a stored done: close it explicitly
-                self.replace(float(rw[e][-1]), True)
-            self.add_episode(0)
+        if filepath is None or os.path.isdir(filepath) is False:
+            print("Replay buffer not found!! filepath: ", filepath)
+            raise SystemExit                       # the reference calls quit()
+        ld = lambda name: np.load(filepath + name + ".npy", allow_pickle=True)
+        st, ac, ns, rw, nd = (ld(k).astype("object") for k in ("state", "action", "next_state", "reward", "not_done"))
+        episodes = ld("episodes").astype("object")
+        info = ld("episodes_info")
+        if os.path.isfile(filepath + "orientation_indexes.npy"):
+            self.orientation_indexes = ld("orientation_indexes").astype("object").tolist()
+        if self.size != 0:
+            for e in range(len(st)):
+                if len(st[e]) == 0:
+                    continue
+                self.add_episode(1)
+                for t in range(len(st[e])):
+                    self.add(st[e][t], ac[e][t], ns[e][t], rw[e][t], 1.0 - float(nd[e][t]) if t == len(st[e]) - 1 else 0.0)
+                if float(nd[e][-1]) != 0.0:          # an episode saved without a stored done: close it explicitly
+                    self.replace(float(rw[e][-1]), True)
+                self.add_episode(0)
+            return ""
+        rows = len(st)
+        longest = max([len(e) for e in st] + [1])
+        self._set_capacity(max(self.max_episode + int(info[0]), rows))
+        if longest > self.T:
+            self._alloc(longest)
+        for e in range(rows):
+            ln = len(st[e])
+            if ln:
+                self.state[e, :ln] = torch.as_tensor(np.asarray(list(st[e]), dtype=np.float32).reshape(ln, self.state_dim)).to(self.device)
+                self.action[e, :ln] = torch.as_tensor(np.asarray(list(ac[e]), dtype=np.float32).reshape(ln, self.action_dim)).to(self.device)
+                self.next_state[e, :ln] = torch.as_tensor(np.asarray(list(ns[e]), dtype=np.float32).reshape(ln, self.state_dim)).to(self.device)
+                self.reward[e, :ln] = torch.as_tensor(np.asarray(list(rw[e]), dtype=np.float32).reshape(ln)).to(self.device)
+                self.not_done[e, :ln] = torch.as_tensor(np.asarray(list(nd[e]), dtype=np.float32).reshape(ln)).to(self.device)
+            self.lengths[e] = ln
+        self.len_dev.copy_(torch.from_numpy(self.lengths))
+        self.episodes = episodes.tolist()
+        self.size += int(info[1])
+        self.episodes_count += int(info[2])
+        self.replay_ep_num += int(info[3])
+        if rows != self.replay_ep_num + 1:
+            raise ValueError(f"{filepath}: {rows} per-episode entries for replay_ep_num {self.replay_ep_num} (expected closed episodes + 1)")
+        if int(self.lengths[self._row(rows - 1)]) == 0:      # "if there is a trailing empty entry [], remove it"
+            self.remove_episode(-1)
+        return ""

@@ -94,6 +94,13 @@ void kgo_env_reset(const KgoModel *m, KgoEnv *e, int shape, const double hand_eu
 /* action: 4 values [wrist, f1, f2, f3].  returns done (incl. TimeLimit). info3 = finger,grasp,lift */
 int kgo_env_step(const KgoModel *m, KgoEnv *e, const double action[4], double obs[KGO_NOBS],
                  double *reward, double info3[3]);
+/* 6-d actions [slide_x, slide_y, slide_z, f1, f2, f3] (ENV:1502-1503, 1518-1522) and reset with slide start positions */
+int kgo_env_step6(const KgoModel *m, KgoEnv *e, const double action[6], double obs[KGO_NOBS],
+                  double *reward, double info3[3]);
+void kgo_env_reset_pose(const KgoModel *m, KgoEnv *e, int shape, const double hand_euler[3],
+                        const double obj_pos[3], const double *hand_pos, double obs[KGO_NOBS]);
+void kgo_ctrl_from_action6(const KgoData *d, const double action[6], double ctrl[KGO_NU]);
+void kgo_hand_location(const KgoData *d_prev, int orient, double hand[3]);
 void kgo_set_rays_every_substep(int on);
 void kgo_get_obs(const KgoModel *m, const KgoState *s, const KgoData *d, int global_rep, double *obs /*82 or 74*/);
 void kgo_ctrl_from_action(const KgoData *d, const double action[4], double ctrl[KGO_NU]);

@@ -74,6 +74,11 @@ def lib():
         L.kgo_env_reset.argtypes = [C.c_void_p, C.POINTER(Env), C.c_int, C.POINTER(d), C.POINTER(d), C.POINTER(d)]
         L.kgo_env_step.argtypes = [C.c_void_p, C.POINTER(Env), C.POINTER(d), C.POINTER(d), C.POINTER(d), C.POINTER(d)]
         L.kgo_env_step.restype = C.c_int
+        L.kgo_env_reset_pose.argtypes = [C.c_void_p, C.POINTER(Env), C.c_int, C.POINTER(d), C.POINTER(d), C.POINTER(d), C.POINTER(d)]
+        L.kgo_env_step6.argtypes = [C.c_void_p, C.POINTER(Env), C.POINTER(d), C.POINTER(d), C.POINTER(d), C.POINTER(d)]
+        L.kgo_env_step6.restype = C.c_int
+        L.kgo_ctrl_from_action6.argtypes = [C.POINTER(Data), C.POINTER(d), C.POINTER(d)]
+        L.kgo_hand_location.argtypes = [C.POINTER(Data), C.c_int, C.POINTER(d)]
         L.kgo_get_obs.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(Data), C.c_int, C.POINTER(d)]
         L.kgo_ctrl_from_action.argtypes = [C.POINTER(Data), C.POINTER(d), C.POINTER(d)]
         L.kgo_expert_action.argtypes = [C.POINTER(Env), C.POINTER(d), C.c_int, C.POINTER(d), C.POINTER(C.c_int)]
@@ -131,17 +136,29 @@ class Model:
         lib().kgo_get_obs(self.h, C.byref(s), C.byref(dat), 1 if global_rep else 0, out.ctypes.data_as(C.POINTER(d)))
         return out[:74] if global_rep else out
 
-    def env_reset(self, shape, hand_euler, obj_pos):
+    def env_reset(self, shape, hand_euler, obj_pos, hand_pos=None):
         e = Env()
         obs = np.zeros(NOBS)
         _, eu = _p(hand_euler); _, o = _p(obj_pos)
-        lib().kgo_env_reset(self.h, C.byref(e), shape, eu, o, obs.ctypes.data_as(C.POINTER(d)))
+        if hand_pos is None:
+            lib().kgo_env_reset(self.h, C.byref(e), shape, eu, o, obs.ctypes.data_as(C.POINTER(d)))
+        else:
+            _, hp = _p(hand_pos)
+            lib().kgo_env_reset_pose(self.h, C.byref(e), shape, eu, o, hp, obs.ctypes.data_as(C.POINTER(d)))
         return e, obs
 
+    def hand_location(self, prev_data, orient):
+        """determine_hand_location (ENV:1286-1307) from the previous episode's last forward pass (None = fresh env)."""
+        out = np.zeros(3)
+        lib().kgo_hand_location(None if prev_data is None else C.byref(prev_data), int(orient), out.ctypes.data_as(C.POINTER(d)))
+        return out
+
     def env_step(self, e, action):
+        """action: 4 values [wrist, f1, f2, f3] or 6 values [slide_x, slide_y, slide_z, f1, f2, f3]."""
         obs = np.zeros(NOBS); rew = d(); info = np.zeros(3)
-        _, a = _p(action)
-        done = lib().kgo_env_step(self.h, C.byref(e), a, obs.ctypes.data_as(C.POINTER(d)), C.byref(rew), info.ctypes.data_as(C.POINTER(d)))
+        a_, a = _p(action)
+        fn = lib().kgo_env_step6 if len(a_) == 6 else lib().kgo_env_step
+        done = fn(self.h, C.byref(e), a, obs.ctypes.data_as(C.POINTER(d)), C.byref(rew), info.ctypes.data_as(C.POINTER(d)))
         return obs, rew.value, bool(done), info
 
     def expert_action(self, e, obs, mode):

@@ -130,22 +130,43 @@ void kgo_get_obs(const KgoModel *m, const KgoState *s, const KgoData *d, int glo
     obs[n++] = dp; /* 82 */
 }
 
-/* ENV:1501-1534: ctrl from the 4-d action */
-void kgo_ctrl_from_action(const KgoData *d, const double action[4], double ctrl[KGO_NU]) {
+/* ENV:1501-1534: ctrl from the 6-d action [slide_x, slide_y, slide_z, f1, f2, f3] */
+void kgo_ctrl_from_action6(const KgoData *d, const double action[6], double ctrl[KGO_NU]) {
     HandFrame h;
     hand_frame(d, &h);
-    double a6[3] = {0, 0, action[0]}, g[3] = {0, 0, 0.733 * 10 / 25}, stuff[3], sv[3];
-    mulmv3(stuff, h.R, g);
+    double g[3] = {0, 0, 0.733 * 10 / 25}, stuff[3], sv[3];
+    mulmv3(stuff, h.R, g);                 /* ENV:1511-1515 */
     stuff[0] = -stuff[0]; stuff[1] = -stuff[1];
-    mulmv3(sv, h.R, a6);
+    mulmv3(sv, h.R, action);               /* ENV:1518-1522 (both branches negate x and y) */
     sv[0] = -sv[0]; sv[1] = -sv[1];
-    for (int i = 0; i < 3; i++) { ctrl[2 * i] = sv[i]; ctrl[2 * i + 1] = stuff[i]; ctrl[6 + i] = action[1 + i]; }
+    for (int i = 0; i < 3; i++) { ctrl[2 * i] = sv[i]; ctrl[2 * i + 1] = stuff[i]; ctrl[6 + i] = action[3 + i]; }
+}
+/* the 4-d action [wrist, f1, f2, f3] is padded to [0, 0, wrist, f1, f2, f3] (ENV:1502-1503) */
+void kgo_ctrl_from_action(const KgoData *d, const double action[4], double ctrl[KGO_NU]) {
+    double a6[6] = {0, 0, action[0], action[1], action[2], action[3]};
+    kgo_ctrl_from_action6(d, a6, ctrl);
+}
+/* determine_hand_location (ENV:1286-1307): slide start positions from the Tfw of the PREVIOUS episode (d_prev = its last
+ * forward pass; NULL = a freshly constructed env, Tfw = 0).  orient: 0 normal, 1 rotated, 2 top; obj_size 'm' (ENV:62). */
+void kgo_hand_location(const KgoData *d_prev, int orient, double hand[3]) {
+    hand[0] = hand[1] = hand[2] = 0;
+    if (orient == 0 || !d_prev) return;
+    HandFrame h;
+    hand_frame(d_prev, &h);
+    double vt[3] = {-0.005, -0.155, 0.14 + 0.06}, vr[3] = {0.051, -0.075, 0.06}, loc[3];
+    mulmv3(loc, h.R, orient == 2 ? vt : vr);
+    hand[0] = -loc[0]; hand[1] = -loc[1]; hand[2] = loc[2];
 }
 
 void kgo_env_reset(const KgoModel *m, KgoEnv *e, int shape, const double hand_euler[3], const double obj_pos[3], double obs[KGO_NOBS]) {
+    kgo_env_reset_pose(m, e, shape, hand_euler, obj_pos, NULL, obs);
+}
+/* hand_pos = qpos[0:3] as _set_state (ENV:692-703) receives them from determine_hand_location; NULL = zeros */
+void kgo_env_reset_pose(const KgoModel *m, KgoEnv *e, int shape, const double hand_euler[3], const double obj_pos[3], const double *hand_pos, double obs[KGO_NOBS]) {
     double ctrl[KGO_NU] = {0};
     memset(e, 0, sizeof *e);
     kgo_state_init(m, &e->st, shape, hand_euler, obj_pos);
+    if (hand_pos) for (int c = 0; c < 3; c++) e->st.qpos[c] = hand_pos[c];
     kgo_forward(m, &e->st, ctrl, KGO_RAYS, &e->d);
     /* centroid fix-up, ENV:1382-1389 */
     double del[3];
@@ -166,8 +187,12 @@ static int g_rays_every_substep = 0;
 void kgo_set_rays_every_substep(int on) { g_rays_every_substep = on; }
 
 int kgo_env_step(const KgoModel *m, KgoEnv *e, const double action[4], double obs[KGO_NOBS], double *reward, double info3[3]) {
+    double a6[6] = {0, 0, action[0], action[1], action[2], action[3]};
+    return kgo_env_step6(m, e, a6, obs, reward, info3);
+}
+int kgo_env_step6(const KgoModel *m, KgoEnv *e, const double action[6], double obs[KGO_NOBS], double *reward, double info3[3]) {
     double ctrl[KGO_NU];
-    kgo_ctrl_from_action(&e->d, action, ctrl);
+    kgo_ctrl_from_action6(&e->d, action, ctrl);
     for (int k = 0; k < 15; k++) kgo_step(m, &e->st, ctrl, (k == 14 || g_rays_every_substep) ? KGO_RAYS : 0, &e->d);
     kgo_get_obs(m, &e->st, &e->d, 0, obs);
     /* _get_reward, ENV:661-666 on global obs[23] = object geom z */

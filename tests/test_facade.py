@@ -1,5 +1,6 @@
 """The single-env facade with the reference's signatures (gym_kinova_gripper KinovaGripper_Env: ENV:1310-1410 reset,
-ENV:1495-1552 step, the accessors main_DDPGfD.py / expert_data.py call) on the host emulation, against the oracle."""
+ENV:1495-1552 step, the accessors main_DDPGfD.py / expert_data.py call) against the oracle -- on the host emulation (CPU
+suite) and on the CUDA library (-m gpu)."""
 import numpy as np
 import pytest
 
@@ -9,8 +10,9 @@ from kinovagrasping_b200.modelcard import SHAPES
 
 
 @pytest.fixture()
-def facade():
-    e = kenv.make("gym_kinova_gripper:kinovagripper-v0", device=0, lib=_emu_lib())
+def facade(backend):
+    kenv._MEM_FILES.clear()
+    e = kenv.make("gym_kinova_gripper:kinovagripper-v0", device=0, lib=backend)
     yield e
     e.close()
 
@@ -20,6 +22,26 @@ def test_make_rejects_other_ids_and_arm_model():
         kenv.make("CartPole-v1", lib=_emu_lib())
     with pytest.raises(ValueError):
         kenv.KinovaGripper_Env(arm_or_end_effector="arm", lib=_emu_lib())
+
+
+def test_shape_list_files_outlive_the_env_object(backend):
+    """MAIN:381 builds a new env per episode and relies on ./objects.csv for the rest of the Latin square (ENV:961-999):
+    the in-memory stand-in for that file is shared by all env objects, incl. the reference's quirks -- a missing file is
+    "not empty" (ENV:885-886), and generating on demand leaves the keys in the list twice (ENV:966-981)."""
+    kenv._MEM_FILES.clear()
+    keys = ["CubeS", "CylinderB", "Cone2S"]
+    seen = []
+    for ep in range(7):
+        e = kenv.make(lib=backend)
+        assert e.check_obj_file_empty("objects.csv") is False
+        e.reset(shape_keys=keys, hand_orientation="normal")
+        seen.append(e.get_random_shape())
+        if ep == 0:
+            assert len(e.get_obj_keys()) == 2 * 20000 - 1
+        e.close()
+    full = kenv.latin_square_keys(keys, 20000)
+    assert seen == (full + full)[::-1][:7]
+    assert len(kenv._MEM_FILES["objects.csv"]) == 2 * 20000 - 7
 
 
 def test_reset_and_step_signatures_match_reference(facade, oracle):
@@ -41,14 +63,34 @@ def test_reset_and_step_signatures_match_reference(facade, oracle):
     ref_env, ref_obs = oracle.env_reset(shape_id, row[6:9].astype(np.float64), np.array(obj, dtype=np.float64))
     assert np.abs(np.array(state) - ref_obs).max() < 1e-5
     assert e.Tfw.shape == (4, 4) and abs(np.linalg.det(e.Tfw[:3, :3]) - 1.0) < 1e-5
-    # a 6-d action [0, 0, wrist, f1, f2, f3] is cut to its last four entries (ENV:1502-1503)
-    nxt, reward, done, info = e.step([0.0, 0.0, 0.0, 0.4, 0.4, 0.4])
-    ref_obs, r, d, _ = oracle.env_step(ref_env, np.array([0.0, 0.4, 0.4, 0.4]))
+    # determine_hand_location ran with the all-zero Tfw of a new env (ENV:110): the slides start at 0 whatever the orientation
+    assert np.abs(e.h.get_state_host()[0][0:3]).max() == 0.0
+    # a 6-d action: action[0:3] is the slide vector (ENV:1518), a 4-d one is padded to [0, 0, wrist, f1, f2, f3] (ENV:1502-1503)
+    nxt, reward, done, info = e.step([0.05, -0.03, 0.0, 0.4, 0.4, 0.4])
+    ref_obs, r, d, _ = oracle.env_step(ref_env, np.array([0.05, -0.03, 0.0, 0.4, 0.4, 0.4]))
     assert isinstance(nxt, list) and len(nxt) == 82 and isinstance(reward, float) and isinstance(done, bool)
     assert set(info) == {"finger_reward", "grasp_reward", "lift_reward"} and info["finger_reward"] == 0.0
     assert np.abs(np.array(nxt) - ref_obs).max() < 2e-4 and reward == r and done == d
     assert e._get_dot_product() == pytest.approx(nxt[81])
     assert e._get_obs() == nxt
+    assert np.abs(e.h.get_state_host()[0][0:2]).max() > 1e-3        # the x / y slide components were not dropped
+    nxt, reward, done, info = e.step([0.3, 0.4, 0.4, 0.4])
+    ref_obs, r, d, _ = oracle.env_step(ref_env, np.array([0.3, 0.4, 0.4, 0.4]))
+    assert np.abs(np.array(nxt) - ref_obs).max() < 2e-4 and reward == r and done == d
+    # second episode on the SAME env object (expert_data.py:696 reuses one env): 'top' / 'rotated' starts now use the Tfw this
+    # episode left behind (ENV:1299-1305), 'normal' starts stay at 0
+    prev_data = ref_env.d
+    for _ in range(6):
+        state = e.reset(shape_keys=["CubeS", "CubeB", "Vase1S"], hand_orientation="random")
+        orient = ["normal", "rotated", "top"].index(e.get_orientation())
+        shape_id = SHAPES.index(e.get_random_shape())
+        row = e.card.pose("train")[shape_id, orient][1:][e.get_orientation_idx()]
+        hand = oracle.hand_location(prev_data, orient)
+        assert np.abs(e.h.get_state_host()[0][0:3, 0] - hand).max() < 1e-6
+        assert (orient == 0) == (np.abs(hand).max() == 0.0)
+        ref_env, ref_obs = oracle.env_reset(shape_id, row[6:9].astype(np.float64), np.array(e.get_obj_coords(), dtype=np.float64), hand_pos=hand)
+        assert np.abs(np.array(state) - ref_obs).max() < 1e-5
+        prev_data = ref_env.d
 
 
 def test_timelimit_and_global_obs(facade):
@@ -72,6 +114,7 @@ def test_timelimit_and_global_obs(facade):
 def test_vector_env_global_obs_view():
     import torch
     from kinovagrasping_b200 import shard
+    kenv._MEM_FILES.clear()
     env = shard.make_sharded_env(5, 0, 1, "cpu", lib=_emu_lib())
     g = env.enable_global_obs()
     obs = env.reset(("CubeS", "Cone1B"), "random", variant="A", seed=9)

@@ -215,7 +215,42 @@ def main():
             pl = np.zeros(31, dtype=bool); pl[:len(seq)] = lifts
             exp_recs["mode"].append(md); exp_recs["obs"].append(pad); exp_recs["action"].append(pa)
             exp_recs["lift"].append(pl); exp_recs["len"].append(len(seq))
-    # synthetic perturbations so rare branches (range < 0.06 averaging, gravity argmax cases) are covered
+    # synthetic perturbations of recorded kinematics so that the branch BOUNDARIES of experimental_sensor (ENV:290-343) are
+    # pinned, not only their interiors: palm ranges exactly at / just around 0.06 (strict `<`), every subset of the five
+    # palm rays below the threshold, misses (-1 -> 6), and palm frames turned so that each of the three
+    # argmax(|gravity_local|) cases -- incl. near-ties between two axes -- is hit
+    base = [i for i in range(len(recs["shape"]))][::97]
+    def turned(ax, ang):
+        c, s_ = np.cos(ang), np.sin(ang)
+        R = np.eye(3); a, b = [(1, 2), (0, 2), (0, 1)][ax]
+        R[a, a] = c; R[a, b] = -s_; R[b, a] = s_; R[b, b] = c
+        return R
+    nsyn = 0
+    for k, i in enumerate(base):
+        shape = int(recs["shape"][i])
+        gx, gm, sx, hx, sd = (np.array(recs[n][i]).copy() for n in ("geom_xpos", "geom_xmat", "site_xpos", "hand_xpos", "sensordata"))
+        variants = []
+        for mask in range(32):                                   # which palm rays are "close"
+            v = sd.copy()
+            for j in range(5):
+                v[9 + j] = (0.01 + 0.009 * j) if (mask >> j) & 1 else (0.06 if j % 2 else 0.0601 + 0.01 * j)
+            variants.append((gm, v))
+        for val in (0.0599999, 0.06, 0.0600001, -1.0):
+            v = sd.copy(); v[9:14] = val; v[14:26] = -1.0 if val < 0 else v[14:26]
+            variants.append((gm, v))
+        for ax in range(3):
+            for ang in (np.pi / 4 - 1e-3, np.pi / 4 + 1e-3, np.pi / 2, 1.1):
+                g2 = gm.copy(); g2[1] = (turned(ax, ang) @ gm[1].reshape(3, 3)).reshape(9)
+                variants.append((g2, sd))
+        for g2, v in variants[k % 3::3]:                         # a third of them per base record keeps the fixture small
+            class _D:
+                pass
+            D = _D()
+            D.arr = lambda name, shp=None, _g=g2, _v=v: {"geom_xpos": gx, "geom_xmat": _g, "site_xpos": sx, "sensordata": _v,
+                                                          "xpos": np.vstack([np.zeros(3), hx, np.zeros((7, 3))])}[name]
+            record(shape, D)
+            nsyn += 1
+    print("synthetic perturbation records", nsyn)
     np.savez_compressed(os.path.join(OUT, "obs_golden.npz"), **{k: np.array(v) for k, v in recs.items()})
     np.savez_compressed(os.path.join(OUT, "expert_golden.npz"), **{k: np.array(v) for k, v in exp_recs.items()})
     print("obs records", len(recs["shape"]), "expert sequences", len(exp_recs["mode"]))
