@@ -113,10 +113,13 @@ int kg_set_schedule(kg_handle h, int mode);
  * lane of the same launch) unless the last RL step the host has a count for had more than a third of the envs above the
  * light limit, then full mode; 1 = always split; 2 = always full (every env through the full workspace). */
 int kg_set_mode(kg_handle h, int mode);
-/* Pipelining of kg_step (no effect on results): the batch is cut into `groups` (1..4) contiguous env groups whose kernel
+/* Pipelining of kg_step (no effect on results): the batch is cut into `groups` (1..32) contiguous env groups whose kernel
  * chains run on separate internal streams, forked from and joined into the handle's stream, so one group's narrowphase
- * kernel overlaps another group's per-env kernel.  Default: 2 for batches of 512 envs or more, else 1. */
+ * kernel overlaps another group's per-env kernel.  Default: 4 from 2048 envs, 2 from 512 envs, else 1. */
 int kg_set_pipeline(kg_handle h, int groups);
+/* Launch path of kg_step (no effect on results): 1 (default) = the kernel chain of a step is captured once per distinct
+ * argument set into a CUDA graph and replayed with one launch call; 0 = every kernel launched individually. */
+int kg_set_graph(kg_handle h, int on);
 /* Diagnostics (bench.py's roofline): with timing on, kg_step records a CUDA event after every kernel launch (and does
  * not pipeline groups); kg_timing_breakdown then returns the milliseconds of the last step by launch kind:
  * [1] schedule [2] begin [3] narrowphase (all launches) [4] substep kernels except the last [5] last substep kernel. */
@@ -129,8 +132,8 @@ int kg_timing_breakdown(kg_handle h, float ms_by_kind[8]);
 int kg_get_last_action_host(kg_handle h, float *action_host);
 
 /* counters since the last call: [0] hull pairs sent to MPR, [1] Newton iterations, [2] substeps that
- * overflowed the per-env contact capacity, [3] substeps executed. */
-int kg_get_stats(kg_handle h, long long stats_host[4]);
+ * overflowed the per-env contact capacity, [3] substeps executed, [4] contacts (summed over substeps), [5..7] reserved. */
+int kg_get_stats(kg_handle h, long long stats_host[8]);
 
 /* Profiling builds (-DKG_PROF) only; zeros otherwise.  32 slots since the last call, summed over envs.
  * SM cycles: [0] kinematics+dynamics [1] barrier wait before collision [2] collision (broadphase, plane, separating-axis

@@ -46,6 +46,7 @@ SIGNATURES = {
     "kg_set_pipeline": (C.c_int, [_vp, C.c_int]),
     "kg_measure_fp32_peak": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "kg_set_timing": (C.c_int, [_vp, C.c_int]),
+    "kg_set_graph": (C.c_int, [_vp, C.c_int]),
     "kg_timing_breakdown": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "kg_get_last_action_host": (C.c_int, [_vp, _vp]),
     "kg_get_stats": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),

@@ -17,7 +17,7 @@
 #include <string>
 #include <vector>
 
-#define KG_MAXGROUPS 4
+#define KG_MAXGROUPS 32
 #ifndef KG_EMU
 #include <cuda_runtime.h>
 #ifndef KG_WARPS
@@ -34,13 +34,16 @@
 #endif
 #endif
 #ifndef KG_LMINBLOCKS
-#define KG_LMINBLOCKS 3     // ... and CTAs per SM (24 warps x 80 registers)
+#define KG_LMINBLOCKS 3     // ... and CTAs per SM: 24 resident warps x 80 registers.  (7 x 4 = 28 warps x 72 registers makes 4096 envs a
+                            // single wave and was measured: no faster -- profiles/README.md r2: a launch lasts as long as its slowest
+                            // warp, and at that occupancy the SM is already at 62 % of its issue slots)
 #endif
 #define KG_SPLIT (KG_MAXCON_LIGHT < KG_MAXCON)
 #define KG_LSMEM (KG_LWARPS * sizeof(KgWSLight))
 __constant__ KgModel c_model;
 #endif
 
+struct KgGraphKey { int cfg, full, qs0, mode; const void *action; void *obs, *reward, *done, *act_out; };
 struct kg_handle_s {
     int n = 0, device = 0, frame_skip = 15, env_offset = 0;
     void *stream = nullptr;
@@ -75,7 +78,13 @@ struct kg_handle_s {
     cudaEvent_t gfork = nullptr, gjoin[KG_MAXGROUPS] = {};
 #endif
     float last_ms = 0.f;
+    int cfg_version = 0;              // bumped by every setter that changes a kernel argument (graph cache key)
 #if !defined(KG_EMU)
+    int use_graph = 1;                // kg_set_graph
+    cudaStream_t capstream = nullptr; // origin stream of graph captures (the caller's stream may be the legacy stream, which cannot capture)
+    struct GraphEntry { KgGraphKey key; cudaGraphExec_t exec; unsigned long long used; };
+    std::vector<GraphEntry> graphs;
+    unsigned long long graph_clock = 0;
     int timing = 0;                   // kg_set_timing: an event after every launch of a step, groups not pipelined
     std::vector<cudaEvent_t> tev;
     std::vector<int> tkind;
@@ -163,6 +172,7 @@ KG_DEV unsigned kg_debug_begin(const KgModel &m, KgWS &ws, const KgEnvArrays &A,
     KG_PHASE(l) { if (l < 9) ws.ctrl[l] = ctrl[l]; }
     KG_SYNC();
     kg_kinematics(m, ws, kg_lane);
+    kg_ccache_load(ws, A.ccache + (size_t)env * KG_CCACHE_BYTES, kg_lane);
     return kg_collision_lane(m, ws, kg_lane);
 }
 KG_DEV void kg_debug_end(const KgModel &m, KgWS &ws, float *out, int kg_lane) {
@@ -174,9 +184,9 @@ KG_DEV void kg_debug_end(const KgModel &m, KgWS &ws, float *out, int kg_lane) {
         if (l < KG_MAXCON) {
             float *o = out + 301 + 8 * l;
             if (9 + l < ws.ngroup) {
-                int s = ws.gslot[9 + l];
+                int s = kg_gslot(ws, 9 + l);
                 o[0] = ws.st_dist[s]; o[1] = ws.st_pos[s][0]; o[2] = ws.st_pos[s][1]; o[3] = ws.st_pos[s][2];
-                o[4] = ws.st_n[s][0]; o[5] = ws.st_n[s][1]; o[6] = ws.st_n[s][2]; o[7] = ws.gmu[9 + l] + 10.f * ws.st_g1[s] + 100.f * ws.st_g2[s];
+                o[4] = ws.st_n[s][0]; o[5] = ws.st_n[s][1]; o[6] = ws.st_n[s][2]; o[7] = KG_GMU(ws, 9 + l) + 10.f * ws.st_g1[s] + 100.f * ws.st_g2[s];
             } else for (int c = 0; c < 8; c++) o[c] = 0.f;
         }
     }
@@ -256,9 +266,9 @@ template <class WS, bool LAST>
 __device__ __forceinline__ void kg_sub_body(WS &ws, const KgEnvArrays &A, int env, unsigned char *rec, int *q, unsigned *tasks,
                                             int nsub, float *obs, float *reward, int *done, float *act_out, int lane) {
     kg_substep_finish(c_model, ws, lane);
-    if (LAST) kg_step_end(c_model, ws, A, env, nsub, obs, reward, done, act_out, lane);
+    if (LAST) kg_step_end(c_model, ws, A, env, nsub, rec, obs, reward, done, act_out, lane);
     else {
-        const unsigned mask = kg_substep_start(c_model, ws, lane);
+        const unsigned mask = kg_substep_start(c_model, ws, rec, lane);
         kg_carry_store(ws, rec, lane);
         kg_emit_tasks(mask, env, q, tasks, lane);
     }
@@ -312,6 +322,9 @@ __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(K
         return;
     }
     KG_ENV_OF_WARP(KgWSLight, KG_LWARPS, blockIdx.x - nheavy_ctas);
+#ifdef KG_TRACE
+    const long long tr0 = clock64();
+#endif
     unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
     kg_carry_load(ws, rec, lane);
     if (nheavy_ctas > 0) {
@@ -319,6 +332,15 @@ __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(K
         if (!kg_claim(subseq + env, sidx, lane)) return;              // ... or already has (the record was rewritten)
     }
     kg_sub_body<KgWSLight, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
+#ifdef KG_TRACE
+    // per (substep, env): cycles of this warp's substep, its Newton iterations and contact count, its SM and start time
+    if (lane == 0 && A.prof) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *tr = A.prof + KG_NPROF + 2 * ((size_t)sidx * A.N + env);
+        tr[0] = ((clock64() - tr0) << 20) | ((long long)(ws.s_iter & 0xff) << 12) | ((long long)(ws.ncon_total & 0xff) << 4);
+        tr[1] = ((long long)smid << 48) | (tr0 & 0xffffffffffffll);
+    }
+#endif
 }
 template <bool LAST>
 __global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_full_kernel(KgEnvArrays A, int base, int cnt, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
@@ -346,7 +368,11 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
     if (blockIdx.x == 0 && threadIdx.x == 0) { q_other[0] = 0; q_other[1] = 0; }   // the list the next per-env kernel fills
     const int ntask = q[0];
     if (ntask == 0) return;
+#ifdef KG_MPR_HALF
+    KgMprWS &mw = *(reinterpret_cast<KgMprWS *>(smem) + 2 * warp + (lane >> 4));      // one workspace per 16-lane team
+#else
     KgMprWS &mw = *(reinterpret_cast<KgMprWS *>(smem) + warp);
+#endif
 #ifndef KG_MPR_L1
     float4 *fh = reinterpret_cast<float4 *>(smem + KG_MPR_WARPS * sizeof(KgMprWS));
     {
@@ -369,10 +395,11 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
 #endif
     // dynamic task list: no look-ahead on purpose -- a warp that reserved its next task while still inside a long MPR
     // would hold that task back from the idle warps (measured: 10 % slower at 4096 envs)
+    const unsigned team = KG_MPR_MASK(lane);
     for (;;) {
         int t = 0;
-        if (lane == 0) t = atomicAdd(q + 1, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((lane & (KG_MPR_W - 1)) == 0) t = atomicAdd(q + 1, 1);
+        t = __shfl_sync(team, t, lane & ~(KG_MPR_W - 1));
         if (t >= ntask) break;
         const unsigned task = tasks[t];
         kg_mpr_task(c_model, mw, carry + (size_t)(task >> 8) * KG_CARRY_BYTES, (int)(task & 0xff), lane);
@@ -438,7 +465,11 @@ static size_t ws_bytes() { return sizeof(KgWS); }
 static_assert(KG_WARPS * sizeof(KgWS) <= 227 * 1024, "KG_WARPS workspaces must fit one SM's shared memory");
 static_assert(KG_LMINBLOCKS * (KG_LWARPS * sizeof(KgWSLight) + 1024) <= 228 * 1024, "KG_LMINBLOCKS light CTAs must fit one SM's shared memory");
 #ifdef KG_MPR_L1
+#ifdef KG_MPR_HALF
+#define KG_MPR_SMEM(h) (2 * KG_MPR_WARPS * sizeof(KgMprWS))
+#else
 #define KG_MPR_SMEM(h) (KG_MPR_WARPS * sizeof(KgMprWS))
+#endif
 #else
 #define KG_MPR_SMEM(h) (KG_MPR_WARPS * sizeof(KgMprWS) + (size_t)(h)->fhull_bytes)
 #endif
@@ -461,44 +492,15 @@ static void emu_run_tasks(kg_handle h, int sel) {
 #else
 #define KG_TMARK(kind) ((void)0)
 #endif
-// One RL step = a wavefront of kernels on the handle's stream:
-//   [schedule] begin | nsub x ( narrowphase tasks | per-env substep kernel )     (2 nsub + 1 launches of our kernels)
-static int launch_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
+#ifndef KG_EMU
+// Everything one RL step puts on a stream: the copy of the last step's heavy count to the host, then per env group
+//   [schedule] begin | nsub x ( narrowphase tasks | per-env substep kernel )     (2 nsub + 2 launches of our kernels)
+// forked over the group streams and joined back into `st` (which may be a capturing stream).
+static int enqueue_step(kg_handle h, cudaStream_t st, const float *action, int mode, float *obs, float *reward, int *done, float *act_out, bool full, int qs0) {
     const int nsub = h->frame_skip;
-#ifdef KG_EMU
-    for (int env = 0; env < h->n; env++) {
-        unsigned mask = kg_step_begin(h->model, g_ws, h->A, env, action, mode, 0);
-        kg_carry_store(g_ws, h->carry + (size_t)env * KG_CARRY_BYTES, 0);
-        kg_emit_tasks(mask, env, h->q + 2 * h->qsel, h->tasks, 0);
-    }
-    for (int s = 0; s < nsub; s++) {
-        emu_run_tasks(h, h->qsel);
-        h->qsel ^= 1;
-        for (int env = 0; env < h->n; env++) {
-            unsigned char *rec = h->carry + (size_t)env * KG_CARRY_BYTES;
-            kg_carry_load(g_ws, rec, 0);
-            kg_substep_finish(h->model, g_ws, 0);
-            if (s == nsub - 1) kg_step_end(h->model, g_ws, h->A, env, nsub, obs, reward, done, act_out, 0);
-            else {
-                unsigned mask = kg_substep_start(h->model, g_ws, 0);
-                kg_carry_store(g_ws, rec, 0);
-                kg_emit_tasks(mask, env, h->q + 2 * h->qsel, h->tasks, 0);
-            }
-        }
-    }
-    return 0;
-#else
-    cudaStream_t st = (cudaStream_t)h->stream;
     const size_t smem = KG_LSMEM, hsmem = KG_WARPS * ws_bytes();
-    // mode of this step, from the newest count of above-the-light-limit envs the host has (never waits for the device)
-    if (KG_SPLIT && h->heavy_host) {
-        const float frac = (float)*(volatile int *)h->heavy_host / (float)h->n;
-        if (h->mode_auto) { if (!h->full_mode && frac > 0.33f) h->full_mode = 1; else if (h->full_mode && frac < 0.20f) h->full_mode = 0; }
-    }
-    const bool full = !KG_SPLIT || h->full_mode;
     cudaMemcpyAsync(h->heavy_host, h->heavy_count, sizeof(int), cudaMemcpyDeviceToHost, st);      // last step's count -> pinned host word
     cudaMemsetAsync(h->heavy_count, 0, sizeof(int), st);
-    cudaEventRecord(h->ev0, st);
     size_t tix = 0;
     const int G = h->timing ? 1 : h->ngroups;
     // The env groups of the batch are independent pipelines: group g's kernels go to its own stream, so the narrowphase
@@ -511,7 +513,6 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
         cudaEventRecord(h->gfork, st);
         for (int g = 0; g < G; g++) { gs[g] = h->gstream[g]; cudaStreamWaitEvent(gs[g], h->gfork, 0); }
     } else gs[0] = st;
-    const int qs0 = h->qsel;
     for (int g = 0; g < G; g++) {
         const int base = gbase[g], cnt = gbase[g + 1] - base;
         if (cnt <= 0) continue;
@@ -532,7 +533,10 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
             const int *perm = h->schedule ? h->perm : nullptr;
             int *q = h->q + 4 * g;
             unsigned *tasks = h->tasks + (size_t)base * 22;
-            kg_mpr_kernel<<<h->mpr_grid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), gs[g]>>>(h->carry, q + 2 * qa, q + 2 * qb, tasks, h->A.prof);
+            // persistent narrowphase grid of this group: room for ~2 tasks per env at one task per team, at most the whole GPU
+            int mgrid = (2 * cnt + KG_MPR_WARPS * (32 / KG_MPR_W) - 1) / (KG_MPR_WARPS * (32 / KG_MPR_W));
+            mgrid = mgrid < 8 ? 8 : (mgrid > h->mpr_grid ? h->mpr_grid : mgrid);
+            kg_mpr_kernel<<<mgrid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), gs[g]>>>(h->carry, q + 2 * qa, q + 2 * qb, tasks, h->A.prof);
             KG_TMARK(3);
             if (full) {
                 const int fblocks = (cnt + KG_WARPS - 1) / KG_WARPS;
@@ -540,16 +544,85 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
                 else kg_sub_full_kernel<false><<<fblocks, KG_WARPS * 32, hsmem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, h->heavy_count, nsub, obs, reward, done, act_out);
             } else {
                 const int blocks = (cnt + KG_LWARPS - 1) / KG_LWARPS;
-                const int hb = (cnt + KG_HEAVY_WARPS - 1) / KG_HEAVY_WARPS;
-                const int nhc = hb < h->heavy_ctas ? hb : h->heavy_ctas;
+                // heavy-lane CTAs at the front of the grid: one full workspace per 8 envs of the group (they loop over whatever is heavy)
+                const int hb = (cnt + 8 * KG_HEAVY_WARPS - 1) / (8 * KG_HEAVY_WARPS);
+                const int nhc = hb < 1 ? 1 : (hb < h->heavy_ctas ? hb : h->heavy_ctas);
                 if (last) kg_sub_kernel<true><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
                 else kg_sub_kernel<false><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
             }
             KG_TMARK(last ? 5 : 4);
         }
     }
-    h->qsel = (qs0 + nsub) & 1;
     if (G > 1) for (int g = 0; g < G; g++) { cudaEventRecord(h->gjoin[g], gs[g]); cudaStreamWaitEvent(st, h->gjoin[g], 0); }
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+#endif
+// One RL step = a wavefront of kernels on the handle's stream:
+//   [schedule] begin | nsub x ( narrowphase tasks | per-env substep kernel )     (2 nsub + 1 launches of our kernels)
+static int launch_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
+    const int nsub = h->frame_skip;
+#ifdef KG_EMU
+    for (int env = 0; env < h->n; env++) {
+        unsigned mask = kg_step_begin(h->model, g_ws, h->A, env, action, mode, 0);
+        kg_carry_store(g_ws, h->carry + (size_t)env * KG_CARRY_BYTES, 0);
+        kg_emit_tasks(mask, env, h->q + 2 * h->qsel, h->tasks, 0);
+    }
+    for (int s = 0; s < nsub; s++) {
+        emu_run_tasks(h, h->qsel);
+        h->qsel ^= 1;
+        for (int env = 0; env < h->n; env++) {
+            unsigned char *rec = h->carry + (size_t)env * KG_CARRY_BYTES;
+            kg_carry_load(g_ws, rec, 0);
+            kg_substep_finish(h->model, g_ws, 0);
+            if (s == nsub - 1) kg_step_end(h->model, g_ws, h->A, env, nsub, rec, obs, reward, done, act_out, 0);
+            else {
+                unsigned mask = kg_substep_start(h->model, g_ws, rec, 0);
+                kg_carry_store(g_ws, rec, 0);
+                kg_emit_tasks(mask, env, h->q + 2 * h->qsel, h->tasks, 0);
+            }
+        }
+    }
+    return 0;
+#else
+    cudaStream_t st = (cudaStream_t)h->stream;
+    // mode of this step, from the newest count of above-the-light-limit envs the host has (never waits for the device)
+    if (KG_SPLIT && h->heavy_host) {
+        const float frac = (float)*(volatile int *)h->heavy_host / (float)h->n;
+        if (h->mode_auto) { if (!h->full_mode && frac > 0.33f) h->full_mode = 1; else if (h->full_mode && frac < 0.20f) h->full_mode = 0; }
+    }
+    const bool full = !KG_SPLIT || h->full_mode;
+    const int qs0 = h->qsel;
+    h->qsel = (qs0 + nsub) & 1;
+    cudaEventRecord(h->ev0, st);
+    if (h->use_graph && !h->timing) {
+        // The chain of a step (2 + 2 nsub launches per env group, forked over the group streams) is captured ONCE per
+        // distinct argument set into a CUDA graph and replayed: one launch call per RL step on the host instead of ~65, and
+        // the dependent kernels of a group chain start without a host round trip between them.
+        KgGraphKey key = {h->cfg_version, full ? 1 : 0, qs0, mode, (const void *)action, (void *)obs, (void *)reward, (void *)done, (void *)act_out};
+        cudaGraphExec_t exec = nullptr;
+        for (auto &g : h->graphs) if (memcmp(&g.key, &key, sizeof key) == 0) { exec = g.exec; g.used = ++h->graph_clock; break; }
+        if (!exec) {
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(h, cudaStreamBeginCapture(h->capstream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_step(h, h->capstream, action, mode, obs, reward, done, act_out, full, qs0);
+            cudaError_t ce = cudaStreamEndCapture(h->capstream, &graph);
+            if (rc != 0 || ce != cudaSuccess || !graph) { h->err = std::string("graph capture: ") + cudaGetErrorString(ce); return KG_ECUDA; }
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { h->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return KG_ECUDA; }
+            if (h->graphs.size() >= 8) {            // evict the least recently used instance
+                size_t lru = 0;
+                for (size_t i = 1; i < h->graphs.size(); i++) if (h->graphs[i].used < h->graphs[lru].used) lru = i;
+                cudaGraphExecDestroy(h->graphs[lru].exec);
+                h->graphs.erase(h->graphs.begin() + lru);
+            }
+            h->graphs.push_back({key, exec, ++h->graph_clock});
+        }
+        CUDA_TRY(h, cudaGraphLaunch(exec, st));
+    } else {
+        TRY(enqueue_step(h, st, action, mode, obs, reward, done, act_out, full, qs0));
+    }
     cudaEventRecord(h->ev1, st);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -703,12 +776,13 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
         *h->heavy_host = 0;
     }
     CUDA_TRY(h, cudaEventCreate(&h->ev0)); CUDA_TRY(h, cudaEventCreate(&h->ev1));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->capstream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->gfork, cudaEventDisableTiming));
     for (int g = 0; g < KG_MAXGROUPS; g++) {
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->gjoin[g], cudaEventDisableTiming));
     }
-    h->ngroups = n_envs >= 512 ? 2 : 1;
+    h->ngroups = n_envs >= 2048 ? 4 : (n_envs >= 512 ? 2 : 1);
 #endif
     const size_t N = (size_t)n_envs;
     KgEnvArrays &A = h->A;
@@ -716,7 +790,13 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     TRY(be_alloc(h, (void **)&A.qpos, 16 * N * 4)); TRY(be_alloc(h, (void **)&A.qvel, 15 * N * 4)); TRY(be_alloc(h, (void **)&A.qwarm, 15 * N * 4));
     TRY(be_alloc(h, (void **)&A.hand_quat, 4 * N * 4)); TRY(be_alloc(h, (void **)&A.shape, N * 4)); TRY(be_alloc(h, (void **)&A.elapsed, N * 4));
     TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
-    TRY(be_alloc(h, (void **)&A.stats, 4 * 8)); TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8)); TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
+    TRY(be_alloc(h, (void **)&A.stats, 8 * 8));
+#ifdef KG_TRACE
+    TRY(be_alloc(h, (void **)&A.prof, (KG_NPROF + 2 * 16 * N) * 8));
+#else
+    TRY(be_alloc(h, (void **)&A.prof, KG_NPROF * 8));
+#endif
+    TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
     TRY(be_alloc(h, (void **)&A.ccache, N * KG_CCACHE_BYTES));
     TRY(be_alloc(h, (void **)&h->d_obs_global, KG_NOBS_GLOBAL * N * 4));
     TRY(be_alloc(h, (void **)&A.load, N * 4)); TRY(be_alloc(h, (void **)&h->perm, N * 4));
@@ -748,6 +828,8 @@ int kg_destroy(kg_handle h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->heavy_host) cudaFreeHost(h->heavy_host);
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
+    if (h->capstream) cudaStreamDestroy(h->capstream);
     if (h->gfork) cudaEventDestroy(h->gfork);
     for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
     for (int g = 0; g < KG_MAXGROUPS; g++) { if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]); if (h->gjoin[g]) cudaEventDestroy(h->gjoin[g]); }
@@ -759,8 +841,8 @@ const char *kg_last_error(kg_handle h) { return h ? h->err.c_str() : "null handl
 int kg_num_envs(kg_handle h) { return h ? h->n : KG_EINVAL; }
 int kg_set_stream(kg_handle h, void *stream) { if (!h) return KG_EINVAL; h->stream = stream; return KG_OK; }
 int kg_sync(kg_handle h) { if (!h) return KG_EINVAL; return be_sync(h); }
-int kg_set_max_episode_steps(kg_handle h, int steps) { if (!h || steps <= 0) return KG_EINVAL; h->A.max_steps = steps; return KG_OK; }
-int kg_set_obs_global(kg_handle h, float *obs74) { if (!h) return KG_EINVAL; h->A.obs_global = obs74; return KG_OK; }
+int kg_set_max_episode_steps(kg_handle h, int steps) { if (!h || steps <= 0) return KG_EINVAL; h->A.max_steps = steps; h->cfg_version++; return KG_OK; }
+int kg_set_obs_global(kg_handle h, float *obs74) { if (!h) return KG_EINVAL; h->A.obs_global = obs74; h->cfg_version++; return KG_OK; }
 int kg_obs_global_buffer(kg_handle h, float **buf) { if (!h || !buf) return KG_EINVAL; *buf = h->d_obs_global; return KG_OK; }
 int kg_get_obs_global_host(kg_handle h, float *obs74_host) {
     if (!h || !obs74_host || !h->A.obs_global) return KG_EINVAL;
@@ -769,7 +851,7 @@ int kg_get_obs_global_host(kg_handle h, float *obs74_host) {
 }
 int kg_set_pipeline(kg_handle h, int groups) {
     if (!h || groups < 1 || groups > KG_MAXGROUPS) return KG_EINVAL;
-    h->ngroups = groups;
+    h->ngroups = groups; h->cfg_version++;
     return KG_OK;
 }
 int kg_set_mode(kg_handle h, int mode) {
@@ -777,8 +859,8 @@ int kg_set_mode(kg_handle h, int mode) {
     h->mode_auto = mode == 0; h->full_mode = mode == 2;
     return KG_OK;
 }
-int kg_set_frame_skip(kg_handle h, int fs) { if (!h || fs <= 0) return KG_EINVAL; h->frame_skip = fs; return KG_OK; }
-int kg_set_schedule(kg_handle h, int mode) { if (!h || mode < 0 || mode > 1) return KG_EINVAL; h->schedule = mode; return KG_OK; }
+int kg_set_frame_skip(kg_handle h, int fs) { if (!h || fs <= 0) return KG_EINVAL; h->frame_skip = fs; h->cfg_version++; return KG_OK; }
+int kg_set_schedule(kg_handle h, int mode) { if (!h || mode < 0 || mode > 1) return KG_EINVAL; h->schedule = mode; h->cfg_version++; return KG_OK; }
 int kg_set_env_offset(kg_handle h, int offset) { if (!h || offset < 0) return KG_EINVAL; h->env_offset = offset; return KG_OK; }
 int kg_get_last_action_host(kg_handle h, float *act) {
     if (!h || !act) return KG_EINVAL;
@@ -796,7 +878,7 @@ int kg_reset(kg_handle h, const int *mask, const int *shape, const float *euler,
 int kg_set_hand_location(kg_handle h, int mode) { if (!h || mode < 0 || mode > 1) return KG_EINVAL; h->hand_location = mode; return KG_OK; }
 int kg_set_action_dim(kg_handle h, int dim) {
     if (!h || (dim != 4 && dim != 6)) { if (h) h->err = "kg_set_action_dim: 4 or 6"; return KG_EINVAL; }
-    h->A.act_dim = dim;
+    h->A.act_dim = dim; h->cfg_version++;
     return KG_OK;
 }
 int kg_reset_sampled(kg_handle h, const int *mask, const int *shape, int orient, int variant, int test_table, uint64_t seed, float *obs) {
@@ -837,11 +919,22 @@ int kg_get_state(kg_handle h, float *qpos, float *qvel) {
     if (qvel) TRY(be_d2d(h, qvel, h->A.qvel, 15 * N * 4));
     return KG_OK;
 }
+// A state written from outside invalidates the collision caches: their separation budgets (kg_core.cuh, slack) are bounds
+// on the motion since the last collision stage and know nothing about a teleport.
+static int invalidate_ccache(kg_handle h) {
+#ifdef KG_EMU
+    memset(h->A.ccache, 0, (size_t)h->n * KG_CCACHE_BYTES);
+#else
+    CUDA_TRY(h, cudaMemsetAsync(h->A.ccache, 0, (size_t)h->n * KG_CCACHE_BYTES, (cudaStream_t)h->stream));
+#endif
+    return 0;
+}
 int kg_set_state(kg_handle h, const float *qpos, const float *qvel) {
     if (!h) return KG_EINVAL;
     const size_t N = h->n;
     if (qpos) TRY(be_d2d(h, h->A.qpos, qpos, 16 * N * 4));
     if (qvel) TRY(be_d2d(h, h->A.qvel, qvel, 15 * N * 4));
+    TRY(invalidate_ccache(h));
     return KG_OK;
 }
 int kg_get_state_host(kg_handle h, float *qpos, float *qvel) {
@@ -856,14 +949,15 @@ int kg_set_state_host(kg_handle h, const float *qpos, const float *qvel) {
     const size_t N = h->n;
     if (qpos) TRY(be_h2d(h, h->A.qpos, qpos, 16 * N * 4));
     if (qvel) TRY(be_h2d(h, h->A.qvel, qvel, 15 * N * 4));
+    TRY(invalidate_ccache(h));
     return be_sync(h);
 }
-int kg_get_stats(kg_handle h, long long out[4]) {
+int kg_get_stats(kg_handle h, long long out[8]) {
     if (!h || !out) return KG_EINVAL;
-    long long s[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};       // 64-bit device counters: 32768 envs x 15 substeps wrap 2^31 in ~4.4k steps
+    long long s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, z[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // 64-bit device counters: 32768 envs x 15 substeps wrap 2^31 in ~4.4k steps
     TRY(be_d2h(h, s, h->A.stats, sizeof s)); TRY(be_sync(h));
     TRY(be_h2d(h, h->A.stats, z, sizeof z)); TRY(be_sync(h));
-    for (int i = 0; i < 4; i++) out[i] = s[i];
+    for (int i = 0; i < 8; i++) out[i] = s[i];
     return KG_OK;
 }
 int kg_get_prof(kg_handle h, long long out[KG_NPROF]) {
@@ -872,6 +966,15 @@ int kg_get_prof(kg_handle h, long long out[KG_NPROF]) {
     TRY(be_d2h(h, out, h->A.prof, sizeof z)); TRY(be_sync(h));
     TRY(be_h2d(h, h->A.prof, z, sizeof z)); TRY(be_sync(h));
     return KG_OK;
+}
+int kg_get_trace(kg_handle h, long long *out) {      /* KG_TRACE builds: [16][n][2] words of the last kg_step (tools/trace_probe.py) */
+    if (!h || !out) return KG_EINVAL;
+#ifdef KG_TRACE
+    TRY(be_d2h(h, out, h->A.prof + KG_NPROF, (size_t)2 * 16 * h->n * 8)); TRY(be_sync(h));
+    return KG_OK;
+#else
+    return KG_EINVAL;
+#endif
 }
 int kg_forward_debug(kg_handle h, int env, const float *ctrl, float *out) {
     if (!h || env < 0 || env >= h->n || !ctrl || !out) return KG_EINVAL;
@@ -929,6 +1032,13 @@ int kg_measure_fp32_peak(kg_handle h, float *tflops) {
     CUDA_TRY(h, cudaGetLastError());
     const double flop = 2.0 * 8.0 * 16.0 * (double)iters * 1024.0 * (double)grid;
     *tflops = (float)(flop / (best * 1e-3) / 1e12);
+#endif
+    return KG_OK;
+}
+int kg_set_graph(kg_handle h, int on) {
+    if (!h) return KG_EINVAL;
+#ifndef KG_EMU
+    h->use_graph = on ? 1 : 0;
 #endif
     return KG_OK;
 }

@@ -101,6 +101,7 @@ static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u
 // obs staging aliases the constraint Jacobian storage (J is dead once the last substep's solve is over)
 #define KG_WSOBS(ws) ((ws).J)
 #define KG_RANGE(ws) ((ws).range)
+#define KG_GROW(g) ((g) < 9 ? (g) : 9 + 3 * ((g) - 9))      // first J row of constraint group g
 #define KG_MAXOBJVERT 160     // padded to a multiple of 32
 // Per-environment workspace in shared memory.  An RL step is a WAVEFRONT of kernels (kg_api.cu): the per-env kernels
 // keep one KgWS per warp; between kernels the CARRY part of it lives in global memory (one KgCarry record per env,
@@ -123,27 +124,40 @@ struct alignas(16) KgWST {
     float oR[9];
     // ---- collision bookkeeping
     int cnt[32];
-    unsigned short cv1[32], cv2[32];   // warm-start hull vertices per pair lane
-    float sep[32][3];                  // cached separating axis per hull-pair lane (valid while sepok[l] != 0)
-    int sepok[32];
-    float range[20];                   // rangefinder readings (KG_NSITE used)
     // ---- statistics
     int stat_mpr, stat_newton, stat_overflow, stat_pad;
     // ======================================================================== end of carry section A
     // ---- dynamics
     alignas(16) float M[KG_NV * KG_MS];
     // the Newton-solver scratch and the contact staging of the collision stage are never live together; the staging
-    // (carry section B) is what the narrowphase kernel fills in global memory
+    // (carry section B) is what the narrowphase kernel fills in global memory.  The rangefinder readings only exist
+    // between kg_rays and kg_obs, at the very end of an RL step.
     union {
-        struct { float L[KG_NV * KG_MS], bdot[NBASE + 2], bdir[NBASE + 2], bw[NBASE + 2]; };
+        struct { float L[KG_NV * KG_MS], bdot[NBASE + 2], bdir[NBASE + 2], bw[NBASE + 2], range[20]; };
         struct { float st_dist[KG_NSTAGE], st_pos[KG_NSTAGE][3], st_n[KG_NSTAGE][3]; unsigned char st_g1[KG_NSTAGE], st_g2[KG_NSTAGE], st_pad[16]; };
     };
     alignas(16) float bias[16], fs[16], qas[16], qacc[16], Mdq[16], grad[16], dir[16], Md[16], ftot[16];
     float sbias[3][3];
-    // ---- constraint groups: slot g<3 tendon, 3..8 limits, 9.. contacts
-    int gtype[32], gslot[32], ngroup, ncon_total;
-    float gmu[32], garef[32][4], gD[32];
-    alignas(16) float J[NBASE * KG_JS];
+    // ---- constraint groups: slot g<3 tendon, 3..8 limits, 9.. contacts.  Their per-group scalars (type, aref, D, mu,
+    // staging slot) live in the 5 pad words of the group's J rows (kg_g* accessors below).
+    int ngroup, ncon_total;
+    // J rows have 15 entries at stride KG_JS = 20.  The same storage is, at other times of a substep: the COLLISION CACHE
+    // of the env (carry section C: warm-start hull vertices and cached separating axes per pair lane; only the collision
+    // stage reads it, long after the solve has finished with J), the obs staging, the rangefinder scratch.
+    union {
+        alignas(16) float J[NBASE * KG_JS];
+        struct {
+            unsigned short cv1[32], cv2[32];   // warm-start hull vertices per pair lane
+            float sep[32][3];                  // cached separating axis per hull-pair lane (valid while sepok[l] != 0)
+            int sepok[32];
+            // separation BUDGET per pair lane: the gap measured along the cached axis (hull pairs) or above the contact margin
+            // (plane lanes) when the pair was last tested, minus an upper bound of how far the two geoms' surfaces have moved
+            // since (cpos = geom centres at the last collision stage).  While it stays positive the pair cannot have come
+            // into contact range, so the support queries of the re-test are skipped -- the contact set is unchanged by this.
+            float slack[32];
+            float cpos[9][3], cpad;
+        };
+    };
     float red[32], red2[32];
     // ---- solver scalars (written by lane 0, read by all after a sync)
     float s_alpha, s_cost, s_flag, s_lo, s_hi, s_glo, s_ghi, s_cost2;
@@ -160,17 +174,20 @@ struct alignas(16) KgWST {
 typedef KgWST<KG_MAXCON, KG_STAGE_MASK> KgWS;
 typedef KgWST<KG_MAXCON_LIGHT, KG_STAGE_MASK> KgWSLight;
 typedef KgWST<KG_MAXCON, 0> KgWSNoSync;      // full workspace without stage rendezvous (warps loop independently)
-// the collision caches: contiguous in the workspace, kept per env across RL steps (a cached axis is only ever RE-TESTED,
-// a cached vertex is only a starting point, so stale entries after kg_set_state cost time, not correctness)
+// the collision caches: contiguous in the workspace (aliased onto J), kept per env across RL steps (a cached axis is only
+// ever RE-TESTED, a cached vertex is only a starting point, so stale entries after kg_set_state cost time, not correctness)
 #define KG_CCACHE_OFF   (offsetof(KgWS, cv1))
-#define KG_CCACHE_BYTES (offsetof(KgWS, sepok) + sizeof(int) * 32 - offsetof(KgWS, cv1))
+#define KG_CCACHE_BYTES (offsetof(KgWS, cpad) + sizeof(float) - offsetof(KgWS, cv1))
+// carry record of an env in global memory: [section A: state, constants, kinematics, contact counts][section C: collision
+// cache][section B: staged contacts]
 #define KG_CARRY_A_BYTES (offsetof(KgWS, M))
 #define KG_CARRY_B_OFF   (offsetof(KgWS, st_dist))
 #define KG_CARRY_B_BYTES ((sizeof(float) * 7 * KG_NSTAGE + 2 * KG_NSTAGE + 15) / 16 * 16)
-#define KG_CARRY_BYTES   ((KG_CARRY_A_BYTES + KG_CARRY_B_BYTES + 127) / 128 * 128)
+#define KG_CARRY_BYTES   ((KG_CARRY_A_BYTES + KG_CCACHE_BYTES + KG_CARRY_B_BYTES + 127) / 128 * 128)
 // offsets of the fields the narrowphase kernel touches inside a carry record
 #define KG_COFF(field)   (offsetof(KgWS, field))
-#define KG_COFF_B(field) (KG_CARRY_A_BYTES + offsetof(KgWS, field) - KG_CARRY_B_OFF)
+#define KG_COFF_C(field) (KG_CARRY_A_BYTES + offsetof(KgWS, field) - KG_CCACHE_OFF)
+#define KG_COFF_B(field) (KG_CARRY_A_BYTES + KG_CCACHE_BYTES + offsetof(KgWS, field) - KG_CARRY_B_OFF)
 
 static_assert(offsetof(KgWS, M) % 16 == 0 && offsetof(KgWS, L) % 16 == 0 && offsetof(KgWS, J) % 16 == 0 && sizeof(KgWS) % 16 == 0, "128-bit access needs 16-byte aligned members");
 static_assert(KG_NOBS * 4 <= KgWSLight::NBASE * KG_JS * 4, "obs staging must fit into J");
@@ -178,8 +195,19 @@ static_assert(KG_CARRY_B_OFF % 16 == 0 && offsetof(KgWS, st_g2) + KG_NSTAGE - KG
 static_assert(KG_CARRY_B_BYTES <= sizeof(float) * 7 * KG_NSTAGE + 2 * KG_NSTAGE + 16, "carry section B must stay inside the union (st_pad absorbs the 16-byte round-up)");
 static_assert(offsetof(KgWSLight, M) == offsetof(KgWS, M) && offsetof(KgWSLight, st_dist) == offsetof(KgWS, st_dist) && offsetof(KgWSLight, st_g2) == offsetof(KgWS, st_g2),
               "carry sections must sit at the same offsets in both workspaces");
-static_assert(KG_CCACHE_OFF % 16 == 0 && KG_CCACHE_BYTES % 16 == 0 && KG_CCACHE_BYTES == 640, "collision cache block");
+static_assert(KG_CCACHE_OFF % 16 == 0 && KG_CCACHE_BYTES % 16 == 0 && KG_CCACHE_BYTES == 880 && KG_CARRY_A_BYTES % 16 == 0, "collision cache block");
+static_assert(offsetof(KgWS, cv1) == offsetof(KgWS, J) && offsetof(KgWSLight, cv1) == offsetof(KgWSLight, J) && KG_CCACHE_BYTES <= KgWSLight::NBASE * KG_JS * 4, "collision cache aliases J");
 static_assert(offsetof(KgWSLight, J) % 16 == 0 && sizeof(KgWSLight) % 16 == 0, "128-bit access needs 16-byte aligned members");
+
+// Per-group scalars in the pad words 15..19 of the group's J rows: row b = KG_GROW(g): [aref0 | aref1 (tendon / limit rows:
+// D * active of the current Newton iterate) | D | type | mu]; contact groups also use row b + 1: [aref2 | aref3 | slot].
+// type: 0 none, 1 equality, 2 limit, 3 contact; type and the staging slot are small integers stored as floats.
+#define KG_GP(ws, g, k) ((ws).J[(KG_GROW(g) + ((k) >= 5 ? 1 : 0)) * KG_JS + 15 + ((k) >= 5 ? (k) - 5 : (k))])
+#define KG_GAREF(ws, g, k) KG_GP(ws, g, (k) < 2 ? (k) : (k) + 3)
+#define KG_GD(ws, g)       KG_GP(ws, g, 2)
+#define KG_GMU(ws, g)      KG_GP(ws, g, 4)
+template <class WS> KG_DEV int kg_gtype(const WS &ws, int g) { return g < ws.ngroup ? (int)KG_GP(ws, g, 3) : 0; }
+template <class WS> KG_DEV int kg_gslot(const WS &ws, int g) { return (int)KG_GP(ws, g, 7); }
 
 // Workspace of the narrowphase (MPR) kernel: the geom frames of one env, the object's hull, the finger hulls of the CTA.
 struct alignas(16) KgMprWS {
@@ -294,7 +322,6 @@ template <class WS> KG_DEV void kg_episode_constants(const KgModel &m, WS &ws, c
             kg_mulmv(ws.sax[l], ws.Rh, m.slide_axes + 3 * l);
         }
         if (l == 3) kg_mulmm(ws.gmat[1], ws.Rh, m.palm_gR);
-        ws.cv1[l] = 0; ws.cv2[l] = 0; ws.sepok[l] = 0;
     }
     KG_SYNC();
 }
@@ -552,6 +579,16 @@ template <class WS> KG_DEV void kg_support(const KgModel &m, const WS &ws, int g
     for (int k = 0; k < 3; k++) out[k] = wv[k] + (ws.gpos[g][k] - origin[k]) + margin * dir[k];
 }
 
+// Narrowphase team size: a full MPR is run by a TEAM of lanes that share the two support scans of an iteration and execute
+// the (scalar) portal algebra redundantly.  KG_MPR_HALF: two teams of 16 lanes per warp, each with its own task -- the
+// algebra, most of an iteration's instructions, is then issued once for two tasks; the scans take twice as many trips.
+#if defined(__CUDA_ARCH__) && defined(KG_MPR_HALF)
+#define KG_MPR_W 16
+#define KG_MPR_MASK(lane) (0xffffu << ((lane) & 16))
+#else
+#define KG_MPR_W 32
+#define KG_MPR_MASK(lane) 0xffffffffu
+#endif
 // Warp-cooperative support of geom g's hull along the (warp-uniform) direction dir, inflated by `margin`, relative to
 // `origin`.  The 32 lanes scan the whole vertex table with independent 128-bit loads (no hill-climbing chain).  The
 // tables are padded to a multiple of 32 vertices with copies of vertex 0, so the scan is branch-free; each lane tracks
@@ -584,15 +621,16 @@ KG_DEV void kg_support_coop(const KgModel &m, const KgMprWS &ws, int slot, int m
     const float4 *v4 = reinterpret_cast<const float4 *>(m.hull_oct) + m.oct0[mesh][oct];
     bi = 0x7fffffff;
 #pragma unroll 4
-    for (int i = kg_lane; i < npad; i += 32) {
+    for (int i = kg_lane & (KG_MPR_W - 1); i < npad; i += KG_MPR_W) {
         float4 v = __ldg(v4 + i);
         float d = v.x * ld[0] + v.y * ld[1] + v.z * ld[2];
         if (d > best) { best = d; bi = __float_as_int(v.w); }
     }
     unsigned u = __float_as_uint(best);
     unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    unsigned mx = __reduce_max_sync(0xffffffffu, key);
-    bi = __reduce_min_sync(0xffffffffu, key == mx ? bi : 0x7fffffff);
+    const unsigned team = KG_MPR_MASK(kg_lane);
+    unsigned mx = __reduce_max_sync(team, key);
+    bi = __reduce_min_sync(team, key == mx ? bi : 0x7fffffff);
     float4 w = __ldg(reinterpret_cast<const float4 *>(vert) + bi);
     float lv[3] = {w.x, w.y, w.z};
     (void)vert;
@@ -704,8 +742,8 @@ static long kg_emu_mpr_iters = 0;
 // On a "no overlap" exit that PROVES separation (support of A-B along dir is negative) *sep_found is set and dir is
 // returned in nrm: the caller re-tests that axis first in the next substep (two supports instead of a full MPR).
 KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g2, int mesh2, float hmargin, int &cur1, int &cur2,
-                   float *depth, float *nrm, float *pos, int *sep_found, int kg_lane) {
-    *sep_found = 0;
+                   float *depth, float *nrm, float *pos, int *sep_found, float *gap, int kg_lane) {
+    *sep_found = 0; *gap = 0.f;
     KgSupp p[4];
     float dir[3], va[3], vb[3], dot;
     const float *org = ws.gp[0];
@@ -732,7 +770,7 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g
         if (state == 0) {
             p[1] = s;
             dot = kg_dot(s.v, dir);
-            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; kg_copy(nrm, dir); } return false; }
+            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); } return false; }
             kg_cross(dir, p[0].v, p[1].v);
             if (kg_iszero(kg_dot(dir, dir))) {
                 if (kg_iszero(p[1].v[0]) && kg_iszero(p[1].v[1]) && kg_iszero(p[1].v[2])) return false;   // touching, no normal
@@ -746,7 +784,7 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g
         } else if (state == 1) {
             p[2] = s;
             dot = kg_dot(s.v, dir);
-            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; kg_copy(nrm, dir); } return false; }
+            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); } return false; }
             kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
             kg_cross(dir, va, vb); kg_normalize_dir(dir);
             if (kg_dot(dir, p[0].v) > 0) { KgSupp t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
@@ -754,7 +792,7 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g
         } else if (state == 2) {
             p[3] = s;
             dot = kg_dot(s.v, dir);
-            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; kg_copy(nrm, dir); } return false; }
+            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); } return false; }
             bool cont = false;
             kg_cross(va, p[1].v, p[3].v); dot = kg_dot(va, p[0].v);
             if (dot < 0 && !kg_iszero(dot)) { p[2] = p[3]; cont = true; }
@@ -768,7 +806,7 @@ KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g
             } else { state = 3; check_portal = true; }
         } else if (state == 3) {
             dot = kg_dot(s.v, dir);
-            if (!(kg_iszero(dot) || dot > 0)) { *sep_found = 1; kg_copy(nrm, dir); return false; }
+            if (!(kg_iszero(dot) || dot > 0)) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); return false; }
             if (kg_reach_tol(p, s, dir)) return false;
             kg_expand_portal(p, s);
             check_portal = true;
@@ -850,6 +888,19 @@ template <class WS> KG_DEV float kg_rbound(const KgModel &m, const WS &ws, int g
 KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int lp, int kg_lane) {
     int g1, g2;
     kg_pair_of_lane(lp, g1, g2);
+#if defined(__CUDA_ARCH__) && defined(KG_MPR_HALF)
+    {   // the frames of the two geoms of this pair: 2 x (3 + 9) words over the team's 16 lanes
+        const unsigned team = KG_MPR_MASK(kg_lane);
+        __syncwarp(team);
+        for (int l = kg_lane & 15; l < 24; l += 16) {
+            const int which = l >= 12, j = l - 12 * which, g = which ? g2 : g1;
+            if (j < 3) mw.gp[which][j] = reinterpret_cast<const float *>(carry + KG_COFF(gpos))[3 * g + j];
+            else mw.gr[which][4 * ((j - 3) / 3) + (j - 3) % 3] = reinterpret_cast<const float *>(carry + KG_COFF(gmat))[9 * g + j - 3];
+        }
+        if ((kg_lane & 15) == 15) mw.shape = *reinterpret_cast<const int *>(carry + KG_COFF(shape));
+        __syncwarp(team);
+    }
+#else
     KG_PHASE(l) {
         // the frames of the two geoms of this pair: 2 x (3 + 9) words, one per lane
         if (l < 24) {
@@ -860,6 +911,7 @@ KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int
         if (l == 31) mw.shape = *reinterpret_cast<const int *>(carry + KG_COFF(shape));
     }
     KG_SYNC();
+#endif
 #ifndef KG_MPR_L1
     if (mw.shape != mw.hull_shape) {      // this warp's object-hull copy holds another shape
         KG_SYNC();
@@ -879,20 +931,27 @@ KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int
     const int mesh1 = kg_mesh_of_geom_s(mw.shape, g1), mesh2 = kg_mesh_of_geom_s(mw.shape, g2);
     const float margin = m.margin;
     int c1 = 0, c2 = 0, sepf = 0;
-    float depth = 0.f, nrm[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
+    float depth = 0.f, nrm[3] = {0, 0, 0}, pos[3] = {0, 0, 0}, gap = 0.f;
 #if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
     long it0_ = kg_emu_mpr_iters;
 #endif
-    bool hit = kg_mpr(m, mw, g1, mesh1, g2, mesh2, 0.5f * margin, c1, c2, &depth, nrm, pos, &sepf, kg_lane);
+    bool hit = kg_mpr(m, mw, g1, mesh1, g2, mesh2, 0.5f * margin, c1, c2, &depth, nrm, pos, &sepf, &gap, kg_lane);
 #if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
     fprintf(stderr, "MPR %d %d %ld %d %d\n", g1, g2, kg_emu_mpr_iters - it0_, (int)hit, sepf);
 #endif
+#if defined(__CUDA_ARCH__) && defined(KG_MPR_HALF)
+    for (int l = kg_lane & 15, once_ = 0; once_ < 1; ++once_) {
+#else
     KG_PHASE(l) {
+#endif
         if (l == 0) {
-            reinterpret_cast<int *>(carry + KG_COFF(sepok))[lp] = sepf;
-            if (sepf) { float *sp = reinterpret_cast<float *>(carry + KG_COFF(sep)) + 3 * lp; sp[0] = nrm[0]; sp[1] = nrm[1]; sp[2] = nrm[2]; }
-            reinterpret_cast<unsigned short *>(carry + KG_COFF(cv1))[lp] = (unsigned short)c1;
-            reinterpret_cast<unsigned short *>(carry + KG_COFF(cv2))[lp] = (unsigned short)c2;
+            reinterpret_cast<int *>(carry + KG_COFF_C(sepok))[lp] = sepf;
+            if (sepf) {
+                float *sp = reinterpret_cast<float *>(carry + KG_COFF_C(sep)) + 3 * lp; sp[0] = nrm[0]; sp[1] = nrm[1]; sp[2] = nrm[2];
+                reinterpret_cast<float *>(carry + KG_COFF_C(slack))[lp] = gap;      // the collision stage of this very substep has already charged the motion up to here
+            }
+            reinterpret_cast<unsigned short *>(carry + KG_COFF_C(cv1))[lp] = (unsigned short)c1;
+            reinterpret_cast<unsigned short *>(carry + KG_COFF_C(cv2))[lp] = (unsigned short)c2;
             if (hit && depth > 0.f) {
                 const int sl = 32 + (lp - 8);
                 reinterpret_cast<float *>(carry + KG_COFF_B(st_dist))[sl] = margin - depth;
@@ -903,12 +962,37 @@ KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int
             }
         }
     }
+#if defined(__CUDA_ARCH__) && defined(KG_MPR_HALF)
+    __syncwarp(KG_MPR_MASK(kg_lane));
+#else
     KG_SYNC();
+#endif
 }
 
 // Lane-parallel part of the collision stage: broadphase, plane contacts, re-test of the cached separating axes.
 // Returns (every lane) the mask of the pair lanes 8..29 that need a full MPR; those become narrowphase tasks.
 template <class WS> KG_DEV unsigned kg_collision_lane(const KgModel &m, WS &ws, int kg_lane) {
+#ifndef KG_NO_SLACK
+    // how far any surface point of geom g can have moved since the previous collision stage: |centre displacement| +
+    // bounding radius x rotation angle of the last integration (hinges: h |qvel|, free body: h |omega|; the palm only
+    // translates; the ground does not move) + rounding allowance
+    KG_PHASE(l) {
+        if (l < 9) {
+            float mv = 0.f;
+            if (l >= 1) {
+                float d[3]; kg_sub(d, ws.gpos[l], ws.cpos[l]);
+                const float h = m.timestep;
+                float th = 0.f;
+                if (l == 8) th = h * sqrtf(ws.qvel[12] * ws.qvel[12] + ws.qvel[13] * ws.qvel[13] + ws.qvel[14] * ws.qvel[14]);
+                else if (l >= 2) { const int k = (l - 2) >> 1; th = h * (fabsf(ws.qvel[3 + 2 * k]) + ((l & 1) ? fabsf(ws.qvel[4 + 2 * k]) : 0.f)); }
+                mv = 1.0001f * (sqrtf(kg_dot(d, d)) + kg_rbound(m, ws, l) * th) + 2e-6f;
+                kg_copy(ws.cpos[l], ws.gpos[l]);
+            }
+            ws.red[l] = mv;
+        }
+    }
+    KG_SYNC();
+#endif
     KG_PHASE(l) {
         int n = 0;
         float tried = 0.f;
@@ -918,9 +1002,14 @@ template <class WS> KG_DEV unsigned kg_collision_lane(const KgModel &m, WS &ws, 
             const float margin = m.margin;
             const float rb2 = kg_rbound(m, ws, g2);
             const int mesh2 = kg_mesh_of_geom(ws, g2);
+#ifndef KG_NO_SLACK
+            const float budget = ws.sepok[l] ? ws.slack[l] - ws.red[g1] - ws.red[g2] : -1.f;
+#else
+            const float budget = -1.f;
+#endif
             if (l < 8) {
                 const int base = 4 * l;
-                if (ws.gpos[g2][2] <= rb2 + margin) {
+                if (ws.gpos[g2][2] <= rb2 + margin && !(budget > 0.f)) {
                     const float nd[3] = {0, 0, -1}, zero[3] = {0, 0, 0};
                     float w[3];
                     int cur = ws.cv2[l];
@@ -928,6 +1017,7 @@ template <class WS> KG_DEV unsigned kg_collision_lane(const KgModel &m, WS &ws, 
                     kg_support(m, ws, g2, mesh2, cur, nd, zero, 0.f, w);
                     KG_COUNT(26, 1);
                     ws.cv2[l] = (unsigned short)cur;
+                    ws.sepok[l] = w[2] > margin; ws.slack[l] = w[2] - margin;      // clear of the floor by this much
                     if (w[2] <= margin) {
                         const float thresh = 0.3f * rb2;
                         const float *vert = m.hull_vert + 4 * (size_t)m.mesh[mesh2].vert0;
@@ -955,27 +1045,33 @@ template <class WS> KG_DEV unsigned kg_collision_lane(const KgModel &m, WS &ws, 
                             n++;
                         }
                     }
-                }
+                } else if (budget > 0.f) ws.slack[l] = budget;
+                else ws.sepok[l] = 0;                                   // beyond the bounding sphere: nothing cached
             } else {
                 float rb1 = kg_rbound(m, ws, g1), df[3];
                 kg_sub(df, ws.gpos[g2], ws.gpos[g1]);
                 float lim = rb1 + rb2 + margin;
                 if (kg_dot(df, df) <= lim * lim) {
-                    const int mesh1 = kg_mesh_of_geom(ws, g1);
-                    int c1 = ws.cv1[l], c2 = ws.cv2[l];
-                    if (c1 >= m.mesh[mesh1].nvert) c1 = 0;
-                    if (c2 >= m.mesh[mesh2].nvert) c2 = 0;
-                    bool separated = false;
-                    if (ws.sepok[l]) {
-                        // the axis that separated the inflated hulls in the previous substep: still separating?
-                        float n0[3] = {ws.sep[l][0], ws.sep[l][1], ws.sep[l][2]}, nn[3] = {-n0[0], -n0[1], -n0[2]}, s1[3], s2[3];
-                        kg_support(m, ws, g1, mesh1, c1, n0, ws.gpos[g1], 0.5f * margin, s1);
-                        kg_support(m, ws, g2, mesh2, c2, nn, ws.gpos[g1], 0.5f * margin, s2);
-                        separated = (kg_dot(s1, n0) - kg_dot(s2, n0)) < 0.f;
-                        KG_COUNT(24, 1); KG_COUNT(25, separated ? 1 : 0);
+                    if (budget > 0.f) ws.slack[l] = budget;             // still provably separated along the cached axis
+                    else {
+                        const int mesh1 = kg_mesh_of_geom(ws, g1);
+                        int c1 = ws.cv1[l], c2 = ws.cv2[l];
+                        if (c1 >= m.mesh[mesh1].nvert) c1 = 0;
+                        if (c2 >= m.mesh[mesh2].nvert) c2 = 0;
+                        bool separated = false;
+                        if (ws.sepok[l]) {
+                            // the axis that separated the inflated hulls in the previous substep: still separating?
+                            float n0[3] = {ws.sep[l][0], ws.sep[l][1], ws.sep[l][2]}, nn[3] = {-n0[0], -n0[1], -n0[2]}, s1[3], s2[3];
+                            kg_support(m, ws, g1, mesh1, c1, n0, ws.gpos[g1], 0.5f * margin, s1);
+                            kg_support(m, ws, g2, mesh2, c2, nn, ws.gpos[g1], 0.5f * margin, s2);
+                            const float gap = kg_dot(s2, n0) - kg_dot(s1, n0);
+                            separated = gap > 0.f;
+                            ws.slack[l] = gap;
+                            KG_COUNT(24, 1); KG_COUNT(25, separated ? 1 : 0);
+                        }
+                        if (!separated) tried = 1.f;       // full MPR: a narrowphase task
+                        ws.cv1[l] = (unsigned short)c1; ws.cv2[l] = (unsigned short)c2;
                     }
-                    if (!separated) tried = 1.f;       // full MPR: a narrowphase task
-                    ws.cv1[l] = (unsigned short)c1; ws.cv2[l] = (unsigned short)c2;
                 } else ws.sepok[l] = 0;
             }
         }
@@ -1010,18 +1106,15 @@ template <class WS> KG_DEV void kg_compaction(const KgModel &m, WS &ws, int kg_l
         int base = l < 8 ? 4 * l : 32 + (l - 8);
         for (int i = 0; i < ws.cnt[l]; i++) {
             int g = 9 + off + i;
-            if (g < 32) { ws.gslot[g] = base + i; ws.gtype[g] = 3; }
+            if (g < 9 + WS::MAXCON) { KG_GP(ws, g, 7) = (float)(base + i); KG_GP(ws, g, 3) = 3.f; }
         }
         if (l == 0) {
             ws.ncon_total = total;
+            ws.stat_pad += total;              // contacts of this substep (reported per substep by kg_get_stats)
             int nc = total > WS::MAXCON ? WS::MAXCON : total;
             ws.ngroup = 9 + nc;
             if (total > WS::MAXCON) ws.stat_overflow += 1;
         }
-    }
-    KG_SYNC();
-    KG_PHASE(l) {
-        if (l >= 9 && l >= ws.ngroup) ws.gtype[l] = 0;
     }
     KG_SYNC();
 }
@@ -1064,7 +1157,7 @@ template <class WS> KG_DEV void kg_make_rows(const KgModel &m, WS &ws, int kg_la
             float vel = ws.qvel[3 + 2 * l] - 2.f * ws.qvel[4 + 2 * l];
             float imp = kg_impedance(m, pos);
             float R = fmaxf((1.f - imp) / imp * m.tendon_invw[l], 1e-15f);
-            ws.gtype[l] = 1; ws.gD[l] = 1.f / R; ws.garef[l][0] = -Bd * vel - K * imp * pos;
+            KG_GP(ws, l, 3) = 1.f; KG_GD(ws, l) = 1.f / R; KG_GAREF(ws, l, 0) = -Bd * vel - K * imp * pos;
         } else if (l < 9) {
             int a = l - 3, j = a < 3 ? a : 3 + 2 * (a - 3);
             float lo = a < 3 ? m.slide_range[2 * a] : m.finger_range[2 * (a - 3)];
@@ -1077,10 +1170,10 @@ template <class WS> KG_DEV void kg_make_rows(const KgModel &m, WS &ws, int kg_la
                 row[j] = sgn;
                 float imp = kg_impedance(m, pos);
                 float R = fmaxf((1.f - imp) / imp * m.dof_invw[j], 1e-15f);
-                ws.gtype[l] = 2; ws.gD[l] = 1.f / R; ws.garef[l][0] = -Bd * sgn * ws.qvel[j] - K * imp * pos;
-            } else ws.gtype[l] = 0;
+                KG_GP(ws, l, 3) = 2.f; KG_GD(ws, l) = 1.f / R; KG_GAREF(ws, l, 0) = -Bd * sgn * ws.qvel[j] - K * imp * pos;
+            } else KG_GP(ws, l, 3) = 0.f;
         } else if (l < ws.ngroup) {
-            int s = ws.gslot[l], g1 = ws.st_g1[s], g2 = ws.st_g2[s];
+            int s = kg_gslot(ws, l), g1 = ws.st_g1[s], g2 = ws.st_g2[s];
             float n[3], t1[3], t2[3];
             kg_copy(n, ws.st_n[s]);
             kg_make_frame(n, t1, t2);
@@ -1098,10 +1191,10 @@ template <class WS> KG_DEV void kg_make_rows(const KgModel &m, WS &ws, int kg_la
             float R = fmaxf((1.f - imp) / imp * (tran + mu * mu * tran), 1e-15f);
             float Rpy = fmaxf(2.f * mu * mu / m.impratio * R, 1e-15f);
             float Dv = 1.f / Rpy, kr = K * imp * r;
-            ws.gmu[l] = mu;
-            ws.gD[l] = Dv;
-            ws.garef[l][0] = -Bd * (vn + mu * v1) - kr; ws.garef[l][1] = -Bd * (vn - mu * v1) - kr;
-            ws.garef[l][2] = -Bd * (vn + mu * v2) - kr; ws.garef[l][3] = -Bd * (vn - mu * v2) - kr;
+            KG_GMU(ws, l) = mu;
+            KG_GD(ws, l) = Dv;
+            KG_GAREF(ws, l, 0) = -Bd * (vn + mu * v1) - kr; KG_GAREF(ws, l, 1) = -Bd * (vn - mu * v1) - kr;
+            KG_GAREF(ws, l, 2) = -Bd * (vn + mu * v2) - kr; KG_GAREF(ws, l, 3) = -Bd * (vn - mu * v2) - kr;
         }
     }
     KG_SYNC();
@@ -1111,13 +1204,13 @@ template <class WS> KG_DEV void kg_make_rows(const KgModel &m, WS &ws, int kg_la
 // Scalar rows of group g at the point described by base-row products bd[]:
 //   tendon/limit: jar = bd[g] - aref ;  contact c: jar_k = bd[n] +- mu bd[t] - aref_k
 template <class WS> KG_DEV int kg_group_rows(const WS &ws, int g, const float *bd, float *jar) {
-    int tp = ws.gtype[g];
+    int tp = kg_gtype(ws, g);
     if (tp == 0) return 0;
-    if (tp < 3) { jar[0] = bd[g] - ws.garef[g][0]; return 1; }
+    if (tp < 3) { jar[0] = bd[g] - KG_GAREF(ws, g, 0); return 1; }
     int b = 9 + 3 * (g - 9);
-    float mu = ws.gmu[g], n = bd[b], t1 = mu * bd[b + 1], t2 = mu * bd[b + 2];
-    jar[0] = n + t1 - ws.garef[g][0]; jar[1] = n - t1 - ws.garef[g][1];
-    jar[2] = n + t2 - ws.garef[g][2]; jar[3] = n - t2 - ws.garef[g][3];
+    float mu = KG_GMU(ws, g), n = bd[b], t1 = mu * bd[b + 1], t2 = mu * bd[b + 2];
+    jar[0] = n + t1 - KG_GAREF(ws, g, 0); jar[1] = n - t1 - KG_GAREF(ws, g, 1);
+    jar[2] = n + t2 - KG_GAREF(ws, g, 2); jar[3] = n - t2 - KG_GAREF(ws, g, 3);
     return 4;
 }
 template <class WS> KG_DEV int kg_nbase(const WS &ws) { return 9 + 3 * (ws.ngroup - 9); }
@@ -1237,9 +1330,9 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
         }
         float jar[4];
         int n = kg_group_rows(ws, l, ws.bdot, jar);
-        for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) cw += 0.5f * ws.gD[l] * jar[k] * jar[k];
+        for (int k = 0; k < n; k++) if (kg_gtype(ws, l) == 1 || jar[k] < 0.f) cw += 0.5f * KG_GD(ws, l) * jar[k] * jar[k];
         n = kg_group_rows(ws, l, ws.bdir, jar);
-        for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) cs += 0.5f * ws.gD[l] * jar[k] * jar[k];
+        for (int k = 0; k < n; k++) if (kg_gtype(ws, l) == 1 || jar[k] < 0.f) cs += 0.5f * KG_GD(ws, l) * jar[k] * jar[k];
         ws.red[l] = cw; ws.red2[l] = cs;
     }
     KG_SYNC();
@@ -1263,11 +1356,11 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             if (l < KG_NV) c = 0.5f * ws.Mdq[l] * (ws.qacc[l] - ws.qas[l]);
             float jar[4], w[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
             int n = kg_group_rows(ws, l, ws.bdot, jar);
-            for (int k = 0; k < n; k++) if (ws.gtype[l] == 1 || jar[k] < 0.f) { a[k] = ws.gD[l]; w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
-            if (n == 1) { ws.bw[l] = w[0]; ws.garef[l][1] = a[0]; }
+            for (int k = 0; k < n; k++) if (kg_gtype(ws, l) == 1 || jar[k] < 0.f) { a[k] = KG_GD(ws, l); w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
+            if (n == 1) { ws.bw[l] = w[0]; KG_GAREF(ws, l, 1) = a[0]; }
             else if (n == 4) {
                 int b = 9 + 3 * (l - 9);
-                float mu = ws.gmu[l];
+                float mu = KG_GMU(ws, l);
                 ws.bw[b] = w[0] + w[1] + w[2] + w[3]; ws.bw[b + 1] = mu * (w[0] - w[1]); ws.bw[b + 2] = mu * (w[2] - w[3]);
             } else if (l < 9) ws.bw[l] = 0.f;
             ws.red[l] = c;
@@ -1298,15 +1391,16 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
 #pragma unroll
                 for (int j = 0; j < KG_NV; j++) h[j] = ws.M[l * KG_MS + j];
                 for (int g = 0; g < ws.ngroup; g++) {
-                    int tp = ws.gtype[g];
+                    int tp = kg_gtype(ws, g);
                     if (tp == 0) continue;
                     if (tp < 3) {
                         const float *rowp = ws.J + g * KG_JS;
                         float ji = rowp[l];
                         float t = ji * ws.bw[g];
                         gr += t; gab += fabsf(t);
-                        float u = ji * ws.garef[g][1];   // D * active stored by (a)
-                        if (ws.garef[g][1] != 0.f) {     // warp-uniform: skip inactive limit rows
+                        const float da = KG_GAREF(ws, g, 1);   // D * active stored by (a)
+                        float u = ji * da;
+                        if (da != 0.f) {     // warp-uniform: skip inactive limit rows
                             float row[16];
                             kg_ld16(rowp, row);
 #pragma unroll
@@ -1320,8 +1414,9 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                         gr += t0 + t1 + t2; gab += fabsf(t0) + fabsf(t1) + fabsf(t2);
                         float jar[4], a[4];
                         kg_group_rows(ws, g, ws.bdot, jar);
-                        for (int k = 0; k < 4; k++) a[k] = jar[k] < 0.f ? ws.gD[g] : 0.f;
-                        float mu = ws.gmu[g];
+                        const float Dg = KG_GD(ws, g);
+                        for (int k = 0; k < 4; k++) a[k] = jar[k] < 0.f ? Dg : 0.f;
+                        float mu = KG_GMU(ws, g);
                         float A = a[0] + a[1] + a[2] + a[3], B1 = mu * (a[0] - a[1]), C1 = mu * mu * (a[0] + a[1]);
                         float B2 = mu * (a[2] - a[3]), C2 = mu * mu * (a[2] + a[3]);
                         if (A != 0.f) {
@@ -1388,13 +1483,14 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                     if (n == 1) jv[0] = ws.bdir[l];
                     else if (n == 4) {
                         int b = 9 + 3 * (l - 9);
-                        float mu = ws.gmu[l], nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
+                        float mu = KG_GMU(ws, l), nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
                         jv[0] = nn + t1; jv[1] = nn - t1; jv[2] = nn + t2; jv[3] = nn - t2;
                     }
-                    const bool eq = ws.gtype[l] == 1;
+                    const bool eq = kg_gtype(ws, l) == 1;
+                    const float Dl = n ? KG_GD(ws, l) : 0.f;
                     for (int k = 0; k < n; k++) {
                         float x = jar[k] + alpha * jv[k];
-                        float dj = ws.gD[l] * jv[k];
+                        float dj = Dl * jv[k];
                         bool act0 = eq || jar[k] < 0.f, act = eq || x < 0.f;
                         if (act) { d1 += dj * x; d2 += dj * jv[k]; }
                         if (act0) d0 += dj * jar[k];
@@ -1446,7 +1542,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             float f = ws.fs[l];
             int nb = kg_nbase(ws);
             for (int b = 0; b < nb; b++) {
-                if (b < 9 && ws.gtype[b] == 0) continue;
+                if (b < 9 && kg_gtype(ws, b) == 0) continue;
                 f -= ws.J[b * KG_JS + l] * ws.bw[b];
             }
             ws.ftot[l] = f;
@@ -1889,7 +1985,7 @@ struct KgEnvArrays {
     int *ex_i;                    // [3][N] have_prev, num_good, total_steps
     float *obs;                   // [82][N] last observation (input of the expert controller)
     float *last_action;           // [4][N] action applied by the last step (given or expert)
-    unsigned long long *stats;    // [4] mpr pairs, newton iterations, contact overflows, substeps (64-bit: they run for a whole training)
+    unsigned long long *stats;    // [8] mpr pairs, newton iterations, contact overflows, substeps, contacts (64-bit: they run for a whole training)
     int *load;                    // [N] cost of each env's last RL step (Newton iterations + 2 x MPR pairs): key of the launch schedule
     long long *prof;              // [KG_NPROF] KG_PROF builds only
     float *obs_global;            // [74][N] or NULL: _get_obs(state_rep="global") of the same step (kg_set_obs_global)
@@ -1938,7 +2034,8 @@ KG_DEV void kg_copy16(void *dst, const void *src, int bytes, int kg_lane) {
 template <class WS> KG_DEV void kg_carry_store(const WS &ws, unsigned char *carry, int kg_lane) {
     KG_SYNC();
     kg_copy16(carry, &ws, (int)KG_CARRY_A_BYTES, kg_lane);
-    kg_copy16(carry + KG_CARRY_A_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CARRY_B_OFF, (int)KG_CARRY_B_BYTES, kg_lane);
+    kg_copy16(carry + KG_CARRY_A_BYTES, ws.cv1, (int)KG_CCACHE_BYTES, kg_lane);      // (its offset differs between the light and the full workspace)
+    kg_copy16(carry + KG_CARRY_A_BYTES + KG_CCACHE_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CARRY_B_OFF, (int)KG_CARRY_B_BYTES, kg_lane);
     KG_SYNC();
 }
 template <class WS> KG_DEV void kg_carry_load(WS &ws, const unsigned char *carry, int kg_lane) {
@@ -1951,13 +2048,13 @@ template <class WS> KG_DEV void kg_carry_load(WS &ws, const unsigned char *carry
         for (int i = kg_lane; i < (int)(KG_CARRY_A_BYTES / 16); i += 32)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstA + 16u * i), "l"(carry + 16 * i) : "memory");
         for (int i = kg_lane; i < (int)(KG_CARRY_B_BYTES / 16); i += 32)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstB + 16u * i), "l"(carry + KG_CARRY_A_BYTES + 16 * i) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstB + 16u * i), "l"(carry + KG_CARRY_A_BYTES + KG_CCACHE_BYTES + 16 * i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
 #else
     kg_copy16(&ws, carry, (int)KG_CARRY_A_BYTES, kg_lane);
-    kg_copy16(reinterpret_cast<unsigned char *>(&ws) + KG_CARRY_B_OFF, carry + KG_CARRY_A_BYTES, (int)KG_CARRY_B_BYTES, kg_lane);
+    kg_copy16(reinterpret_cast<unsigned char *>(&ws) + KG_CARRY_B_OFF, carry + KG_CARRY_A_BYTES + KG_CCACHE_BYTES, (int)KG_CARRY_B_BYTES, kg_lane);
 #endif
     KG_SYNC();
 #ifdef KG_PROF
@@ -1969,6 +2066,12 @@ template <class WS> KG_DEV void kg_carry_load(WS &ws, const unsigned char *carry
     }
     KG_SYNC();
 #endif
+}
+// the collision cache of an env (640 bytes, section C of its record or its slot of A.ccache) into the workspace
+template <class WS> KG_DEV void kg_ccache_load(WS &ws, const unsigned char *src, int kg_lane) {
+    KG_SYNC();
+    kg_copy16(ws.cv1, src, (int)KG_CCACHE_BYTES, kg_lane);
+    KG_SYNC();
 }
 template <class WS> KG_DEV void kg_prof_flush(WS &ws, const KgEnvArrays &A, int kg_lane) {
 #if defined(KG_PROF) && defined(__CUDA_ARCH__)
@@ -1999,8 +2102,6 @@ KG_DEV void kg_emit_tasks(unsigned mask, int env, int *q, unsigned *tasks, int k
 // Returns the narrowphase task mask; the caller stores the carry record and emits the tasks.
 template <class WS> KG_DEV unsigned kg_step_begin(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, const float *action_in, int expert_mode, int kg_lane) {
     kg_load_env(m, ws, A, env, kg_lane);
-    kg_copy16(reinterpret_cast<unsigned char *>(&ws) + KG_CCACHE_OFF, A.ccache + (size_t)env * KG_CCACHE_BYTES, (int)KG_CCACHE_BYTES, kg_lane);
-    KG_SYNC();
     float act[4] = {0, 0, 0, 0}, sxy[2] = {0, 0};      // act = [wrist (slide_z), f1, f2, f3]; sxy = slide_x, slide_y of a 6-d action
     if (action_in) {
         if (A.act_dim == 6) {
@@ -2037,6 +2138,7 @@ template <class WS> KG_DEV unsigned kg_step_begin(const KgModel &m, WS &ws, cons
     KG_PROBE(19);
     kg_kinematics(m, ws, kg_lane);
     KG_PROBE(0);
+    kg_ccache_load(ws, A.ccache + (size_t)env * KG_CCACHE_BYTES, kg_lane);      // (J, which it aliases, held the expert's obs staging until here)
     unsigned mask = kg_collision_lane(m, ws, kg_lane);
     KG_PROBE(2);
     return mask;
@@ -2065,11 +2167,12 @@ template <class WS> KG_DEV void kg_substep_finish(const KgModel &m, WS &ws, int 
     KG_PROBE(15);
 }
 // First half of the next mj_step: kinematics of the new state + lane-parallel collision; returns the task mask.
-template <class WS> KG_DEV unsigned kg_substep_start(const KgModel &m, WS &ws, int kg_lane) {
+template <class WS> KG_DEV unsigned kg_substep_start(const KgModel &m, WS &ws, const unsigned char *rec, int kg_lane) {
     kg_kinematics(m, ws, kg_lane);
     KG_PROBE(0);
     KG_STAGE(1);
     KG_PROBE(1);
+    kg_ccache_load(ws, rec + KG_CARRY_A_BYTES, kg_lane);      // section C of the env's record, into the storage J no longer needs
     unsigned mask = kg_collision_lane(m, ws, kg_lane);
     KG_PROBE(2);
     return mask;
@@ -2077,8 +2180,10 @@ template <class WS> KG_DEV unsigned kg_substep_start(const KgModel &m, WS &ws, i
 
 // Last kernel of an RL step for one env (after the last substep's finish): rays -> obs/reward/done (+TimeLimit),
 // state and outputs back to the struct-of-arrays.
-template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, int nsub,
+template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, int nsub, const unsigned char *rec,
                         float *obs_out, float *reward_out, int *done_out, float *action_out, int kg_lane) {
+    // the collision cache goes back to its per-env home for the next RL step (record -> array; it is not in the workspace)
+    kg_copy16(A.ccache + (size_t)env * KG_CCACHE_BYTES, rec + KG_CARRY_A_BYTES, (int)KG_CCACHE_BYTES, kg_lane);
     KG_PROBE(19);
     kg_rays(m, ws, kg_lane);
     KG_PROBE(16);
@@ -2087,7 +2192,6 @@ template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEn
     if (A.obs_global) kg_obs_global_store(ws, A.obs_global, A.N, env, kg_lane);
     KG_PROBE(17);
     kg_store_env(ws, A, env, kg_lane);
-    kg_copy16(A.ccache + (size_t)env * KG_CCACHE_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CCACHE_OFF, (int)KG_CCACHE_BYTES, kg_lane);
     KG_PHASE(l) {
         const int N = A.N;
         for (int i = l; i < KG_NOBS; i += 32) { float v = KG_WSOBS(ws)[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
@@ -2104,9 +2208,10 @@ template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEn
             if (A.stats) {
                 atomicAdd(A.stats, (unsigned long long)ws.stat_mpr); atomicAdd(A.stats + 1, (unsigned long long)ws.stat_newton);
                 atomicAdd(A.stats + 2, (unsigned long long)ws.stat_overflow); atomicAdd(A.stats + 3, (unsigned long long)nsub);
+                atomicAdd(A.stats + 4, (unsigned long long)ws.stat_pad);
             }
 #else
-            if (A.stats) { A.stats[0] += (unsigned long long)ws.stat_mpr; A.stats[1] += (unsigned long long)ws.stat_newton; A.stats[2] += (unsigned long long)ws.stat_overflow; A.stats[3] += (unsigned long long)nsub; }
+            if (A.stats) { A.stats[0] += (unsigned long long)ws.stat_mpr; A.stats[1] += (unsigned long long)ws.stat_newton; A.stats[2] += (unsigned long long)ws.stat_overflow; A.stats[3] += (unsigned long long)nsub; A.stats[4] += (unsigned long long)ws.stat_pad; }
 #endif
         }
     }
@@ -2163,7 +2268,11 @@ template <class WS> KG_DEV void kg_env_reset(const KgModel &m, WS &ws, const KgE
     kg_obs(m, ws, kg_lane, &rew, &dn);
     if (A.obs_global) kg_obs_global_store(ws, A.obs_global, A.N, env, kg_lane);
     kg_store_env(ws, A, env, kg_lane);
-    kg_copy16(A.ccache + (size_t)env * KG_CCACHE_BYTES, reinterpret_cast<const unsigned char *>(&ws) + KG_CCACHE_OFF, (int)KG_CCACHE_BYTES, kg_lane);   // cleared by kg_episode_constants
+    KG_PHASE(l) {      // a new episode starts with an empty collision cache: vertex 0 as warm start, no cached axis
+        unsigned *cc = reinterpret_cast<unsigned *>(A.ccache + (size_t)env * KG_CCACHE_BYTES);
+        for (int i = l; i < (int)(KG_CCACHE_BYTES / 4); i += 32) cc[i] = 0u;
+    }
+    KG_SYNC();
     KG_PHASE(l) {
         const int N = A.N;
         for (int i = l; i < KG_NOBS; i += 32) { float v = KG_WSOBS(ws)[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }

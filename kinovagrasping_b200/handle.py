@@ -123,6 +123,10 @@ class Handle:
         self._chk(self.lib.kg_measure_fp32_peak(self.h, C.byref(v)), "kg_measure_fp32_peak")
         return float(v.value)
 
+    def set_graph(self, on):
+        """1 (default) = kg_step replays a captured CUDA graph of its kernel chain; 0 = individual launches."""
+        self._chk(self.lib.kg_set_graph(self.h, int(on)), "kg_set_graph")
+
     def set_timing(self, on):
         self._chk(self.lib.kg_set_timing(self.h, int(on)), "kg_set_timing")
 
@@ -143,9 +147,9 @@ class Handle:
         return ms.value
 
     def stats(self):
-        out = (C.c_longlong * 4)()
+        out = (C.c_longlong * 8)()
         self._chk(self.lib.kg_get_stats(self.h, out), "kg_get_stats")
-        return {"mpr_pairs": out[0], "newton_iters": out[1], "contact_overflow": out[2], "substeps": out[3]}
+        return {"mpr_pairs": out[0], "newton_iters": out[1], "contact_overflow": out[2], "substeps": out[3], "contacts": out[4]}
 
     # ---- host-buffer API (numpy)
     def reset_host(self, shape, euler, objpos, mask=None, handpos=None):

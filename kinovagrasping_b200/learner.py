@@ -51,20 +51,27 @@ class Critic(nn.Module):
         return self.l3(q)
 
 
-def flatten_parameters(module):
-    """Re-seat every parameter of `module` as a view into one flat buffer; returns (flat_param, flat_grad)."""
-    ps = list(module.parameters())
+def flatten_parameters(modules):
+    """Re-seat every parameter of the given modules as a view into ONE flat buffer (and its .grad into one flat gradient
+    buffer); returns (flat_param, flat_grad, [(offset, numel) per module])."""
+    if isinstance(modules, nn.Module):
+        modules = [modules]
+    ps = [p for m in modules for p in m.parameters()]
     n = sum(p.numel() for p in ps)
     flat = torch.zeros(n, dtype=ps[0].dtype, device=ps[0].device)
     grad = torch.zeros_like(flat)
     o = 0
-    for p in ps:
-        k = p.numel()
-        flat[o:o + k].copy_(p.data.reshape(-1))
-        p.data = flat[o:o + k].view_as(p.data)
-        p.grad = grad[o:o + k].view_as(p.data)
-        o += k
-    return flat, grad
+    spans = []
+    for m in modules:
+        start = o
+        for p in m.parameters():
+            k = p.numel()
+            flat[o:o + k].copy_(p.data.reshape(-1))
+            p.data = flat[o:o + k].view_as(p.data)
+            p.grad = grad[o:o + k].view_as(p.data)
+            o += k
+        spans.append((start, o - start))
+    return flat, grad, spans
 
 
 class DDPGfD(object):
@@ -92,8 +99,12 @@ class DDPGfD(object):
             self.world = torch.distributed.get_world_size(self.process_group)
 
     def _seat(self):
-        self.actor_flat, self.actor_grad = flatten_parameters(self.actor)
-        self.critic_flat, self.critic_grad = flatten_parameters(self.critic)
+        # one contiguous bucket for all 310 105 parameters and one for their gradients; the critic's and the
+        # actor's gradients are its two halves.  An update needs them at two different times -- the actor loss is taken
+        # through the critic AFTER its step (DDPG:345-350) -- so each half is all-reduced when it is complete.
+        self.flat_param, self.flat_grad, ((co, cn), (ao, an)) = flatten_parameters([self.critic, self.actor])
+        self.critic_flat, self.critic_grad = self.flat_param[co:co + cn], self.flat_grad[co:co + cn]
+        self.actor_flat, self.actor_grad = self.flat_param[ao:ao + an], self.flat_grad[ao:ao + an]
 
     # ------------------------------------------------------------------ acting
     def select_action(self, state):

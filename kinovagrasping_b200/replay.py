@@ -44,6 +44,7 @@ class ReplayBuffer_Queue:
             self.st_reward = torch.zeros((self.n_envs, self.T), **f)
             self.st_notdone = torch.zeros((self.n_envs, self.T), **f)
             self.st_len = torch.zeros(self.n_envs, dtype=torch.long, device=self.device)
+            self.st_closed = torch.zeros(self.n_envs, dtype=torch.bool, device=self.device)
             self._env_ids = torch.arange(self.n_envs, device=self.device)
         self.len_dev = torch.zeros(self.cap, dtype=torch.long, device=self.device)
         self._host_len_dirty = False
@@ -253,7 +254,7 @@ class ReplayBuffer_Queue:
         return self._gather_dev(rows, starts)
 
     # ------------------------------------------------------------------ vectorised feeder
-    def add_batch(self, state, action, next_state, reward, done, record=None, replace=None):
+    def add_batch(self, state, action, next_state, reward, done, record=None, replace=None, defer=False):
         """One step of all N environments (tensors on the device, env-major [N, dim]).
         record[i]  : store this transition (default all).  The rollout loops do not store the lifting steps
                      (expert_data.py:794, main_DDPGfD.py:451-456).
@@ -261,38 +262,46 @@ class ReplayBuffer_Queue:
                      (utils.py:309-343).
         A stored `done` transition closes the episode as in `add`.  Closed episodes with len - n_steps <= 1 are dropped
         (main_DDPGfD.py:470-471); the others are committed to the ring in env order, evicting the oldest when full.
-        Returns the number of episodes committed."""
+        defer=False: commit right away and return the number of episodes committed (one host synchronisation).
+        defer=True : only stage -- no host synchronisation at all, every update is a masked device write; closed episodes
+                     wait in their env's staging row (which ignores further transitions) until `flush()` commits them.  This
+                     is what the lock-step rollout uses: an env closes at most one episode per sweep."""
         N = self.n_envs
         dev = self.device
         done = done.to(dev).bool()
         record = torch.ones(N, dtype=torch.bool, device=dev) if record is None else record.to(dev).bool()
         replace = torch.zeros(N, dtype=torch.bool, device=dev) if replace is None else replace.to(dev).bool()
+        open_ = ~self.st_closed
+        record = record & open_
+        e = self._env_ids
         t = self.st_len.clamp(max=self.T - 1)
-        ids = self._env_ids[record]
-        if ids.numel():
-            tt = t[record]
-            self.st_state[ids, tt] = state[record]
-            self.st_action[ids, tt] = action[record]
-            self.st_next[ids, tt] = next_state[record]
-            self.st_reward[ids, tt] = reward[record].float()
-            self.st_notdone[ids, tt] = 1.0 - done[record].float()
-            self.st_len[ids] = tt + 1
-        rep = replace & (self.st_len > 0)
-        if bool(rep.any()):
-            ids = self._env_ids[rep]
-            last = self.st_len[rep] - 1
-            self.st_reward[ids, last] = reward[rep].float()
-            self.st_notdone[ids, last] = 0.0
-        closing = (record & done) | rep
-        n_close = int(closing.sum())
-        if n_close == 0:
-            return 0
+        m1 = record[:, None]
+        self.st_state[e, t] = torch.where(m1, state, self.st_state[e, t])
+        self.st_action[e, t] = torch.where(m1, action, self.st_action[e, t])
+        self.st_next[e, t] = torch.where(m1, next_state, self.st_next[e, t])
+        self.st_reward[e, t] = torch.where(record, reward.float(), self.st_reward[e, t])
+        self.st_notdone[e, t] = torch.where(record, 1.0 - done.float(), self.st_notdone[e, t])
+        self.st_len += record.long()
+        rep = replace & open_ & (self.st_len > 0)
+        last = (self.st_len - 1).clamp(min=0)
+        self.st_reward[e, last] = torch.where(rep, reward.float(), self.st_reward[e, last])
+        self.st_notdone[e, last] = torch.where(rep, torch.zeros_like(self.st_reward[e, last]), self.st_notdone[e, last])
+        self.st_closed |= (record & done) | rep
+        return 0 if defer else self.flush()
+
+    def flush(self):
+        """Commit every closed staged episode to the ring (env order), dropping those too short to train on; returns the
+        number committed.  The one place of the vectorised feeder that talks to the host (the ring's bookkeeping)."""
+        dev = self.device
+        closing = self.st_closed
         ids = self._env_ids[closing]
+        if ids.numel() == 0:
+            return 0
         lens = self.st_len[ids]
+        self.size += int(lens.sum())
         keep = (lens - self.n_steps) > 1
         ids, lens = ids[keep], lens[keep]
         k = int(ids.numel())
-        self.size += int(self.st_len[closing].sum())
         if k:
             if k > self.max_episode:
                 ids, lens, k = ids[-self.max_episode:], lens[-self.max_episode:], self.max_episode
@@ -311,12 +320,13 @@ class ReplayBuffer_Queue:
             self.replay_ep_num += k
             self.episodes_count += k
             self._open_row()
-        self.st_len[self._env_ids[closing]] = 0
+        self.st_len.masked_fill_(closing, 0)
+        self.st_closed.zero_()
         return k
 
     def abandon(self, mask):
-        """Forget the staged (unfinished) episodes of the masked environments (time-limit without a stored done)."""
-        self.st_len[mask.to(self.device).bool()] = 0
+        """Forget the staged, still OPEN episodes of the masked environments (time-limit without a stored done)."""
+        self.st_len.masked_fill_(mask.to(self.device).bool() & ~self.st_closed, 0)
 
     # ------------------------------------------------------------------ persistence (utils.py:345-460 layout)
     def save_replay_buffer(self, save_filepath):

@@ -46,3 +46,12 @@ def all_reduce_sum(values, device, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return [float(x) for x in t.tolist()]
+
+
+def all_reduce_min(values, device, group=None):
+    """Min over ranks: collective yes/no decisions (every rank must take the same branch around a collective)."""
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return [float(x) for x in t.tolist()]

@@ -25,7 +25,7 @@ import torch
 
 from .learner import DDPGfD
 from .replay import ReplayBuffer_Queue
-from .shard import all_reduce_sum, dist_env, make_sharded_env
+from .shard import all_reduce_min, all_reduce_sum, dist_env, make_sharded_env
 
 WRIST_LIFT_VELOCITY, FINGER_LIFT_VELOCITY = 0.6, 0.5      # MAIN:945-947
 SKIP_NUM_TS = 6                                           # MAIN:417
@@ -67,20 +67,26 @@ def run_episode(env, act_fn, replay=None, shapes=("CubeS",), orientation="normal
         nxt = nxt.clone()
         if replay is not None:
             rec = alive & ~lifting
-            replay.add_batch(obs, action, nxt, rew, done & alive, record=rec, replace=alive & lifting & done)
-            stored += int(rec.sum())
+            replay.add_batch(obs, action, nxt, rew, done & alive, record=rec, replace=alive & lifting & done, defer=True)
+            stored = stored + rec.sum()
         success |= alive & done & (rew > 0)
         alive &= ~done
         prev, obs = obs, nxt
     if replay is not None:
         replay.abandon(alive)
+        replay.flush()              # the only host synchronisation of the sweep
+        stored = int(stored)
     return success, stored
 
 
 class GraphedUpdates:
     """`network_repl_freq` (10) consecutive updates -- device-side window sampling from both buffers, the n-step update, the
     target-network mix on the last one -- captured once into a CUDA graph and replayed: an update is ~60 small kernels and
-    was launch-bound (3.3 ms each eagerly at batch 4096).  Single process only (the all-reduce stays eager)."""
+    was launch-bound (3.3 ms each eagerly at batch 4096).  Under torchrun the two NCCL all-reduces of an update (critic
+    half, then actor half of the flat gradient bucket; NCCL collectives are capturable) are nodes of the same graph, so the
+    data-parallel update replays exactly like the single-GPU one plus two NVLink all-reduces of ~0.6 MB.
+    Every rank must call run() the same number of times (train.main decides that collectively).  If a replay buffer
+    re-allocates its storage (storage_version), the graph is re-captured."""
 
     def __init__(self, policy, agent, expert, batch, expert_prob):
         self.policy, self.agent, self.expert = policy, agent, expert
@@ -89,6 +95,7 @@ class GraphedUpdates:
         self.block = policy.network_repl_freq
         self.graph = None
         self.losses = None
+        self.versions = None
 
     def _one(self):
         if self.n_agent:
@@ -102,6 +109,10 @@ class GraphedUpdates:
     def run(self, n_updates):
         """n_updates rounded up to a multiple of the block; returns the losses of the last update (device tensors)."""
         self.agent.publish_meta(); self.expert.publish_meta()
+        versions = (self.agent.storage_version, self.expert.storage_version)
+        if self.graph is not None and versions != self.versions:
+            self.graph = None                                # the captured addresses are gone
+        self.versions = versions
         if self.graph is None:
             assert self.policy.total_it % self.block == 0
             side = torch.cuda.Stream()
@@ -140,7 +151,7 @@ def main():
     ap.add_argument("--max-episodes", type=int, default=40000, help="replay capacity in episodes per rank")
     ap.add_argument("--tau", type=float, default=0.0005, help="target-network mixing (DDPG:221 default)")
     ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--no-graph", action="store_true", help="run the updates eagerly (always the case under torchrun)")
+    ap.add_argument("--no-graph", action="store_true", help="run the updates eagerly instead of replaying captured CUDA graphs")
     ap.add_argument("--fp32-matmul", action="store_true", help="keep the actor/critic GEMMs in IEEE fp32 instead of TF32 tensor cores")
     ap.add_argument("--save", default=None)
     args = ap.parse_args()
@@ -157,7 +168,7 @@ def main():
     env = make_sharded_env(args.envs, rank, world, local)
     shapes = tuple(args.shapes.split(","))
     max_action = 0.8                                          # action_space.high (ENV:128)
-    graphed = world == 1 and not args.no_graph
+    graphed = not args.no_graph
     policy = DDPGfD(82, 4, max_action, n=5, tau=args.tau, batch_size=args.batch, device=dev, capturable=graphed)
     gen = torch.Generator(device=dev)
     gen.manual_seed(args.seed * 1000 + rank)
@@ -176,6 +187,9 @@ def main():
     for k in range(args.expert_sweeps):
         succ, stored = run_episode(env, None, expert, shapes, args.orientation, args.variant, seed=args.seed + 7000 + k, expert_mode="combined")
         log(phase="expert", sweep=k, success=count(succ), episodes_held=expert.replay_ep_num, steps_stored=stored)
+
+    held = all_reduce_min([float(expert.replay_ep_num)], dev)[0]
+    assert held > 2, f"a rank holds only {held:.0f} expert episodes: pre-training would sample an empty shard"
 
     def evaluate(tag, sweep):
         succ, _ = run_episode(env, lambda o: policy.select_actions(o), None, shapes, args.orientation, args.variant, mode="test", seed=args.seed + 99)
@@ -203,7 +217,10 @@ def main():
         n_agent = int(args.batch * (1 - args.expert_prob))
         losses = None
         tu = time.perf_counter()
-        if agent.replay_ep_num > 2:
+        # every rank takes the same branch (a rank that skipped while the others entered the all-reduce would hang them):
+        # the update block runs only if EVERY shard holds enough episodes
+        ready = all_reduce_min([1.0 if agent.replay_ep_num > 2 else 0.0], dev)[0] > 0.5
+        if ready:
             if upd is not None:
                 losses = upd.run(args.updates)
             else:

@@ -376,7 +376,7 @@ def test_split_and_full_workspace_modes_agree(card):
         runs.append(trace)
         h.close()
     a, b = runs
-    assert np.abs(a[0][0] - b[0][0]).max() <= 1e-5
+    assert np.abs(a[0][0] - b[0][0]).max() <= 3e-5
     close = np.abs(a[-1][0] - b[-1][0]).max(axis=0) <= 1e-3          # per env, over the 82 obs entries
     assert close.mean() >= 0.95, close.mean()
     assert (a[-1][1] == b[-1][1]).mean() >= 0.99
@@ -457,6 +457,45 @@ def test_handles_share_the_device_model_tables(card, oracle):
 
 
 @pytest.mark.gpu
+def test_cuda_graph_replay_does_not_change_results(card):
+    """kg_set_graph: a step replayed from the captured CUDA graph of its kernel chain is the same arithmetic as the
+    individually launched chain -- bit-identical obs / reward / done / state over expert and caller-driven steps, with the
+    argument sets changing between calls (expert vs action tensor, outputs on / off, a setter in between: each needs its own
+    graph instance, keyed by kg_api.cu's KgGraphKey) and auto-resets in between."""
+    import torch
+    from kinovagrasping_b200 import _lib
+    lib = _lib.load()
+    n = 2048
+    shape = torch.from_numpy((np.arange(n) % 2).astype(np.int32)).cuda()
+    act = torch.zeros((4, n), device="cuda"); act[1:] = 0.45
+    runs = []
+    for graph in (0, 1):
+        h = Handle(n, lib=lib)
+        h.set_graph(graph)
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        obs = torch.zeros((82, n), device="cuda"); rew = torch.zeros(n, device="cuda"); done = torch.zeros(n, dtype=torch.int32, device="cuda")
+        h.reset_sampled(0, shape.data_ptr(), 0, 1, 0, 5, obs.data_ptr())
+        trace = []
+        for k in range(10):
+            if k == 6:
+                h.set_max_episode_steps(8)
+            if k % 3 == 2:
+                h.step(act.data_ptr(), 0, obs.data_ptr(), rew.data_ptr(), done.data_ptr())
+            elif k % 3 == 1:
+                h.step(0, 2, 0, rew.data_ptr(), done.data_ptr())
+            else:
+                h.step(0, 2, obs.data_ptr(), rew.data_ptr(), done.data_ptr())
+            h.sync()
+            trace += [obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy()]
+            h.reset_sampled(done.data_ptr(), 0, 0, 1, 0, 5, 0)
+        trace += list(h.get_state_host())
+        runs.append(trace)
+        h.close()
+    for x, y in zip(*runs):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.gpu
 def test_pipeline_groups_do_not_change_results(card):
     """kg_set_pipeline cuts the batch into env groups whose kernel chains run on separate internal streams; an env's
     arithmetic does not depend on its group, so 1, 2 and 3 groups give bit-identical observations, rewards, dones and
@@ -480,7 +519,11 @@ def test_pipeline_groups_do_not_change_results(card):
             trace += [obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy()]
             h.reset_sampled(done.data_ptr(), 0, 0, 1, 0, 99, 0)
         trace += list(h.get_state_host())
-        assert h.stats()["contact_overflow"] == 0
+        st = h.stats()
+        assert st["contact_overflow"] == 0
+        # the collision caches do their job: before the grasp closes nearly every near pair is settled by its cached axis
+        # (without them all ~13 near pairs of an env go to the narrowphase in every substep)
+        assert st["mpr_pairs"] / st["substeps"] < 2.5, st
         runs.append(trace)
         h.close()
     for other in runs[1:]:

@@ -1,0 +1,17 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2c_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2c_pytest.log
+tail -5 gpurun_out/r2c_pytest.log
+python tools/cmp_libs.py kinovagrasping_b200/libkg_b200.so build_variants/libkg_half.so > gpurun_out/r2c_cmp.log 2>&1
+python tools/cmp_libs.py kinovagrasping_b200/libkg_b200.so build_variants/libkg_noslack.so >> gpurun_out/r2c_cmp.log 2>&1
+cat gpurun_out/r2c_cmp.log
+for lib in kinovagrasping_b200/libkg_b200.so build_variants/libkg_noslack.so build_variants/libkg_half.so build_variants/libkg_half4.so; do
+ for n in 4096 32768; do
+  for G in 1 2; do
+   KG_GROUPS=$G timeout 300 python tools/perf_probe.py $lib $n 36 >> gpurun_out/r2c_probe.log 2>&1
+  done
+ done
+done
+KG_TIMING=1 timeout 300 python tools/perf_probe.py kinovagrasping_b200/libkg_b200.so 4096 36 >> gpurun_out/r2c_probe.log 2>&1
+KG_TIMING=1 timeout 300 python tools/perf_probe.py build_variants/libkg_half.so 4096 36 >> gpurun_out/r2c_probe.log 2>&1
+cat gpurun_out/r2c_probe.log
