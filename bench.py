@@ -317,7 +317,7 @@ def run_ours(args):
     except Exception:                                          # never let the roofline denominator break the bench line
         fp32_peak_measured = 0.0
     sub_ms = float(np.mean([b["substep"] for b in brk])) / (SUBSTEPS - 1)
-    share = {k: float(np.mean([b[k] for b in brk])) for k in ("schedule", "begin", "narrowphase", "substep", "last")}
+    share = {k: float(np.mean([b[k] for b in brk])) for k in ("schedule", "begin", "narrowphase", "substep", "last", "rays")}
 
     # ---- e2e: host buffers through the C ABI (kg_step_host): pinned actions in, obs/reward/done out, every step
     act_h = torch.zeros((4, n), dtype=torch.float32).pin_memory()
@@ -406,9 +406,9 @@ def run_ours(args):
                            "l2": "flushed between timed steps by a 256 MiB write (excluded from the timed spans); state is 2.4 MB per 4096 envs",
                            "parallelism": "env-sharded x%d, no data-path collective" % world},
                 "e2e": {"value": e2e_value, "unit": "physics substeps/s", "h2d_bytes_per_step": 16 * n + 4 * n, "d2h_bytes_per_step": (82 + 2) * 4 * n, "steps": e2e_steps},
-                # kernels per step: per env group kg_schedule_kernel + kg_begin_kernel + 15 x (kg_mpr_kernel + kg_sub_kernel), + kg_reset_kernel
+                # kernels per step: per env group kg_schedule_kernel + kg_begin_kernel + 15 x (kg_mpr_kernel + kg_sub_kernel) + kg_rays_kernel, + kg_reset_kernel
                 # (the chain of a step is replayed as ONE CUDA graph launch)
-                "gpu_launches": (groups * (2 + 2 * SUBSTEPS) + 1) * steps_total,
+                "gpu_launches": (groups * (3 + 2 * SUBSTEPS) + 1) * steps_total,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(n),
                              "peak_source": peak_src, "kernel": "kg_sub_kernel<false> (one physics substep over the batch; 14 of the 31 launches per group of a step)",
                              "kernel_ms": sub_ms, "step_chain_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,

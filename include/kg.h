@@ -122,7 +122,8 @@ int kg_set_pipeline(kg_handle h, int groups);
 int kg_set_graph(kg_handle h, int on);
 /* Diagnostics (bench.py's roofline): with timing on, kg_step records a CUDA event after every kernel launch (and does
  * not pipeline groups); kg_timing_breakdown then returns the milliseconds of the last step by launch kind:
- * [1] schedule [2] begin [3] narrowphase (all launches) [4] substep kernels except the last [5] last substep kernel. */
+ * [1] schedule [2] begin [3] narrowphase (all launches) [4] substep kernels except the last [5] last substep kernel
+ * [6] rangefinder kernel (in timing mode it runs inline; normally on a side stream next to the last narrowphase + substep). */
 /* FP32 FMA microbenchmark on the handle's device (8 independent chains per thread, 2 x 1024 threads per SM): the measured
  * denominator of bench.py's FP32 roofline fraction, in TFLOP/s (2 flop per FMA).  0 in the test-only emulation. */
 int kg_measure_fp32_peak(kg_handle h, float *tflops);

@@ -74,8 +74,8 @@ struct kg_handle_s {
     float *d_obs_global = nullptr;    // [74][n] internal buffer kg_obs_global_buffer hands out
 #ifndef KG_EMU
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaStream_t gstream[KG_MAXGROUPS] = {};
-    cudaEvent_t gfork = nullptr, gjoin[KG_MAXGROUPS] = {};
+    cudaStream_t gstream[KG_MAXGROUPS] = {}, rstream[KG_MAXGROUPS] = {};
+    cudaEvent_t gfork = nullptr, gjoin[KG_MAXGROUPS] = {}, gray0[KG_MAXGROUPS] = {}, gray1[KG_MAXGROUPS] = {};
 #endif
     float last_ms = 0.f;
     int cfg_version = 0;              // bumped by every setter that changes a kernel argument (graph cache key)
@@ -181,7 +181,7 @@ KG_DEV void kg_debug_end(const KgModel &m, KgWS &ws, float *out, int kg_lane) {
     kg_make_rows(m, ws, kg_lane);
     KG_PHASE(l) {      // the contact staging shares storage with the solver scratch: dump it before the solve
         if (l == 0) out[300] = (float)ws.ncon_total;
-        if (l < KG_MAXCON) {
+        if (l < 23) {                        // the dump has room for 23 contacts (kg.h)
             float *o = out + 301 + 8 * l;
             if (9 + l < ws.ngroup) {
                 int s = kg_gslot(ws, 9 + l);
@@ -266,7 +266,7 @@ template <class WS, bool LAST>
 __device__ __forceinline__ void kg_sub_body(WS &ws, const KgEnvArrays &A, int env, unsigned char *rec, int *q, unsigned *tasks,
                                             int nsub, float *obs, float *reward, int *done, float *act_out, int lane) {
     kg_substep_finish(c_model, ws, lane);
-    if (LAST) kg_step_end(c_model, ws, A, env, nsub, rec, obs, reward, done, act_out, lane);
+    if (LAST) kg_step_end(c_model, ws, A, env, nsub, rec, A.ranges, obs, reward, done, act_out, lane);
     else {
         const unsigned mask = kg_substep_start(c_model, ws, rec, lane);
         kg_carry_store(ws, rec, lane);
@@ -286,39 +286,47 @@ __device__ __forceinline__ bool kg_claim(int *seq, int sidx, int lane) {
     if (lane == 0) ok = atomicCAS(seq, sidx, sidx + 1) == sidx;
     return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
-#define KG_HEAVY_WARPS ((int)(KG_LSMEM / sizeof(KgWSNoSync)))     // full workspaces that fit a light CTA's shared memory
+#define KG_HEAVY_WARPS ((int)(KG_LSMEM / sizeof(KgWSNoSync)))                          // heavy-lane workspaces that fit a light CTA's shared memory
+#define KG_FHEAVY_WARPS ((int)(KG_WARPS * sizeof(KgWS) / sizeof(KgWSNoSync)))         // ... a full-mode CTA's
+// The heavy lane: the first `nheavy_ctas` CTAs of a per-env substep grid hold KgWSNoSync workspaces (rows for every contact
+// the model can have), scan the contact counts of all envs of the group and run the substeps whose count exceeds `limit`,
+// the capacity of the workspace the other CTAs of this launch use.  Persistent warps, no stage rendezvous.
+template <bool LAST>
+__device__ __forceinline__ void kg_heavy_lane(unsigned char *smem, int nwarps, int limit, const KgEnvArrays &A, int base, int cnt, unsigned char *carry, int *q, unsigned *tasks,
+                                              int nheavy_ctas, int *heavy_count, int *subseq, int sidx, int nsub, float *obs, float *reward, int *done, float *act_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= nwarps) return;
+    KgWSNoSync &ws = *(reinterpret_cast<KgWSNoSync *>(smem) + warp);
+    const int W = nheavy_ctas * nwarps;
+    int nh = 0;
+    const int end = base + cnt;
+    for (int e0 = base + blockIdx.x * nwarps + warp; e0 < end; e0 += 4 * W) {
+        int c[4];      // four independent count loads in flight
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int env = e0 + k * W;
+            c[k] = env < end ? reinterpret_cast<const int *>(carry + (size_t)env * KG_CARRY_BYTES + KG_COFF(cnt))[lane] : 0;
+        }
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+            if (kg_warp_sum(c[k]) <= limit) continue;
+            const int env = e0 + k * W;
+            if (!kg_claim(subseq + env, sidx, lane)) continue;
+            unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
+            kg_carry_load(ws, rec, lane);
+            kg_sub_body<KgWSNoSync, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
+            __syncwarp();
+            nh++;
+        }
+    }
+    if (LAST && nh && lane == 0 && limit == KG_MAXCON_LIGHT) atomicAdd(heavy_count, nh);      // what the host picks the mode of later steps from
+}
 template <bool LAST>
 __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(KgEnvArrays A, int base, int cnt, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
                                                                                int nheavy_ctas, int *heavy_count, int *subseq, int sidx, int nsub, float *obs, float *reward, int *done, float *act_out) {
     if ((int)blockIdx.x < nheavy_ctas) {
-        // ---- heavy lane: persistent warps with full workspaces (no stage rendezvous: they loop independently)
-        extern __shared__ __align__(16) unsigned char smem[];
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (warp >= KG_HEAVY_WARPS) return;
-        KgWSNoSync &ws = *(reinterpret_cast<KgWSNoSync *>(smem) + warp);
-        const int W = nheavy_ctas * KG_HEAVY_WARPS;
-        int nh = 0;
-        const int end = base + cnt;
-        for (int e0 = base + blockIdx.x * KG_HEAVY_WARPS + warp; e0 < end; e0 += 4 * W) {
-            int c[4];      // four independent count loads in flight
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int env = e0 + k * W;
-                c[k] = env < end ? reinterpret_cast<const int *>(carry + (size_t)env * KG_CARRY_BYTES + KG_COFF(cnt))[lane] : 0;
-            }
-#pragma unroll 1
-            for (int k = 0; k < 4; k++) {
-                if (kg_warp_sum(c[k]) <= KG_MAXCON_LIGHT) continue;
-                const int env = e0 + k * W;
-                if (!kg_claim(subseq + env, sidx, lane)) continue;
-                unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
-                kg_carry_load(ws, rec, lane);
-                kg_sub_body<KgWSNoSync, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
-                __syncwarp();
-                nh++;
-            }
-        }
-        if (LAST && nh && lane == 0) atomicAdd(heavy_count, nh);      // what the host picks the mode of later steps from
+        extern __shared__ __align__(16) unsigned char smem_h[];
+        kg_heavy_lane<LAST>(smem_h, KG_HEAVY_WARPS, KG_MAXCON_LIGHT, A, base, cnt, carry, q, tasks, nheavy_ctas, heavy_count, subseq, sidx, nsub, obs, reward, done, act_out);
         return;
     }
     KG_ENV_OF_WARP(KgWSLight, KG_LWARPS, blockIdx.x - nheavy_ctas);
@@ -327,10 +335,8 @@ __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(K
 #endif
     unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
     kg_carry_load(ws, rec, lane);
-    if (nheavy_ctas > 0) {
-        if (kg_warp_sum(ws.cnt[lane]) > KG_MAXCON_LIGHT) return;      // the heavy lane runs this one
-        if (!kg_claim(subseq + env, sidx, lane)) return;              // ... or already has (the record was rewritten)
-    }
+    if (kg_warp_sum(ws.cnt[lane]) > KG_MAXCON_LIGHT) return;      // the heavy lane runs this one
+    if (!kg_claim(subseq + env, sidx, lane)) return;              // ... or already has (the record was rewritten)
     kg_sub_body<KgWSLight, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
 #ifdef KG_TRACE
     // per (substep, env): cycles of this warp's substep, its Newton iterations and contact count, its SM and start time
@@ -342,16 +348,23 @@ __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(K
     }
 #endif
 }
+// FULL mode: every env through the full workspace (KG_MAXCON contacts); the rare substep with even more contacts goes to the
+// heavy lane of the same launch, exactly as in split mode.
 template <bool LAST>
 __global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_full_kernel(KgEnvArrays A, int base, int cnt, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
-                                                                                  int *heavy_count, int nsub, float *obs, float *reward, int *done, float *act_out) {
-    KG_ENV_OF_WARP(KgWS, KG_WARPS, blockIdx.x);
+                                                                                  int nheavy_ctas, int *heavy_count, int *subseq, int sidx, int nsub, float *obs, float *reward, int *done, float *act_out) {
+    if ((int)blockIdx.x < nheavy_ctas) {
+        extern __shared__ __align__(16) unsigned char smem_h[];
+        kg_heavy_lane<LAST>(smem_h, KG_FHEAVY_WARPS, KG_MAXCON, A, base, cnt, carry, q, tasks, nheavy_ctas, heavy_count, subseq, sidx, nsub, obs, reward, done, act_out);
+        return;
+    }
+    KG_ENV_OF_WARP(KgWS, KG_WARPS, blockIdx.x - nheavy_ctas);
     unsigned char *rec = carry + (size_t)env * KG_CARRY_BYTES;
     kg_carry_load(ws, rec, lane);
-    if (LAST) {
-        const int total = kg_warp_sum(ws.cnt[lane]);
-        if ((slot & 15) == 0 && total > KG_MAXCON_LIGHT && lane == 0) atomicAdd(heavy_count, 16);     // 1-in-16 sample of the same count
-    }
+    const int total = kg_warp_sum(ws.cnt[lane]);
+    if (LAST && (slot & 15) == 0 && total > KG_MAXCON_LIGHT && lane == 0) atomicAdd(heavy_count, 16);     // 1-in-16 sample of the split-mode count
+    if (total > KG_MAXCON) return;                                // the heavy lane runs this one
+    if (!kg_claim(subseq + env, sidx, lane)) return;
     kg_sub_body<KgWS, LAST>(ws, A, env, rec, q, tasks, nsub, obs, reward, done, act_out, lane);
 }
 // ---- narrowphase kernel: persistent warps pull (env, pair) tasks from the global list; every task is one full MPR run
@@ -416,6 +429,53 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
 #endif
 }
 
+// ---- rangefinder kernel: the 17 rays of an RL step for a whole env group, one LANE per (site, geom) pair -- 5 warps per env,
+// a warp = 4 sites x the 8 mesh geoms.  The rays see the kinematics of the last substep's INPUT state (mj_step traces them in
+// its forward pass, before integrating: SURVEY 8a O-note), i.e. what the env's carry record holds once the second-to-last
+// per-env kernel has stored it, so this kernel runs on a side stream NEXT TO the last narrowphase + per-env kernel instead of
+// inside the latter: a BVH traversal is a chain of dependent loads, and here ~0.5 M independent ones hide each other's latency
+// (in the per-env kernel 32 lanes of one warp did, and the step's last launch took 2.5x a normal substep).  Same arithmetic
+// per pair as kg_rays, and the nearest hit is a min, so the readings are bit-identical.
+#define KG_RAY_WARPS 5
+__global__ void __launch_bounds__(KG_RAY_WARPS * 32) kg_rays_kernel(const unsigned char *carry, int base, int N, float *ranges) {
+    __shared__ __align__(16) unsigned char rec[KG_CARRY_A_BYTES];
+    const int env = base + blockIdx.x;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(carry + (size_t)env * KG_CARRY_BYTES);
+        uint4 *dst = reinterpret_cast<uint4 *>(rec);
+        for (int i = threadIdx.x; i < (int)(KG_CARRY_A_BYTES / 16); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const KgWSLight &ws = *reinterpret_cast<const KgWSLight *>(rec);      // only carry section A of it exists here (state, constants, kinematics)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = 4 * warp + (lane >> 3), g = 1 + (lane & 7);
+    unsigned best = KG_RAY_NONE;
+    if (i < KG_NSITE) {
+        float p[3], v[3];
+        kg_site_pose(c_model, ws, i, p, v);
+        if ((lane & 7) == 0 && v[2] < -1e-15f) {      // the floor (mj_ray's plane case), once per site
+            const float x = -p[2] / v[2];
+            if (x >= 0.f && fabsf(p[0] + x * v[0]) <= 2.f && fabsf(p[1] + x * v[1]) <= 2.f) best = __float_as_uint(fabsf(x));
+        }
+        const int sb = c_model.site_body[i];
+        const int own = sb == 0 ? 1 : (sb <= 3 ? 2 * sb : 2 * (sb - 3) + 1);
+        if (g != own) {
+            const float *size = g == 8 ? c_model.shape[ws.shape].size : (g == 1 ? c_model.hand_size : ((g & 1) ? c_model.hand_size + 6 : c_model.hand_size + 3));
+            float lp[3], lv[3];
+            kg_ray_local(ws.gpos[g], ws.gmat[g], p, v, lp, lv);
+            if (!(kg_ray_box(size, lp, lv) < 0.f)) {
+                const float x = kg_ray_mesh_bvh(c_model, kg_mesh_of_geom(ws, g), lp, lv);
+                if (x >= 0.f) best = min(best, __float_as_uint(fabsf(x)));
+            }
+        }
+    }
+    // nearest hit of a site = min over its 8 lanes (distances are non-negative floats: their bit patterns order like integers)
+    best = min(best, __shfl_xor_sync(0xffffffffu, best, 1));
+    best = min(best, __shfl_xor_sync(0xffffffffu, best, 2));
+    best = min(best, __shfl_xor_sync(0xffffffffu, best, 4));
+    if (i < KG_NSITE && (lane & 7) == 0) ranges[i * N + env] = best == KG_RAY_NONE ? -1.f : __uint_as_float(best);
+}
+
 __global__ void __launch_bounds__(KG_LWARPS * 32) kg_reset_kernel(KgEnvArrays A, const int *mask, const int *shape, const float *euler, const float *objp, const float *handp,
                                                                  int sampled, int orient, int variant, int test_table, int hand_location, unsigned long long seed, int *ep_count, int env_offset, float *obs) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -463,6 +523,7 @@ static KgMprWS g_mw;
 static size_t ws_bytes() { return sizeof(KgWS); }
 #ifndef KG_EMU
 static_assert(KG_WARPS * sizeof(KgWS) <= 227 * 1024, "KG_WARPS workspaces must fit one SM's shared memory");
+static_assert(KG_LSMEM >= 2 * sizeof(KgWSNoSync), "a light CTA's shared memory must hold at least two heavy-lane workspaces");
 static_assert(KG_LMINBLOCKS * (KG_LWARPS * sizeof(KgWSLight) + 1024) <= 228 * 1024, "KG_LMINBLOCKS light CTAs must fit one SM's shared memory");
 #ifdef KG_MPR_L1
 #ifdef KG_MPR_HALF
@@ -503,6 +564,11 @@ static int enqueue_step(kg_handle h, cudaStream_t st, const float *action, int m
     cudaMemsetAsync(h->heavy_count, 0, sizeof(int), st);
     size_t tix = 0;
     const int G = h->timing ? 1 : h->ngroups;
+    // the ray kernel of group g, forked off the group's stream once its last carry records are written (timing mode: inline)
+#define KG_RAYS(g) do { const int rb_ = gbase[g], rc_ = gbase[(g) + 1] - rb_; \
+        if (h->timing) { kg_rays_kernel<<<rc_, KG_RAY_WARPS * 32, 0, gs[g]>>>(h->carry, rb_, h->n, h->A.ranges); KG_TMARK(6); } \
+        else { cudaEventRecord(h->gray0[g], gs[g]); cudaStreamWaitEvent(h->rstream[g], h->gray0[g], 0); \
+               kg_rays_kernel<<<rc_, KG_RAY_WARPS * 32, 0, h->rstream[g]>>>(h->carry, rb_, h->n, h->A.ranges); cudaEventRecord(h->gray1[g], h->rstream[g]); } } while (0)
     // The env groups of the batch are independent pipelines: group g's kernels go to its own stream, so the narrowphase
     // kernel of one group (latency-bound, few registers) overlaps the per-env kernel of another (and the launch gaps and
     // the tail of every kernel are covered by the other groups' work).  Fork from / join into the caller's stream.
@@ -523,6 +589,7 @@ static int enqueue_step(kg_handle h, cudaStream_t st, const float *action, int m
         KG_TMARK(1);
         kg_begin_kernel<<<blocks, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, action, mode, h->carry, h->q + 4 * g + 2 * qs0, h->tasks + (size_t)base * 22, h->subseq);
         KG_TMARK(2);
+        if (nsub == 1) KG_RAYS(g);
     }
     for (int s = 0; s < nsub; s++) {
         const int qa = (qs0 + s) & 1, qb = qa ^ 1;
@@ -538,22 +605,27 @@ static int enqueue_step(kg_handle h, cudaStream_t st, const float *action, int m
             mgrid = mgrid < 8 ? 8 : (mgrid > h->mpr_grid ? h->mpr_grid : mgrid);
             kg_mpr_kernel<<<mgrid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), gs[g]>>>(h->carry, q + 2 * qa, q + 2 * qb, tasks, h->A.prof);
             KG_TMARK(3);
+            if (last && !h->timing) cudaStreamWaitEvent(gs[g], h->gray1[g], 0);      // this group's rays are in
             if (full) {
                 const int fblocks = (cnt + KG_WARPS - 1) / KG_WARPS;
-                if (last) kg_sub_full_kernel<true><<<fblocks, KG_WARPS * 32, hsmem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, h->heavy_count, nsub, obs, reward, done, act_out);
-                else kg_sub_full_kernel<false><<<fblocks, KG_WARPS * 32, hsmem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, h->heavy_count, nsub, obs, reward, done, act_out);
+                const int hb = (cnt + 64 * KG_FHEAVY_WARPS - 1) / (64 * KG_FHEAVY_WARPS);      // more than KG_MAXCON contacts is rare: a thin lane
+                const int nhc = hb < 1 ? 1 : (hb < h->heavy_ctas ? hb : h->heavy_ctas);
+                if (last) kg_sub_full_kernel<true><<<fblocks + nhc, KG_WARPS * 32, hsmem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
+                else kg_sub_full_kernel<false><<<fblocks + nhc, KG_WARPS * 32, hsmem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
             } else {
                 const int blocks = (cnt + KG_LWARPS - 1) / KG_LWARPS;
-                // heavy-lane CTAs at the front of the grid: one full workspace per 8 envs of the group (they loop over whatever is heavy)
+                // heavy-lane CTAs at the front of the grid: one workspace per 8 envs of the group (they loop over whatever is heavy)
                 const int hb = (cnt + 8 * KG_HEAVY_WARPS - 1) / (8 * KG_HEAVY_WARPS);
                 const int nhc = hb < 1 ? 1 : (hb < h->heavy_ctas ? hb : h->heavy_ctas);
                 if (last) kg_sub_kernel<true><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
                 else kg_sub_kernel<false><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
             }
             KG_TMARK(last ? 5 : 4);
+            if (s == nsub - 2) KG_RAYS(g);
         }
     }
     if (G > 1) for (int g = 0; g < G; g++) { cudaEventRecord(h->gjoin[g], gs[g]); cudaStreamWaitEvent(st, h->gjoin[g], 0); }
+#undef KG_RAYS
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
@@ -575,7 +647,7 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
             unsigned char *rec = h->carry + (size_t)env * KG_CARRY_BYTES;
             kg_carry_load(g_ws, rec, 0);
             kg_substep_finish(h->model, g_ws, 0);
-            if (s == nsub - 1) kg_step_end(h->model, g_ws, h->A, env, nsub, rec, obs, reward, done, act_out, 0);
+            if (s == nsub - 1) kg_step_end(h->model, g_ws, h->A, env, nsub, rec, nullptr, obs, reward, done, act_out, 0);
             else {
                 unsigned mask = kg_substep_start(h->model, g_ws, rec, 0);
                 kg_carry_store(g_ws, rec, 0);
@@ -780,7 +852,10 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->gfork, cudaEventDisableTiming));
     for (int g = 0; g < KG_MAXGROUPS; g++) {
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->rstream[g], cudaStreamNonBlocking));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->gjoin[g], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->gray0[g], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->gray1[g], cudaEventDisableTiming));
     }
     h->ngroups = n_envs >= 2048 ? 4 : (n_envs >= 512 ? 2 : 1);
 #endif
@@ -798,6 +873,9 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
 #endif
     TRY(be_alloc(h, (void **)&h->ep_count, N * 4));
     TRY(be_alloc(h, (void **)&A.ccache, N * KG_CCACHE_BYTES));
+#ifndef KG_EMU
+    TRY(be_alloc(h, (void **)&A.ranges, KG_NSITE * N * 4));
+#endif
     TRY(be_alloc(h, (void **)&h->d_obs_global, KG_NOBS_GLOBAL * N * 4));
     TRY(be_alloc(h, (void **)&A.load, N * 4)); TRY(be_alloc(h, (void **)&h->perm, N * 4));
     TRY(be_alloc(h, (void **)&h->carry, N * KG_CARRY_BYTES)); TRY(be_alloc(h, (void **)&h->tasks, N * 22 * 4)); TRY(be_alloc(h, (void **)&h->q, 4 * 4 * KG_MAXGROUPS));
@@ -832,7 +910,13 @@ int kg_destroy(kg_handle h) {
     if (h->capstream) cudaStreamDestroy(h->capstream);
     if (h->gfork) cudaEventDestroy(h->gfork);
     for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
-    for (int g = 0; g < KG_MAXGROUPS; g++) { if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]); if (h->gjoin[g]) cudaEventDestroy(h->gjoin[g]); }
+    for (int g = 0; g < KG_MAXGROUPS; g++) {
+        if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
+        if (h->rstream[g]) cudaStreamDestroy(h->rstream[g]);
+        if (h->gjoin[g]) cudaEventDestroy(h->gjoin[g]);
+        if (h->gray0[g]) cudaEventDestroy(h->gray0[g]);
+        if (h->gray1[g]) cudaEventDestroy(h->gray1[g]);
+    }
 #endif
     delete h;
     return KG_OK;

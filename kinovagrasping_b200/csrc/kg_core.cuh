@@ -173,7 +173,12 @@ struct alignas(16) KgWST {
 // sections do not depend on the row count, so a record written through one workspace loads into the other.
 typedef KgWST<KG_MAXCON, KG_STAGE_MASK> KgWS;
 typedef KgWST<KG_MAXCON_LIGHT, KG_STAGE_MASK> KgWSLight;
-typedef KgWST<KG_MAXCON, 0> KgWSNoSync;      // full workspace without stage rendezvous (warps loop independently)
+// The HEAVY LANE's workspace: rows for every contact this model can have at once (8 plane lanes x 4 + 22 hull pairs = 54,
+// i.e. 63 constraint groups, two per lane), no stage rendezvous (its warps loop over envs independently).  Whatever exceeds
+// the workspace of the kernel it runs in -- more than KG_MAXCON_LIGHT contacts in split mode, more than KG_MAXCON in full
+// mode -- is run there, so no contact is ever dropped (MuJoCo never drops one for this model: nconmax >> 54).
+#define KG_MAXCON_ALL 54
+typedef KgWST<KG_MAXCON_ALL, 0> KgWSNoSync;
 // the collision caches: contiguous in the workspace (aliased onto J), kept per env across RL steps (a cached axis is only
 // ever RE-TESTED, a cached vertex is only a starting point, so stale entries after kg_set_state cost time, not correctness)
 #define KG_CCACHE_OFF   (offsetof(KgWS, cv1))
@@ -1149,52 +1154,55 @@ template <class WS> KG_NOINL void kg_jac_add(const WS &ws, int g, const float *p
 template <class WS> KG_DEV void kg_make_rows(const KgModel &m, WS &ws, int kg_lane) {
     KG_PHASE(l) {
         const float K = m.solK, Bd = m.solB;
-        if (l < 3) {
-            float *row = ws.J + l * KG_JS;
-            for (int j = 0; j < KG_NV; j++) row[j] = 0.f;
-            row[3 + 2 * l] = 1.f; row[4 + 2 * l] = -2.f;
-            float pos = ws.qpos[3 + 2 * l] - 2.f * ws.qpos[4 + 2 * l];
-            float vel = ws.qvel[3 + 2 * l] - 2.f * ws.qvel[4 + 2 * l];
-            float imp = kg_impedance(m, pos);
-            float R = fmaxf((1.f - imp) / imp * m.tendon_invw[l], 1e-15f);
-            KG_GP(ws, l, 3) = 1.f; KG_GD(ws, l) = 1.f / R; KG_GAREF(ws, l, 0) = -Bd * vel - K * imp * pos;
-        } else if (l < 9) {
-            int a = l - 3, j = a < 3 ? a : 3 + 2 * (a - 3);
-            float lo = a < 3 ? m.slide_range[2 * a] : m.finger_range[2 * (a - 3)];
-            float hi = a < 3 ? m.slide_range[2 * a + 1] : m.finger_range[2 * (a - 3) + 1];
-            float q = ws.qpos[j], sgn = 0.f, pos = 0.f;
-            if (q - lo < 0.f) { sgn = 1.f; pos = q - lo; } else if (hi - q < 0.f) { sgn = -1.f; pos = hi - q; }
-            float *row = ws.J + l * KG_JS;
-            for (int jj = 0; jj < KG_NV; jj++) row[jj] = 0.f;
-            if (sgn != 0.f) {
-                row[j] = sgn;
+        // a lane owns group l and, in workspaces with more than 32 groups, group l + 32 as well
+        for (int g = l; g < 9 + WS::MAXCON; g += 32) {
+            if (g < 3) {
+                float *row = ws.J + g * KG_JS;
+                for (int j = 0; j < KG_NV; j++) row[j] = 0.f;
+                row[3 + 2 * g] = 1.f; row[4 + 2 * g] = -2.f;
+                float pos = ws.qpos[3 + 2 * g] - 2.f * ws.qpos[4 + 2 * g];
+                float vel = ws.qvel[3 + 2 * g] - 2.f * ws.qvel[4 + 2 * g];
                 float imp = kg_impedance(m, pos);
-                float R = fmaxf((1.f - imp) / imp * m.dof_invw[j], 1e-15f);
-                KG_GP(ws, l, 3) = 2.f; KG_GD(ws, l) = 1.f / R; KG_GAREF(ws, l, 0) = -Bd * sgn * ws.qvel[j] - K * imp * pos;
-            } else KG_GP(ws, l, 3) = 0.f;
-        } else if (l < ws.ngroup) {
-            int s = kg_gslot(ws, l), g1 = ws.st_g1[s], g2 = ws.st_g2[s];
-            float n[3], t1[3], t2[3];
-            kg_copy(n, ws.st_n[s]);
-            kg_make_frame(n, t1, t2);
-            float *rn = ws.J + (9 + 3 * (l - 9)) * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
-            for (int j = 0; j < KG_NV; j++) { rn[j] = 0.f; r1[j] = 0.f; r2[j] = 0.f; }
-            const float *p = ws.st_pos[s];
-            kg_jac_add(ws, g2, p, n, 1.f, rn); kg_jac_add(ws, g1, p, n, -1.f, rn);
-            kg_jac_add(ws, g2, p, t1, 1.f, r1); kg_jac_add(ws, g1, p, t1, -1.f, r1);
-            kg_jac_add(ws, g2, p, t2, 1.f, r2); kg_jac_add(ws, g1, p, t2, -1.f, r2);
-            float vn = 0, v1 = 0, v2 = 0;
-            for (int j = 0; j < KG_NV; j++) { float v = ws.qvel[j]; vn += rn[j] * v; v1 += r1[j] * v; v2 += r2[j] * v; }
-            float mu = m.pair_mu[s < 32 ? (s >> 2) : 8 + (s - 32)], dist = ws.st_dist[s], r = dist - m.margin;   // staging slot -> pair lane
-            float tran = (g1 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g1]) + (g2 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g2]);
-            float imp = kg_impedance(m, r);
-            float R = fmaxf((1.f - imp) / imp * (tran + mu * mu * tran), 1e-15f);
-            float Rpy = fmaxf(2.f * mu * mu / m.impratio * R, 1e-15f);
-            float Dv = 1.f / Rpy, kr = K * imp * r;
-            KG_GMU(ws, l) = mu;
-            KG_GD(ws, l) = Dv;
-            KG_GAREF(ws, l, 0) = -Bd * (vn + mu * v1) - kr; KG_GAREF(ws, l, 1) = -Bd * (vn - mu * v1) - kr;
-            KG_GAREF(ws, l, 2) = -Bd * (vn + mu * v2) - kr; KG_GAREF(ws, l, 3) = -Bd * (vn - mu * v2) - kr;
+                float R = fmaxf((1.f - imp) / imp * m.tendon_invw[g], 1e-15f);
+                KG_GP(ws, g, 3) = 1.f; KG_GD(ws, g) = 1.f / R; KG_GAREF(ws, g, 0) = -Bd * vel - K * imp * pos;
+            } else if (g < 9) {
+                int a = g - 3, j = a < 3 ? a : 3 + 2 * (a - 3);
+                float lo = a < 3 ? m.slide_range[2 * a] : m.finger_range[2 * (a - 3)];
+                float hi = a < 3 ? m.slide_range[2 * a + 1] : m.finger_range[2 * (a - 3) + 1];
+                float q = ws.qpos[j], sgn = 0.f, pos = 0.f;
+                if (q - lo < 0.f) { sgn = 1.f; pos = q - lo; } else if (hi - q < 0.f) { sgn = -1.f; pos = hi - q; }
+                float *row = ws.J + g * KG_JS;
+                for (int jj = 0; jj < KG_NV; jj++) row[jj] = 0.f;
+                if (sgn != 0.f) {
+                    row[j] = sgn;
+                    float imp = kg_impedance(m, pos);
+                    float R = fmaxf((1.f - imp) / imp * m.dof_invw[j], 1e-15f);
+                    KG_GP(ws, g, 3) = 2.f; KG_GD(ws, g) = 1.f / R; KG_GAREF(ws, g, 0) = -Bd * sgn * ws.qvel[j] - K * imp * pos;
+                } else KG_GP(ws, g, 3) = 0.f;
+            } else if (g < ws.ngroup) {
+                int s = kg_gslot(ws, g), g1 = ws.st_g1[s], g2 = ws.st_g2[s];
+                float n[3], t1[3], t2[3];
+                kg_copy(n, ws.st_n[s]);
+                kg_make_frame(n, t1, t2);
+                float *rn = ws.J + (9 + 3 * (g - 9)) * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
+                for (int j = 0; j < KG_NV; j++) { rn[j] = 0.f; r1[j] = 0.f; r2[j] = 0.f; }
+                const float *p = ws.st_pos[s];
+                kg_jac_add(ws, g2, p, n, 1.f, rn); kg_jac_add(ws, g1, p, n, -1.f, rn);
+                kg_jac_add(ws, g2, p, t1, 1.f, r1); kg_jac_add(ws, g1, p, t1, -1.f, r1);
+                kg_jac_add(ws, g2, p, t2, 1.f, r2); kg_jac_add(ws, g1, p, t2, -1.f, r2);
+                float vn = 0, v1 = 0, v2 = 0;
+                for (int j = 0; j < KG_NV; j++) { float v = ws.qvel[j]; vn += rn[j] * v; v1 += r1[j] * v; v2 += r2[j] * v; }
+                float mu = m.pair_mu[s < 32 ? (s >> 2) : 8 + (s - 32)], dist = ws.st_dist[s], r = dist - m.margin;   // staging slot -> pair lane
+                float tran = (g1 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g1]) + (g2 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g2]);
+                float imp = kg_impedance(m, r);
+                float R = fmaxf((1.f - imp) / imp * (tran + mu * mu * tran), 1e-15f);
+                float Rpy = fmaxf(2.f * mu * mu / m.impratio * R, 1e-15f);
+                float Dv = 1.f / Rpy, kr = K * imp * r;
+                KG_GMU(ws, g) = mu;
+                KG_GD(ws, g) = Dv;
+                KG_GAREF(ws, g, 0) = -Bd * (vn + mu * v1) - kr; KG_GAREF(ws, g, 1) = -Bd * (vn - mu * v1) - kr;
+                KG_GAREF(ws, g, 2) = -Bd * (vn + mu * v2) - kr; KG_GAREF(ws, g, 3) = -Bd * (vn - mu * v2) - kr;
+            }
         }
     }
     KG_SYNC();
@@ -1328,11 +1336,13 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             ws.Mdq[l] = s;
             cw = 0.5f * s * (ws.qwarm[l] - ws.qas[l]);
         }
-        float jar[4];
-        int n = kg_group_rows(ws, l, ws.bdot, jar);
-        for (int k = 0; k < n; k++) if (kg_gtype(ws, l) == 1 || jar[k] < 0.f) cw += 0.5f * KG_GD(ws, l) * jar[k] * jar[k];
-        n = kg_group_rows(ws, l, ws.bdir, jar);
-        for (int k = 0; k < n; k++) if (kg_gtype(ws, l) == 1 || jar[k] < 0.f) cs += 0.5f * KG_GD(ws, l) * jar[k] * jar[k];
+        for (int g = l; g < 9 + WS::MAXCON; g += 32) {
+            float jar[4];
+            int n = kg_group_rows(ws, g, ws.bdot, jar);
+            for (int k = 0; k < n; k++) if (kg_gtype(ws, g) == 1 || jar[k] < 0.f) cw += 0.5f * KG_GD(ws, g) * jar[k] * jar[k];
+            n = kg_group_rows(ws, g, ws.bdir, jar);
+            for (int k = 0; k < n; k++) if (kg_gtype(ws, g) == 1 || jar[k] < 0.f) cs += 0.5f * KG_GD(ws, g) * jar[k] * jar[k];
+        }
         ws.red[l] = cw; ws.red2[l] = cs;
     }
     KG_SYNC();
@@ -1354,15 +1364,17 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
         KG_PHASE(l) {
             float c = 0.f;
             if (l < KG_NV) c = 0.5f * ws.Mdq[l] * (ws.qacc[l] - ws.qas[l]);
-            float jar[4], w[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
-            int n = kg_group_rows(ws, l, ws.bdot, jar);
-            for (int k = 0; k < n; k++) if (kg_gtype(ws, l) == 1 || jar[k] < 0.f) { a[k] = KG_GD(ws, l); w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
-            if (n == 1) { ws.bw[l] = w[0]; KG_GAREF(ws, l, 1) = a[0]; }
-            else if (n == 4) {
-                int b = 9 + 3 * (l - 9);
-                float mu = KG_GMU(ws, l);
-                ws.bw[b] = w[0] + w[1] + w[2] + w[3]; ws.bw[b + 1] = mu * (w[0] - w[1]); ws.bw[b + 2] = mu * (w[2] - w[3]);
-            } else if (l < 9) ws.bw[l] = 0.f;
+            for (int g = l; g < 9 + WS::MAXCON; g += 32) {
+                float jar[4], w[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
+                int n = kg_group_rows(ws, g, ws.bdot, jar);
+                for (int k = 0; k < n; k++) if (kg_gtype(ws, g) == 1 || jar[k] < 0.f) { a[k] = KG_GD(ws, g); w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
+                if (n == 1) { ws.bw[g] = w[0]; KG_GAREF(ws, g, 1) = a[0]; }
+                else if (n == 4) {
+                    int b = 9 + 3 * (g - 9);
+                    float mu = KG_GMU(ws, g);
+                    ws.bw[b] = w[0] + w[1] + w[2] + w[3]; ws.bw[b + 1] = mu * (w[0] - w[1]); ws.bw[b + 2] = mu * (w[2] - w[3]);
+                } else if (g < 9) ws.bw[g] = 0.f;
+            }
             ws.red[l] = c;
         }
         KG_SYNC();
@@ -1477,24 +1489,27 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             for (int ls = 0; ls < KG_LS_MAXIT; ls++) {
                 if (kg_lane == 0) KG_COUNT(27, 1);
                 KG_PHASE(l) {
-                    float d1 = 0.f, d2 = 0.f, d0 = 0.f, jar[4], jv[4];
+                    float d1 = 0.f, d2 = 0.f, d0 = 0.f;
                     int nchg = 0;
-                    int n = kg_group_rows(ws, l, ws.bdot, jar);
-                    if (n == 1) jv[0] = ws.bdir[l];
-                    else if (n == 4) {
-                        int b = 9 + 3 * (l - 9);
-                        float mu = KG_GMU(ws, l), nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
-                        jv[0] = nn + t1; jv[1] = nn - t1; jv[2] = nn + t2; jv[3] = nn - t2;
-                    }
-                    const bool eq = kg_gtype(ws, l) == 1;
-                    const float Dl = n ? KG_GD(ws, l) : 0.f;
-                    for (int k = 0; k < n; k++) {
-                        float x = jar[k] + alpha * jv[k];
-                        float dj = Dl * jv[k];
-                        bool act0 = eq || jar[k] < 0.f, act = eq || x < 0.f;
-                        if (act) { d1 += dj * x; d2 += dj * jv[k]; }
-                        if (act0) d0 += dj * jar[k];
-                        nchg += (act != act0);
+                    for (int g = l; g < 9 + WS::MAXCON; g += 32) {
+                        float jar[4], jv[4];
+                        int n = kg_group_rows(ws, g, ws.bdot, jar);
+                        if (n == 1) jv[0] = ws.bdir[g];
+                        else if (n == 4) {
+                            int b = 9 + 3 * (g - 9);
+                            float mu = KG_GMU(ws, g), nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
+                            jv[0] = nn + t1; jv[1] = nn - t1; jv[2] = nn + t2; jv[3] = nn - t2;
+                        }
+                        const bool eq = kg_gtype(ws, g) == 1;
+                        const float Dl = n ? KG_GD(ws, g) : 0.f;
+                        for (int k = 0; k < n; k++) {
+                            float x = jar[k] + alpha * jv[k];
+                            float dj = Dl * jv[k];
+                            bool act0 = eq || jar[k] < 0.f, act = eq || x < 0.f;
+                            if (act) { d1 += dj * x; d2 += dj * jv[k]; }
+                            if (act0) d0 += dj * jar[k];
+                            nchg += (act != act0);
+                        }
                     }
                     ws.red[l] = d1; ws.red2[l] = d2;
                     if (ls == 0) { ws.cnt[l] = nchg; ws.mv_red3[l] = d0; }
@@ -1989,6 +2004,7 @@ struct KgEnvArrays {
     int *load;                    // [N] cost of each env's last RL step (Newton iterations + 2 x MPR pairs): key of the launch schedule
     long long *prof;              // [KG_NPROF] KG_PROF builds only
     float *obs_global;            // [74][N] or NULL: _get_obs(state_rep="global") of the same step (kg_set_obs_global)
+    float *ranges;                // [KG_NSITE][N] rangefinder readings of the current RL step, written by the batch-wide ray kernel (GPU path)
     unsigned char *ccache;        // [N][KG_CCACHE_BYTES] collision caches (warm-start vertices, separating axes) kept across RL steps
     int N, max_steps;
     int act_dim;                  // 4 = [wrist, f1, f2, f3], 6 = [slide_x, slide_y, slide_z, f1, f2, f3] (ENV:1502-1503)
@@ -2180,12 +2196,15 @@ template <class WS> KG_DEV unsigned kg_substep_start(const KgModel &m, WS &ws, c
 
 // Last kernel of an RL step for one env (after the last substep's finish): rays -> obs/reward/done (+TimeLimit),
 // state and outputs back to the struct-of-arrays.
-template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, int nsub, const unsigned char *rec,
+template <class WS> KG_DEV void kg_step_end(const KgModel &m, WS &ws, const KgEnvArrays &A, int env, int nsub, const unsigned char *rec, const float *ranges,
                         float *obs_out, float *reward_out, int *done_out, float *action_out, int kg_lane) {
     // the collision cache goes back to its per-env home for the next RL step (record -> array; it is not in the workspace)
     kg_copy16(A.ccache + (size_t)env * KG_CCACHE_BYTES, rec + KG_CARRY_A_BYTES, (int)KG_CCACHE_BYTES, kg_lane);
     KG_PROBE(19);
-    kg_rays(m, ws, kg_lane);
+    if (ranges) {      // the batch-wide ray kernel (kg_api.cu) already traced this step's 17 rays from the same kinematics
+        KG_PHASE(l) { if (l < KG_NSITE) KG_RANGE(ws)[l] = ranges[l * A.N + env]; }
+        KG_SYNC();
+    } else kg_rays(m, ws, kg_lane);
     KG_PROBE(16);
     float rew = 0.f; int dn = 0;
     kg_obs(m, ws, kg_lane, &rew, &dn);

@@ -131,10 +131,10 @@ class Handle:
         self._chk(self.lib.kg_set_timing(self.h, int(on)), "kg_set_timing")
 
     def timing_breakdown(self):
-        """ms of the last step by launch kind (timing on): schedule, begin, narrowphase, substep, last."""
+        """ms of the last step by launch kind (timing on): schedule, begin, narrowphase, substep, last, rays."""
         b = (C.c_float * 8)()
         self._chk(self.lib.kg_timing_breakdown(self.h, b), "kg_timing_breakdown")
-        return {"schedule": b[1], "begin": b[2], "narrowphase": b[3], "substep": b[4], "last": b[5]}
+        return {"schedule": b[1], "begin": b[2], "narrowphase": b[3], "substep": b[4], "last": b[5], "rays": b[6]}
 
     def last_action_host(self):
         a = np.zeros((4, self.n), dtype=np.float32)

@@ -531,6 +531,52 @@ def test_pipeline_groups_do_not_change_results(card):
             assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_no_contact_is_dropped_above_the_full_workspace(backend, oracle, card, mode):
+    """MuJoCo never drops a contact for this model, the round-1 kernels did above 23.  A hand pressed flat on the
+    floor with folded fingers has 25+ contacts (plane lanes of the palm and all six finger geoms + the object): more than
+    the light (8) AND the full (23) workspace hold.  One physics substep from that state, in split mode and in full mode:
+    the heavy lane of the launch runs it with rows for all 54 possible contacts -- kg_get_stats reports no overflow, the
+    contact count equals the oracle's, and the next velocities agree with the oracle's step."""
+    emu = backend._name.endswith("libkg_emu.so")
+    if emu and mode == 2:
+        pytest.skip("the emulation has one workspace only")
+    n = 4
+    shape = np.array([9, 9, 0, 0], dtype=np.int32)
+    euler = np.tile(np.array([[-1.57], [0.0], [-1.57]], dtype=np.float32), (1, n))
+    objp = np.tile(np.array([[0.0], [0.0], [0.03]], dtype=np.float32), (1, n))
+    objp[:, 3] = card.pose("train")[0, 0, 7, 0:3]      # env 3: an ordinary start (object standing on the floor)
+    h = Handle(n, lib=backend)
+    h.set_mode(mode); h.set_frame_skip(1); h.set_max_episode_steps(10 ** 6)
+    h.reset_host(shape, euler, objp)
+    qp, qv = h.get_state_host()
+    qp[0], qp[1], qp[2] = 0.0, -0.04, -0.08
+    qp[3] = qp[5] = qp[7] = 1.2; qp[4] = qp[6] = qp[8] = 0.6
+    qp[0:9, 3] = 0.0                                   # env 3: open hand above the object (an ordinary substep next to the heavy ones)
+    h.set_state_host(qp, qv)
+    h.stats()
+    obs, rew, done = h.step_host(np.zeros((4, n), dtype=np.float32), 0)
+    st = h.stats()
+    assert st["contact_overflow"] == 0 and st["substeps"] == n
+    qp2, qv2 = h.get_state_host()
+    ncons = []
+    for i in range(n):
+        s = oracle.state(int(shape[i]), euler[:, i].astype(np.float64), objp[:, i].astype(np.float64))
+        for k in range(16): s.qpos[k] = float(qp[k, i])
+        for k in range(15): s.qvel[k] = float(qv[k, i])
+        import ctypes as C
+        D0 = oracle.forward(s)
+        c = np.zeros(9); a = np.zeros(4); dp = C.POINTER(C.c_double)
+        kgo.lib().kgo_ctrl_from_action(C.byref(D0), a.ctypes.data_as(dp), c.ctypes.data_as(dp))
+        D = oracle.step(s, c)
+        ncons.append(D.ncon)
+        ref_v = np.array(s.qvel)
+        assert np.abs(qv2[:, i] - ref_v).max() < 2e-3 * max(1.0, np.abs(ref_v).max()), (i, D.ncon, np.abs(qv2[:, i] - ref_v).max(), np.abs(ref_v).max())
+    assert max(ncons[:3]) > 23 and ncons[3] <= 8, ncons
+    assert st["contacts"] == sum(ncons), (st, ncons)
+    h.close()
+
+
 def test_global_frame_obs_parity(backend, oracle, card):
     """_get_obs(state_rep="global"): the 74-value world-frame layout written next to the local one (kg_set_obs_global)
     against the oracle (itself pinned to the reference's own _get_obs in test_oracle_golden), after reset for all shapes and

@@ -25,4 +25,5 @@ for path in sys.argv[1:3]:
     out.append((tr, st)); h.close()
 same = all(np.array_equal(x, y) for x, y in zip(out[0][0], out[1][0]))
 worst = max(float(np.abs(x - y).max()) for x, y in zip(out[0][0], out[1][0]))
-print(f"{sys.argv[1]} vs {sys.argv[2]}: bit-identical {same}, max |diff| {worst:.3e}; stats {out[0][1]} | {out[1][1]}")
+frac = float(np.mean(np.abs(out[0][0][-4] - out[1][0][-4]).max(axis=0) <= 1e-3))       # envs whose last obs agree
+print(f"{sys.argv[1]} vs {sys.argv[2]}: bit-identical {same}, envs with |obs diff| <= 1e-3 after the last step {frac:.4f}, max |diff| {worst:.3e}; stats {out[0][1]} | {out[1][1]}")

@@ -39,7 +39,7 @@ for t in range(steps):
     ms.append(h.last_step_ms())
     if os.environ.get("KG_TIMING"):
         d = h.timing_breakdown()
-        brk.append([0.0, d["schedule"], d["begin"], d["narrowphase"], d["substep"], d["last"]])
+        brk.append([0.0, d["schedule"], d["begin"], d["narrowphase"], d["substep"], d["last"], d.get("rays", 0.0)])
     h.reset_sampled(done.data_ptr(), 0, orient, variant, 0, 1234, 0)
 h.sync()
 st = h.stats()
@@ -51,9 +51,9 @@ print(f"{os.path.basename(sys.argv[1]):28s} sched {sched} envs {n} kernel ms: me
       f"-> {n * 15 / ms[3:].mean() * 1e3:.3e} substeps/s | mpr/sub {st['mpr_pairs'] / st['substeps']:.2f} newton/sub {st['newton_iters'] / st['substeps']:.2f} ovf {st['contact_overflow']}"
       f" mode {mode} groups {groups} graph {os.environ.get('KG_GRAPH', 'default')}")
 if brk:
-    names = ["", "schedule", "begin", "narrowphase", "substep", "last"]
+    names = ["", "schedule", "begin", "narrowphase", "substep", "last", "rays"]
     for t in (5, 18):
-        if t < len(brk): print(f"   step {t}: total {ms[t]:.3f} ms | " + "  ".join(f"{names[k]} {brk[t][k]:.3f}" for k in range(1, 6)))
+        if t < len(brk): print(f"   step {t}: total {ms[t]:.3f} ms | " + "  ".join(f"{names[k]} {brk[t][k]:.3f}" for k in range(1, 7)))
 if os.environ.get("KG_SERIES"): print("   ms per step:", " ".join(f"{x:.2f}" for x in ms))
 tot = sum(prof[:20])
 if tot:
