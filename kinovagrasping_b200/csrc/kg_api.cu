@@ -40,6 +40,9 @@
 #endif
 #define KG_SPLIT (KG_MAXCON_LIGHT < KG_MAXCON)
 #define KG_LSMEM (KG_LWARPS * sizeof(KgWSLight))
+#if KG_MPR_TEAMS > 1 && !defined(KG_MPR_L1)
+#error "narrowphase teams need the hull tables on the read-only L1 path (KG_MPR_L1)"
+#endif
 __constant__ KgModel c_model;
 #endif
 
@@ -381,13 +384,9 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
     if (blockIdx.x == 0 && threadIdx.x == 0) { q_other[0] = 0; q_other[1] = 0; }   // the list the next per-env kernel fills
     const int ntask = q[0];
     if (ntask == 0) return;
-#ifdef KG_MPR_HALF
-    KgMprWS &mw = *(reinterpret_cast<KgMprWS *>(smem) + 2 * warp + (lane >> 4));      // one workspace per 16-lane team
-#else
-    KgMprWS &mw = *(reinterpret_cast<KgMprWS *>(smem) + warp);
-#endif
+    KgMprWS &mw = *(reinterpret_cast<KgMprWS *>(smem) + KG_MPR_TEAMS * warp + lane / KG_MPR_W);      // one workspace per team
 #ifndef KG_MPR_L1
-    float4 *fh = reinterpret_cast<float4 *>(smem + KG_MPR_WARPS * sizeof(KgMprWS));
+    float4 *fh = reinterpret_cast<float4 *>(smem + KG_MPR_TEAMS * KG_MPR_WARPS * sizeof(KgMprWS));
     {
         const int n4 = c_model.hnpad[1] + c_model.hnpad[2];
         const float4 *src = reinterpret_cast<const float4 *>(c_model.hull_pad) + c_model.hpad0[1];
@@ -406,13 +405,14 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
 #ifdef KG_PROF
     long long t0 = clock64(), nt = 0;
 #endif
+    const unsigned team = KG_MPR_MASK(lane);
+#if KG_MPR_TEAMS == 1
     // dynamic task list: no look-ahead on purpose -- a warp that reserved its next task while still inside a long MPR
     // would hold that task back from the idle warps (measured: 10 % slower at 4096 envs)
-    const unsigned team = KG_MPR_MASK(lane);
     for (;;) {
         int t = 0;
-        if ((lane & (KG_MPR_W - 1)) == 0) t = atomicAdd(q + 1, 1);
-        t = __shfl_sync(team, t, lane & ~(KG_MPR_W - 1));
+        if (lane == 0) t = atomicAdd(q + 1, 1);
+        t = __shfl_sync(team, t, 0);
         if (t >= ntask) break;
         const unsigned task = tasks[t];
         kg_mpr_task(c_model, mw, carry + (size_t)(task >> 8) * KG_CARRY_BYTES, (int)(task & 0xff), lane);
@@ -420,6 +420,47 @@ __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_ke
         nt++;
 #endif
     }
+#else
+    // KG_MPR_TEAMS teams per warp in LOCKSTEP: every trip of this loop each team either picks up a new task or advances its
+    // MPR by one iteration, then the warp meets again -- so teams that are in the same state of the algorithm execute its
+    // (scalar, redundant) portal algebra as one instruction stream.
+    KgMprIt it;
+    unsigned char *rec = nullptr;
+    int lp = 0, g1 = 0, g2 = 0, mesh1 = 0, mesh2 = 0, c1 = 0, c2 = 0;
+    bool active = false, exhausted = false;
+    for (;;) {
+        if (!active && !exhausted) {
+            int t = 0;
+            if ((lane & (KG_MPR_W - 1)) == 0) t = atomicAdd(q + 1, 1);
+            t = __shfl_sync(team, t, lane & ~(KG_MPR_W - 1));
+            if (t >= ntask) exhausted = true;
+            else {
+                const unsigned task = tasks[t];
+                rec = carry + (size_t)(task >> 8) * KG_CARRY_BYTES; lp = (int)(task & 0xff);
+                kg_pair_of_lane(lp, g1, g2);
+                kg_mpr_stage(mw, rec, g1, g2, lane);
+                mesh1 = kg_mesh_of_geom_s(mw.shape, g1); mesh2 = kg_mesh_of_geom_s(mw.shape, g2);
+                c1 = 0; c2 = 0;
+                kg_mpr_init(mw, it);
+                active = true;
+#ifdef KG_PROF
+                nt++;
+#endif
+            }
+        }
+        if (__all_sync(0xffffffffu, !active)) break;
+        if (active) {
+            int sepf = 0;
+            float depth = 0.f, nrm[3] = {0, 0, 0}, pos[3] = {0, 0, 0}, gap = 0.f;
+            const int r = kg_mpr_iter(c_model, mw, it, mesh1, mesh2, 0.5f * c_model.margin, c1, c2, &depth, nrm, pos, &sepf, &gap, lane);
+            if (r) {
+                kg_mpr_file(c_model, mw, rec, lp, g1, g2, r == 1, depth, nrm, pos, sepf, gap, c1, c2, lane);
+                active = false;
+            }
+        }
+        __syncwarp();
+    }
+#endif
 #ifdef KG_PROF
     __syncwarp();
     if (prof) {
@@ -526,13 +567,9 @@ static_assert(KG_WARPS * sizeof(KgWS) <= 227 * 1024, "KG_WARPS workspaces must f
 static_assert(KG_LSMEM >= 2 * sizeof(KgWSNoSync), "a light CTA's shared memory must hold at least two heavy-lane workspaces");
 static_assert(KG_LMINBLOCKS * (KG_LWARPS * sizeof(KgWSLight) + 1024) <= 228 * 1024, "KG_LMINBLOCKS light CTAs must fit one SM's shared memory");
 #ifdef KG_MPR_L1
-#ifdef KG_MPR_HALF
-#define KG_MPR_SMEM(h) (2 * KG_MPR_WARPS * sizeof(KgMprWS))
+#define KG_MPR_SMEM(h) (KG_MPR_TEAMS * KG_MPR_WARPS * sizeof(KgMprWS))
 #else
-#define KG_MPR_SMEM(h) (KG_MPR_WARPS * sizeof(KgMprWS))
-#endif
-#else
-#define KG_MPR_SMEM(h) (KG_MPR_WARPS * sizeof(KgMprWS) + (size_t)(h)->fhull_bytes)
+#define KG_MPR_SMEM(h) (KG_MPR_TEAMS * KG_MPR_WARPS * sizeof(KgMprWS) + (size_t)(h)->fhull_bytes)
 #endif
 #endif
 
@@ -601,7 +638,7 @@ static int enqueue_step(kg_handle h, cudaStream_t st, const float *action, int m
             int *q = h->q + 4 * g;
             unsigned *tasks = h->tasks + (size_t)base * 22;
             // persistent narrowphase grid of this group: room for ~2 tasks per env at one task per team, at most the whole GPU
-            int mgrid = (2 * cnt + KG_MPR_WARPS * (32 / KG_MPR_W) - 1) / (KG_MPR_WARPS * (32 / KG_MPR_W));
+            int mgrid = (2 * cnt + KG_MPR_WARPS * KG_MPR_TEAMS - 1) / (KG_MPR_WARPS * KG_MPR_TEAMS);
             mgrid = mgrid < 8 ? 8 : (mgrid > h->mpr_grid ? h->mpr_grid : mgrid);
             kg_mpr_kernel<<<mgrid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), gs[g]>>>(h->carry, q + 2 * qa, q + 2 * qb, tasks, h->A.prof);
             KG_TMARK(3);

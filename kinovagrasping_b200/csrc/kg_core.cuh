@@ -585,11 +585,17 @@ template <class WS> KG_DEV void kg_support(const KgModel &m, const WS &ws, int g
 }
 
 // Narrowphase team size: a full MPR is run by a TEAM of lanes that share the two support scans of an iteration and execute
-// the (scalar) portal algebra redundantly.  KG_MPR_HALF: two teams of 16 lanes per warp, each with its own task -- the
-// algebra, most of an iteration's instructions, is then issued once for two tasks; the scans take twice as many trips.
-#if defined(__CUDA_ARCH__) && defined(KG_MPR_HALF)
-#define KG_MPR_W 16
-#define KG_MPR_MASK(lane) (0xffffu << ((lane) & 16))
+// the (scalar) portal algebra redundantly.  KG_MPR_TEAMS = 2 or 4: that many teams (16 / 8 lanes) per warp, each with its own
+// task, advancing ONE MPR iteration per trip of the kernel's loop with a warp-wide rendezvous after it -- teams in the same
+// state of the algorithm then issue the algebra, most of an iteration's instructions, once for all of them; the scans take
+// more trips.  (Teams that merely share a warp without the rendezvous drift apart and issue everything separately: measured,
+// no gain.)
+#ifndef KG_MPR_TEAMS
+#define KG_MPR_TEAMS 1
+#endif
+#if defined(__CUDA_ARCH__)
+#define KG_MPR_W (32 / KG_MPR_TEAMS)
+#define KG_MPR_MASK(lane) (KG_MPR_TEAMS == 1 ? 0xffffffffu : (((1u << (KG_MPR_W & 31)) - 1u) << ((lane) & ~(KG_MPR_W - 1))))
 #else
 #define KG_MPR_W 32
 #define KG_MPR_MASK(lane) 0xffffffffu
@@ -746,116 +752,131 @@ static long kg_emu_mpr_iters = 0;
 // findPenetr) so that the hill-climbing support code exists once in the instruction stream.
 // On a "no overlap" exit that PROVES separation (support of A-B along dir is negative) *sep_found is set and dir is
 // returned in nrm: the caller re-tests that axis first in the next substep (two supports instead of a full MPR).
-KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g2, int mesh2, float hmargin, int &cur1, int &cur2,
-                   float *depth, float *nrm, float *pos, int *sep_found, float *gap, int kg_lane) {
-    *sep_found = 0; *gap = 0.f;
-    KgSupp p[4];
-    float dir[3], va[3], vb[3], dot;
+struct KgMprIt { KgSupp p[4]; float dir[3]; int state, it, guard; };
+KG_DEV void kg_mpr_init(const KgMprWS &ws, KgMprIt &q) {
+    q.p[0].v1[0] = q.p[0].v1[1] = q.p[0].v1[2] = 0.f;
+    kg_sub(q.p[0].v, ws.gp[0], ws.gp[1]);
+    if (kg_iszero(q.p[0].v[0]) && kg_iszero(q.p[0].v[1]) && kg_iszero(q.p[0].v[2])) q.p[0].v[0] += KG_CCD_EPS * 10;
+    for (int c = 0; c < 3; c++) q.dir[c] = -q.p[0].v[c];
+    kg_normalize_dir(q.dir);
+    q.state = 0; q.it = 0; q.guard = 0;
+}
+// ONE iteration of the state machine (one support evaluation of the Minkowski difference): 0 = go on, 1 = penetration found
+// (depth, nrm, pos set), 2 = no contact (*sep_found / *gap / nrm set when separation along nrm was proven).
+KG_DEV int kg_mpr_iter(const KgModel &m, const KgMprWS &ws, KgMprIt &q, int mesh1, int mesh2, float hmargin, int &cur1, int &cur2,
+                       float *depth, float *nrm, float *pos, int *sep_found, float *gap, int kg_lane) {
+    KgSupp *p = q.p;
+    float *dir = q.dir;
+    float va[3], vb[3], dot;
     const float *org = ws.gp[0];
-    p[0].v1[0] = p[0].v1[1] = p[0].v1[2] = 0.f;
-    kg_sub(p[0].v, ws.gp[0], ws.gp[1]);
-    if (kg_iszero(p[0].v[0]) && kg_iszero(p[0].v[1]) && kg_iszero(p[0].v[2])) p[0].v[0] += KG_CCD_EPS * 10;
-    for (int c = 0; c < 3; c++) dir[c] = -p[0].v[c];
-    kg_normalize_dir(dir);
-    int state = 0, it = 0;
-    if (kg_lane == 0) KG_COUNT(22, 1);
-    for (int guard = 0; guard < 400; guard++) {
-        KgSupp s;
-        if (kg_lane == 0) KG_COUNT(23, 1);
+    if (++q.guard > 400) return 2;
+    KgSupp s;
+    if (kg_lane == 0) KG_COUNT(23, 1);
 #if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
-        kg_emu_mpr_iters++;
+    kg_emu_mpr_iters++;
 #endif
-        {
-            float nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
-            kg_support_coop(m, ws, 0, mesh1, dir, org, hmargin, s.v1, &cur1, kg_lane);
-            kg_support_coop(m, ws, 1, mesh2, nd, org, hmargin, v2, &cur2, kg_lane);
-            kg_sub(s.v, s.v1, v2);
+    {
+        float nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
+        kg_support_coop(m, ws, 0, mesh1, dir, org, hmargin, s.v1, &cur1, kg_lane);
+        kg_support_coop(m, ws, 1, mesh2, nd, org, hmargin, v2, &cur2, kg_lane);
+        kg_sub(s.v, s.v1, v2);
+    }
+    bool check_portal = false;
+    if (q.state == 0) {
+        p[1] = s;
+        dot = kg_dot(s.v, dir);
+        if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); } return 2; }
+        kg_cross(dir, p[0].v, p[1].v);
+        if (kg_iszero(kg_dot(dir, dir))) {
+            if (kg_iszero(p[1].v[0]) && kg_iszero(p[1].v[1]) && kg_iszero(p[1].v[2])) return 2;   // touching, no normal
+            *depth = sqrtf(kg_dot(p[1].v, p[1].v));
+            kg_copy(nrm, p[1].v); kg_normalize(nrm);
+            for (int c = 0; c < 3; c++) pos[c] = p[1].v1[c] - 0.5f * p[1].v[c];
+            return 1;
         }
-        bool check_portal = false;
-        if (state == 0) {
-            p[1] = s;
-            dot = kg_dot(s.v, dir);
-            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); } return false; }
-            kg_cross(dir, p[0].v, p[1].v);
-            if (kg_iszero(kg_dot(dir, dir))) {
-                if (kg_iszero(p[1].v[0]) && kg_iszero(p[1].v[1]) && kg_iszero(p[1].v[2])) return false;   // touching, no normal
-                *depth = sqrtf(kg_dot(p[1].v, p[1].v));
-                kg_copy(nrm, p[1].v); kg_normalize(nrm);
-                for (int c = 0; c < 3; c++) pos[c] = p[1].v1[c] - 0.5f * p[1].v[c];
-                return true;
-            }
-            kg_normalize_dir(dir);
-            state = 1;
-        } else if (state == 1) {
-            p[2] = s;
-            dot = kg_dot(s.v, dir);
-            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); } return false; }
+        kg_normalize_dir(dir);
+        q.state = 1;
+    } else if (q.state == 1) {
+        p[2] = s;
+        dot = kg_dot(s.v, dir);
+        if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); } return 2; }
+        kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
+        kg_cross(dir, va, vb); kg_normalize_dir(dir);
+        if (kg_dot(dir, p[0].v) > 0) { KgSupp t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+        q.state = 2;
+    } else if (q.state == 2) {
+        p[3] = s;
+        dot = kg_dot(s.v, dir);
+        if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); } return 2; }
+        bool cont = false;
+        kg_cross(va, p[1].v, p[3].v); dot = kg_dot(va, p[0].v);
+        if (dot < 0 && !kg_iszero(dot)) { p[2] = p[3]; cont = true; }
+        if (!cont) {
+            kg_cross(va, p[3].v, p[2].v); dot = kg_dot(va, p[0].v);
+            if (dot < 0 && !kg_iszero(dot)) { p[1] = p[3]; cont = true; }
+        }
+        if (cont) {
             kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
             kg_cross(dir, va, vb); kg_normalize_dir(dir);
-            if (kg_dot(dir, p[0].v) > 0) { KgSupp t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
-            state = 2;
-        } else if (state == 2) {
-            p[3] = s;
-            dot = kg_dot(s.v, dir);
-            if (kg_iszero(dot) || dot < 0) { if (dot < 0) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); } return false; }
-            bool cont = false;
-            kg_cross(va, p[1].v, p[3].v); dot = kg_dot(va, p[0].v);
-            if (dot < 0 && !kg_iszero(dot)) { p[2] = p[3]; cont = true; }
-            if (!cont) {
-                kg_cross(va, p[3].v, p[2].v); dot = kg_dot(va, p[0].v);
-                if (dot < 0 && !kg_iszero(dot)) { p[1] = p[3]; cont = true; }
+        } else { q.state = 3; check_portal = true; }
+    } else if (q.state == 3) {
+        dot = kg_dot(s.v, dir);
+        if (!(kg_iszero(dot) || dot > 0)) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); return 2; }
+        if (kg_reach_tol(p, s, dir)) return 2;
+        kg_expand_portal(p, s);
+        check_portal = true;
+    } else {
+        if (kg_reach_tol(p, s, dir) || q.it > KG_MPR_ITER) {
+            float w[3];
+            *depth = sqrtf(kg_tri_dist2(p[1].v, p[2].v, p[3].v, w));
+            if (kg_iszero(w[0]) && kg_iszero(w[1]) && kg_iszero(w[2])) kg_copy(w, dir);
+            kg_copy(nrm, w); kg_normalize(nrm);
+            // findPos: barycentric coordinates of the origin in the portal tetrahedron
+            float b[4], t[3], sum;
+            kg_cross(t, p[1].v, p[2].v); b[0] = kg_dot(t, p[3].v);
+            kg_cross(t, p[3].v, p[2].v); b[1] = kg_dot(t, p[0].v);
+            kg_cross(t, p[0].v, p[1].v); b[2] = kg_dot(t, p[3].v);
+            kg_cross(t, p[2].v, p[1].v); b[3] = kg_dot(t, p[0].v);
+            sum = b[0] + b[1] + b[2] + b[3];
+            if (kg_iszero(sum) || sum < 0) {
+                kg_portal_dir(p, dir);
+                b[0] = 0;
+                kg_cross(t, p[2].v, p[3].v); b[1] = kg_dot(t, dir);
+                kg_cross(t, p[3].v, p[1].v); b[2] = kg_dot(t, dir);
+                kg_cross(t, p[1].v, p[2].v); b[3] = kg_dot(t, dir);
+                sum = b[1] + b[2] + b[3];
             }
-            if (cont) {
-                kg_sub(va, p[1].v, p[0].v); kg_sub(vb, p[2].v, p[0].v);
-                kg_cross(dir, va, vb); kg_normalize_dir(dir);
-            } else { state = 3; check_portal = true; }
-        } else if (state == 3) {
-            dot = kg_dot(s.v, dir);
-            if (!(kg_iszero(dot) || dot > 0)) { *sep_found = 1; *gap = -dot; kg_copy(nrm, dir); return false; }
-            if (kg_reach_tol(p, s, dir)) return false;
-            kg_expand_portal(p, s);
-            check_portal = true;
-        } else {
-            if (kg_reach_tol(p, s, dir) || it > KG_MPR_ITER) {
-                float w[3];
-                *depth = sqrtf(kg_tri_dist2(p[1].v, p[2].v, p[3].v, w));
-                if (kg_iszero(w[0]) && kg_iszero(w[1]) && kg_iszero(w[2])) kg_copy(w, dir);
-                kg_copy(nrm, w); kg_normalize(nrm);
-                // findPos: barycentric coordinates of the origin in the portal tetrahedron
-                float b[4], t[3], sum;
-                kg_cross(t, p[1].v, p[2].v); b[0] = kg_dot(t, p[3].v);
-                kg_cross(t, p[3].v, p[2].v); b[1] = kg_dot(t, p[0].v);
-                kg_cross(t, p[0].v, p[1].v); b[2] = kg_dot(t, p[3].v);
-                kg_cross(t, p[2].v, p[1].v); b[3] = kg_dot(t, p[0].v);
-                sum = b[0] + b[1] + b[2] + b[3];
-                if (kg_iszero(sum) || sum < 0) {
-                    kg_portal_dir(p, dir);
-                    b[0] = 0;
-                    kg_cross(t, p[2].v, p[3].v); b[1] = kg_dot(t, dir);
-                    kg_cross(t, p[3].v, p[1].v); b[2] = kg_dot(t, dir);
-                    kg_cross(t, p[1].v, p[2].v); b[3] = kg_dot(t, dir);
-                    sum = b[1] + b[2] + b[3];
-                }
-                float inv = 1.0f / sum;
-                for (int c = 0; c < 3; c++) {
-                    float s1 = 0, sv = 0;
-                    for (int i = 0; i < 4; i++) { s1 += b[i] * p[i].v1[c]; sv += b[i] * p[i].v[c]; }
-                    pos[c] = (s1 - 0.5f * sv) * inv;   // (p1 + p2)/2 with p2 = p1 - v
-                }
-                return true;
+            float inv = 1.0f / sum;
+            for (int c = 0; c < 3; c++) {
+                float s1 = 0, sv = 0;
+                for (int i = 0; i < 4; i++) { s1 += b[i] * p[i].v1[c]; sv += b[i] * p[i].v[c]; }
+                pos[c] = (s1 - 0.5f * sv) * inv;   // (p1 + p2)/2 with p2 = p1 - v
             }
-            kg_expand_portal(p, s);
-            it++;
-            kg_portal_dir(p, dir);
+            return 1;
         }
-        if (check_portal) {
-            // refinePortal's loop head: does the portal already enclose the origin ray?
-            kg_portal_dir(p, dir);
-            dot = kg_dot(dir, p[1].v);
-            if (kg_iszero(dot) || dot > 0) state = 4;   // findPenetr starts with this same portal direction
-        }
+        kg_expand_portal(p, s);
+        q.it++;
+        kg_portal_dir(p, dir);
     }
-    return false;
+    if (check_portal) {
+        // refinePortal's loop head: does the portal already enclose the origin ray?
+        kg_portal_dir(p, dir);
+        dot = kg_dot(dir, p[1].v);
+        if (kg_iszero(dot) || dot > 0) q.state = 4;   // findPenetr starts with this same portal direction
+    }
+    return 0;
+}
+KG_DEV bool kg_mpr(const KgModel &m, const KgMprWS &ws, int g1, int mesh1, int g2, int mesh2, float hmargin, int &cur1, int &cur2,
+                   float *depth, float *nrm, float *pos, int *sep_found, float *gap, int kg_lane) {
+    (void)g1; (void)g2;
+    *sep_found = 0; *gap = 0.f;
+    KgMprIt q;
+    kg_mpr_init(ws, q);
+    if (kg_lane == 0) KG_COUNT(22, 1);
+    for (;;) {
+        const int r = kg_mpr_iter(m, ws, q, mesh1, mesh2, hmargin, cur1, cur2, depth, nrm, pos, sep_found, gap, kg_lane);
+        if (r) return r == 1;
+    }
 }
 
 // mju_makeFrame on frame[0:3] = normal
@@ -890,33 +911,61 @@ template <class WS> KG_DEV float kg_rbound(const KgModel &m, const WS &ws, int g
 // One narrowphase task: full MPR of pair lane lp of env `env` (warp-uniform: all 32 lanes run the portal algebra and
 // share the cooperative support scans).  The geom frames come from the env's carry record, the result is filed there
 // by lane 0: separating axis / warm-start vertices, and on a hit the contact in staging slot 32 + (lp - 8).
-KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int lp, int kg_lane) {
-    int g1, g2;
-    kg_pair_of_lane(lp, g1, g2);
-#if defined(__CUDA_ARCH__) && defined(KG_MPR_HALF)
-    {   // the frames of the two geoms of this pair: 2 x (3 + 9) words over the team's 16 lanes
-        const unsigned team = KG_MPR_MASK(kg_lane);
-        __syncwarp(team);
-        for (int l = kg_lane & 15; l < 24; l += 16) {
-            const int which = l >= 12, j = l - 12 * which, g = which ? g2 : g1;
-            if (j < 3) mw.gp[which][j] = reinterpret_cast<const float *>(carry + KG_COFF(gpos))[3 * g + j];
-            else mw.gr[which][4 * ((j - 3) / 3) + (j - 3) % 3] = reinterpret_cast<const float *>(carry + KG_COFF(gmat))[9 * g + j - 3];
-        }
-        if ((kg_lane & 15) == 15) mw.shape = *reinterpret_cast<const int *>(carry + KG_COFF(shape));
-        __syncwarp(team);
-    }
+// the frames of a task's two geoms (2 x (3 + 9) words) from the env's carry record into the team's workspace
+KG_DEV void kg_mpr_stage(KgMprWS &mw, const unsigned char *carry, int g1, int g2, int kg_lane) {
+#if defined(__CUDA_ARCH__)
+    const unsigned team = KG_MPR_MASK(kg_lane);
+    __syncwarp(team);
+    for (int l = kg_lane & (KG_MPR_W - 1); l < 25; l += KG_MPR_W) {
 #else
     KG_PHASE(l) {
-        // the frames of the two geoms of this pair: 2 x (3 + 9) words, one per lane
+#endif
         if (l < 24) {
             const int which = l >= 12, j = l - 12 * which, g = which ? g2 : g1;
             if (j < 3) mw.gp[which][j] = reinterpret_cast<const float *>(carry + KG_COFF(gpos))[3 * g + j];
             else mw.gr[which][4 * ((j - 3) / 3) + (j - 3) % 3] = reinterpret_cast<const float *>(carry + KG_COFF(gmat))[9 * g + j - 3];
         }
-        if (l == 31) mw.shape = *reinterpret_cast<const int *>(carry + KG_COFF(shape));
+        if (l == 24) mw.shape = *reinterpret_cast<const int *>(carry + KG_COFF(shape));
     }
+#if defined(__CUDA_ARCH__)
+    __syncwarp(team);
+#else
     KG_SYNC();
 #endif
+}
+// file the result of pair lane lp in the env's carry record (the team's first lane): separating axis / budget / warm-start
+// vertices, and on a hit the contact in staging slot 32 + (lp - 8)
+KG_DEV void kg_mpr_file(const KgModel &m, const KgMprWS &mw, unsigned char *carry, int lp, int g1, int g2, bool hit, float depth, const float *nrm, const float *pos,
+                        int sepf, float gap, int c1, int c2, int kg_lane) {
+#if defined(__CUDA_ARCH__)
+    if ((kg_lane & (KG_MPR_W - 1)) == 0) {
+#else
+    (void)kg_lane;
+    {
+#endif
+        const float margin = m.margin;
+        reinterpret_cast<int *>(carry + KG_COFF_C(sepok))[lp] = sepf;
+        if (sepf) {
+            float *sp = reinterpret_cast<float *>(carry + KG_COFF_C(sep)) + 3 * lp; sp[0] = nrm[0]; sp[1] = nrm[1]; sp[2] = nrm[2];
+            reinterpret_cast<float *>(carry + KG_COFF_C(slack))[lp] = gap;      // the collision stage of this very substep has already charged the motion up to here
+        }
+        reinterpret_cast<unsigned short *>(carry + KG_COFF_C(cv1))[lp] = (unsigned short)c1;
+        reinterpret_cast<unsigned short *>(carry + KG_COFF_C(cv2))[lp] = (unsigned short)c2;
+        if (hit && depth > 0.f) {
+            const int sl = 32 + (lp - 8);
+            reinterpret_cast<float *>(carry + KG_COFF_B(st_dist))[sl] = margin - depth;
+            float *sp = reinterpret_cast<float *>(carry + KG_COFF_B(st_pos)) + 3 * sl, *sn = reinterpret_cast<float *>(carry + KG_COFF_B(st_n)) + 3 * sl;
+            for (int c = 0; c < 3; c++) { sp[c] = pos[c] + mw.gp[0][c]; sn[c] = nrm[c]; }
+            (carry + KG_COFF_B(st_g1))[sl] = (unsigned char)g1; (carry + KG_COFF_B(st_g2))[sl] = (unsigned char)g2;
+            reinterpret_cast<int *>(carry + KG_COFF(cnt))[lp] = 1;
+        }
+    }
+}
+// One narrowphase task from start to end: full MPR of pair lane lp of an env, by one team.
+KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int lp, int kg_lane) {
+    int g1, g2;
+    kg_pair_of_lane(lp, g1, g2);
+    kg_mpr_stage(mw, carry, g1, g2, kg_lane);
 #ifndef KG_MPR_L1
     if (mw.shape != mw.hull_shape) {      // this warp's object-hull copy holds another shape
         KG_SYNC();
@@ -934,40 +983,17 @@ KG_DEV void kg_mpr_task(const KgModel &m, KgMprWS &mw, unsigned char *carry, int
     }
 #endif
     const int mesh1 = kg_mesh_of_geom_s(mw.shape, g1), mesh2 = kg_mesh_of_geom_s(mw.shape, g2);
-    const float margin = m.margin;
     int c1 = 0, c2 = 0, sepf = 0;
     float depth = 0.f, nrm[3] = {0, 0, 0}, pos[3] = {0, 0, 0}, gap = 0.f;
 #if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
     long it0_ = kg_emu_mpr_iters;
 #endif
-    bool hit = kg_mpr(m, mw, g1, mesh1, g2, mesh2, 0.5f * margin, c1, c2, &depth, nrm, pos, &sepf, &gap, kg_lane);
+    bool hit = kg_mpr(m, mw, g1, mesh1, g2, mesh2, 0.5f * m.margin, c1, c2, &depth, nrm, pos, &sepf, &gap, kg_lane);
 #if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
     fprintf(stderr, "MPR %d %d %ld %d %d\n", g1, g2, kg_emu_mpr_iters - it0_, (int)hit, sepf);
 #endif
-#if defined(__CUDA_ARCH__) && defined(KG_MPR_HALF)
-    for (int l = kg_lane & 15, once_ = 0; once_ < 1; ++once_) {
-#else
-    KG_PHASE(l) {
-#endif
-        if (l == 0) {
-            reinterpret_cast<int *>(carry + KG_COFF_C(sepok))[lp] = sepf;
-            if (sepf) {
-                float *sp = reinterpret_cast<float *>(carry + KG_COFF_C(sep)) + 3 * lp; sp[0] = nrm[0]; sp[1] = nrm[1]; sp[2] = nrm[2];
-                reinterpret_cast<float *>(carry + KG_COFF_C(slack))[lp] = gap;      // the collision stage of this very substep has already charged the motion up to here
-            }
-            reinterpret_cast<unsigned short *>(carry + KG_COFF_C(cv1))[lp] = (unsigned short)c1;
-            reinterpret_cast<unsigned short *>(carry + KG_COFF_C(cv2))[lp] = (unsigned short)c2;
-            if (hit && depth > 0.f) {
-                const int sl = 32 + (lp - 8);
-                reinterpret_cast<float *>(carry + KG_COFF_B(st_dist))[sl] = margin - depth;
-                float *sp = reinterpret_cast<float *>(carry + KG_COFF_B(st_pos)) + 3 * sl, *sn = reinterpret_cast<float *>(carry + KG_COFF_B(st_n)) + 3 * sl;
-                for (int c = 0; c < 3; c++) { sp[c] = pos[c] + mw.gp[0][c]; sn[c] = nrm[c]; }
-                (carry + KG_COFF_B(st_g1))[sl] = (unsigned char)g1; (carry + KG_COFF_B(st_g2))[sl] = (unsigned char)g2;
-                reinterpret_cast<int *>(carry + KG_COFF(cnt))[lp] = 1;
-            }
-        }
-    }
-#if defined(__CUDA_ARCH__) && defined(KG_MPR_HALF)
+    kg_mpr_file(m, mw, carry, lp, g1, g2, hit, depth, nrm, pos, sepf, gap, c1, c2, kg_lane);
+#if defined(__CUDA_ARCH__)
     __syncwarp(KG_MPR_MASK(kg_lane));
 #else
     KG_SYNC();

@@ -197,12 +197,16 @@ def main():
 
     evaluate("untrained", 0)
     losses = None
+    graphs = []
     if graphed and args.pretrain_updates:                     # pre-training: demonstrations only (DDPG:227-229)
-        losses = GraphedUpdates(policy, agent, expert, args.batch, 1.0).run(args.pretrain_updates)
+        graphs.append(GraphedUpdates(policy, agent, expert, args.batch, 1.0))
+        losses = graphs[-1].run(args.pretrain_updates)
     else:
         for _ in range(args.pretrain_updates):
             losses = policy.train_on_batch(*expert.sample_windows(args.batch, generator=gen))
     upd = GraphedUpdates(policy, agent, expert, args.batch, args.expert_prob) if graphed else None
+    if upd is not None:
+        graphs.append(upd)
     if args.pretrain_updates:
         log(phase="pretrain", updates=args.pretrain_updates, losses=[float(x) for x in losses])
         evaluate("pretrained", 0)
@@ -239,7 +243,15 @@ def main():
     if args.save and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.save)), exist_ok=True)
         policy.save(args.save)
+    # captured graphs hold NCCL work: release them before the process group goes (destroy_process_group otherwise waits forever)
+    for g in graphs:
+        if g.graph is not None:
+            g.graph.reset()
+        g.graph = None
+    del graphs, upd
+    torch.cuda.synchronize()
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
