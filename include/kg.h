@@ -55,6 +55,10 @@ int kg_reset_pose(kg_handle h, const int *mask_dev, const int *shape_dev, const 
                   const float *objpos_dev, const float *handpos_dev, float *obs_dev);
 int kg_reset_pose_host(kg_handle h, const int *mask_host, const int *shape_host, const float *euler_host,
                        const float *objpos_host, const float *handpos_host, float *obs_host);
+/* Shape schedule of kg_reset_sampled when shape_dev is NULL (replaces the Latin-square list the reference keeps in
+ * objects.csv, kinova_gripper_env.py:895-999): episode e of global env i gets keys[(i + e) mod nkeys], shape ids in model-card
+ * order; every env cycles through the keys and every episode index sees them uniformly.  nkeys = 0: envs keep their shape. */
+int kg_set_shape_cycle(kg_handle h, const int *keys_host, int nkeys);
 /* determine_hand_location for kg_reset_sampled: 0 (default) = slides start at 0 -- what main_DDPGfD.py gets, because it
  * builds a new env per episode (MAIN:381) and a new env's Tfw is all zeros (ENV:110); 1 = what expert_data.py gets, which
  * reuses one env (EXP:696): the offsets are computed from the Tfw of the env's PREVIOUS episode (none for its first). */

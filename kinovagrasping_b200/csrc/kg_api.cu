@@ -68,6 +68,7 @@ struct kg_handle_s {
     int *heavy_host = nullptr;        // pinned host copy of the previous step's count (read without synchronising)
     int heavy_ctas = 1;               // heavy-lane CTAs at the front of every split-mode substep grid
     int hand_location = 0;            // kg_set_hand_location
+    int *cycle = nullptr; int cycle_n = 0;      // kg_set_shape_cycle: Latin-square shape schedule over (env, episode)
     int full_mode = 0, mode_auto = 1; // 1 = every env through the full workspace; chosen per step from heavy_host unless pinned
     std::vector<void *> allocs;
     // scratch for the *_host entry points
@@ -518,14 +519,17 @@ __global__ void __launch_bounds__(KG_RAY_WARPS * 32) kg_rays_kernel(const unsign
 }
 
 __global__ void __launch_bounds__(KG_LWARPS * 32) kg_reset_kernel(KgEnvArrays A, const int *mask, const int *shape, const float *euler, const float *objp, const float *handp,
-                                                                 int sampled, int orient, int variant, int test_table, int hand_location, unsigned long long seed, int *ep_count, int env_offset, float *obs) {
+                                                                 int sampled, int orient, int variant, int test_table, int hand_location, unsigned long long seed, int *ep_count, int env_offset,
+                                                                 const int *cycle, int cycle_n, float *obs) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * KG_LWARPS + warp;
     if (env >= A.N) return;
     if (mask && mask[env] == 0) return;
     KgWSLight &ws = *(reinterpret_cast<KgWSLight *>(smem) + warp);
-    int sh = shape ? shape[env] : A.shape[env];
+    // shape of the new episode: given, or the Latin-square schedule (row = env, column = episode: every env walks through the
+    // keys, every episode index sees them uniformly -- Generate_Latin_Square's property, ENV:895-964), or unchanged
+    int sh = shape ? shape[env] : (sampled && cycle_n > 0 ? cycle[(unsigned)(env + env_offset + ep_count[env]) % (unsigned)cycle_n] : A.shape[env]);
     float e[3], p[3], hp[3] = {0.f, 0.f, 0.f};
     if (sampled) {
         KgSample s = kg_sample_pose(c_model, seed, env + env_offset, ep_count[env], sh, orient, variant, test_table);
@@ -742,7 +746,7 @@ static int launch_reset(kg_handle h, const int *mask, const int *shape, const fl
 #ifdef KG_EMU
     for (int env = 0; env < h->n; env++) {
         if (mask && mask[env] == 0) continue;
-        int sh = shape ? shape[env] : h->A.shape[env];
+        int sh = shape ? shape[env] : (sampled && h->cycle_n > 0 ? h->cycle[(unsigned)(env + h->env_offset + h->ep_count[env]) % (unsigned)h->cycle_n] : h->A.shape[env]);
         float e[3], p[3], hp[3] = {0.f, 0.f, 0.f};
         if (sampled) {
             KgSample s = kg_sample_pose(h->model, seed, env + h->env_offset, h->ep_count[env], sh, orient, variant, test_table);
@@ -760,7 +764,7 @@ static int launch_reset(kg_handle h, const int *mask, const int *shape, const fl
 #else
     cudaStream_t st = (cudaStream_t)h->stream;
     int blocks = (h->n + KG_LWARPS - 1) / KG_LWARPS;
-    kg_reset_kernel<<<blocks, KG_LWARPS * 32, KG_LSMEM, st>>>(h->A, mask, shape, euler, objp, handp, sampled, orient, variant, test_table, h->hand_location, seed, h->ep_count, h->env_offset, obs);
+    kg_reset_kernel<<<blocks, KG_LWARPS * 32, KG_LSMEM, st>>>(h->A, mask, shape, euler, objp, handp, sampled, orient, variant, test_table, h->hand_location, seed, h->ep_count, h->env_offset, h->cycle, h->cycle_n, obs);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 #endif
@@ -995,6 +999,14 @@ int kg_reset_pose(kg_handle h, const int *mask, const int *shape, const float *e
 }
 int kg_reset(kg_handle h, const int *mask, const int *shape, const float *euler, const float *objp, float *obs) {
     return kg_reset_pose(h, mask, shape, euler, objp, nullptr, obs);
+}
+int kg_set_shape_cycle(kg_handle h, const int *keys_host, int nkeys) {
+    if (!h || nkeys < 0 || nkeys > 64 || (nkeys > 0 && !keys_host)) return KG_EINVAL;
+    for (int i = 0; i < nkeys; i++) if (keys_host[i] < 0 || keys_host[i] >= KG_NSHAPE) { h->err = "kg_set_shape_cycle: shape id out of range"; return KG_EINVAL; }
+    if (!h->cycle) TRY(be_alloc(h, (void **)&h->cycle, 64 * 4));
+    if (nkeys > 0) { TRY(be_h2d(h, h->cycle, keys_host, (size_t)nkeys * 4)); TRY(be_sync(h)); }
+    h->cycle_n = nkeys;
+    return KG_OK;
 }
 int kg_set_hand_location(kg_handle h, int mode) { if (!h || mode < 0 || mode > 1) return KG_EINVAL; h->hand_location = mode; return KG_OK; }
 int kg_set_action_dim(kg_handle h, int dim) {

@@ -87,6 +87,13 @@ class VecKinovaGripperEnv:
             self.shape_ids.copy_(self.torch.from_numpy(ids))
         return ids
 
+    def set_shape_cycle(self, shape_keys):
+        """Latin-square schedule on the device (ENV:895-964's property over (env, episode)): from now on a sampled reset that
+        is given no shapes (`reset(mask=...)`, the auto-reset of finished envs) moves env i on to the next key of its row,
+        shape_keys[(i + episode) % len].  An empty list switches it off (envs keep their shape)."""
+        self.h.set_shape_cycle([SHAPES.index(k) for k in shape_keys])
+        self._cycle = len(shape_keys) > 0
+
     def reset(self, shape_keys=("CubeS",), hand_orientation="normal", mode="train", variant="A", seed=0, mask=None):
         """Sampled reset of every env (or those with mask != 0).  hand_orientation: 'normal' | 'random' | 'rotated' | 'top'.
         variant 'A' = code-faithful pose tables, 'B' = SURVEY 8d side-grasp variant.  Returns obs [N, 82]."""
@@ -94,7 +101,8 @@ class VecKinovaGripperEnv:
         if mask is None:
             self.set_shapes(shape_keys)
         m = 0 if mask is None else mask.data_ptr()
-        self.h.reset_sampled(m, self.shape_ids.data_ptr(), orient, 1 if variant == "B" else 0, 1 if mode == "test" else 0,
+        shapes = 0 if (mask is not None and getattr(self, "_cycle", False)) else self.shape_ids.data_ptr()
+        self.h.reset_sampled(m, shapes, orient, 1 if variant == "B" else 0, 1 if mode == "test" else 0,
                              seed, self.obs_soa.data_ptr())
         return self.obs_soa.t()
 

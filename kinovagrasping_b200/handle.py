@@ -62,6 +62,11 @@ class Handle:
         """0 = slides start at 0 (a new env per episode, MAIN:381); 1 = determine_hand_location with the previous episode's Tfw (EXP:696)."""
         self._chk(self.lib.kg_set_hand_location(self.h, int(mode)), "kg_set_hand_location")
 
+    def set_shape_cycle(self, shape_ids):
+        """Latin-square shape schedule for sampled resets with no shape array: episode e of env i -> shape_ids[(i + e) % len]."""
+        a = np.ascontiguousarray(shape_ids, dtype=np.int32).reshape(-1)
+        self._chk(self.lib.kg_set_shape_cycle(self.h, _np_ptr(a) if a.size else None, int(a.size)), "kg_set_shape_cycle")
+
     def set_action_dim(self, dim):
         """4 = [wrist, f1, f2, f3]; 6 = [slide_x, slide_y, slide_z, f1, f2, f3] (ENV:1502-1503)."""
         self._chk(self.lib.kg_set_action_dim(self.h, int(dim)), "kg_set_action_dim")

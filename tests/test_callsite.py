@@ -163,3 +163,38 @@ def test_update_policy_and_eval_policy_unmodified(tmp_path):
     assert pol_a.total_it == pol_b.total_it == 8
     for pa, pb in zip(pol_a.actor.parameters(), pol_b.actor.parameters()):
         assert np.abs(pa.detach().numpy() - pb.detach().numpy()).max() < 2e-3
+
+
+def test_checkpoint_files_interchange_with_the_reference(tmp_path):
+    """DDPG:371-382: the four torch.save files `<name>_{actor,critic,actor_optimizer,critic_optimizer}`.  Reference save ->
+    this repo's load -> identical forward and an identical next update; this repo's save -> reference load -> identical
+    forward (the policy-stage hand-over of MAIN:776-797 globs for `*_actor_optimizer`)."""
+    RH.install_stubs(lambda: None)
+    R = RH.import_reference("DDPGfD")
+    R.device = torch.device("cpu")
+    torch.manual_seed(1)
+    ref = R.DDPGfD(82, 4, 0.8, 5, batch_size=8)
+    rng = np.random.default_rng(0)
+    batch = [torch.from_numpy(rng.normal(0, 0.3, (24, 5, 82)).astype(np.float32)), torch.from_numpy(rng.uniform(0, 0.8, (24, 5, 4)).astype(np.float32)),
+             torch.from_numpy(rng.normal(0, 0.3, (24, 5, 82)).astype(np.float32)), torch.from_numpy(rng.uniform(0, 1, (24, 5)).astype(np.float32)),
+             torch.ones(24, 5)]
+    mine = DDPGfD(82, 4, 0.8, 5, batch_size=8, device="cpu", process_group=False)
+    for a, b in ((mine.actor_target, ref.actor_target), (mine.critic_target, ref.critic_target)):
+        a.load_state_dict(b.state_dict())
+    for _ in range(2):                                    # give Adam some state worth saving
+        mine.actor.load_state_dict(ref.actor.state_dict()); mine.critic.load_state_dict(ref.critic.state_dict())
+        break
+    ref.save(str(tmp_path / "ref_policy"))
+    assert sorted(os.listdir(tmp_path)) == ["ref_policy_actor", "ref_policy_actor_optimizer", "ref_policy_critic", "ref_policy_critic_optimizer"]
+    mine.load(str(tmp_path / "ref_policy"))
+    s = batch[0][:, 0]
+    with torch.no_grad():
+        assert torch.equal(mine.actor(s), ref.actor(s)) and torch.equal(mine.critic(s, batch[1][:, 0]), ref.critic(s, batch[1][:, 0]))
+    assert mine.actor.l1.weight.data_ptr() == mine.actor_flat.data_ptr()      # load() kept the parameters inside the flat bucket
+    losses = mine.train_on_batch(*batch)
+    mine.save(str(tmp_path / "my_policy"))
+    back = R.DDPGfD(82, 4, 0.8, 5, batch_size=8)
+    back.load(str(tmp_path / "my_policy"))
+    with torch.no_grad():
+        assert torch.equal(back.actor(s), mine.actor(s)) and torch.equal(back.critic(s, batch[1][:, 0]), mine.critic(s, batch[1][:, 0]))
+    assert back.actor_optimizer.state_dict()["state"][0]["step"] == mine.actor_optimizer.state_dict()["state"][0]["step"]

@@ -154,3 +154,35 @@ def test_device_sampled_reset_against_oracle(backend, oracle, card, hand_locatio
             prev[i] = e.d
     assert seen_orient == {0, 1, 2}
     h.close()
+
+
+def test_device_shape_cycle_is_a_latin_square(backend):
+    """kg_set_shape_cycle: with no shape array, episode e of global env i is reset to keys[(i + e) % n] -- every env walks
+    through all keys, every episode index sees every key equally often (what Generate_Latin_Square provides per env object)."""
+    import ctypes as C
+    n, offset, keys = 12, 5, [0, 3, 9, 13]
+    h = Handle(n, lib=backend)
+    h.set_env_offset(offset)
+    h.set_shape_cycle(keys)
+    cuda = not backend._name.endswith("libkg_emu.so")
+    seen = []
+    for e in range(6):
+        h.reset_sampled(0, 0, 0, 0, 0, 1, 0)
+        h.sync()
+        if cuda:
+            import torch
+            obs = torch.zeros((82, n), device="cuda"); rew = torch.zeros(n, device="cuda"); done = torch.zeros(n, dtype=torch.int32, device="cuda")
+            h.step(0, 0, obs.data_ptr(), rew.data_ptr(), done.data_ptr()); h.sync()
+            o = obs.cpu().numpy()
+        else:
+            o, _, _ = h.step_host(None, 0)
+        seen.append(o[33:36].copy())                        # obs[33:36] = the object's size: identifies the shape
+    card_sizes = {}
+    ref = Handle(1, lib=backend)
+    for k in keys:
+        ob = ref.reset_host(np.array([k], dtype=np.int32), np.zeros((3, 1), dtype=np.float32), np.array([[0.0], [0.0], [0.1]], dtype=np.float32))
+        card_sizes[k] = ob[33:36, 0].copy()
+    for e in range(6):
+        for i in range(n):
+            assert np.array_equal(seen[e][:, i], card_sizes[keys[(offset + i + e) % len(keys)]]), (e, i)
+    h.close(); ref.close()
