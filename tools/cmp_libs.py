@@ -13,14 +13,16 @@ out = []
 for path in sys.argv[1:3]:
     lib = _lib.bind(C.CDLL(os.path.abspath(path)))
     h = Handle(n, lib=lib)
-    sh = torch.from_numpy((np.arange(n) % 2).astype(np.int32)).cuda()
+    shapes = [int(x) for x in os.environ.get("KG_SHAPES", "0,1").split(",")]
+    orient, mode = int(os.environ.get("KG_ORIENT", "0")), int(os.environ.get("KG_MODE", "2"))
+    sh = torch.from_numpy(np.array(shapes, np.int32)[np.arange(n) % len(shapes)]).cuda()
     obs = torch.zeros((82, n), device="cuda"); rew = torch.zeros(n, device="cuda"); done = torch.zeros(n, dtype=torch.int32, device="cuda")
-    h.reset_sampled(0, sh.data_ptr(), 0, 1, 0, 1234, obs.data_ptr())
+    h.reset_sampled(0, sh.data_ptr(), orient, 1, 0, 1234, obs.data_ptr())
     tr = []
     for _ in range(steps):
-        h.step(0, 2, obs.data_ptr(), rew.data_ptr(), done.data_ptr()); h.sync()
+        h.step(0, mode, obs.data_ptr(), rew.data_ptr(), done.data_ptr()); h.sync()
         tr += [obs.cpu().numpy().copy(), rew.cpu().numpy().copy()]
-        h.reset_sampled(done.data_ptr(), 0, 0, 1, 0, 1234, 0)
+        h.reset_sampled(done.data_ptr(), 0, orient, 1, 0, 1234, 0)
     tr += list(h.get_state_host()); st = h.stats()
     out.append((tr, st)); h.close()
 same = all(np.array_equal(x, y) for x, y in zip(out[0][0], out[1][0]))
