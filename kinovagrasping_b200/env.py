@@ -230,7 +230,14 @@ class KinovaGripper_Env:
     def get_orientation(self): return self.orientation
     def set_orientation(self, orientation): self.orientation = orientation
     def get_with_grasp_reward(self): return self.with_grasp_reward
-    def set_with_grasp_reward(self, with_grasp): self.with_grasp_reward = with_grasp
+    def set_with_grasp_reward(self, with_grasp):
+        """ENV:643-659 adds +5 once per episode when the pickled sklearn forest (KD/gc_model.pkl) predicts >= 0.3 on
+        local_obs[0:75].  That reward is outside this path (off by default, ENV:104 / MAIN:906) and is NOT built:
+        asking for it fails here instead of quietly returning the lift reward alone."""
+        if with_grasp:
+            raise NotImplementedError("grasp-classifier reward (ENV:643-659, gc_model.pkl) is not part of kinovagrasping_b200; "
+                                      "reset(..., with_grasp=False) is the reference's default")
+        self.with_grasp_reward = False
     def get_coords_filename(self): return self.coords_filename
     def set_coords_filename(self, coords_filename): self.coords_filename = coords_filename
     def get_all_objects(self): return self.all_objects

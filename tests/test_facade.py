@@ -121,3 +121,13 @@ def test_vector_env_global_obs_view():
     assert g.shape == (5, 74) and torch.equal(g[:, 24:67], obs[:, 24:67]) and torch.equal(g[:, 67:74], obs[:, 75:82])
     obs, rew, done, info = env.step(None, "naive")
     assert torch.equal(g[:, 24:67], obs[:, 24:67]) and float(g[:, 23].min()) > 0.0      # object centre above the floor
+
+
+def test_grasp_classifier_reward_is_refused_not_faked(facade):
+    """ENV:643-659: the +5 classifier reward is not built; asking for it must fail loudly, never degrade to lift-only."""
+    with pytest.raises(NotImplementedError):
+        facade.set_with_grasp_reward(True)
+    with pytest.raises(NotImplementedError):
+        facade.reset(shape_keys=["CubeS"], hand_orientation="normal", with_grasp=True)
+    facade.set_with_grasp_reward(False)
+    assert facade.get_with_grasp_reward() is False
