@@ -240,8 +240,8 @@ def test_one_step_parity_all_substeps_statistics(backend, oracle, card):
 
 
 def test_narrowphase_against_oracle(backend, oracle, card):
-    """Contact sets from identical states: same pairs, distance within 5e-6 m, position within 1e-4 m along the normal, normal within the
-    curvature-limited cone: 8 degrees."""
+    """Contact sets from identical states: same pairs, distance within 5e-6 m, position within 1e-4 m along the normal; normals:
+    median < 0.05 degrees and >= 98 % within 0.1 degrees, every one within the curvature-limited cone of 8 degrees."""
     n = 8
     shape, _, objp = _poses(card, n, 11, orient_idx=(0,), shapes=(0, 1, 2, 6))
     _, euler, _ = _poses(card, n, 11, orient_idx=(2,), shapes=(0, 1, 2, 6))
@@ -249,7 +249,7 @@ def test_narrowphase_against_oracle(backend, oracle, card):
     h.set_max_episode_steps(10 ** 6)
     h.reset_host(shape, euler, objp)
     ref = _oracle_reset(oracle, shape, euler, objp)
-    checked = 0; ang_worst = 0.0
+    checked = 0; ang_worst = 0.0; angs = []
     for t in range(24):
         for i in range(n):
             a, _ = oracle.expert_action(ref[i][0], ref[i][1], 0)
@@ -286,9 +286,15 @@ def test_narrowphase_against_oracle(backend, oracle, card):
                 assert abs(float(np.dot(dpos, np.array(lst[0].frame)[:3]))) < 1e-4 and np.abs(dpos).max() < 0.06
                 cosang = float(np.dot(c[4:7], np.array(lst[0].frame)[:3]))
                 ang_worst = max(ang_worst, np.degrees(np.arccos(min(1.0, cosang))))
+                angs.append(np.degrees(np.arccos(min(1.0, cosang))))
                 checked += 1
     assert checked > 100
     assert ang_worst < 8.0, ang_worst
+    angs = np.array(angs)
+    print(f"narrowphase normals, {checked} hull contacts: median {np.median(angs):.4f} deg, p90 {np.percentile(angs, 90):.4f}, p99 {np.percentile(angs, 99):.3f}, max {angs.max():.3f}")
+    # the bulk is tight; the 8-degree bound above is for the rare contact ON an inflated edge, where the normal is free within
+    # the edge's cone and fp32 / fp64 portal refinement stop at different points of it (conditioning)
+    assert np.median(angs) < 0.05 and np.mean(angs < 0.1) >= 0.98, (np.median(angs), np.mean(angs < 0.1))
 
 
 def test_expert_modes_and_rollout_success_parity(backend, oracle, card):
