@@ -152,8 +152,12 @@ int kg_get_prof(kg_handle h, long long slots_host[KG_NPROF]);
 
 /* Test hook: one mj_forward of env `env` with the given ctrl[9]; dumps intermediates to host memory.
  * out layout (floats): M[225] bias[15] fsmooth[15] qacc_smooth[15] qacc[15] ftotal[15] ncon[1]
- * con[23][8]{dist,pos3,n3,mu} geom_xpos[27] geom_xmat[81]  -> 225+75+1+184+108 = 593 floats. */
-#define KG_DEBUG_FLOATS 593
+ * con[23][8]{dist,pos3,n3,mu} geom_xpos[27] geom_xmat[81]  -> 225+75+1+184+108 = 593 floats, then the constraint rows
+ * as the solver holds them (kg_make_rows): [593] ngroup, [594 + 8 g]{type (0 inactive, 1 tendon equality, 2 joint limit,
+ * 3 pyramidal contact), D, mu, aref[4], first base row} for the groups g < 32, [850 + 15 b] the base Jacobian rows b < 78
+ * (a scalar group has one, a contact three: normal, tangent 1, tangent 2; its four rows are n +- mu t1, n +- mu t2).
+ * Groups beyond the dump's 32 (more than 23 contacts) are not dumped. */
+#define KG_DEBUG_FLOATS 2020
 int kg_forward_debug(kg_handle h, int env, const float *ctrl_host, float *out_host);
 /* Test hook: device time of the last kg_step launch in milliseconds (CUDA events on the handle's stream). */
 int kg_last_step_ms(kg_handle h, float *ms);

@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkg_b200.so")
-DEBUG_FLOATS = 593
+DEBUG_FLOATS = 2020
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int)

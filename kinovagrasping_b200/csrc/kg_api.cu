@@ -195,6 +195,19 @@ KG_DEV void kg_debug_end(const KgModel &m, KgWS &ws, float *out, int kg_lane) {
         }
     }
     KG_SYNC();
+    KG_PHASE(l) {      // the rows as the solver is about to see them (kg.h: layout of the dump)
+        if (l == 0) out[593] = (float)ws.ngroup;
+        {
+            float *o = out + 594 + 8 * l;
+            const int tp = kg_gtype(ws, l);
+            o[0] = (float)tp; o[1] = tp ? KG_GD(ws, l) : 0.f; o[2] = tp == 3 ? KG_GMU(ws, l) : 0.f;
+            for (int k = 0; k < 4; k++) o[3 + k] = (tp == 3 || (tp && k == 0)) ? KG_GAREF(ws, l, k) : 0.f;
+            o[7] = (float)(l < 9 ? l : 9 + 3 * (l - 9));
+        }
+        const int nb = kg_nbase(ws) < 78 ? kg_nbase(ws) : 78;
+        for (int i = l; i < 78 * 15; i += 32) out[850 + i] = i / 15 < nb ? ws.J[(i / 15) * KG_JS + (i % 15)] : 0.f;
+    }
+    KG_SYNC();
     kg_solve(m, ws, kg_lane);
     KG_PHASE(l) {
         for (int i = l; i < 225; i += 32) out[i] = ws.M[(i / 15) * KG_MS + (i % 15)];

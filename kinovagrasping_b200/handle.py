@@ -199,4 +199,21 @@ class Handle:
         con = out[301:301 + 8 * 23].reshape(23, 8)
         return {"M": out[:225].reshape(15, 15), "bias": out[225:240], "fsmooth": out[240:255], "qacc_smooth": out[255:270],
                 "qacc": out[270:285], "ftotal": out[285:300], "ncon": ncon, "con": con[:min(ncon, 23)],
-                "geom_xpos": out[485:512].reshape(9, 3), "geom_xmat": out[512:593].reshape(9, 9)}
+                "geom_xpos": out[485:512].reshape(9, 3), "geom_xmat": out[512:593].reshape(9, 9),
+                "ngroup": int(out[593]), "groups": out[594:850].reshape(32, 8), "Jbase": out[850:2020].reshape(78, 15)}
+
+    @staticmethod
+    def explicit_rows(dbg):
+        """The scalar constraint rows of a forward_debug dump, as (kind, J[15], aref, D) in the kernel's group order:
+        kind 1 tendon equality, 2 joint limit, 3 pyramidal contact (four rows per contact: n +- mu t1, n +- mu t2)."""
+        rows = []
+        for g in range(min(dbg["ngroup"], 32)):
+            tp, D, mu = int(dbg["groups"][g, 0]), float(dbg["groups"][g, 1]), float(dbg["groups"][g, 2])
+            b = int(dbg["groups"][g, 7])
+            if tp in (1, 2):
+                rows.append((tp, dbg["Jbase"][b].astype(np.float64), float(dbg["groups"][g, 3]), D))
+            elif tp == 3:
+                n, t1, t2 = (dbg["Jbase"][b + k].astype(np.float64) for k in range(3))
+                for k, J in enumerate((n + mu * t1, n - mu * t1, n + mu * t2, n - mu * t2)):
+                    rows.append((3, J, float(dbg["groups"][g, 3 + k]), D))
+        return rows

@@ -297,6 +297,79 @@ def test_narrowphase_against_oracle(backend, oracle, card):
     assert np.median(angs) < 0.05 and np.mean(angs < 0.1) >= 0.98, (np.median(angs), np.mean(angs < 0.1))
 
 
+def test_constraint_rows_against_oracle(backend, oracle, card):
+    """P6 directly: the scalar constraint rows the solver is handed (efc_J, efc_aref, efc_D of the reference engine;
+    kg_make_rows here, reconstructed from its base rows: a contact's four pyramid rows are n +- mu t1, n +- mu t2) against the
+    oracle's, from identical states along an expert rollout.  Tendon-equality and joint-limit rows depend on the state only:
+    1e-5.  Contact rows inherit the narrowphase's witness point / normal / distance (test_narrowphase_against_oracle), so
+    they are compared where both sides report the same contact set: J to 2e-3 of the row's scale (a 0.03-degree normal on
+    a 0.1 m lever), D to 1e-4 relative, aref to 1e-3 relative + the reference acceleration of a 5e-6 m distance error."""
+    n = 8
+    shape, _, objp = _poses(card, n, 11, orient_idx=(0,), shapes=(0, 1, 2, 6))
+    _, euler, _ = _poses(card, n, 11, orient_idx=(2,), shapes=(0, 1, 2, 6))
+    h = Handle(n, lib=backend)
+    h.set_max_episode_steps(10 ** 6)
+    h.reset_host(shape, euler, objp)
+    ref = _oracle_reset(oracle, shape, euler, objp)
+    stats = {1: [], 2: [], 3: []}
+    nsame = 0; nlimit_states = 0
+    for t in range(24):
+        for i in range(n):
+            a, _ = oracle.expert_action(ref[i][0], ref[i][1], 0)
+            ref[i][1], _, _, _ = oracle.env_step(ref[i][0], a)
+        qp = np.stack([np.array(ref[i][0].st.qpos) for i in range(n)], 1).astype(np.float32)
+        qv = np.stack([np.array(ref[i][0].st.qvel) for i in range(n)], 1).astype(np.float32)
+        if t % 6 == 5:       # push a slide and a finger joint past their limits so that limit rows exist as well
+            qp[2, 0] = 0.5004; qp[3, 1] = -0.0006
+        h.set_state_host(qp, qv)
+        for i in range(n):
+            s = kgo.State.from_buffer_copy(ref[i][0].st)
+            for k in range(16): s.qpos[k] = float(qp[k, i])
+            for k in range(15): s.qvel[k] = float(qv[k, i])
+            ctrl = np.array([0, 0, 0.05, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3])
+            D = oracle.forward(s, ctrl)
+            d = h.forward_debug(i, ctrl)
+            same = D.ncon == d["ncon"] and d["ncon"] <= 23
+            if same:
+                for c in range(D.ncon):
+                    cc = D.con[c]
+                    same = same and any(np.abs(k[1:4] - np.array(cc.pos)).max() < 2e-5 and abs(float(k[0]) - cc.dist) < 2e-6 and
+                                        float(np.dot(k[4:7], np.array(cc.frame)[:3])) > 0.99996 for k in d["con"])
+            if not same:
+                continue
+            nsame += 1
+            mine = Handle.explicit_rows(d)
+            J = np.array(D.efc_J[:D.nefc * 15]).reshape(D.nefc, 15)
+            kind = {0: 1, 1: 2, 2: 3}
+            assert len(mine) == D.nefc, (t, i, len(mine), D.nefc)
+            used = set()
+            for r in range(D.nefc):
+                kd = kind[D.efc_type[r]]
+                cand = [(float(np.abs(m[1] - J[r]).max()), q) for q, m in enumerate(mine) if m[0] == kd and q not in used]
+                assert cand, (t, i, r, kd)
+                dj, q = min(cand)
+                used.add(q)
+                scale = max(1.0, float(np.abs(J[r]).max()))
+                aref, Dv = D.efc_aref[r], D.efc_D[r]
+                stats[kd].append((dj / scale, abs(mine[q][2] - aref), abs(aref), abs(mine[q][3] - Dv) / Dv))
+            if any(D.efc_type[r] == 1 for r in range(D.nefc)):
+                nlimit_states += 1
+    assert nsame > 100 and nlimit_states >= 4, (nsame, nlimit_states)
+    for kd, name in ((1, "tendon"), (2, "limit"), (3, "contact")):
+        a = np.array(stats[kd])
+        print(f"{name} rows {len(a)}: J err max {a[:, 0].max():.2e}, aref abs err max {a[:, 1].max():.2e} (|aref| up to {a[:, 2].max():.1f}), "
+              f"aref rel err max {(a[:, 1] / np.maximum(a[:, 2], 1.0)).max():.2e}, D rel err max {a[:, 3].max():.2e}")
+    for kd in (1, 2):
+        a = np.array(stats[kd])
+        assert len(a) > 0 and a[:, 0].max() < 1e-6 and a[:, 3].max() < 1e-5, kd
+        assert (a[:, 1] / np.maximum(a[:, 2], 1.0)).max() < 1e-5, kd
+    a = np.array(stats[3])
+    K = 1.0 / (0.95 * 0.95 * 0.02 * 0.02)          # stiffness of solref (0.02, 1) at dmax 0.95: d(aref)/d(dist)
+    assert len(a) > 400
+    assert a[:, 0].max() < 2e-3 and a[:, 3].max() < 1e-4, (a[:, 0].max(), a[:, 3].max())
+    assert (a[:, 1] <= 1e-3 * a[:, 2] + K * 5e-6).all(), float((a[:, 1] - 1e-3 * a[:, 2]).max())
+
+
 def test_expert_modes_and_rollout_success_parity(backend, oracle, card):
     """Free-running expert episodes (on-device controller) vs the oracle: the controller's actions follow the validated
     host controller on the kernel's own observations, and lift success agrees within +-2 pp (+ small-sample slack)."""
