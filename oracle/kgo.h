@@ -73,6 +73,9 @@ void kgo_state_init(const KgoModel *m, KgoState *s, int shape, const double hand
                     const double obj_pos[3]);
 /* mj_forward */
 void kgo_forward(const KgoModel *m, const KgoState *s, const double ctrl[KGO_NU], int flags, KgoData *d);
+/* test hook: mj_forward with the contact list given by the caller, ncon x {geom1, geom2, dist, pos[3], normal[3]} */
+void kgo_forward_contacts(const KgoModel *m, const KgoState *s, const double ctrl[KGO_NU], int flags, int ncon,
+                          const double *con, KgoData *d);
 /* mj_step = forward + Euler; d holds the forward results (pre-integration, the staleness of SURVEY 8a O-note) */
 void kgo_step(const KgoModel *m, KgoState *s, const double ctrl[KGO_NU], int flags, KgoData *d);
 

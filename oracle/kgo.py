@@ -70,6 +70,7 @@ def lib():
         L.kgo_model_load.argtypes = [C.c_void_p, C.c_size_t]
         L.kgo_state_init.argtypes = [C.c_void_p, C.POINTER(State), C.c_int, C.POINTER(d), C.POINTER(d)]
         L.kgo_forward.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(d), C.c_int, C.POINTER(Data)]
+        L.kgo_forward_contacts.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(d), C.c_int, C.c_int, C.POINTER(d), C.POINTER(Data)]
         L.kgo_step.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(d), C.c_int, C.POINTER(Data)]
         L.kgo_env_reset.argtypes = [C.c_void_p, C.POINTER(Env), C.c_int, C.POINTER(d), C.POINTER(d), C.POINTER(d)]
         L.kgo_env_step.argtypes = [C.c_void_p, C.POINTER(Env), C.POINTER(d), C.POINTER(d), C.POINTER(d), C.POINTER(d)]
@@ -123,6 +124,15 @@ class Model:
         dat = Data()
         c, cp = _p(np.zeros(NU) if ctrl is None else ctrl)
         lib().kgo_forward(self.h, C.byref(s), cp, 1 if rays else 0, C.byref(dat))
+        return dat
+
+    def forward_contacts(self, s, ctrl, contacts):
+        """mj_forward with a GIVEN contact list: rows of (geom1, geom2, dist, pos[3], normal[3]) -- kgo_forward_contacts."""
+        dat = Data()
+        c, cp = _p(np.zeros(NU) if ctrl is None else ctrl)
+        con = np.ascontiguousarray(contacts, dtype=np.float64).reshape(-1, 9)
+        g, gp = _p(con.ravel() if len(con) else np.zeros(9))
+        lib().kgo_forward_contacts(self.h, C.byref(s), cp, 0, len(con), gp, C.byref(dat))
         return dat
 
     def step(self, s, ctrl=None, rays=False):

@@ -761,11 +761,29 @@ static void solve_newton(const KgoModel *m, const KgoState *s, KgoData *d) {
 }
 
 /* ------------------------------------------------------------------ mj_forward / mj_step */
-void kgo_forward(const KgoModel *m, const KgoState *s, const double ctrl[KGO_NU], int flags, KgoData *d) {
+/* given != NULL: the contact list is taken from the caller (given_n x {geom1, geom2, dist, pos[3], normal[3]}) instead of
+ * the collision stage -- test infrastructure: it lets a parity test hand the oracle the contacts ANOTHER narrowphase
+ * found, so that the constraint rows and the solver are compared on identical input */
+static void forward_impl(const KgoModel *m, const KgoState *s, const double ctrl[KGO_NU], int flags, KgoData *d,
+                         int given_n, const double *given) {
     Kin k;
     kinematics(m, s, d, &k);
     crba_rne(m, s, d, &k);
-    collision(m, s, d);
+    if (!given) collision(m, s, d);
+    else {
+        d->ncon = 0; d->n_mpr = 0; d->n_broad = 0;
+        for (int c = 0; c < given_n && d->ncon < KGO_MAXCON; c++) {
+            const double *g = given + 9 * c;
+            KgoContact *con = &d->con[d->ncon++];
+            memset(con, 0, sizeof *con);
+            con->geom1 = (int)g[0]; con->geom2 = (int)g[1]; con->dist = g[2];
+            copy3(con->pos, g + 3); copy3(con->frame, g + 6);
+            make_frame(con->frame);
+            con->includemargin = m->margin;
+            for (int pi = 0; pi < m->npair; pi++)
+                if (m->pair[pi].g1 == con->geom1 && m->pair[pi].g2 == con->geom2) con->friction = m->pair[pi].friction;
+        }
+    }
     make_constraints(m, s, d, &k);
     /* sensors (position stage): 9 jointpos then 17 rangefinders (XML:247-288) */
     for (int i = 0; i < 3; i++) d->sensordata[i] = s->qpos[i];
@@ -788,6 +806,14 @@ void kgo_forward(const KgoModel *m, const KgoState *s, const double ctrl[KGO_NU]
     } else {
         solve_newton(m, s, d);
     }
+}
+
+void kgo_forward(const KgoModel *m, const KgoState *s, const double ctrl[KGO_NU], int flags, KgoData *d) {
+    forward_impl(m, s, ctrl, flags, d, 0, NULL);
+}
+void kgo_forward_contacts(const KgoModel *m, const KgoState *s, const double ctrl[KGO_NU], int flags, int ncon,
+                          const double *con, KgoData *d) {
+    forward_impl(m, s, ctrl, flags, d, ncon, con);
 }
 
 void kgo_step(const KgoModel *m, KgoState *s, const double ctrl[KGO_NU], int flags, KgoData *d) {

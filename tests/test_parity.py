@@ -297,13 +297,15 @@ def test_narrowphase_against_oracle(backend, oracle, card):
     assert np.median(angs) < 0.05 and np.mean(angs < 0.1) >= 0.98, (np.median(angs), np.mean(angs < 0.1))
 
 
-def test_constraint_rows_against_oracle(backend, oracle, card):
-    """P6 directly: the scalar constraint rows the solver is handed (efc_J, efc_aref, efc_D of the reference engine;
-    kg_make_rows here, reconstructed from its base rows: a contact's four pyramid rows are n +- mu t1, n +- mu t2) against the
-    oracle's, from identical states along an expert rollout.  Tendon-equality and joint-limit rows depend on the state only:
-    1e-5.  Contact rows inherit the narrowphase's witness point / normal / distance (test_narrowphase_against_oracle), so
-    they are compared where both sides report the same contact set: J to 2e-3 of the row's scale (a 0.03-degree normal on
-    a 0.1 m lever), D to 1e-4 relative, aref to 1e-3 relative + the reference acceleration of a 5e-6 m distance error."""
+def test_constraint_rows_and_solver_on_identical_contacts(backend, oracle, card):
+    """P6 and P7 without the narrowphase in between: along an expert rollout the oracle is handed the contact list THE KERNEL
+    found (kgo_forward_contacts: geoms, distance, point, normal) and builds its own rows from it.  Then
+      * every scalar row the solver sees -- efc_J, efc_aref, efc_D of the reference engine; kg_make_rows here, a contact's four
+        pyramid rows reconstructed from its base rows as n +- mu t1, n +- mu t2 -- agrees: J 2e-6 of the row's scale, D 1e-5
+        relative, aref 2e-5 relative to max(1, |aref|) (aref = -B J.v - K d r is a 15-term fp32 dot product scaled by
+        B = 105; tendon equality, joint limit and contact rows alike);
+      * the Newton solver's answer on those rows agrees: qacc within 1e-4 of max(1, |qacc|) on EVERY state, with or
+        without contacts -- the north_star's one-step gate, here free of the narrowphase's conditioning."""
     n = 8
     shape, _, objp = _poses(card, n, 11, orient_idx=(0,), shapes=(0, 1, 2, 6))
     _, euler, _ = _poses(card, n, 11, orient_idx=(2,), shapes=(0, 1, 2, 6))
@@ -312,7 +314,7 @@ def test_constraint_rows_against_oracle(backend, oracle, card):
     h.reset_host(shape, euler, objp)
     ref = _oracle_reset(oracle, shape, euler, objp)
     stats = {1: [], 2: [], 3: []}
-    nsame = 0; nlimit_states = 0
+    qerr = []; ferr = []; nfree = 0
     for t in range(24):
         for i in range(n):
             a, _ = oracle.expert_action(ref[i][0], ref[i][1], 0)
@@ -327,17 +329,15 @@ def test_constraint_rows_against_oracle(backend, oracle, card):
             for k in range(16): s.qpos[k] = float(qp[k, i])
             for k in range(15): s.qvel[k] = float(qv[k, i])
             ctrl = np.array([0, 0, 0.05, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3])
-            D = oracle.forward(s, ctrl)
             d = h.forward_debug(i, ctrl)
-            same = D.ncon == d["ncon"] and d["ncon"] <= 23
-            if same:
-                for c in range(D.ncon):
-                    cc = D.con[c]
-                    same = same and any(np.abs(k[1:4] - np.array(cc.pos)).max() < 2e-5 and abs(float(k[0]) - cc.dist) < 2e-6 and
-                                        float(np.dot(k[4:7], np.array(cc.frame)[:3])) > 0.99996 for k in d["con"])
-            if not same:
-                continue
-            nsame += 1
+            if d["ncon"] > 23:
+                continue                                       # (the dump holds 23 contacts)
+            given = []
+            for c in d["con"]:
+                code = int(round(float(c[7]) * 10)); g2 = code // 1000; g1 = (code // 100) % 10
+                given.append([g1, g2, float(c[0])] + [float(x) for x in c[1:7]])
+            D = oracle.forward_contacts(s, ctrl, np.array(given).reshape(-1, 9))
+            assert D.ncon == d["ncon"]
             mine = Handle.explicit_rows(d)
             J = np.array(D.efc_J[:D.nefc * 15]).reshape(D.nefc, 15)
             kind = {0: 1, 1: 2, 2: 3}
@@ -349,25 +349,24 @@ def test_constraint_rows_against_oracle(backend, oracle, card):
                 assert cand, (t, i, r, kd)
                 dj, q = min(cand)
                 used.add(q)
-                scale = max(1.0, float(np.abs(J[r]).max()))
                 aref, Dv = D.efc_aref[r], D.efc_D[r]
-                stats[kd].append((dj / scale, abs(mine[q][2] - aref), abs(aref), abs(mine[q][3] - Dv) / Dv))
-            if any(D.efc_type[r] == 1 for r in range(D.nefc)):
-                nlimit_states += 1
-    assert nsame > 100 and nlimit_states >= 4, (nsame, nlimit_states)
+                stats[kd].append((dj / max(1.0, float(np.abs(J[r]).max())), abs(mine[q][2] - aref) / max(1.0, abs(aref)), abs(mine[q][3] - Dv) / Dv))
+            qa = D.arr("qacc"); fc = D.arr("qfrc_constraint")
+            eq = float(np.abs(qa - d["qacc"]).max() / max(1.0, np.abs(qa).max()))
+            if D.ncon == 0:
+                nfree += 1
+                assert eq < 1e-4, (t, i, eq)
+            else:
+                qerr.append(eq)
     for kd, name in ((1, "tendon"), (2, "limit"), (3, "contact")):
         a = np.array(stats[kd])
-        print(f"{name} rows {len(a)}: J err max {a[:, 0].max():.2e}, aref abs err max {a[:, 1].max():.2e} (|aref| up to {a[:, 2].max():.1f}), "
-              f"aref rel err max {(a[:, 1] / np.maximum(a[:, 2], 1.0)).max():.2e}, D rel err max {a[:, 3].max():.2e}")
-    for kd in (1, 2):
-        a = np.array(stats[kd])
-        assert len(a) > 0 and a[:, 0].max() < 1e-6 and a[:, 3].max() < 1e-5, kd
-        assert (a[:, 1] / np.maximum(a[:, 2], 1.0)).max() < 1e-5, kd
-    a = np.array(stats[3])
-    K = 1.0 / (0.95 * 0.95 * 0.02 * 0.02)          # stiffness of solref (0.02, 1) at dmax 0.95: d(aref)/d(dist)
-    assert len(a) > 400
-    assert a[:, 0].max() < 2e-3 and a[:, 3].max() < 1e-4, (a[:, 0].max(), a[:, 3].max())
-    assert (a[:, 1] <= 1e-3 * a[:, 2] + K * 5e-6).all(), float((a[:, 1] - 1e-3 * a[:, 2]).max())
+        print(f"{name} rows {len(a)}: J err max {a[:, 0].max():.2e}, aref rel err max {a[:, 1].max():.2e}, D rel err max {a[:, 2].max():.2e}")
+        assert len(a) >= (400 if kd == 3 else 8), (kd, len(a))
+        assert a[:, 0].max() < 2e-6 and a[:, 1].max() < 2e-5 and a[:, 2].max() < 1e-5, (name, a.max(axis=0))
+    qerr = np.array(qerr)
+    print(f"solver on identical rows: {len(qerr)} contact states, qacc within 1e-4: {np.mean(qerr < 1e-4):.4f}, max {qerr.max():.2e}; contact-free states {nfree}")
+    assert len(qerr) > 60 and nfree >= 1
+    assert qerr.max() < 1e-4, (np.mean(qerr < 1e-4), qerr.max())
 
 
 def test_expert_modes_and_rollout_success_parity(backend, oracle, card):
