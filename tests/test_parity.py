@@ -302,8 +302,9 @@ def test_constraint_rows_and_solver_on_identical_contacts(backend, oracle, card)
     found (kgo_forward_contacts: geoms, distance, point, normal) and builds its own rows from it.  Then
       * every scalar row the solver sees -- efc_J, efc_aref, efc_D of the reference engine; kg_make_rows here, a contact's four
         pyramid rows reconstructed from its base rows as n +- mu t1, n +- mu t2 -- agrees: J 2e-6 of the row's scale, D 1e-5
-        relative, aref 2e-5 relative to max(1, |aref|) (aref = -B J.v - K d r is a 15-term fp32 dot product scaled by
-        B = 105; tendon equality, joint limit and contact rows alike);
+        relative, aref within 1e-5 max(1, |aref|) + 16 ulp of B sum_j |J_j v_j| (aref = -B J.v - K d r is a 15-term fp32 dot
+        product scaled by B = 105, so its round-off follows the magnitude of its terms; tendon equality, joint limit and
+        contact rows alike);
       * the Newton solver's answer on those rows agrees: qacc within 1e-4 of max(1, |qacc|) on EVERY state, with or
         without contacts -- the north_star's one-step gate, here free of the narrowphase's conditioning."""
     n = 8
@@ -350,7 +351,11 @@ def test_constraint_rows_and_solver_on_identical_contacts(backend, oracle, card)
                 dj, q = min(cand)
                 used.add(q)
                 aref, Dv = D.efc_aref[r], D.efc_D[r]
-                stats[kd].append((dj / max(1.0, float(np.abs(J[r]).max())), abs(mine[q][2] - aref) / max(1.0, abs(aref)), abs(mine[q][3] - Dv) / Dv))
+                # aref = -B J.v - K d(r) r: an fp32 dot product of 15 terms scaled by B = 2 / (dmax tc) = 105; its round-off is
+                # bounded through the SUM OF THE TERMS' MAGNITUDES (cancellation), not through |aref|
+                cond = 105.3 * float(np.abs(J[r] * qv[:, i].astype(np.float64)).sum())
+                tol = 1e-5 * max(1.0, abs(aref)) + 16 * 2.0 ** -24 * cond
+                stats[kd].append((dj / max(1.0, float(np.abs(J[r]).max())), abs(mine[q][2] - aref) / tol, abs(mine[q][3] - Dv) / Dv))
             qa = D.arr("qacc"); fc = D.arr("qfrc_constraint")
             eq = float(np.abs(qa - d["qacc"]).max() / max(1.0, np.abs(qa).max()))
             if D.ncon == 0:
@@ -360,9 +365,9 @@ def test_constraint_rows_and_solver_on_identical_contacts(backend, oracle, card)
                 qerr.append(eq)
     for kd, name in ((1, "tendon"), (2, "limit"), (3, "contact")):
         a = np.array(stats[kd])
-        print(f"{name} rows {len(a)}: J err max {a[:, 0].max():.2e}, aref rel err max {a[:, 1].max():.2e}, D rel err max {a[:, 2].max():.2e}")
+        print(f"{name} rows {len(a)}: J err max {a[:, 0].max():.2e}, aref err / bound max {a[:, 1].max():.3f}, D rel err max {a[:, 2].max():.2e}")
         assert len(a) >= (400 if kd == 3 else 8), (kd, len(a))
-        assert a[:, 0].max() < 2e-6 and a[:, 1].max() < 2e-5 and a[:, 2].max() < 1e-5, (name, a.max(axis=0))
+        assert a[:, 0].max() < 2e-6 and a[:, 1].max() < 1.0 and a[:, 2].max() < 1e-5, (name, a.max(axis=0))
     qerr = np.array(qerr)
     print(f"solver on identical rows: {len(qerr)} contact states, qacc within 1e-4: {np.mean(qerr < 1e-4):.4f}, max {qerr.max():.2e}; contact-free states {nfree}")
     assert len(qerr) > 60 and nfree >= 1
