@@ -78,6 +78,8 @@ void kgo_forward_contacts(const KgoModel *m, const KgoState *s, const double ctr
                           const double *con, KgoData *d);
 /* mj_step = forward + Euler; d holds the forward results (pre-integration, the staleness of SURVEY 8a O-note) */
 void kgo_step(const KgoModel *m, KgoState *s, const double ctrl[KGO_NU], int flags, KgoData *d);
+void kgo_step_contacts(const KgoModel *m, KgoState *s, const double ctrl[KGO_NU], int flags, int ncon, const double *con,
+                       KgoData *d);
 
 /* ---- env layer (ENV:1495-1552, 438-534, 631-687) */
 typedef struct {

@@ -71,6 +71,7 @@ def lib():
         L.kgo_state_init.argtypes = [C.c_void_p, C.POINTER(State), C.c_int, C.POINTER(d), C.POINTER(d)]
         L.kgo_forward.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(d), C.c_int, C.POINTER(Data)]
         L.kgo_forward_contacts.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(d), C.c_int, C.c_int, C.POINTER(d), C.POINTER(Data)]
+        L.kgo_step_contacts.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(d), C.c_int, C.c_int, C.POINTER(d), C.POINTER(Data)]
         L.kgo_step.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(d), C.c_int, C.POINTER(Data)]
         L.kgo_env_reset.argtypes = [C.c_void_p, C.POINTER(Env), C.c_int, C.POINTER(d), C.POINTER(d), C.POINTER(d)]
         L.kgo_env_step.argtypes = [C.c_void_p, C.POINTER(Env), C.POINTER(d), C.POINTER(d), C.POINTER(d), C.POINTER(d)]
@@ -133,6 +134,15 @@ class Model:
         con = np.ascontiguousarray(contacts, dtype=np.float64).reshape(-1, 9)
         g, gp = _p(con.ravel() if len(con) else np.zeros(9))
         lib().kgo_forward_contacts(self.h, C.byref(s), cp, 0, len(con), gp, C.byref(dat))
+        return dat
+
+    def step_contacts(self, s, ctrl, contacts):
+        """one mj_step (s is advanced in place) with a GIVEN contact list -- kgo_step_contacts."""
+        dat = Data()
+        c, cp = _p(np.zeros(NU) if ctrl is None else ctrl)
+        con = np.ascontiguousarray(contacts, dtype=np.float64).reshape(-1, 9)
+        g, gp = _p(con.ravel() if len(con) else np.zeros(9))
+        lib().kgo_step_contacts(self.h, C.byref(s), cp, 0, len(con), gp, C.byref(dat))
         return dat
 
     def step(self, s, ctrl=None, rays=False):

@@ -816,8 +816,18 @@ void kgo_forward_contacts(const KgoModel *m, const KgoState *s, const double ctr
     forward_impl(m, s, ctrl, flags, d, ncon, con);
 }
 
+static void euler(const KgoModel *m, KgoState *s, KgoData *d);
 void kgo_step(const KgoModel *m, KgoState *s, const double ctrl[KGO_NU], int flags, KgoData *d) {
     kgo_forward(m, s, ctrl, flags, d);
+    euler(m, s, d);
+}
+/* test hook: one mj_step whose contact list is given by the caller (see kgo_forward_contacts) */
+void kgo_step_contacts(const KgoModel *m, KgoState *s, const double ctrl[KGO_NU], int flags, int ncon, const double *con,
+                       KgoData *d) {
+    forward_impl(m, s, ctrl, flags, d, ncon, con);
+    euler(m, s, d);
+}
+static void euler(const KgoModel *m, KgoState *s, KgoData *d) {
     const double h = m->timestep;
     /* mj_Euler: joint damping implicit, (M + h B) a = qfrc_smooth + qfrc_constraint */
     double A[KGO_NV * KGO_NV], a[KGO_NV];
