@@ -1575,6 +1575,9 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             }
             KG_SYNC();
             KG_PROBE(12);
+            // a full step on an unchanged active set is the exact minimiser: nothing the next pass over the rows would
+            // compute is needed any more (the total force below is M qacc)
+            if (exact && iter + 1 < KG_NEWTON_MAXIT) break;
         }
     }
     // ---- total force qfrc_smooth + qfrc_constraint, warm start for the next substep.
