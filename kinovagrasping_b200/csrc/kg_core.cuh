@@ -205,9 +205,11 @@ static_assert(offsetof(KgWS, cv1) == offsetof(KgWS, J) && offsetof(KgWSLight, cv
 static_assert(offsetof(KgWSLight, J) % 16 == 0 && sizeof(KgWSLight) % 16 == 0, "128-bit access needs 16-byte aligned members");
 
 // Per-group scalars in the pad words 15..19 of the group's J rows: row b = KG_GROW(g): [aref0 | aref1 (tendon / limit rows:
-// D * active of the current Newton iterate) | D | type | mu]; contact groups also use row b + 1: [aref2 | aref3 | slot].
+// D * active of the current Newton iterate) | D | type | mu]; contact groups also use row b + 1: [aref2 | aref3 | slot | A | B1]
+// and row b + 2: [C1 | B2 | C2] -- the Hessian coefficients of the group's active rows at the current Newton iterate (KG_GH).
 // type: 0 none, 1 equality, 2 limit, 3 contact; type and the staging slot are small integers stored as floats.
-#define KG_GP(ws, g, k) ((ws).J[(KG_GROW(g) + ((k) >= 5 ? 1 : 0)) * KG_JS + 15 + ((k) >= 5 ? (k) - 5 : (k))])
+#define KG_GP(ws, g, k) ((ws).J[(KG_GROW(g) + (k) / 5) * KG_JS + 15 + (k) % 5])
+#define KG_GH(ws, g, k) KG_GP(ws, g, 8 + (k))      // k = 0..4: A, B1, C1, B2, C2 (contact groups only)
 #define KG_GAREF(ws, g, k) KG_GP(ws, g, (k) < 2 ? (k) : (k) + 3)
 #define KG_GD(ws, g)       KG_GP(ws, g, 2)
 #define KG_GMU(ws, g)      KG_GP(ws, g, 4)
@@ -290,6 +292,25 @@ KG_DEV void kg_ld16(const float *p, float *v) {
     v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y; v[14] = d.z; v[15] = d.w;
 #else
     for (int i = 0; i < 16; i++) v[i] = p[i];
+#endif
+}
+
+// 8 consecutive floats from / to a 16-byte aligned shared-memory address with two 128-bit accesses
+KG_DEV void kg_ld8(const float *p, float *v) {
+#if defined(__CUDA_ARCH__)
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    float4 a = q[0], b = q[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) v[i] = p[i];
+#endif
+}
+KG_DEV void kg_st8(float *p, const float *v) {
+#if defined(__CUDA_ARCH__)
+    float4 *q = reinterpret_cast<float4 *>(p);
+    q[0] = make_float4(v[0], v[1], v[2], v[3]); q[1] = make_float4(v[4], v[5], v[6], v[7]);
+#else
+    for (int i = 0; i < 8; i++) p[i] = v[i];
 #endif
 }
 
@@ -1399,6 +1420,10 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                     int b = 9 + 3 * (g - 9);
                     float mu = KG_GMU(ws, g);
                     ws.bw[b] = w[0] + w[1] + w[2] + w[3]; ws.bw[b + 1] = mu * (w[0] - w[1]); ws.bw[b + 2] = mu * (w[2] - w[3]);
+                    // the group's 3x3 block of J^T D J in the (n, t1, t2) base: [A B1 B2; B1 C1 0; B2 0 C2], for phase (b)
+                    KG_GH(ws, g, 0) = a[0] + a[1] + a[2] + a[3];
+                    KG_GH(ws, g, 1) = mu * (a[0] - a[1]); KG_GH(ws, g, 2) = mu * mu * (a[0] + a[1]);
+                    KG_GH(ws, g, 3) = mu * (a[2] - a[3]); KG_GH(ws, g, 4) = mu * mu * (a[2] + a[3]);
                 } else if (g < 9) ws.bw[g] = 0.f;
             }
             ws.red[l] = c;
@@ -1419,57 +1444,52 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
         KG_SYNC();
         KG_PROBE(8);
         if (ws.s_done) break;
-        // ---- (b) gradient and Hessian (lane = dof / row of H)
+        // ---- (b) gradient and Hessian.  Two lanes per row of H: lane r owns the columns 0..7 of row r, lane 16 + r the
+        // columns 8..14 (each entry accumulates over the groups in the same order whoever owns it); lane r also forms
+        // the gradient entry.  The groups' coefficients come from phase (a).
         KG_PHASE(l) {
             float gsq = 0.f, gab = 0.f;
-            if (l < KG_NV) {
-                float gr = ws.Mdq[l];
+            const int r = l & 15, j0 = (l >> 4) * 8;
+            if (r < KG_NV) {
+                float gr = ws.Mdq[r];
                 gab = fabsf(gr);
-                float h[KG_NV];
-#pragma unroll
-                for (int j = 0; j < KG_NV; j++) h[j] = ws.M[l * KG_MS + j];
+                float h[8];
+                kg_ld8(ws.M + r * KG_MS + j0, h);
                 for (int g = 0; g < ws.ngroup; g++) {
                     int tp = kg_gtype(ws, g);
                     if (tp == 0) continue;
                     if (tp < 3) {
                         const float *rowp = ws.J + g * KG_JS;
-                        float ji = rowp[l];
+                        float ji = rowp[r];
                         float t = ji * ws.bw[g];
                         gr += t; gab += fabsf(t);
                         const float da = KG_GAREF(ws, g, 1);   // D * active stored by (a)
                         float u = ji * da;
                         if (da != 0.f) {     // warp-uniform: skip inactive limit rows
-                            float row[16];
-                            kg_ld16(rowp, row);
+                            float row[8];
+                            kg_ld8(rowp + j0, row);
 #pragma unroll
-                            for (int j = 0; j < KG_NV; j++) h[j] += u * row[j];
+                            for (int j = 0; j < 8; j++) h[j] += u * row[j];
                         }
                     } else {
                         int b = 9 + 3 * (g - 9);
                         const float *rn = ws.J + b * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
-                        float jn = rn[l], j1 = r1[l], j2 = r2[l];
+                        float jn = rn[r], j1 = r1[r], j2 = r2[r];
                         float t0 = jn * ws.bw[b], t1 = j1 * ws.bw[b + 1], t2 = j2 * ws.bw[b + 2];
                         gr += t0 + t1 + t2; gab += fabsf(t0) + fabsf(t1) + fabsf(t2);
-                        float jar[4], a[4];
-                        kg_group_rows(ws, g, ws.bdot, jar);
-                        const float Dg = KG_GD(ws, g);
-                        for (int k = 0; k < 4; k++) a[k] = jar[k] < 0.f ? Dg : 0.f;
-                        float mu = KG_GMU(ws, g);
-                        float A = a[0] + a[1] + a[2] + a[3], B1 = mu * (a[0] - a[1]), C1 = mu * mu * (a[0] + a[1]);
-                        float B2 = mu * (a[2] - a[3]), C2 = mu * mu * (a[2] + a[3]);
+                        const float A = KG_GH(ws, g, 0), B1 = KG_GH(ws, g, 1), C1 = KG_GH(ws, g, 2), B2 = KG_GH(ws, g, 3), C2 = KG_GH(ws, g, 4);
                         if (A != 0.f) {
                             float u = A * jn + B1 * j1 + B2 * j2, v1 = B1 * jn + C1 * j1, v2 = B2 * jn + C2 * j2;
-                            float vn[16], w1[16], w2[16];
-                            kg_ld16(rn, vn); kg_ld16(r1, w1); kg_ld16(r2, w2);
+                            float vn[8], w1[8], w2[8];
+                            kg_ld8(rn + j0, vn); kg_ld8(r1 + j0, w1); kg_ld8(r2 + j0, w2);
 #pragma unroll
-                            for (int j = 0; j < KG_NV; j++) h[j] += u * vn[j] + v1 * w1[j] + v2 * w2[j];
+                            for (int j = 0; j < 8; j++) h[j] += u * vn[j] + v1 * w1[j] + v2 * w2[j];
                         }
                     }
                 }
-                ws.grad[l] = gr;
-                gsq = gr * gr;
-#pragma unroll
-                for (int j = 0; j < KG_NV; j++) ws.L[l * KG_MS + j] = h[j];
+                if (j0 == 0) { ws.grad[r] = gr; gsq = gr * gr; }
+                else { gab = 0.f; h[7] = 0.f; }           // (column 15 is padding; the gradient is lane r's)
+                kg_st8(ws.L + r * KG_MS + j0, h);
             }
             ws.red[l] = gsq; ws.red2[l] = gab * gab;
         }
