@@ -1201,8 +1201,8 @@ template <class WS> KG_NOINL void kg_jac_add(const WS &ws, int g, const float *p
 template <class WS> KG_DEV void kg_make_rows(const KgModel &m, WS &ws, int kg_lane) {
     KG_PHASE(l) {
         const float K = m.solK, Bd = m.solB;
-        // a lane owns group l and, in workspaces with more than 32 groups, group l + 32 as well
-        for (int g = l; g < 9 + WS::MAXCON; g += 32) {
+        if (l < 9) {      // the tendon equalities and the joint limits: a lane per group
+            const int g = l;
             if (g < 3) {
                 float *row = ws.J + g * KG_JS;
                 for (int j = 0; j < KG_NV; j++) row[j] = 0.f;
@@ -1226,30 +1226,45 @@ template <class WS> KG_DEV void kg_make_rows(const KgModel &m, WS &ws, int kg_la
                     float R = fmaxf((1.f - imp) / imp * m.dof_invw[j], 1e-15f);
                     KG_GP(ws, g, 3) = 2.f; KG_GD(ws, g) = 1.f / R; KG_GAREF(ws, g, 0) = -Bd * sgn * ws.qvel[j] - K * imp * pos;
                 } else KG_GP(ws, g, 3) = 0.f;
-            } else if (g < ws.ngroup) {
-                int s = kg_gslot(ws, g), g1 = ws.st_g1[s], g2 = ws.st_g2[s];
-                float n[3], t1[3], t2[3];
-                kg_copy(n, ws.st_n[s]);
-                kg_make_frame(n, t1, t2);
-                float *rn = ws.J + (9 + 3 * (g - 9)) * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
-                for (int j = 0; j < KG_NV; j++) { rn[j] = 0.f; r1[j] = 0.f; r2[j] = 0.f; }
-                const float *p = ws.st_pos[s];
-                kg_jac_add(ws, g2, p, n, 1.f, rn); kg_jac_add(ws, g1, p, n, -1.f, rn);
-                kg_jac_add(ws, g2, p, t1, 1.f, r1); kg_jac_add(ws, g1, p, t1, -1.f, r1);
-                kg_jac_add(ws, g2, p, t2, 1.f, r2); kg_jac_add(ws, g1, p, t2, -1.f, r2);
-                float vn = 0, v1 = 0, v2 = 0;
-                for (int j = 0; j < KG_NV; j++) { float v = ws.qvel[j]; vn += rn[j] * v; v1 += r1[j] * v; v2 += r2[j] * v; }
-                float mu = m.pair_mu[s < 32 ? (s >> 2) : 8 + (s - 32)], dist = ws.st_dist[s], r = dist - m.margin;   // staging slot -> pair lane
-                float tran = (g1 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g1]) + (g2 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g2]);
-                float imp = kg_impedance(m, r);
-                float R = fmaxf((1.f - imp) / imp * (tran + mu * mu * tran), 1e-15f);
-                float Rpy = fmaxf(2.f * mu * mu / m.impratio * R, 1e-15f);
-                float Dv = 1.f / Rpy, kr = K * imp * r;
-                KG_GMU(ws, g) = mu;
-                KG_GD(ws, g) = Dv;
-                KG_GAREF(ws, g, 0) = -Bd * (vn + mu * v1) - kr; KG_GAREF(ws, g, 1) = -Bd * (vn - mu * v1) - kr;
-                KG_GAREF(ws, g, 2) = -Bd * (vn + mu * v2) - kr; KG_GAREF(ws, g, 3) = -Bd * (vn - mu * v2) - kr;
             }
+        }
+        // contacts: a lane per BASE ROW (normal, tangent 1, tangent 2 of each contact) -- lanes 9..31 take the first 23 rows,
+        // lanes 0..8 (busy with the tendon / limit groups above) the next 9, and so on: the Jacobian rows of a contact are
+        // built side by side instead of one after the other.  The row's velocity J.v waits in the row's last pad word for the
+        // phase below (bdot and the rest of the solver scratch still ARE the contact staging read here).
+        const int nb = kg_nbase(ws);
+        for (int b = 9 + ((l + 23) & 31); b < nb; b += 32) {
+            const int g = 9 + (b - 9) / 3, k = (b - 9) % 3;
+            const int s = kg_gslot(ws, g), g1 = ws.st_g1[s], g2 = ws.st_g2[s];
+            float n[3], t1[3], t2[3];
+            kg_copy(n, ws.st_n[s]);
+            kg_make_frame(n, t1, t2);
+            const float *f = k == 0 ? n : (k == 1 ? t1 : t2);
+            float *row = ws.J + b * KG_JS;
+            for (int j = 0; j < KG_NV; j++) row[j] = 0.f;
+            const float *p = ws.st_pos[s];
+            kg_jac_add(ws, g2, p, f, 1.f, row); kg_jac_add(ws, g1, p, f, -1.f, row);
+            float v = 0.f;
+            for (int j = 0; j < KG_NV; j++) v += row[j] * ws.qvel[j];
+            row[KG_JS - 1] = v;
+        }
+    }
+    KG_SYNC();
+    KG_PHASE(l) {
+        const float K = m.solK, Bd = m.solB;
+        for (int g = 9 + l; g < ws.ngroup; g += 32) {
+            const int s = kg_gslot(ws, g), g1 = ws.st_g1[s], g2 = ws.st_g2[s], b = 9 + 3 * (g - 9);
+            const float vn = ws.J[b * KG_JS + KG_JS - 1], v1 = ws.J[(b + 1) * KG_JS + KG_JS - 1], v2 = ws.J[(b + 2) * KG_JS + KG_JS - 1];
+            float mu = m.pair_mu[s < 32 ? (s >> 2) : 8 + (s - 32)], dist = ws.st_dist[s], r = dist - m.margin;   // staging slot -> pair lane
+            float tran = (g1 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g1]) + (g2 == 8 ? m.shape[ws.shape].invw_tran : m.body_invw[g2]);
+            float imp = kg_impedance(m, r);
+            float R = fmaxf((1.f - imp) / imp * (tran + mu * mu * tran), 1e-15f);
+            float Rpy = fmaxf(2.f * mu * mu / m.impratio * R, 1e-15f);
+            float Dv = 1.f / Rpy, kr = K * imp * r;
+            KG_GMU(ws, g) = mu;
+            KG_GD(ws, g) = Dv;
+            KG_GAREF(ws, g, 0) = -Bd * (vn + mu * v1) - kr; KG_GAREF(ws, g, 1) = -Bd * (vn - mu * v1) - kr;
+            KG_GAREF(ws, g, 2) = -Bd * (vn + mu * v2) - kr; KG_GAREF(ws, g, 3) = -Bd * (vn - mu * v2) - kr;
         }
     }
     KG_SYNC();
