@@ -314,6 +314,31 @@ KG_DEV void kg_st8(float *p, const float *v) {
 #endif
 }
 
+// warp total / exclusive prefix of a per-lane int array written in the previous phase (every lane calls these)
+KG_DEV int kg_total_int(const int *v, int l) {
+#if defined(__CUDA_ARCH__)
+    return __reduce_add_sync(0xffffffffu, v[l]);
+#else
+    (void)l;
+    int s = 0;
+    for (int i = 0; i < 32; i++) s += v[i];
+    return s;
+#endif
+}
+KG_DEV void kg_prefix_int(const int *v, int l, int &off, int &total) {
+#if defined(__CUDA_ARCH__)
+    const int x = v[l];
+    int inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += y; }
+    off = inc - x;
+    total = __shfl_sync(0xffffffffu, inc, 31);
+#else
+    off = 0; total = 0;
+    for (int k = 0; k < 32; k++) { int c = v[k]; if (k < l) off += c; total += c; }
+#endif
+}
+
 // warp total of ws.red[] (every lane wrote its partial in the previous phase)
 KG_DEV float kg_total(const float *red, int l) {
 #if defined(__CUDA_ARCH__)
@@ -1153,8 +1178,8 @@ template <class WS> KG_DEV unsigned kg_collision_lane(const KgModel &m, WS &ws, 
 template <class WS> KG_DEV void kg_compaction(const KgModel &m, WS &ws, int kg_lane) {
     (void)m;
     KG_PHASE(l) {
-        int off = 0, total = 0;
-        for (int k = 0; k < 32; k++) { int c = ws.cnt[k]; if (k < l) off += c; total += c; }
+        int off, total;
+        kg_prefix_int(ws.cnt, l, off, total);
         int base = l < 8 ? 4 * l : 32 + (l - 8);
         for (int i = 0; i < ws.cnt[l]; i++) {
             int g = 9 + off + i;
@@ -1534,11 +1559,10 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             ws.red[l] = p1; ws.red2[l] = p2;
         }
         KG_SYNC();
-        KG_PHASE(l) {
-            float p1 = kg_total(ws.red, l), p2 = kg_total(ws.red2, l);
-            if (l == 0) { ws.s_glo = p1; ws.s_ghi = p2; }   // Gauss part of phi'(0), phi''
-        }
-        KG_SYNC();
+        // warp totals are carried in registers: every lane of kg_total's result holds the same value (in the host emulation
+        // the phase body runs once per lane and assigns the same value each time)
+        float gp1 = 0.f, gp2 = 0.f;                         // Gauss part of phi'(0), phi''
+        KG_PHASE(l) { gp1 = kg_total(ws.red, l); gp2 = kg_total(ws.red2, l); }
         KG_PROBE(11);
         // ---- (d) exact line search: root of the piecewise-linear phi'(alpha).  dir is the exact Newton direction of
         // the current quadratic piece, so the first candidate is alpha = 1; if no row changes activity on [0,1] that is
@@ -1546,7 +1570,6 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
         {
             float alpha = 1.f, lo = 0.f, hi = -1.f, g0abs = 0.f, best_alpha = 1.f;
             int exact = 0;
-            const float gp1 = ws.s_glo, gp2 = ws.s_ghi;
             for (int ls = 0; ls < KG_LS_MAXIT; ls++) {
                 if (kg_lane == 0) KG_COUNT(27, 1);
                 KG_PHASE(l) {
@@ -1576,21 +1599,17 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                     if (ls == 0) { ws.cnt[l] = nchg; ws.mv_red3[l] = d0; }
                 }
                 KG_SYNC();
+                float t_lo = 0.f, t_hi = 0.f, t_d0 = 0.f;
+                int t_chg = 0;
                 KG_PHASE(l) {
-                    float d1 = kg_total(ws.red, l), d2 = kg_total(ws.red2, l);
-                    if (ls == 0) {
-                        float d0 = kg_total(ws.mv_red3, l);
-                        int chg = 0;
-                        for (int k = 0; k < 32; k++) chg += ws.cnt[k];
-                        if (l == 0) { ws.s_flag = (float)chg; ws.s_cost2 = d0; }
-                    }
-                    if (l == 0) { ws.s_lo = d1; ws.s_hi = d2; }
+                    t_lo = kg_total(ws.red, l); t_hi = kg_total(ws.red2, l);
+                    if (ls == 0) { t_d0 = kg_total(ws.mv_red3, l); t_chg = kg_total_int(ws.cnt, l); }
                 }
-                KG_SYNC();
-                float gA = gp1 + alpha * gp2 + ws.s_lo, hA = gp2 + ws.s_hi;
+                KG_SYNC();                                        // (red / cnt are rewritten by the next pass)
+                float gA = gp1 + alpha * gp2 + t_lo, hA = gp2 + t_hi;
                 if (ls == 0) {
-                    g0abs = fabsf(gp1 + ws.s_cost2);              // |phi'(0)|
-                    if (ws.s_flag == 0.f) { exact = 1; best_alpha = 1.f; break; }
+                    g0abs = fabsf(gp1 + t_d0);                    // |phi'(0)|
+                    if (t_chg == 0) { exact = 1; best_alpha = 1.f; break; }
                 }
                 best_alpha = alpha;
                 if (fabsf(gA) <= 1e-6f * g0abs) break;
