@@ -1441,11 +1441,14 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             if (use_smooth) ws.Mdq[l] = 0.f;
         }
         if (use_smooth) { int nb = kg_nbase(ws); for (int b = l; b < nb; b += 32) ws.bdot[b] = ws.bdir[b]; }
-        if (l == 0) { ws.s_cost = 3.0e38f; ws.s_done = 0; ws.s_iter = 0; ws.s_exact = 0; }
     }
     KG_SYNC();
     const float scale = m.shape[ws.shape].scale;
     KG_PROBE(7);
+    // the solve's control state lives in registers: every lane of a warp total holds the same value, so every lane takes
+    // the same decisions without a broadcast through shared memory
+    float prev_cost = 3.0e38f;
+    int done = 0, n_iter = 0;
     for (int iter = 0; iter <= KG_NEWTON_MAXIT; iter++) {
         // ---- (a) rows at the current point: cost and the weights w = D * jar of the active rows
         KG_PHASE(l) {
@@ -1469,21 +1472,18 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             ws.red[l] = c;
         }
         KG_SYNC();
-        KG_PHASE(l) {
-            float cost = kg_total(ws.red, l);
-            if (l == 0) {
-                // MuJoCo's test is scale*improvement < 1e-8; in fp32 the cost itself only carries ~2^-23 relative
-                // precision, so an "improvement" below that noise floor is treated as converged as well.  s_exact: the
-                // previous Newton step was a full step on an unchanged active set, i.e. the exact minimiser.
-                float improvement = scale * (ws.s_cost - cost);
-                if (iter > 0 && improvement < tol + 2.4e-7f * scale * fabsf(cost)) ws.s_done = 1;
-                if (ws.s_exact || iter == KG_NEWTON_MAXIT) ws.s_done = 1;
-                ws.s_cost = cost;
-            }
+        {
+            float cost = 0.f;
+            KG_PHASE(l) { cost = kg_total(ws.red, l); }
+            // MuJoCo's test is scale*improvement < 1e-8; in fp32 the cost itself only carries ~2^-23 relative
+            // precision, so an "improvement" below that noise floor is treated as converged as well.
+            const float improvement = scale * (prev_cost - cost);
+            if (iter > 0 && improvement < tol + 2.4e-7f * scale * fabsf(cost)) done = 1;
+            if (iter == KG_NEWTON_MAXIT) done = 1;
+            prev_cost = cost;
         }
-        KG_SYNC();
         KG_PROBE(8);
-        if (ws.s_done) break;
+        if (done) break;
         // ---- (b) gradient and Hessian.  Two lanes per row of H: lane r owns the columns 0..7 of row r, lane 16 + r the
         // columns 8..14 (each entry accumulates over the groups in the same order whoever owns it); lane r also forms
         // the gradient entry.  The groups' coefficients come from phase (a).
@@ -1534,15 +1534,18 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             ws.red[l] = gsq; ws.red2[l] = gab * gab;
         }
         KG_SYNC();
-        KG_PHASE(l) {
-            float gn = kg_total(ws.red, l), ga = kg_total(ws.red2, l);
+        {
+            float gn = 0.f, ga = 0.f;
+            KG_PHASE(l) {
+                gn = kg_total(ws.red, l); ga = kg_total(ws.red2, l);
+                if (l < KG_NV) ws.dir[l] = -ws.grad[l];
+            }
             // gradient test: MuJoCo's absolute 1e-8, or the fp32 rounding floor of the sum that formed the gradient
-            if (l == 0 && (scale * sqrtf(gn) < tol || gn < 1.4e-13f * ga)) ws.s_done = 1;
-            if (l < KG_NV) ws.dir[l] = -ws.grad[l];
+            if (scale * sqrtf(gn) < tol || gn < 1.4e-13f * ga) done = 1;
         }
         KG_SYNC();
         KG_PROBE(9);
-        if (ws.s_done) break;
+        if (done) break;
         kg_chol_factor_solve(ws.L, ws.dir, kg_lane);
         KG_PROBE(10);
         // ---- (c) directional products
@@ -1625,8 +1628,8 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                 if (l < KG_NV) { ws.qacc[l] += al * ws.dir[l]; ws.Mdq[l] += al * ws.Md[l]; }
                 int nb = kg_nbase(ws);
                 for (int b = l; b < nb; b += 32) ws.bdot[b] += al * ws.bdir[b];
-                if (l == 0) { ws.s_iter = iter + 1; ws.s_exact = exact; }
             }
+            n_iter = iter + 1;
             KG_SYNC();
             KG_PROBE(12);
             // a full step on an unchanged active set is the exact minimiser: nothing the next pass over the rows would
@@ -1643,7 +1646,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
     KG_PHASE(l) {
         if (l < KG_NV) {
             float f = ws.fs[l];
-            if (ws.s_iter < KG_NEWTON_MAXIT) f += ws.Mdq[l];
+            if (n_iter < KG_NEWTON_MAXIT) f += ws.Mdq[l];
             else {
                 int nb = kg_nbase(ws);
                 for (int b = 0; b < nb; b++) {
@@ -1654,7 +1657,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             ws.ftot[l] = f;
             ws.qwarm[l] = ws.qacc[l];
         }
-        if (l == 0) ws.stat_newton += ws.s_iter;
+        if (l == 0) { ws.s_iter = n_iter; ws.stat_newton += n_iter; }
 #if !defined(__CUDA_ARCH__) && defined(KG_EMU_HIST)
         if (l == 0) fprintf(stderr, "NEWTON %d %d\n", ws.s_iter, ws.ngroup - 9);
 #endif
