@@ -1328,6 +1328,24 @@ template <class WS> KG_NOINL void kg_base_dots(WS &ws, const float *x, float *ou
     KG_SYNC();
 }
 
+// the same for two vectors at once (one pass over the rows)
+template <class WS> KG_NOINL void kg_base_dots2(WS &ws, const float *x1, float *out1, const float *x2, float *out2, int kg_lane) {
+    KG_PHASE(l) {
+        int nb = kg_nbase(ws);
+        float xv[16], yv[16];
+        kg_ld16(x1, xv); kg_ld16(x2, yv);
+        for (int b = l; b < nb; b += 32) {
+            float row[16];
+            kg_ld16(ws.J + b * KG_JS, row);
+            float s = 0.f, t = 0.f;
+#pragma unroll
+            for (int j = 0; j < KG_NV; j++) { s += row[j] * xv[j]; t += row[j] * yv[j]; }
+            out1[b] = s; out2[b] = t;
+        }
+    }
+    KG_SYNC();
+}
+
 // x <- (M + diag_add I)^-1 x in closed form.  M is block diagonal {hand 9x9, object 6x6}; the hand block is
 // [mu I3, C; C^T, blockdiag(A_1,A_2,A_3)] (slides couple to each finger's 2x2 hinge block, fingers do not couple to
 // each other), the object block is [m' I3, T; T^T, Io'].  Both are eliminated by 3x3 Schur complements: lanes 0..2
@@ -1413,8 +1431,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
     KG_SYNC();
     kg_minv(ws, 0.f, ws.qas, kg_lane);
     // ---- warm start: the cheaper of qacc_warmstart and qacc_smooth
-    kg_base_dots(ws, ws.qwarm, ws.bdot, kg_lane);
-    kg_base_dots(ws, ws.qas, ws.bdir, kg_lane);
+    kg_base_dots2(ws, ws.qwarm, ws.bdot, ws.qas, ws.bdir, kg_lane);
     KG_PHASE(l) {
         float cw = 0.f, cs = 0.f;
         if (l < KG_NV) {
@@ -1549,15 +1566,29 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
         kg_chol_factor_solve(ws.L, ws.dir, kg_lane);
         KG_PROBE(10);
         // ---- (c) directional products
-        kg_base_dots(ws, ws.dir, ws.bdir, kg_lane);
+        // (one phase: base-row products J_b . dir by a lane per base row, M dir by a lane per dof)
         KG_PHASE(l) {
-            float p1 = 0.f, p2 = 0.f;
-            if (l < KG_NV) {
+            float xv[16];
+            kg_ld16(ws.dir, xv);
+            const int nb = kg_nbase(ws);
+            for (int b = l; b < nb; b += 32) {
+                float row[16];
+                kg_ld16(ws.J + b * KG_JS, row);
                 float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < KG_NV; j++) s += ws.M[l * KG_MS + j] * ws.dir[j];
+                for (int j = 0; j < KG_NV; j++) s += row[j] * xv[j];
+                ws.bdir[b] = s;
+            }
+            float p1 = 0.f, p2 = 0.f;
+            if (l < KG_NV) {
+                float mr[16];
+                kg_ld16(ws.M + l * KG_MS, mr);
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < KG_NV; j++) s += mr[j] * xv[j];
                 ws.Md[l] = s;
-                p1 = ws.Mdq[l] * ws.dir[l]; p2 = s * ws.dir[l];
+                const float dl = ws.dir[l];
+                p1 = ws.Mdq[l] * dl; p2 = s * dl;
             }
             ws.red[l] = p1; ws.red2[l] = p2;
         }
