@@ -1346,7 +1346,7 @@ template <class WS> KG_NOINL void kg_base_dots2(WS &ws, const float *x1, float *
     KG_SYNC();
 }
 
-// x <- (M + diag_add I)^-1 x in closed form.  M is block diagonal {hand 9x9, object 6x6}; the hand block is
+// y <- (M + diag_add I)^-1 x in closed form (y != x: lanes read x while others already write y).  M is block diagonal {hand 9x9, object 6x6}; the hand block is
 // [mu I3, C; C^T, blockdiag(A_1,A_2,A_3)] (slides couple to each finger's 2x2 hinge block, fingers do not couple to
 // each other), the object block is [m' I3, T; T^T, Io'].  Both are eliminated by 3x3 Schur complements: lanes 0..2
 // own a finger, lane 3 the object.  (The reference engine does a generic sparse L^T D L here.)
@@ -1357,7 +1357,7 @@ KG_DEV void kg_inv3_sym(const float *S, float *Si) {   // inverse of a symmetric
     Si[1] = (S[0] * S[2] - S[4] * S[4]) * id; Si[5] = (S[3] * S[4] - S[0] * S[5]) * id;
     Si[2] = (S[0] * S[1] - S[3] * S[3]) * id;
 }
-template <class WS> KG_NOINL void kg_minv(WS &ws, float diag_add, float *x, int kg_lane) {
+template <class WS> KG_NOINL void kg_minv(WS &ws, float diag_add, const float *x, float *y, int kg_lane) {
     KG_PHASE(l) {
         if (l < 3) {
             int h1 = 3 + 2 * l, h2 = 4 + 2 * l;
@@ -1394,8 +1394,8 @@ template <class WS> KG_NOINL void kg_minv(WS &ws, float diag_add, float *x, int 
             kg_inv3_sym(S, Si);
             float xr[3] = {Si[0] * rhs[0] + Si[3] * rhs[1] + Si[4] * rhs[2], Si[3] * rhs[0] + Si[1] * rhs[1] + Si[5] * rhs[2],
                            Si[4] * rhs[0] + Si[5] * rhs[1] + Si[2] * rhs[2]};
-            for (int j = 0; j < 3; j++) x[9 + j] = (ft[j] - (T[3 * j] * xr[0] + T[3 * j + 1] * xr[1] + T[3 * j + 2] * xr[2])) * im;
-            for (int i = 0; i < 3; i++) x[12 + i] = xr[i];
+            for (int j = 0; j < 3; j++) y[9 + j] = (ft[j] - (T[3 * j] * xr[0] + T[3 * j + 1] * xr[1] + T[3 * j + 2] * xr[2])) * im;
+            for (int i = 0; i < 3; i++) y[12 + i] = xr[i];
         }
     }
     KG_SYNC();
@@ -1412,14 +1412,10 @@ template <class WS> KG_NOINL void kg_minv(WS &ws, float diag_add, float *x, int 
             int h1 = 3 + 2 * l, h2 = 4 + 2 * l;
             float t1 = 0.f, t2 = 0.f;   // C^T xs
             for (int i = 0; i < 3; i++) { t1 += ws.M[i * KG_MS + h1] * xs[i]; t2 += ws.M[i * KG_MS + h2] * xs[i]; }
-            ws.mv_y[l][0] -= ws.mv_i[l][0] * t1 + ws.mv_i[l][1] * t2;
-            ws.mv_y[l][1] -= ws.mv_i[l][1] * t1 + ws.mv_i[l][2] * t2;
-            if (l == 0) { ws.mv_xs[0] = xs[0]; ws.mv_xs[1] = xs[1]; ws.mv_xs[2] = xs[2]; }
+            y[h1] = ws.mv_y[l][0] - (ws.mv_i[l][0] * t1 + ws.mv_i[l][1] * t2);
+            y[h2] = ws.mv_y[l][1] - (ws.mv_i[l][1] * t1 + ws.mv_i[l][2] * t2);
+            y[l] = l == 0 ? xs[0] : (l == 1 ? xs[1] : xs[2]);      // (every finger lane holds the same xs)
         }
-    }
-    KG_SYNC();
-    KG_PHASE(l) {
-        if (l < 3) { x[l] = ws.mv_xs[l]; x[3 + 2 * l] = ws.mv_y[l][0]; x[4 + 2 * l] = ws.mv_y[l][1]; }
     }
     KG_SYNC();
 }
@@ -1427,9 +1423,7 @@ template <class WS> KG_NOINL void kg_minv(WS &ws, float diag_add, float *x, int 
 template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) {
     const float tol = 1e-8f;
     // ---- unconstrained acceleration
-    KG_PHASE(l) { if (l < KG_NV) ws.qas[l] = ws.fs[l]; }
-    KG_SYNC();
-    kg_minv(ws, 0.f, ws.qas, kg_lane);
+    kg_minv(ws, 0.f, ws.fs, ws.qas, kg_lane);
     // ---- warm start: the cheaper of qacc_warmstart and qacc_smooth
     kg_base_dots2(ws, ws.qwarm, ws.bdot, ws.qas, ws.bdir, kg_lane);
     KG_PHASE(l) {
@@ -1699,10 +1693,10 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
 // ------------------------------------------------------------------------------------------------ P9 Euler
 template <class WS> KG_DEV void kg_euler(const KgModel &m, WS &ws, int kg_lane) {
     const float h = m.timestep;
-    kg_minv(ws, h * m.damping, ws.ftot, kg_lane);     // implicit joint damping: (M + h B) a = f
+    kg_minv(ws, h * m.damping, ws.ftot, ws.Md, kg_lane);     // implicit joint damping: (M + h B) a = f   (Md: free after the solve)
     KG_PHASE(l) {
         if (l < KG_NV) {
-            float v = ws.qvel[l] + h * ws.ftot[l];
+            float v = ws.qvel[l] + h * ws.Md[l];
             ws.qvel[l] = v;
             if (l < 12) ws.qpos[l] += h * v;
         }
