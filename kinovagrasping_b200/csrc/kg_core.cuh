@@ -1084,44 +1084,16 @@ template <class WS> KG_DEV unsigned kg_collision_lane(const KgModel &m, WS &ws, 
 #else
             const float budget = -1.f;
 #endif
+            // Stage 0: what this lane has to look up.  job 1 = plane lane: lowest hull vertex of geom g2; job 2 = hull pair
+            // whose cached separating axis gets re-tested: first the support of g1 along it.  Both kinds of lanes then run
+            // the SAME hill-climbing call side by side (one call site, no serialisation between plane and pair lanes).
+            int job = 0, gA = g2, meshA = mesh2, curA = 0, mesh1 = 0, c2 = 0;
+            float dirA[3] = {0.f, 0.f, -1.f}, orgA[3] = {0.f, 0.f, 0.f}, marginA = 0.f;
             if (l < 8) {
-                const int base = 4 * l;
                 if (ws.gpos[g2][2] <= rb2 + margin && !(budget > 0.f)) {
-                    const float nd[3] = {0, 0, -1}, zero[3] = {0, 0, 0};
-                    float w[3];
-                    int cur = ws.cv2[l];
-                    if (cur >= m.mesh[mesh2].nvert) cur = 0;
-                    kg_support(m, ws, g2, mesh2, cur, nd, zero, 0.f, w);
-                    KG_COUNT(26, 1);
-                    ws.cv2[l] = (unsigned short)cur;
-                    ws.sepok[l] = w[2] > margin; ws.slack[l] = w[2] - margin;      // clear of the floor by this much
-                    if (w[2] <= margin) {
-                        const float thresh = 0.3f * rb2;
-                        const float *vert = m.hull_vert + 4 * (size_t)m.mesh[mesh2].vert0;
-                        const int *adjs = m.adj_start + m.mesh[mesh2].vert0;
-                        int a0 = adjs[cur], a1 = adjs[cur + 1];
-                        for (int c = -1; c < a1 - a0 && n < 4; c++) {
-                            if (c >= 0) {
-                                auto lv = KG_LDG4(vert + 4 * m.adj[a0 + c]);
-                                float lvv[3] = {lv.x, lv.y, lv.z};
-                                kg_mulmv(w, ws.gmat[g2], lvv); kg_add(w, w, ws.gpos[g2]);
-                            }
-                            float dist = w[2];
-                            if (dist > margin) continue;
-                            float cp[3] = {w[0], w[1], w[2] - 0.5f * dist};
-                            bool skip = false;
-                            for (int k = 0; k < n; k++) {
-                                float df[3]; kg_sub(df, cp, ws.st_pos[base + k]);
-                                if (kg_dot(df, df) < thresh * thresh) skip = true;
-                            }
-                            if (skip) continue;
-                            int s = base + n;
-                            ws.st_dist[s] = dist; kg_copy(ws.st_pos[s], cp);
-                            ws.st_n[s][0] = 0; ws.st_n[s][1] = 0; ws.st_n[s][2] = 1;
-                            ws.st_g1[s] = 0; ws.st_g2[s] = (unsigned char)g2;
-                            n++;
-                        }
-                    }
+                    job = 1;
+                    curA = ws.cv2[l];
+                    if (curA >= m.mesh[mesh2].nvert) curA = 0;
                 } else if (budget > 0.f) ws.slack[l] = budget;
                 else ws.sepok[l] = 0;                                   // beyond the bounding sphere: nothing cached
             } else {
@@ -1131,25 +1103,70 @@ template <class WS> KG_DEV unsigned kg_collision_lane(const KgModel &m, WS &ws, 
                 if (kg_dot(df, df) <= lim * lim) {
                     if (budget > 0.f) ws.slack[l] = budget;             // still provably separated along the cached axis
                     else {
-                        const int mesh1 = kg_mesh_of_geom(ws, g1);
-                        int c1 = ws.cv1[l], c2 = ws.cv2[l];
+                        mesh1 = kg_mesh_of_geom(ws, g1);
+                        int c1 = ws.cv1[l];
+                        c2 = ws.cv2[l];
                         if (c1 >= m.mesh[mesh1].nvert) c1 = 0;
                         if (c2 >= m.mesh[mesh2].nvert) c2 = 0;
-                        bool separated = false;
                         if (ws.sepok[l]) {
                             // the axis that separated the inflated hulls in the previous substep: still separating?
-                            float n0[3] = {ws.sep[l][0], ws.sep[l][1], ws.sep[l][2]}, nn[3] = {-n0[0], -n0[1], -n0[2]}, s1[3], s2[3];
-                            kg_support(m, ws, g1, mesh1, c1, n0, ws.gpos[g1], 0.5f * margin, s1);
-                            kg_support(m, ws, g2, mesh2, c2, nn, ws.gpos[g1], 0.5f * margin, s2);
-                            const float gap = kg_dot(s2, n0) - kg_dot(s1, n0);
-                            separated = gap > 0.f;
-                            ws.slack[l] = gap;
-                            KG_COUNT(24, 1); KG_COUNT(25, separated ? 1 : 0);
+                            job = 2; gA = g1; meshA = mesh1; curA = c1; marginA = 0.5f * margin;
+                            for (int k = 0; k < 3; k++) { dirA[k] = ws.sep[l][k]; orgA[k] = ws.gpos[g1][k]; }
+                        } else {
+                            tried = 1.f;                                // nothing cached: full MPR, a narrowphase task
+                            ws.cv1[l] = (unsigned short)c1; ws.cv2[l] = (unsigned short)c2;
                         }
-                        if (!separated) tried = 1.f;       // full MPR: a narrowphase task
-                        ws.cv1[l] = (unsigned short)c1; ws.cv2[l] = (unsigned short)c2;
                     }
                 } else ws.sepok[l] = 0;
+            }
+            // Stage 1
+            float sA[3] = {0.f, 0.f, 0.f};
+            if (job) kg_support(m, ws, gA, meshA, curA, dirA, orgA, marginA, sA);
+            // Stage 2
+            if (job == 1) {
+                const int base = 4 * l;
+                float w[3] = {sA[0], sA[1], sA[2]};
+                const int cur = curA;
+                KG_COUNT(26, 1);
+                ws.cv2[l] = (unsigned short)cur;
+                ws.sepok[l] = w[2] > margin; ws.slack[l] = w[2] - margin;      // clear of the floor by this much
+                if (w[2] <= margin) {
+                    const float thresh = 0.3f * rb2;
+                    const float *vert = m.hull_vert + 4 * (size_t)m.mesh[mesh2].vert0;
+                    const int *adjs = m.adj_start + m.mesh[mesh2].vert0;
+                    int a0 = adjs[cur], a1 = adjs[cur + 1];
+                    for (int c = -1; c < a1 - a0 && n < 4; c++) {
+                        if (c >= 0) {
+                            auto lv = KG_LDG4(vert + 4 * m.adj[a0 + c]);
+                            float lvv[3] = {lv.x, lv.y, lv.z};
+                            kg_mulmv(w, ws.gmat[g2], lvv); kg_add(w, w, ws.gpos[g2]);
+                        }
+                        float dist = w[2];
+                        if (dist > margin) continue;
+                        float cp[3] = {w[0], w[1], w[2] - 0.5f * dist};
+                        bool skip = false;
+                        for (int k = 0; k < n; k++) {
+                            float df[3]; kg_sub(df, cp, ws.st_pos[base + k]);
+                            if (kg_dot(df, df) < thresh * thresh) skip = true;
+                        }
+                        if (skip) continue;
+                        int s = base + n;
+                        ws.st_dist[s] = dist; kg_copy(ws.st_pos[s], cp);
+                        ws.st_n[s][0] = 0; ws.st_n[s][1] = 0; ws.st_n[s][2] = 1;
+                        ws.st_g1[s] = 0; ws.st_g2[s] = (unsigned char)g2;
+                        n++;
+                    }
+                }
+            } else if (job == 2) {
+                const float nn[3] = {-dirA[0], -dirA[1], -dirA[2]};
+                float s2[3];
+                kg_support(m, ws, g2, mesh2, c2, nn, orgA, 0.5f * margin, s2);
+                const float gap = kg_dot(s2, dirA) - kg_dot(sA, dirA);
+                const bool separated = gap > 0.f;
+                ws.slack[l] = gap;
+                KG_COUNT(24, 1); KG_COUNT(25, separated ? 1 : 0);
+                if (!separated) tried = 1.f;           // full MPR: a narrowphase task
+                ws.cv1[l] = (unsigned short)curA; ws.cv2[l] = (unsigned short)c2;
             }
         }
         ws.red2[l] = tried;
