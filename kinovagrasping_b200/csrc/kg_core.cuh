@@ -1523,36 +1523,40 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                 gab = fabsf(gr);
                 float h[8];
                 kg_ld8(ws.M + r * KG_MS + j0, h);
-                for (int g = 0; g < ws.ngroup; g++) {
-                    int tp = kg_gtype(ws, g);
-                    if (tp == 0) continue;
-                    if (tp < 3) {
-                        const float *rowp = ws.J + g * KG_JS;
-                        float ji = rowp[r];
-                        float t = ji * ws.bw[g];
-                        gr += t; gab += fabsf(t);
-                        const float da = KG_GAREF(ws, g, 1);   // D * active stored by (a)
-                        float u = ji * da;
-                        if (da != 0.f) {     // warp-uniform: skip inactive limit rows
-                            float row[8];
-                            kg_ld8(rowp + j0, row);
+                // scalar rows: tendon k has entries on the two hinges of finger k only, a limit row on its own dof only, so a
+                // row of H meets at most one of each (the others would add exact zeros); then every contact in use
+                auto scalar_row = [&](int g) {
+                    const float *rowp = ws.J + g * KG_JS;
+                    float ji = rowp[r];
+                    float t = ji * ws.bw[g];
+                    gr += t; gab += fabsf(t);
+                    const float da = KG_GAREF(ws, g, 1);   // D * active stored by (a)
+                    float u = ji * da;
+                    if (da != 0.f) {
+                        float row[8];
+                        kg_ld8(rowp + j0, row);
 #pragma unroll
-                            for (int j = 0; j < 8; j++) h[j] += u * row[j];
-                        }
-                    } else {
-                        int b = 9 + 3 * (g - 9);
-                        const float *rn = ws.J + b * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
-                        float jn = rn[r], j1 = r1[r], j2 = r2[r];
-                        float t0 = jn * ws.bw[b], t1 = j1 * ws.bw[b + 1], t2 = j2 * ws.bw[b + 2];
-                        gr += t0 + t1 + t2; gab += fabsf(t0) + fabsf(t1) + fabsf(t2);
-                        const float A = KG_GH(ws, g, 0), B1 = KG_GH(ws, g, 1), C1 = KG_GH(ws, g, 2), B2 = KG_GH(ws, g, 3), C2 = KG_GH(ws, g, 4);
-                        if (A != 0.f) {
-                            float u = A * jn + B1 * j1 + B2 * j2, v1 = B1 * jn + C1 * j1, v2 = B2 * jn + C2 * j2;
-                            float vn[8], w1[8], w2[8];
-                            kg_ld8(rn + j0, vn); kg_ld8(r1 + j0, w1); kg_ld8(r2 + j0, w2);
+                        for (int j = 0; j < 8; j++) h[j] += u * row[j];
+                    }
+                };
+                if (r >= 3 && r < 9) scalar_row((r - 3) >> 1);
+                {
+                    const int gl = r < 3 ? 3 + r : ((r < 9 && (r & 1)) ? 6 + ((r - 3) >> 1) : -1);
+                    if (gl >= 0 && kg_gtype(ws, gl) == 2) scalar_row(gl);
+                }
+                for (int g = 9; g < ws.ngroup; g++) {
+                    int b = 9 + 3 * (g - 9);
+                    const float *rn = ws.J + b * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
+                    float jn = rn[r], j1 = r1[r], j2 = r2[r];
+                    float t0 = jn * ws.bw[b], t1 = j1 * ws.bw[b + 1], t2 = j2 * ws.bw[b + 2];
+                    gr += t0 + t1 + t2; gab += fabsf(t0) + fabsf(t1) + fabsf(t2);
+                    const float A = KG_GH(ws, g, 0), B1 = KG_GH(ws, g, 1), C1 = KG_GH(ws, g, 2), B2 = KG_GH(ws, g, 3), C2 = KG_GH(ws, g, 4);
+                    if (A != 0.f) {
+                        float u = A * jn + B1 * j1 + B2 * j2, v1 = B1 * jn + C1 * j1, v2 = B2 * jn + C2 * j2;
+                        float vn[8], w1[8], w2[8];
+                        kg_ld8(rn + j0, vn); kg_ld8(r1 + j0, w1); kg_ld8(r2 + j0, w2);
 #pragma unroll
-                            for (int j = 0; j < 8; j++) h[j] += u * vn[j] + v1 * w1[j] + v2 * w2[j];
-                        }
+                        for (int j = 0; j < 8; j++) h[j] += u * vn[j] + v1 * w1[j] + v2 * w2[j];
                     }
                 }
                 if (j0 == 0) { ws.grad[r] = gr; gsq = gr * gr; }
