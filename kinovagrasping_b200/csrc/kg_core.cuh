@@ -1544,6 +1544,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                     const int gl = r < 3 ? 3 + r : ((r < 9 && (r & 1)) ? 6 + ((r - 3) >> 1) : -1);
                     if (gl >= 0 && kg_gtype(ws, gl) == 2) scalar_row(gl);
                 }
+#pragma unroll 2
                 for (int g = 9; g < ws.ngroup; g++) {
                     int b = 9 + 3 * (g - 9);
                     const float *rn = ws.J + b * KG_JS, *r1 = rn + KG_JS, *r2 = rn + 2 * KG_JS;
