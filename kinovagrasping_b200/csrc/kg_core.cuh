@@ -33,6 +33,9 @@
 #define KG_NOINL __device__ __noinline__
 #define KG_PHASE(l) for (int l = kg_lane, kg_once_ = 0; kg_once_ < 1; ++kg_once_)
 #define KG_SYNC() __syncwarp()
+// a per-lane variable that lives across phases: a register array on the GPU, one slot per lane in the host emulation
+#define KG_LANEVAR(type, name, n) type name[n]
+#define KG_LV(name, l) name
 #define KG_LDG4(p) __ldg((const float4 *)(p))
 #define KG_LDGU4(p) __ldg((const uint4 *)(p))
 #define KG_F2U(x) __float_as_uint(x)
@@ -55,6 +58,8 @@
 static int kg_emu_lane_order = 0;
 #define KG_PHASE(l) for (int kg_i_ = 0, l = kg_emu_lane_order ? 31 : 0; kg_i_ < 32; ++kg_i_, l += kg_emu_lane_order ? -1 : 1)
 #define KG_SYNC() ((void)0)
+#define KG_LANEVAR(type, name, n) type name[32][n]
+#define KG_LV(name, l) name[l]
 struct kg_float4 { float x, y, z, w; };
 struct kg_uint4 { unsigned x, y, z, w; };
 #define KG_LDG4(p) (*(const kg_float4 *)(p))
@@ -1620,28 +1625,50 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
         {
             float alpha = 1.f, lo = 0.f, hi = -1.f, g0abs = 0.f, best_alpha = 1.f;
             int exact = 0;
+            // what a lane's rows contribute does not change between the trial steps: residuals at the current point (jar),
+            // their slopes along dir (jv), D and the equality flag are taken once and kept per lane; rows a group does not
+            // have are zero-filled (they add exact zeros)
+            constexpr int NG = (9 + WS::MAXCON + 31) / 32;
+            KG_LANEVAR(float, lsq, NG * 9);
+            KG_LANEVAR(int, lse, NG);
+            KG_PHASE(l) {
+#pragma unroll
+                for (int gi = 0; gi < NG; gi++) {
+                    const int g = l + 32 * gi;
+                    float jar[4] = {0.f, 0.f, 0.f, 0.f}, jv[4] = {0.f, 0.f, 0.f, 0.f};
+                    int n = 0;
+                    if (g < 9 + WS::MAXCON) n = kg_group_rows(ws, g, ws.bdot, jar);
+                    if (n == 1) jv[0] = ws.bdir[g];
+                    else if (n == 4) {
+                        int b = 9 + 3 * (g - 9);
+                        float mu = KG_GMU(ws, g), nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
+                        jv[0] = nn + t1; jv[1] = nn - t1; jv[2] = nn + t2; jv[3] = nn - t2;
+                    }
+                    float *q = KG_LV(lsq, l) + 9 * gi;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { q[k] = k < n ? jar[k] : 0.f; q[4 + k] = k < n ? jv[k] : 0.f; }
+                    q[8] = n ? KG_GD(ws, g) : 0.f;
+                    KG_LV(lse, l)[gi] = n && kg_gtype(ws, g) == 1;
+                }
+            }
             for (int ls = 0; ls < KG_LS_MAXIT; ls++) {
                 if (kg_lane == 0) KG_COUNT(27, 1);
                 KG_PHASE(l) {
                     float d1 = 0.f, d2 = 0.f, d0 = 0.f;
                     int nchg = 0;
-                    for (int g = l; g < 9 + WS::MAXCON; g += 32) {
-                        float jar[4], jv[4];
-                        int n = kg_group_rows(ws, g, ws.bdot, jar);
-                        if (n == 1) jv[0] = ws.bdir[g];
-                        else if (n == 4) {
-                            int b = 9 + 3 * (g - 9);
-                            float mu = KG_GMU(ws, g), nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
-                            jv[0] = nn + t1; jv[1] = nn - t1; jv[2] = nn + t2; jv[3] = nn - t2;
-                        }
-                        const bool eq = kg_gtype(ws, g) == 1;
-                        const float Dl = n ? KG_GD(ws, g) : 0.f;
-                        for (int k = 0; k < n; k++) {
-                            float x = jar[k] + alpha * jv[k];
-                            float dj = Dl * jv[k];
-                            bool act0 = eq || jar[k] < 0.f, act = eq || x < 0.f;
-                            if (act) { d1 += dj * x; d2 += dj * jv[k]; }
-                            if (act0) d0 += dj * jar[k];
+#pragma unroll
+                    for (int gi = 0; gi < NG; gi++) {
+                        const float *q = KG_LV(lsq, l) + 9 * gi;
+                        const bool eq = KG_LV(lse, l)[gi] != 0;
+                        const float Dl = q[8];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const float jr = q[k], jvk = q[4 + k];
+                            float x = jr + alpha * jvk;
+                            float dj = Dl * jvk;
+                            bool act0 = eq || jr < 0.f, act = eq || x < 0.f;
+                            if (act) { d1 += dj * x; d2 += dj * jvk; }
+                            if (act0) d0 += dj * jr;
                             nchg += (act != act0);
                         }
                     }
