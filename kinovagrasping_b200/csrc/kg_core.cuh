@@ -1226,8 +1226,10 @@ KG_DEV float kg_impedance(const KgModel &m, float r) {
     return m.dmin + y * (m.dmax - m.dmin);
 }
 // translational Jacobian row of the point p on the body carrying geom g, projected on f, ADDED with sign sg
-template <class WS> KG_NOINL void kg_jac_add(const WS &ws, int g, const float *p, const float *f, float sg, float *row) {
+// (f by value: a pointer into the caller's registers would put them on the stack)
+template <class WS> KG_NOINL void kg_jac_add(const WS &ws, int g, const float *p, float fx, float fy, float fz, float sg, float *row) {
     if (g == 0) return;
+    const float f[3] = {fx, fy, fz};
     if (g == 8) {
         float r[3], t[3];
         for (int c = 0; c < 3; c++) { row[9 + c] += sg * f[c]; r[c] = p[c] - ws.qpos[9 + c]; }
@@ -1286,13 +1288,15 @@ template <class WS> KG_DEV void kg_make_rows(const KgModel &m, WS &ws, int kg_la
             float n[3], t1[3], t2[3];
             kg_copy(n, ws.st_n[s]);
             kg_make_frame(n, t1, t2);
-            const float *f = k == 0 ? n : (k == 1 ? t1 : t2);
+            const float fx = k == 0 ? n[0] : (k == 1 ? t1[0] : t2[0]), fy = k == 0 ? n[1] : (k == 1 ? t1[1] : t2[1]), fz = k == 0 ? n[2] : (k == 1 ? t1[2] : t2[2]);
             float *row = ws.J + b * KG_JS;
             for (int j = 0; j < KG_NV; j++) row[j] = 0.f;
             const float *p = ws.st_pos[s];
-            kg_jac_add(ws, g2, p, f, 1.f, row); kg_jac_add(ws, g1, p, f, -1.f, row);
-            float v = 0.f;
-            for (int j = 0; j < KG_NV; j++) v += row[j] * ws.qvel[j];
+            kg_jac_add(ws, g2, p, fx, fy, fz, 1.f, row); kg_jac_add(ws, g1, p, fx, fy, fz, -1.f, row);
+            float v = 0.f, rr[16], qv[16];
+            kg_ld16(row, rr); kg_ld16(ws.qvel, qv);
+#pragma unroll
+            for (int j = 0; j < KG_NV; j++) v += rr[j] * qv[j];
             row[KG_JS - 1] = v;
         }
     }
@@ -1451,8 +1455,10 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
     KG_PHASE(l) {
         float cw = 0.f, cs = 0.f;
         if (l < KG_NV) {
-            float s = 0.f;
-            for (int j = 0; j < KG_NV; j++) s += ws.M[l * KG_MS + j] * (ws.qwarm[j] - ws.qas[j]);
+            float s = 0.f, mr[16], qw[16], qs[16];
+            kg_ld16(ws.M + l * KG_MS, mr); kg_ld16(ws.qwarm, qw); kg_ld16(ws.qas, qs);
+#pragma unroll
+            for (int j = 0; j < KG_NV; j++) s += mr[j] * (qw[j] - qs[j]);
             ws.Mdq[l] = s;
             cw = 0.5f * s * (ws.qwarm[l] - ws.qas[l]);
         }
