@@ -1488,15 +1488,32 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
     // the same decisions without a broadcast through shared memory
     float prev_cost = 3.0e38f;
     int done = 0, n_iter = 0;
+    // per lane, for the group(s) it owns: the residuals jar[4] of the rows at the current point (phase (a); rows the group
+    // does not have are zero), their slopes jv[4] along the Newton direction (line search), D (0 = no rows), equality flag
+    constexpr int NG = (9 + WS::MAXCON + 31) / 32;
+    KG_LANEVAR(float, lsq, NG * 9);
+    KG_LANEVAR(int, lse, NG);
     for (int iter = 0; iter <= KG_NEWTON_MAXIT; iter++) {
         // ---- (a) rows at the current point: cost and the weights w = D * jar of the active rows
         KG_PHASE(l) {
             float c = 0.f;
             if (l < KG_NV) c = 0.5f * ws.Mdq[l] * (ws.qacc[l] - ws.qas[l]);
-            for (int g = l; g < 9 + WS::MAXCON; g += 32) {
-                float jar[4], w[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
-                int n = kg_group_rows(ws, g, ws.bdot, jar);
-                for (int k = 0; k < n; k++) if (kg_gtype(ws, g) == 1 || jar[k] < 0.f) { a[k] = KG_GD(ws, g); w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
+#pragma unroll
+            for (int gi = 0; gi < NG; gi++) {
+                const int g = l + 32 * gi;
+                float jar[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
+                int n = 0;
+                if (g < 9 + WS::MAXCON) n = kg_group_rows(ws, g, ws.bdot, jar);
+                const bool eq = n && kg_gtype(ws, g) == 1;
+                const float Dg = n ? KG_GD(ws, g) : 0.f;
+                {
+                    float *q = KG_LV(lsq, l) + 9 * gi;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) q[k] = k < n ? jar[k] : 0.f;
+                    q[8] = Dg;
+                    KG_LV(lse, l)[gi] = eq;
+                }
+                for (int k = 0; k < n; k++) if (eq || jar[k] < 0.f) { a[k] = Dg; w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
                 if (n == 1) { ws.bw[g] = w[0]; KG_GAREF(ws, g, 1) = a[0]; }
                 else if (n == 4) {
                     int b = 9 + 3 * (g - 9);
@@ -1631,30 +1648,24 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
         {
             float alpha = 1.f, lo = 0.f, hi = -1.f, g0abs = 0.f, best_alpha = 1.f;
             int exact = 0;
-            // what a lane's rows contribute does not change between the trial steps: residuals at the current point (jar),
-            // their slopes along dir (jv), D and the equality flag are taken once and kept per lane; rows a group does not
-            // have are zero-filled (they add exact zeros)
-            constexpr int NG = (9 + WS::MAXCON + 31) / 32;
-            KG_LANEVAR(float, lsq, NG * 9);
-            KG_LANEVAR(int, lse, NG);
+            // what a lane's rows contribute does not change between the trial steps: the residuals at the current point are
+            // phase (a)'s, their slopes along dir (jv) are taken once here; rows a group does not have add exact zeros
             KG_PHASE(l) {
 #pragma unroll
                 for (int gi = 0; gi < NG; gi++) {
                     const int g = l + 32 * gi;
-                    float jar[4] = {0.f, 0.f, 0.f, 0.f}, jv[4] = {0.f, 0.f, 0.f, 0.f};
-                    int n = 0;
-                    if (g < 9 + WS::MAXCON) n = kg_group_rows(ws, g, ws.bdot, jar);
-                    if (n == 1) jv[0] = ws.bdir[g];
-                    else if (n == 4) {
-                        int b = 9 + 3 * (g - 9);
-                        float mu = KG_GMU(ws, g), nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
-                        jv[0] = nn + t1; jv[1] = nn - t1; jv[2] = nn + t2; jv[3] = nn - t2;
-                    }
                     float *q = KG_LV(lsq, l) + 9 * gi;
+                    float jv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (q[8] != 0.f) {
+                        if (g < 9) jv[0] = ws.bdir[g];
+                        else {
+                            int b = 9 + 3 * (g - 9);
+                            float mu = KG_GMU(ws, g), nn = ws.bdir[b], t1 = mu * ws.bdir[b + 1], t2 = mu * ws.bdir[b + 2];
+                            jv[0] = nn + t1; jv[1] = nn - t1; jv[2] = nn + t2; jv[3] = nn - t2;
+                        }
+                    }
 #pragma unroll
-                    for (int k = 0; k < 4; k++) { q[k] = k < n ? jar[k] : 0.f; q[4 + k] = k < n ? jv[k] : 0.f; }
-                    q[8] = n ? KG_GD(ws, g) : 0.f;
-                    KG_LV(lse, l)[gi] = n && kg_gtype(ws, g) == 1;
+                    for (int k = 0; k < 4; k++) q[4 + k] = jv[k];
                 }
             }
             for (int ls = 0; ls < KG_LS_MAXIT; ls++) {

@@ -464,29 +464,42 @@ def test_launch_schedule_does_not_change_results(card):
 def test_split_and_full_workspace_modes_agree(card):
     """kg_set_mode: the light-workspace kernels with their heavy lane (mode 1) and the full-workspace kernels (mode 2) run
     the same arithmetic on the same carry records; they are separate template instantiations, so fp32 rounding may differ in
-    the last bit.  One RL step agrees to 1e-5 everywhere; a 10-step expert rollout into contact (cones and vases, where
-    single substeps exceed the light workspace's 8 contacts) still agrees for the bulk of the envs, and rewards match."""
+    the last bits, and contact dynamics amplifies that over a free rollout.  So the two are held together in LOCK STEP: every
+    RL step both start from mode 1's state (written into both, which also invalidates both collision caches) and take the
+    action mode 1's on-device expert chose; a 12-step expert rollout into contact on cones and vases, where single substeps
+    exceed the light workspace's 8 contacts.  Per (step, env) the 82 obs entries agree to 1e-4 for >= 98 % (median < 1e-5),
+    rewards and done flags are equal for >= 99.5 %."""
+    import torch
     from kinovagrasping_b200 import _lib
     lib = _lib.load()
     n = 700
     shape, euler, objp = _poses(card, n, 5, orient_idx=(2,), shapes=(0, 1, 6, 9, 10, 13))
-    runs = []
-    for mode in (1, 2):
-        h = Handle(n, lib=lib)
-        h.set_mode(mode)
-        h.reset_host(shape, euler, objp)
-        trace = []
-        for _ in range(10):
-            obs, rew, done = h.step_host(None, 2)
-            trace.append((obs.copy(), rew.copy(), done.copy()))
-        assert h.stats()["contact_overflow"] == 0
-        runs.append(trace)
-        h.close()
-    a, b = runs
-    assert np.abs(a[0][0] - b[0][0]).max() <= 3e-5
-    close = np.abs(a[-1][0] - b[-1][0]).max(axis=0) <= 1e-3          # per env, over the 82 obs entries
-    assert close.mean() >= 0.95, close.mean()
-    assert (a[-1][1] == b[-1][1]).mean() >= 0.99
+    A = Handle(n, lib=lib); A.set_mode(1)
+    B = Handle(n, lib=lib); B.set_mode(2)
+    A.reset_host(shape, euler, objp); B.reset_host(shape, euler, objp)
+    dev = "cuda"
+    oA = torch.zeros((82, n), device=dev); oB = torch.zeros((82, n), device=dev)
+    rA = torch.zeros(n, device=dev); rB = torch.zeros(n, device=dev)
+    dA = torch.zeros(n, dtype=torch.int32, device=dev); dB = torch.zeros(n, dtype=torch.int32, device=dev)
+    act = torch.zeros((4, n), device=dev)
+    diffs = []; same = []
+    for t in range(12):
+        qp, qv = A.get_state_host()
+        A.set_state_host(qp, qv); B.set_state_host(qp, qv)
+        A.step(0, 2, oA.data_ptr(), rA.data_ptr(), dA.data_ptr(), act.data_ptr()); A.sync()
+        B.step(act.data_ptr(), 0, oB.data_ptr(), rB.data_ptr(), dB.data_ptr()); B.sync()
+        diffs.append((oA - oB).abs().max(dim=0).values.cpu().numpy())
+        same.append(float(((rA == rB) & (dA == dB)).float().mean()))
+    sa, sb = A.stats(), B.stats()
+    assert sa["contact_overflow"] == 0 and sb["contact_overflow"] == 0
+    assert sa["contacts"] / sa["substeps"] > 2.0                        # the rollout really is in contact
+    diffs = np.stack(diffs)
+    print(f"split vs full workspace, lock step: obs diff median {np.median(diffs):.2e}, within 1e-4: {(diffs <= 1e-4).mean():.4f}, "
+          f"within 1e-3: {(diffs <= 1e-3).mean():.4f}, max {diffs.max():.2e}; reward/done equal: min over steps {min(same):.4f}")
+    assert diffs[0].max() <= 3e-5
+    assert np.median(diffs) < 1e-5 and (diffs <= 1e-4).mean() >= 0.98, (np.median(diffs), (diffs <= 1e-4).mean())
+    assert min(same) >= 0.995, same
+    A.close(); B.close()
 
 
 @pytest.mark.gpu
