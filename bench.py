@@ -341,7 +341,7 @@ def run_ours(args):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
-    groups = 4 if n >= 2048 else (2 if n >= 512 else 1)          # kg_set_pipeline default
+    groups = 2 if n >= 32768 else (4 if n >= 2048 else (2 if n >= 512 else 1))          # kg_set_pipeline default
 
     # ---- extra workloads for the record (rank 0, single GPU only): the other pose-table variant and the 32768-env batch
     extra = {}

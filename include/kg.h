@@ -119,7 +119,7 @@ int kg_set_schedule(kg_handle h, int mode);
 int kg_set_mode(kg_handle h, int mode);
 /* Pipelining of kg_step (no effect on results): the batch is cut into `groups` (1..32) contiguous env groups whose kernel
  * chains run on separate internal streams, forked from and joined into the handle's stream, so one group's narrowphase
- * kernel overlaps another group's per-env kernel.  Default: 4 from 2048 envs, 2 from 512 envs, else 1. */
+ * kernel overlaps another group's per-env kernel.  Default: 2 from 32768 envs, 4 from 2048 envs, 2 from 512 envs, else 1. */
 int kg_set_pipeline(kg_handle h, int groups);
 /* Launch path of kg_step (no effect on results): 1 (default) = the kernel chain of a step is captured once per distinct
  * argument set into a CUDA graph and replayed with one launch call; 0 = every kernel launched individually. */

@@ -911,7 +911,8 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->gray0[g], cudaEventDisableTiming));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->gray1[g], cudaEventDisableTiming));
     }
-    h->ngroups = n_envs >= 2048 ? 4 : (n_envs >= 512 ? 2 : 1);
+    // pipelined env groups (kg_set_pipeline overrides): measured optimum 4 at 4096 envs, 2 once every group's launch is several waves
+    h->ngroups = n_envs >= 32768 ? 2 : (n_envs >= 2048 ? 4 : (n_envs >= 512 ? 2 : 1));
 #endif
     const size_t N = (size_t)n_envs;
     KgEnvArrays &A = h->A;
