@@ -523,19 +523,27 @@ def test_heavy_lane_claims_each_substep_once_large_grid(card):
         h.set_mode(mode); h.set_schedule(0)
         obs = torch.zeros((82, n), device="cuda"); rew = torch.zeros(n, device="cuda"); done = torch.zeros(n, dtype=torch.int32, device="cuda")
         h.reset_sampled(0, shape.data_ptr(), 2, 0, 0, 77, obs.data_ptr())
-        for _ in range(steps):
+        first = None
+        for t in range(steps):
             h.step(0, 2, obs.data_ptr(), rew.data_ptr(), done.data_ptr())
+            if t == 0:
+                h.sync(); first = obs.cpu().numpy().copy()
         h.sync()
         st = h.stats()
         assert st["substeps"] == n * 15 * steps, st
-        runs.append((obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy()) + tuple(h.get_state_host()) + (st,))
+        runs.append((obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy()) + tuple(h.get_state_host()) + (st, first))
         h.close()
     a, b, c = runs
     for x, y in zip(a[:5], b[:5]):
         assert np.array_equal(x, y)
-    assert a[5] == b[5]
+    assert a[5] == b[5] and np.array_equal(a[6], b[6])
+    # (c): after ONE RL step the two instantiations differ by rounding only; after 8 free steps contact dynamics has amplified
+    # that in some envs (test_split_and_full_workspace_modes_agree holds the two together step by step instead)
+    d1 = np.abs(a[6] - c[6]).max(axis=0)
     close = np.abs(a[0] - c[0]).max(axis=0) <= 1e-3
-    assert close.mean() >= 0.95, close.mean()
+    print(f"split vs full, 32768 envs: after 1 step within 1e-4: {(d1 <= 1e-4).mean():.4f} (median {np.median(d1):.1e}); after {steps} free steps within 1e-3: {close.mean():.4f}; rewards equal {(a[1] == c[1]).mean():.4f}")
+    assert (d1 <= 1e-4).mean() >= 0.99, (d1 <= 1e-4).mean()
+    assert close.mean() >= 0.85, close.mean()
     assert (a[1] == c[1]).mean() >= 0.99
 
 
