@@ -1452,6 +1452,13 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
     kg_minv(ws, 0.f, ws.fs, ws.qas, kg_lane);
     // ---- warm start: the cheaper of qacc_warmstart and qacc_smooth
     kg_base_dots2(ws, ws.qwarm, ws.bdot, ws.qas, ws.bdir, kg_lane);
+    // per lane, for the group(s) it owns: the residuals jar[4] of the rows at the current point (rows the group does not have
+    // are zero), their slopes jv[4] along the Newton direction (line search), D (0 = no rows), equality flag; lss = the
+    // residuals at qacc_smooth until the start point is chosen
+    constexpr int NG = (9 + WS::MAXCON + 31) / 32;
+    KG_LANEVAR(float, lsq, NG * 9);
+    KG_LANEVAR(float, lss, NG * 4);
+    KG_LANEVAR(int, lse, NG);
     KG_PHASE(l) {
         float cw = 0.f, cs = 0.f;
         if (l < KG_NV) {
@@ -1462,12 +1469,21 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             ws.Mdq[l] = s;
             cw = 0.5f * s * (ws.qwarm[l] - ws.qas[l]);
         }
-        for (int g = l; g < 9 + WS::MAXCON; g += 32) {
-            float jar[4];
-            int n = kg_group_rows(ws, g, ws.bdot, jar);
-            for (int k = 0; k < n; k++) if (kg_gtype(ws, g) == 1 || jar[k] < 0.f) cw += 0.5f * KG_GD(ws, g) * jar[k] * jar[k];
-            n = kg_group_rows(ws, g, ws.bdir, jar);
-            for (int k = 0; k < n; k++) if (kg_gtype(ws, g) == 1 || jar[k] < 0.f) cs += 0.5f * KG_GD(ws, g) * jar[k] * jar[k];
+#pragma unroll
+        for (int gi = 0; gi < NG; gi++) {
+            const int g = l + 32 * gi;
+            float jw[4] = {0, 0, 0, 0}, js[4] = {0, 0, 0, 0};
+            int n = 0;
+            if (g < 9 + WS::MAXCON) { n = kg_group_rows(ws, g, ws.bdot, jw); kg_group_rows(ws, g, ws.bdir, js); }
+            const bool eq = n && kg_gtype(ws, g) == 1;
+            const float Dg = n ? KG_GD(ws, g) : 0.f;
+            for (int k = 0; k < n; k++) if (eq || jw[k] < 0.f) cw += 0.5f * Dg * jw[k] * jw[k];
+            for (int k = 0; k < n; k++) if (eq || js[k] < 0.f) cs += 0.5f * Dg * js[k] * js[k];
+            float *q = KG_LV(lsq, l) + 9 * gi, *qs = KG_LV(lss, l) + 4 * gi;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { q[k] = k < n ? jw[k] : 0.f; qs[k] = k < n ? js[k] : 0.f; }
+            q[8] = Dg;
+            KG_LV(lse, l)[gi] = eq;
         }
         ws.red[l] = cw; ws.red2[l] = cs;
     }
@@ -1479,7 +1495,12 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             ws.qacc[l] = use_smooth ? ws.qas[l] : ws.qwarm[l];
             if (use_smooth) ws.Mdq[l] = 0.f;
         }
-        if (use_smooth) { int nb = kg_nbase(ws); for (int b = l; b < nb; b += 32) ws.bdot[b] = ws.bdir[b]; }
+        if (use_smooth) {
+            int nb = kg_nbase(ws);
+            for (int b = l; b < nb; b += 32) ws.bdot[b] = ws.bdir[b];
+#pragma unroll
+            for (int k = 0; k < 4 * NG; k++) KG_LV(lsq, l)[9 * (k / 4) + (k & 3)] = KG_LV(lss, l)[k];
+        }
     }
     KG_SYNC();
     const float scale = m.shape[ws.shape].scale;
@@ -1488,11 +1509,6 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
     // the same decisions without a broadcast through shared memory
     float prev_cost = 3.0e38f;
     int done = 0, n_iter = 0;
-    // per lane, for the group(s) it owns: the residuals jar[4] of the rows at the current point (phase (a); rows the group
-    // does not have are zero), their slopes jv[4] along the Newton direction (line search), D (0 = no rows), equality flag
-    constexpr int NG = (9 + WS::MAXCON + 31) / 32;
-    KG_LANEVAR(float, lsq, NG * 9);
-    KG_LANEVAR(int, lse, NG);
     for (int iter = 0; iter <= KG_NEWTON_MAXIT; iter++) {
         // ---- (a) rows at the current point: cost and the weights w = D * jar of the active rows
         KG_PHASE(l) {
@@ -1501,19 +1517,21 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
 #pragma unroll
             for (int gi = 0; gi < NG; gi++) {
                 const int g = l + 32 * gi;
-                float jar[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
-                int n = 0;
-                if (g < 9 + WS::MAXCON) n = kg_group_rows(ws, g, ws.bdot, jar);
-                const bool eq = n && kg_gtype(ws, g) == 1;
-                const float Dg = n ? KG_GD(ws, g) : 0.f;
-                {
-                    float *q = KG_LV(lsq, l) + 9 * gi;
+                float jar[4], w[4] = {0, 0, 0, 0}, a[4] = {0, 0, 0, 0};
+                float *q = KG_LV(lsq, l) + 9 * gi;
+                const float Dg = q[8];                                  // (D and the equality flag do not change during the solve)
+                const bool eq = KG_LV(lse, l)[gi] != 0;
+                const int n = Dg != 0.f ? (g < 9 ? 1 : 4) : 0;
+                if (iter > 0 && n) {                                    // (iteration 0 starts from the warm-start evaluation above)
+                    float jn[4] = {0, 0, 0, 0};
+                    kg_group_rows(ws, g, ws.bdot, jn);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) q[k] = k < n ? jar[k] : 0.f;
-                    q[8] = Dg;
-                    KG_LV(lse, l)[gi] = eq;
+                    for (int k = 0; k < 4; k++) q[k] = k < n ? jn[k] : 0.f;
                 }
-                for (int k = 0; k < n; k++) if (eq || jar[k] < 0.f) { a[k] = Dg; w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) jar[k] = q[k];
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (k < n && (eq || jar[k] < 0.f)) { a[k] = Dg; w[k] = a[k] * jar[k]; c += 0.5f * w[k] * jar[k]; }
                 if (n == 1) { ws.bw[g] = w[0]; KG_GAREF(ws, g, 1) = a[0]; }
                 else if (n == 4) {
                     int b = 9 + 3 * (g - 9);
