@@ -1383,7 +1383,7 @@ KG_DEV void kg_inv3_sym(const float *S, float *Si) {   // inverse of a symmetric
     Si[1] = (S[0] * S[2] - S[4] * S[4]) * id; Si[5] = (S[3] * S[4] - S[0] * S[5]) * id;
     Si[2] = (S[0] * S[1] - S[3] * S[3]) * id;
 }
-template <class WS> KG_NOINL void kg_minv(WS &ws, float diag_add, const float *x, float *y, int kg_lane) {
+template <class WS> KG_NOINL void kg_minv(const KgModel &m, WS &ws, float diag_add, const float *x, float *y, int kg_lane) {
     KG_PHASE(l) {
         if (l < 3) {
             int h1 = 3 + 2 * l, h2 = 4 + 2 * l;
@@ -1407,17 +1407,13 @@ template <class WS> KG_NOINL void kg_minv(WS &ws, float diag_add, const float *x
         } else if (l == 3) {
             // object: x_t = (f_t - T x_r)/m',  (Io' - T^T T / m') x_r = f_r - T^T f_t / m'
             float mp = ws.M[9 * KG_MS + 9] + diag_add, im = 1.0f / mp;
-            float T[9], S[6], rhs[3];
+            // the Schur complement Io' - T^T T / m' does not depend on the pose (T = -m R [c]x, R^T R = I): its inverse is a
+            // per-shape constant of the model card, one for each of the two diagonal shifts this function is called with
+            float T[9], rhs[3];
             for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) T[3 * j + i] = ws.M[(9 + j) * KG_MS + 12 + i];
-            const int ii[6] = {0, 1, 2, 0, 0, 1}, jj[6] = {0, 1, 2, 1, 2, 2};
-            for (int e = 0; e < 6; e++) {
-                float tt = T[ii[e]] * T[jj[e]] + T[3 + ii[e]] * T[3 + jj[e]] + T[6 + ii[e]] * T[6 + jj[e]];
-                S[e] = ws.M[(12 + ii[e]) * KG_MS + 12 + jj[e]] + (ii[e] == jj[e] ? diag_add : 0.f) - tt * im;
-            }
             float ft[3] = {x[9], x[10], x[11]};
             for (int i = 0; i < 3; i++) rhs[i] = x[12 + i] - (T[i] * ft[0] + T[3 + i] * ft[1] + T[6 + i] * ft[2]) * im;
-            float Si[6];
-            kg_inv3_sym(S, Si);
+            const float *Si = m.shape[ws.shape].Sinv[diag_add != 0.f ? 1 : 0];
             float xr[3] = {Si[0] * rhs[0] + Si[3] * rhs[1] + Si[4] * rhs[2], Si[3] * rhs[0] + Si[1] * rhs[1] + Si[5] * rhs[2],
                            Si[4] * rhs[0] + Si[5] * rhs[1] + Si[2] * rhs[2]};
             for (int j = 0; j < 3; j++) y[9 + j] = (ft[j] - (T[3 * j] * xr[0] + T[3 * j + 1] * xr[1] + T[3 * j + 2] * xr[2])) * im;
@@ -1449,7 +1445,7 @@ template <class WS> KG_NOINL void kg_minv(WS &ws, float diag_add, const float *x
 template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) {
     const float tol = 1e-8f;
     // ---- unconstrained acceleration
-    kg_minv(ws, 0.f, ws.fs, ws.qas, kg_lane);
+    kg_minv(m, ws, 0.f, ws.fs, ws.qas, kg_lane);
     // ---- warm start: the cheaper of qacc_warmstart and qacc_smooth
     kg_base_dots2(ws, ws.qwarm, ws.bdot, ws.qas, ws.bdir, kg_lane);
     // per lane, for the group(s) it owns: the residuals jar[4] of the rows at the current point (rows the group does not have
@@ -1777,7 +1773,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
 // ------------------------------------------------------------------------------------------------ P9 Euler
 template <class WS> KG_DEV void kg_euler(const KgModel &m, WS &ws, int kg_lane) {
     const float h = m.timestep;
-    kg_minv(ws, h * m.damping, ws.ftot, ws.Md, kg_lane);     // implicit joint damping: (M + h B) a = f   (Md: free after the solve)
+    kg_minv(m, ws, h * m.damping, ws.ftot, ws.Md, kg_lane);     // implicit joint damping: (M + h B) a = f   (Md: free after the solve)
     KG_PHASE(l) {
         if (l < KG_NV) {
             float v = ws.qvel[l] + h * ws.Md[l];

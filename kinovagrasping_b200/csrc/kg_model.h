@@ -27,6 +27,8 @@ struct KgShape {
     float Io[6];          // inertia about the body origin, body frame (+ nothing else)
     float invw_tran;      // body_invweight0 (translational)
     float scale;          // 1 / (meaninertia * nv): Newton tolerance scaling
+    float Sinv[2][6];     // inverse Schur complement of the object's 6x6 mass block (rotational part after eliminating the
+                          // translation): CONSTANT in the body frame, [0] for M, [1] for M + timestep * damping (kg_minv)
 };
 
 struct KgModel {
@@ -170,6 +172,18 @@ inline std::string kg_load_model(const void *blob_, size_t nbytes, KgModel *m, K
         double t = tr + 3 * (opt[5] + opt[4]);
         for (int i = 0; i < 3; i++) t += Io[4 * i] + opt[4];
         sh.scale = (float)(1.0 / (t / 15.0 * 15.0));
+        // object block of M (+ d I): [mp I, T; T^T, Io + (arm + d) I] with T = -m R [c]x, so T^T T = m^2 (|c|^2 I - c c^T) whatever R is
+        for (int which = 0; which < 2; which++) {
+            const double d = which ? opt[0] * opt[3] : 0.0, mp = opt[5] + opt[4] + d;
+            double S[9], Si[9];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
+                S[3 * i + j] = Io[3 * i + j] + (i == j ? opt[4] + d : 0.0) - opt[5] * opt[5] / mp * ((i == j ? cc : 0) - c[i] * c[j]);
+            const double det = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+            Si[0] = (S[4] * S[8] - S[5] * S[7]) / det; Si[1] = (S[2] * S[7] - S[1] * S[8]) / det; Si[2] = (S[1] * S[5] - S[2] * S[4]) / det;
+            Si[4] = (S[0] * S[8] - S[2] * S[6]) / det; Si[5] = (S[2] * S[3] - S[0] * S[5]) / det; Si[8] = (S[0] * S[4] - S[1] * S[3]) / det;
+            Si[3] = Si[1]; Si[6] = Si[2]; Si[7] = Si[5];
+            for (int i = 0; i < 6; i++) sh.Sinv[which][i] = (float)Si[ix[i]];
+        }
         // _get_obj_size (ENV:706-746), single-geom object
         double sz[3] = {c[8], c[9], c[10]};
         if (sz[2] == 0) { sz[2] = sz[1]; sz[1] = sz[0]; }
