@@ -36,6 +36,13 @@
 // a per-lane variable that lives across phases: a register array on the GPU, one slot per lane in the host emulation
 #define KG_LANEVAR(type, name, n) type name[n]
 #define KG_LV(name, l) name
+// a per-lane partial and its warp total: registers and shuffles on the GPU (no trip through shared memory, no warp sync
+// between writing and summing), one slot per lane in the host emulation; same butterfly order as kg_total
+#define KG_PARTIAL(name) float name = 0.f
+#define KG_PARTIAL_I(name) int name = 0
+#define KG_PUT(name, l, v) name = (v)
+#define KG_SUM(name, l) kg_total_reg(name)
+#define KG_SUM_I(name, l) __reduce_add_sync(0xffffffffu, name)
 #define KG_LDG4(p) __ldg((const float4 *)(p))
 #define KG_LDGU4(p) __ldg((const uint4 *)(p))
 #define KG_F2U(x) __float_as_uint(x)
@@ -60,6 +67,11 @@ static int kg_emu_lane_order = 0;
 #define KG_SYNC() ((void)0)
 #define KG_LANEVAR(type, name, n) type name[32][n]
 #define KG_LV(name, l) name[l]
+#define KG_PARTIAL(name) float name[32]
+#define KG_PARTIAL_I(name) int name[32]
+#define KG_PUT(name, l, v) name[l] = (v)
+#define KG_SUM(name, l) kg_total(name, l)
+#define KG_SUM_I(name, l) kg_total_int(name, l)
 struct kg_float4 { float x, y, z, w; };
 struct kg_uint4 { unsigned x, y, z, w; };
 #define KG_LDG4(p) (*(const kg_float4 *)(p))
@@ -344,6 +356,14 @@ KG_DEV void kg_prefix_int(const int *v, int l, int &off, int &total) {
 #endif
 }
 
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float kg_total_reg(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+#endif
 // warp total of ws.red[] (every lane wrote its partial in the previous phase)
 KG_DEV float kg_total(const float *red, int l) {
 #if defined(__CUDA_ARCH__)
@@ -1455,6 +1475,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
     KG_LANEVAR(float, lsq, NG * 9);
     KG_LANEVAR(float, lss, NG * 4);
     KG_LANEVAR(int, lse, NG);
+    KG_PARTIAL(pcw); KG_PARTIAL(pcs);
     KG_PHASE(l) {
         float cw = 0.f, cs = 0.f;
         if (l < KG_NV) {
@@ -1481,11 +1502,11 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             q[8] = Dg;
             KG_LV(lse, l)[gi] = eq;
         }
-        ws.red[l] = cw; ws.red2[l] = cs;
+        KG_PUT(pcw, l, cw); KG_PUT(pcs, l, cs);
     }
-    KG_SYNC();
+    KG_SYNC();                                                  // (Mdq written above is read below by other lanes? no: own lane; kept for bdot/bdir)
     KG_PHASE(l) {
-        float cw = kg_total(ws.red, l), cs = kg_total(ws.red2, l);
+        float cw = KG_SUM(pcw, l), cs = KG_SUM(pcs, l);
         bool use_smooth = cs < cw;
         if (l < KG_NV) {
             ws.qacc[l] = use_smooth ? ws.qas[l] : ws.qwarm[l];
@@ -1507,6 +1528,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
     int done = 0, n_iter = 0;
     for (int iter = 0; iter <= KG_NEWTON_MAXIT; iter++) {
         // ---- (a) rows at the current point: cost and the weights w = D * jar of the active rows
+        KG_PARTIAL(pc);
         KG_PHASE(l) {
             float c = 0.f;
             if (l < KG_NV) c = 0.5f * ws.Mdq[l] * (ws.qacc[l] - ws.qas[l]);
@@ -1539,12 +1561,12 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                     KG_GH(ws, g, 3) = mu * (a[2] - a[3]); KG_GH(ws, g, 4) = mu * mu * (a[2] + a[3]);
                 } else if (g < 9) ws.bw[g] = 0.f;
             }
-            ws.red[l] = c;
+            KG_PUT(pc, l, c);
         }
-        KG_SYNC();
+        KG_SYNC();                                              // (bw and the groups' coefficients go to phase (b))
         {
             float cost = 0.f;
-            KG_PHASE(l) { cost = kg_total(ws.red, l); }
+            KG_PHASE(l) { cost = KG_SUM(pc, l); }
             // MuJoCo's test is scale*improvement < 1e-8; in fp32 the cost itself only carries ~2^-23 relative
             // precision, so an "improvement" below that noise floor is treated as converged as well.
             const float improvement = scale * (prev_cost - cost);
@@ -1557,6 +1579,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
         // ---- (b) gradient and Hessian.  Two lanes per row of H: lane r owns the columns 0..7 of row r, lane 16 + r the
         // columns 8..14 (each entry accumulates over the groups in the same order whoever owns it); lane r also forms
         // the gradient entry.  The groups' coefficients come from phase (a).
+        KG_PARTIAL(pgs); KG_PARTIAL(pga);
         KG_PHASE(l) {
             float gsq = 0.f, gab = 0.f;
             const int r = l & 15, j0 = (l >> 4) * 8;
@@ -1606,13 +1629,13 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                 else { gab = 0.f; h[7] = 0.f; }           // (column 15 is padding; the gradient is lane r's)
                 kg_st8(ws.L + r * KG_MS + j0, h);
             }
-            ws.red[l] = gsq; ws.red2[l] = gab * gab;
+            KG_PUT(pgs, l, gsq); KG_PUT(pga, l, gab * gab);
         }
-        KG_SYNC();
+        KG_SYNC();                                              // (grad, L)
         {
             float gn = 0.f, ga = 0.f;
             KG_PHASE(l) {
-                gn = kg_total(ws.red, l); ga = kg_total(ws.red2, l);
+                gn = KG_SUM(pgs, l); ga = KG_SUM(pga, l);
                 if (l < KG_NV) ws.dir[l] = -ws.grad[l];
             }
             // gradient test: MuJoCo's absolute 1e-8, or the fp32 rounding floor of the sum that formed the gradient
@@ -1625,6 +1648,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
         KG_PROBE(10);
         // ---- (c) directional products
         // (one phase: base-row products J_b . dir by a lane per base row, M dir by a lane per dof)
+        KG_PARTIAL(pp1); KG_PARTIAL(pp2);
         KG_PHASE(l) {
             float xv[16];
             kg_ld16(ws.dir, xv);
@@ -1648,13 +1672,13 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                 const float dl = ws.dir[l];
                 p1 = ws.Mdq[l] * dl; p2 = s * dl;
             }
-            ws.red[l] = p1; ws.red2[l] = p2;
+            KG_PUT(pp1, l, p1); KG_PUT(pp2, l, p2);
         }
-        KG_SYNC();
+        KG_SYNC();                                              // (bdir, Md)
         // warp totals are carried in registers: every lane of kg_total's result holds the same value (in the host emulation
         // the phase body runs once per lane and assigns the same value each time)
         float gp1 = 0.f, gp2 = 0.f;                         // Gauss part of phi'(0), phi''
-        KG_PHASE(l) { gp1 = kg_total(ws.red, l); gp2 = kg_total(ws.red2, l); }
+        KG_PHASE(l) { gp1 = KG_SUM(pp1, l); gp2 = KG_SUM(pp2, l); }
         KG_PROBE(11);
         // ---- (d) exact line search: root of the piecewise-linear phi'(alpha).  dir is the exact Newton direction of
         // the current quadratic piece, so the first candidate is alpha = 1; if no row changes activity on [0,1] that is
@@ -1684,6 +1708,7 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
             }
             for (int ls = 0; ls < KG_LS_MAXIT; ls++) {
                 if (kg_lane == 0) KG_COUNT(27, 1);
+                KG_PARTIAL(pd1); KG_PARTIAL(pd2); KG_PARTIAL(pd0); KG_PARTIAL_I(pch);
                 KG_PHASE(l) {
                     float d1 = 0.f, d2 = 0.f, d0 = 0.f;
                     int nchg = 0;
@@ -1703,17 +1728,14 @@ template <class WS> KG_DEV void kg_solve(const KgModel &m, WS &ws, int kg_lane) 
                             nchg += (act != act0);
                         }
                     }
-                    ws.red[l] = d1; ws.red2[l] = d2;
-                    if (ls == 0) { ws.cnt[l] = nchg; ws.mv_red3[l] = d0; }
+                    KG_PUT(pd1, l, d1); KG_PUT(pd2, l, d2); KG_PUT(pd0, l, d0); KG_PUT(pch, l, nchg);
                 }
-                KG_SYNC();
                 float t_lo = 0.f, t_hi = 0.f, t_d0 = 0.f;
                 int t_chg = 0;
                 KG_PHASE(l) {
-                    t_lo = kg_total(ws.red, l); t_hi = kg_total(ws.red2, l);
-                    if (ls == 0) { t_d0 = kg_total(ws.mv_red3, l); t_chg = kg_total_int(ws.cnt, l); }
+                    t_lo = KG_SUM(pd1, l); t_hi = KG_SUM(pd2, l);
+                    if (ls == 0) { t_d0 = KG_SUM(pd0, l); t_chg = KG_SUM_I(pch, l); }
                 }
-                KG_SYNC();                                        // (red / cnt are rewritten by the next pass)
                 float gA = gp1 + alpha * gp2 + t_lo, hA = gp2 + t_hi;
                 if (ls == 0) {
                     g0abs = fabsf(gp1 + t_d0);                    // |phi'(0)|
