@@ -407,29 +407,31 @@ template <class WS> KG_DEV void kg_kinematics(const KgModel &m, WS &ws, int kg_l
     KG_PHASE(l) {
         float hp[3];
         for (int c = 0; c < 3; c++) hp[c] = m.l7_pos[c] + ws.sax[0][c] * ws.qpos[0] + ws.sax[1][c] * ws.qpos[1] + ws.sax[2][c] * ws.qpos[2];
-        if (l < 3) {
-            const float *Bk = ws.B[l];
-            float q1 = ws.qpos[3 + 2 * l], q2 = ws.qpos[4 + 2 * l];
+        if (l < 6) {
+            // one lane per finger LINK (0..2 proximal, 3..5 distal of finger k), the same instruction stream for both kinds:
+            // R = the link's rotation (R1 or R2), P = its joint position (p1 or p2)
+            const int k = l < 3 ? l : l - 3;
+            const bool distal = l >= 3;
+            const float *Bk = ws.B[k];
+            float q1 = ws.qpos[3 + 2 * k], q2 = ws.qpos[4 + 2 * k];
             float s1, c1, s2, c2;
             sincosf(q1, &s1, &c1);
-            sincosf(q1 + q2, &s2, &c2);
-            float R1[9], R2[9];
+            sincosf(distal ? q1 + q2 : q1, &s2, &c2);
+            float R1[9], R[9];
             for (int r = 0; r < 3; r++) {
                 float b0 = Bk[3 * r], b1 = Bk[3 * r + 1], b2 = Bk[3 * r + 2];
                 R1[3 * r] = c1 * b0 + s1 * b1; R1[3 * r + 1] = -s1 * b0 + c1 * b1; R1[3 * r + 2] = b2;
-                R2[3 * r] = c2 * b0 + s2 * b1; R2[3 * r + 1] = -s2 * b0 + c2 * b1; R2[3 * r + 2] = b2;
+                R[3 * r] = c2 * b0 + s2 * b1; R[3 * r + 1] = -s2 * b0 + c2 * b1; R[3 * r + 2] = b2;
             }
             float t[3], p1[3], p2[3];
-            kg_add(p1, hp, ws.fo[l]);
+            kg_add(p1, hp, ws.fo[k]);
             kg_mulmv(t, R1, m.tip_pos); kg_add(p2, p1, t);
-            kg_copy(ws.p1[l], p1); kg_copy(ws.p2[l], p2);
-            kg_mulmv(t, R1, m.link_com); kg_add(ws.c1[l], p1, t);
-            kg_mulmv(t, R2, m.link_com); kg_add(ws.c2[l], p2, t);
-            kg_mulmv(t, R1, m.prox_gpos); kg_add(ws.gpos[2 + 2 * l], p1, t);
-            kg_mulmv(t, R2, m.dist_gpos); kg_add(ws.gpos[3 + 2 * l], p2, t);
-            kg_mulmm(ws.gmat[2 + 2 * l], R1, m.prox_gR);
-            kg_mulmm(ws.gmat[3 + 2 * l], R2, m.dist_gR);
-        } else if (l == 3) {
+            if (!distal) { kg_copy(ws.p1[k], p1); kg_copy(ws.p2[k], p2); }
+            float Pv[3] = {distal ? p2[0] : p1[0], distal ? p2[1] : p1[1], distal ? p2[2] : p1[2]};
+            kg_mulmv(t, R, m.link_com); kg_add(distal ? ws.c2[k] : ws.c1[k], Pv, t);
+            kg_mulmv(t, R, distal ? m.dist_gpos : m.prox_gpos); kg_add(ws.gpos[2 + 2 * k + (distal ? 1 : 0)], Pv, t);
+            kg_mulmm(ws.gmat[2 + 2 * k + (distal ? 1 : 0)], R, distal ? m.dist_gR : m.prox_gR);
+        } else if (l == 6) {
             float q[4] = {ws.qpos[12], ws.qpos[13], ws.qpos[14], ws.qpos[15]};
             float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
             float inv = 1.0f / n;
@@ -440,13 +442,14 @@ template <class WS> KG_DEV void kg_kinematics(const KgModel &m, WS &ws, int kg_l
             kg_mulmv(t, ws.oR, sh.gpos);
             for (int c = 0; c < 3; c++) ws.gpos[8][c] = ws.qpos[9 + c] + t[c];
             kg_mulmm(ws.gmat[8], ws.oR, sh.gR);
-        } else if (l == 4) {
+        } else if (l == 7) {
             float t[3];
             kg_mulmv(t, ws.Rh, m.palm_gpos);
             kg_add(ws.gpos[1], hp, t);
             kg_copy(ws.hp, hp);
-        } else if (l >= 5 && l < 14) {
-            ws.sens_q[l - 5] = (l - 5) < 3 ? ws.qpos[l - 5] : ((l - 5) < 6 ? ws.qpos[3 + 2 * (l - 8)] : ws.qpos[4 + 2 * (l - 11)]);
+        } else if (l >= 8 && l < 17) {
+            const int i = l - 8;
+            ws.sens_q[i] = i < 3 ? ws.qpos[i] : (i < 6 ? ws.qpos[3 + 2 * (i - 3)] : ws.qpos[4 + 2 * (i - 6)]);
         }
     }
     KG_SYNC();
