@@ -837,7 +837,7 @@ static int model_acquire(kg_handle h, int device, const void *blob, size_t nbyte
         if (ce == cudaSuccess) ce = cudaMalloc(&p_, b_ ? b_ : 4); \
         if (ce == cudaSuccess) { dm.allocs.push_back(p_); ce = cudaMemcpy(p_, (vec).data(), b_, cudaMemcpyHostToDevice); } \
         m.field = (decltype(m.field))p_; } while (0)
-    UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(adj8, t.adj8); UP(hull_pad, t.hull_pad); UP(hull_oct, t.hull_oct); UP(tri, t.tri);
+    UP(hull_vert, t.hull_vert); UP(adj_start, t.adj_start); UP(adj, t.adj); UP(adj8, t.adj8); UP(nbr8, t.nbr8); UP(hull_pad, t.hull_pad); UP(hull_oct, t.hull_oct); UP(tri, t.tri);
     UP(bvh_node, t.bvh_node); UP(pose_train, t.pose_train); UP(pose_test, t.pose_test);
 #undef UP
     if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(c_model, &m, sizeof(KgModel));
@@ -868,7 +868,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     std::string e = kg_load_model(blob, nbytes, &h->model, &t);
     if (!e.empty()) { h->err = "model card: " + e; return KG_EMODEL; }
     KgModel &m = h->model;
-    m.hull_vert = t.hull_vert.data(); m.adj_start = t.adj_start.data(); m.adj = t.adj.data(); m.adj8 = t.adj8.data(); m.hull_pad = t.hull_pad.data(); m.hull_oct = t.hull_oct.data(); m.tri = t.tri.data();
+    m.hull_vert = t.hull_vert.data(); m.adj_start = t.adj_start.data(); m.adj = t.adj.data(); m.adj8 = t.adj8.data(); m.nbr8 = t.nbr8.data(); m.hull_pad = t.hull_pad.data(); m.hull_oct = t.hull_oct.data(); m.tri = t.tri.data();
     m.bvh_node = t.bvh_node.data();
     m.pose_train = t.pose_train.data(); m.pose_test = t.pose_test.data();
     g_mw.fhull = m.hull_pad + 4 * (size_t)m.hpad0[1];     // host emulation: no staging copy

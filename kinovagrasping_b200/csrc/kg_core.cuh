@@ -622,6 +622,7 @@ template <class WS> KG_DEV void kg_support(const KgModel &m, const WS &ws, int g
     const KgMesh &mi = m.mesh[mesh];
     const float *vert = m.hull_vert + 4 * (size_t)mi.vert0;
     const unsigned short *adj8 = m.adj8;
+    const float *nbr8 = m.nbr8;
     const float *R = ws.gmat[g];
     float ld[3];
     kg_multmv(ld, R, dir);
@@ -631,8 +632,8 @@ template <class WS> KG_DEV void kg_support(const KgModel &m, const WS &ws, int g
     float bx = v.x, by = v.y, bz = v.z;
     unsigned info = KG_F2U(v.w);
     for (int guard = 0; guard < 1024; guard++) {
-        // one hill-climbing move: the 8 neighbours of a chunk are fetched with independent 128-bit loads, so a move costs
-        // two dependent memory latencies (ids, vertices) whatever the degree; ties keep the first neighbour in list order
+        // one hill-climbing move: the ids and the vertex records of a chunk's 8 neighbours are addressed from the chunk index
+        // alone (nbr8), so a move costs ONE memory latency whatever the degree; ties keep the first neighbour in list order
         const int ch0 = (int)(info & 0xffffffu), nch = (int)(info >> 24);
         int nxt = c;
         for (int k = 0; k < nch; k++) {
@@ -640,7 +641,7 @@ template <class WS> KG_DEV void kg_support(const KgModel &m, const WS &ws, int g
             const unsigned id[8] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16, q.z & 0xffffu, q.z >> 16, q.w & 0xffffu, q.w >> 16};
             decltype(v) w[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) w[i] = KG_LDG4(vert + 4 * id[i]);
+            for (int i = 0; i < 8; i++) w[i] = KG_LDG4(nbr8 + 4 * (8 * (size_t)(ch0 + k) + i));
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 float d = w[i].x * ld[0] + w[i].y * ld[1] + w[i].z * ld[2];

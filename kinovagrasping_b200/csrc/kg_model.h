@@ -58,6 +58,7 @@ struct KgModel {
     const float *hull_oct;
     int oct0[KG_NMESH][8], octn[KG_NMESH][8];
     const unsigned short *adj8;    // neighbour lists in 16-byte chunks of 8 mesh-local vertex ids, padded with the vertex itself
+    const float *nbr8;             // the same chunks with the neighbours' vertex records (xyzw as in hull_vert) inline: 128 bytes per chunk
     const int *adj_start;
     const unsigned short *adj;
     const float *tri;              // 9 floats per triangle, BVH leaf order
@@ -71,6 +72,7 @@ struct KgHostTables {
     std::vector<float> hull_vert, hull_pad, hull_oct, tri, bvh_node, pose_train, pose_test;
     std::vector<int> adj_start;
     std::vector<unsigned short> adj, adj8;
+    std::vector<float> nbr8;
 };
 
 namespace kgdetail {
@@ -231,6 +233,20 @@ inline std::string kg_load_model(const void *blob_, size_t nbytes, KgModel *m, K
             for (uint32_t i = 0; i < nch * 8; i++) t->adj8.push_back(a0 + (int)i < a1 ? t->adj[a0 + i] : (unsigned short)v);
             uint32_t info = first | (nch << 24);
             std::memcpy(&t->hull_vert[4 * (size_t)(mk.vert0 + v) + 3], &info, 4);
+        }
+    }
+    // ... and the neighbours' vertex records next to each other, so that a hill-climbing move is ONE dependent memory level
+    // (ids and vertices of a chunk are addressed from the chunk index alone)
+    for (int k = 0; k < KG_NMESH; k++) {
+        const KgMesh &mk = m->mesh[k];
+        for (int v = 0; v < mk.nvert; v++) {
+            uint32_t info; std::memcpy(&info, &t->hull_vert[4 * (size_t)(mk.vert0 + v) + 3], 4);
+            const uint32_t first = info & 0xffffffu, nch = info >> 24;
+            if (t->nbr8.size() < 32 * (size_t)(first + nch)) t->nbr8.resize(32 * (size_t)(first + nch));
+            for (uint32_t i = 0; i < nch * 8; i++) {
+                const int u = t->adj8[8 * (size_t)first + i];
+                for (int c = 0; c < 4; c++) t->nbr8[4 * (8 * (size_t)first + i) + c] = t->hull_vert[4 * (size_t)(mk.vert0 + u) + c];
+            }
         }
     }
     for (int k = 0; k < KG_NMESH; k++) {
