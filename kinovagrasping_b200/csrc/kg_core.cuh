@@ -633,15 +633,18 @@ template <class WS> KG_DEV void kg_support(const KgModel &m, const WS &ws, int g
     unsigned info = KG_F2U(v.w);
     for (int guard = 0; guard < 1024; guard++) {
         // one hill-climbing move: the ids and the vertex records of a chunk's 8 neighbours are addressed from the chunk index
-        // alone (nbr8), so a move costs ONE memory latency whatever the degree; ties keep the first neighbour in list order
-        const int ch0 = (int)(info & 0xffffffu), nch = (int)(info >> 24);
+        // alone, and the first chunk of a vertex from the vertex index alone -- so the evaluation of the warm-start vertex
+        // (its record and its neighbours load together) and every move cost ONE memory latency whatever the degree;
+        // ties keep the first neighbour in list order
+        const int ovf0 = (int)(info & 0xffffffu), novf = (int)(info >> 24);
         int nxt = c;
-        for (int k = 0; k < nch; k++) {
-            auto q = KG_LDGU4(adj8 + 8 * (size_t)(ch0 + k));
+        for (int k = 0; k <= novf; k++) {
+            const size_t ci = k == 0 ? (size_t)(mi.vert0 + c) : (size_t)(ovf0 + k - 1);
+            auto q = KG_LDGU4(adj8 + 8 * ci);
             const unsigned id[8] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16, q.z & 0xffffu, q.z >> 16, q.w & 0xffffu, q.w >> 16};
             decltype(v) w[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) w[i] = KG_LDG4(nbr8 + 4 * (8 * (size_t)(ch0 + k) + i));
+            for (int i = 0; i < 8; i++) w[i] = KG_LDG4(nbr8 + 4 * (8 * ci + i));
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 float d = w[i].x * ld[0] + w[i].y * ld[1] + w[i].z * ld[2];

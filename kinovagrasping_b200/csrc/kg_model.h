@@ -2,6 +2,7 @@
 // Replaces what mujoco_py.load_model_from_path + MjSim build on every reset
 // (kinova_gripper_env.py:878-879, 1002-1003) with one immutable table set per GPU.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -49,7 +50,7 @@ struct KgModel {
     KgShape shape[KG_NSHAPE];
     KgMesh mesh[KG_NMESH];
     // big read-only tables (device pointers on the GPU, host pointers in the emulation build)
-    const float *hull_vert;        // xyzw per vertex, 128-bit loads; w = bits of (first adj8 chunk | n chunks << 24)
+    const float *hull_vert;        // xyzw per vertex, 128-bit loads; w = bits of (first OVERFLOW chunk | n overflow chunks << 24); chunk 0 = the vertex's global index
     const float *hull_pad;         // the same vertices, every mesh padded to a multiple of 32 with copies of its vertex 0 (branch-free scans)
     int hpad0[KG_NMESH], hnpad[KG_NMESH];
     // per mesh and direction octant (bit c set = component c negative): the vertices that can be a support vertex for SOME
@@ -57,7 +58,7 @@ struct KgModel {
     // copies of the list's first entry.  Exact: the arg-max of a scan over the list equals the arg-max over the mesh.
     const float *hull_oct;
     int oct0[KG_NMESH][8], octn[KG_NMESH][8];
-    const unsigned short *adj8;    // neighbour lists in 16-byte chunks of 8 mesh-local vertex ids, padded with the vertex itself
+    const unsigned short *adj8;    // neighbour lists in 16-byte chunks of 8 mesh-local vertex ids, padded with the vertex itself; chunk gv = first chunk of vertex gv
     const float *nbr8;             // the same chunks with the neighbours' vertex records (xyzw as in hull_vert) inline: 128 bytes per chunk
     const int *adj_start;
     const unsigned short *adj;
@@ -224,28 +225,40 @@ inline std::string kg_load_model(const void *blob_, size_t nbytes, KgModel *m, K
     for (size_t i = 0; i < hv->count / 3; i++) for (int c = 0; c < 3; c++) t->hull_vert[4 * i + c] = (float)hvd[3 * i + c];
     ip = I("hull_adj_start", &n); KG_NEED(ip); t->adj_start.assign(ip, ip + n);
     ip = I("hull_adj", &n); KG_NEED(ip); t->adj.resize(n); for (size_t i = 0; i < n; i++) t->adj[i] = (unsigned short)ip[i];
-    // chunked neighbour lists: one 128-bit load brings 8 neighbour ids, whose vertices are then fetched in parallel
-    for (int k = 0; k < KG_NMESH; k++) {
-        const KgMesh &mk = m->mesh[k];
-        for (int v = 0; v < mk.nvert; v++) {
-            int a0 = t->adj_start[mk.vert0 + v], a1 = t->adj_start[mk.vert0 + v + 1];
-            uint32_t first = (uint32_t)(t->adj8.size() / 8), nch = (uint32_t)((a1 - a0 + 7) / 8);
-            for (uint32_t i = 0; i < nch * 8; i++) t->adj8.push_back(a0 + (int)i < a1 ? t->adj[a0 + i] : (unsigned short)v);
-            uint32_t info = first | (nch << 24);
-            std::memcpy(&t->hull_vert[4 * (size_t)(mk.vert0 + v) + 3], &info, 4);
+    // chunked neighbour lists: a chunk = 8 neighbour ids (adj8, 16 bytes) + their vertex records (nbr8, 128 bytes), padded
+    // with the vertex itself.  The FIRST chunk of vertex gv (global index) is chunk gv, so it is addressed from the vertex
+    // index alone and loads together with the vertex record; vertices with more than 8 neighbours continue in overflow
+    // chunks appended behind, referenced by hull_vert.w = bits of (first overflow chunk | n overflow chunks << 24).
+    {
+        size_t nvtot = 0;
+        for (int k = 0; k < KG_NMESH; k++) nvtot = std::max(nvtot, (size_t)(m->mesh[k].vert0 + m->mesh[k].nvert));
+        t->adj8.assign(8 * nvtot, 0);
+        for (int k = 0; k < KG_NMESH; k++) {
+            const KgMesh &mk = m->mesh[k];
+            for (int v = 0; v < mk.nvert; v++) {
+                const size_t gv = (size_t)mk.vert0 + v;
+                const int a0 = t->adj_start[gv], a1 = t->adj_start[gv + 1];
+                for (int i = 0; i < 8; i++) t->adj8[8 * gv + i] = a0 + i < a1 ? t->adj[a0 + i] : (unsigned short)v;
+                const uint32_t novf = a1 - a0 > 8 ? (uint32_t)((a1 - a0 - 8 + 7) / 8) : 0u, first = (uint32_t)(t->adj8.size() / 8);
+                for (uint32_t i = 0; i < novf * 8; i++) t->adj8.push_back(a0 + 8 + (int)i < a1 ? t->adj[a0 + 8 + i] : (unsigned short)v);
+                const uint32_t info = (novf ? first : 0u) | (novf << 24);
+                std::memcpy(&t->hull_vert[4 * gv + 3], &info, 4);
+            }
         }
-    }
-    // ... and the neighbours' vertex records next to each other, so that a hill-climbing move is ONE dependent memory level
-    // (ids and vertices of a chunk are addressed from the chunk index alone)
-    for (int k = 0; k < KG_NMESH; k++) {
-        const KgMesh &mk = m->mesh[k];
-        for (int v = 0; v < mk.nvert; v++) {
-            uint32_t info; std::memcpy(&info, &t->hull_vert[4 * (size_t)(mk.vert0 + v) + 3], 4);
-            const uint32_t first = info & 0xffffffu, nch = info >> 24;
-            if (t->nbr8.size() < 32 * (size_t)(first + nch)) t->nbr8.resize(32 * (size_t)(first + nch));
-            for (uint32_t i = 0; i < nch * 8; i++) {
-                const int u = t->adj8[8 * (size_t)first + i];
-                for (int c = 0; c < 4; c++) t->nbr8[4 * (8 * (size_t)first + i) + c] = t->hull_vert[4 * (size_t)(mk.vert0 + u) + c];
+        t->nbr8.assign(4 * t->adj8.size(), 0.f);
+        for (int k = 0; k < KG_NMESH; k++) {
+            const KgMesh &mk = m->mesh[k];
+            for (int v = 0; v < mk.nvert; v++) {
+                const size_t gv = (size_t)mk.vert0 + v;
+                uint32_t info; std::memcpy(&info, &t->hull_vert[4 * gv + 3], 4);
+                const uint32_t first = info & 0xffffffu, novf = info >> 24;
+                for (uint32_t ch = 0; ch <= novf; ch++) {
+                    const size_t ci = ch == 0 ? gv : (size_t)first + ch - 1;
+                    for (int i = 0; i < 8; i++) {
+                        const int u = t->adj8[8 * ci + i];
+                        for (int c = 0; c < 4; c++) t->nbr8[4 * (8 * ci + i) + c] = t->hull_vert[4 * ((size_t)mk.vert0 + u) + c];
+                    }
+                }
             }
         }
     }
