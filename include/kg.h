@@ -133,6 +133,20 @@ int kg_set_graph(kg_handle h, int on);
 int kg_measure_fp32_peak(kg_handle h, float *tflops);
 int kg_set_timing(kg_handle h, int on);
 int kg_timing_breakdown(kg_handle h, float ms_by_kind[8]);
+/* Grasp-classifier reward (kinova_gripper_env.py:248 `self.Grasp_net = pickle.load(.../gc_model.pkl)`, 643-659
+ * `_get_reward(with_grasp_reward)`, 791 set_with_grasp_reward, 1327 reset(with_grasp=...), 1372 Grasp_Reward=False).
+ * kg_set_grasp_forest: the RandomForestClassifier's trees as the data blob tools/extract_forest.py writes
+ * (kinovagrasping_b200/assets/gc_forest.bin; host memory, copied).  kg_set_grasp_reward(1): every kg_step then labels
+ * obs[0:75] of each env with the forest and adds 5.0 to the reward the first time per episode the label is >= 0.3
+ * (label = scikit-learn's RandomForestClassifier.predict, bit-exact); every kg_reset* clears the per-episode flag of the
+ * envs it resets.  kg_get_grasp_reward_host: info["grasp_reward"] of the last step (float[n]) and the Grasp_Reward flags
+ * (int[n]); either may be NULL. */
+int kg_set_grasp_forest(kg_handle h, const void *forest_blob, size_t nbytes);
+int kg_set_grasp_reward(kg_handle h, int on);
+int kg_get_grasp_reward_host(kg_handle h, float *grasp_host, int *given_host);
+/* Grasp_net.predict (ENV:651) on caller-supplied samples with the kernels the step uses: x_host = float[n_features][m]
+ * (feature-major, m <= n_envs), label_host = float[m] class labels.  Needs kg_set_grasp_forest. */
+int kg_grasp_predict_host(kg_handle h, const float *x_host, int m, float *label_host);
 /* The action the last kg_step applied (the caller's, or the on-device expert's: get_action, expert_data.py:610). float[4][n]. */
 int kg_get_last_action_host(kg_handle h, float *action_host);
 

@@ -50,6 +50,10 @@ SIGNATURES = {
     "kg_set_graph": (C.c_int, [_vp, C.c_int]),
     "kg_timing_breakdown": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "kg_get_last_action_host": (C.c_int, [_vp, _vp]),
+    "kg_set_grasp_forest": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "kg_set_grasp_reward": (C.c_int, [_vp, C.c_int]),
+    "kg_get_grasp_reward_host": (C.c_int, [_vp, _vp, _vp]),
+    "kg_grasp_predict_host": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "kg_get_stats": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "kg_get_prof": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "kg_forward_debug": (C.c_int, [_vp, C.c_int, _vp, _vp]),

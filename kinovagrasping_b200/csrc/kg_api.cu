@@ -10,6 +10,7 @@
 #define KG_MPR_L1      // narrowphase kernel reads the hull tables through the read-only L1 path (no shared-memory staging: +2 % measured)
 #endif
 #include "kg_core.cuh"
+#include "kg_forest.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -76,6 +77,10 @@ struct kg_handle_s {
     int *d_done = nullptr, *d_mask = nullptr, *d_shape = nullptr;
     float *d_debug = nullptr, *d_ctrl = nullptr;
     float *d_obs_global = nullptr;    // [74][n] internal buffer kg_obs_global_buffer hands out
+    KgForest forest = {};             // kg_set_grasp_forest: the grasp classifier's trees (device tables owned by this handle)
+    int grasp_on = 0;                 // kg_set_grasp_reward: with_grasp_reward (ENV:104, 791)
+    int *d_leaf = nullptr;            // [n_trees][n] leaf reached by every (tree, env) of the current step
+    float *d_grasp = nullptr;         // [n] grasp_reward of the last step (info["grasp_reward"], ENV:684)
 #ifndef KG_EMU
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t gstream[KG_MAXGROUPS] = {}, rstream[KG_MAXGROUPS] = {};
@@ -680,6 +685,12 @@ static int enqueue_step(kg_handle h, cudaStream_t st, const float *action, int m
     }
     if (G > 1) for (int g = 0; g < G; g++) { cudaEventRecord(h->gjoin[g], gs[g]); cudaStreamWaitEvent(st, h->gjoin[g], 0); }
 #undef KG_RAYS
+    if (h->grasp_on) {      // grasp-classifier reward on the obs the last per-env kernels just wrote (kg_forest.cuh)
+        const int nt = h->forest.n_trees * h->n;
+        kg_forest_leaf_kernel<<<(nt + 255) / 256, 256, 0, st>>>(h->forest, h->A.obs, h->n, h->d_leaf);
+        kg_grasp_decide_kernel<<<(h->n + 255) / 256, 256, 0, st>>>(h->forest, h->d_leaf, h->n, h->A.grasp_given, reward, h->d_grasp);
+        KG_TMARK(7);
+    }
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
@@ -708,6 +719,10 @@ static int launch_step(kg_handle h, const float *action, int mode, float *obs, f
                 kg_emit_tasks(mask, env, h->q + 2 * h->qsel, h->tasks, 0);
             }
         }
+    }
+    if (h->grasp_on) {
+        for (int t = 0; t < h->forest.n_trees; t++) for (int env = 0; env < h->n; env++) h->d_leaf[(size_t)t * h->n + env] = kg_forest_leaf(h->forest, t, h->A.obs, h->n, env);
+        for (int env = 0; env < h->n; env++) kg_grasp_decide(h->forest, h->d_leaf, h->n, env, h->A.grasp_given, reward, h->d_grasp);
     }
     return 0;
 #else
@@ -919,6 +934,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     A.N = n_envs; A.max_steps = 30; A.act_dim = 4;
     TRY(be_alloc(h, (void **)&A.qpos, 16 * N * 4)); TRY(be_alloc(h, (void **)&A.qvel, 15 * N * 4)); TRY(be_alloc(h, (void **)&A.qwarm, 15 * N * 4));
     TRY(be_alloc(h, (void **)&A.hand_quat, 4 * N * 4)); TRY(be_alloc(h, (void **)&A.shape, N * 4)); TRY(be_alloc(h, (void **)&A.elapsed, N * 4));
+    TRY(be_alloc(h, (void **)&A.grasp_given, N * 4)); TRY(be_alloc(h, (void **)&h->d_grasp, N * 4));
     TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
     TRY(be_alloc(h, (void **)&A.stats, 8 * 8));
 #ifdef KG_TRACE
@@ -1031,6 +1047,84 @@ int kg_set_action_dim(kg_handle h, int dim) {
 int kg_reset_sampled(kg_handle h, const int *mask, const int *shape, int orient, int variant, int test_table, uint64_t seed, float *obs) {
     if (!h || orient < 0 || orient > 3 || variant < 0 || variant > 1) { if (h) h->err = "kg_reset_sampled: bad orient/variant"; return KG_EINVAL; }
     return launch_reset(h, mask, shape, nullptr, nullptr, nullptr, 1, orient, variant, test_table ? 1 : 0, (unsigned long long)seed, obs);
+}
+// Grasp-classifier reward.  blob = assets/gc_forest.bin (tools/extract_forest.py: the trees of the RandomForestClassifier the
+// reference unpickles at ENV:248).  The tables are copied; the blob may be freed after the call.
+int kg_set_grasp_forest(kg_handle h, const void *blob_, size_t nbytes) {
+    if (!h || !blob_) return KG_EINVAL;
+    using namespace kgdetail;
+    const unsigned char *blob = (const unsigned char *)blob_;
+    if (nbytes < 16 || std::memcmp(blob, "KGMC0001", 8) != 0) { h->err = "grasp forest: bad magic"; return KG_EMODEL; }
+    auto sec = [&](const char *n, uint32_t dtype, size_t esz) -> const Sec * {
+        const Sec *s = find(blob, n);
+        return (s && s->dtype == dtype && s->offset + (size_t)s->count * esz <= nbytes) ? s : nullptr;
+    };
+    const Sec *meta = sec("forest_meta", 1, 4);
+    if (!meta || meta->count != 4) { h->err = "grasp forest: no forest_meta"; return KG_EMODEL; }
+    const int *mv = (const int *)(blob + meta->offset);
+    KgForest F = {};
+    F.n_trees = mv[0]; F.n_features = mv[1]; F.n_classes = mv[2]; F.n_nodes = mv[3];
+    const Sec *root = sec("tree_root", 1, 4), *fe = sec("node_feature", 1, 4), *le = sec("node_left", 1, 4), *ri = sec("node_right", 1, 4);
+    const Sec *th = sec("node_thresh", 0, 8), *pr = sec("node_proba", 0, 8), *cl = sec("classes", 0, 8);
+    if (F.n_trees < 1 || F.n_classes < 1 || F.n_nodes < 1 || F.n_features < 1 || F.n_features > 75 || !root || !fe || !le || !ri || !th || !pr || !cl ||
+        root->count != (uint32_t)F.n_trees + 1 || fe->count != (uint32_t)F.n_nodes || le->count != fe->count || ri->count != fe->count || th->count != fe->count ||
+        pr->count != (size_t)F.n_nodes * F.n_classes || cl->count != (uint32_t)F.n_classes) { h->err = "grasp forest: inconsistent sections (features must be obs[0:75])"; return KG_EMODEL; }
+    // every walk must end: children inside their tree and behind their parent (sklearn numbers nodes in construction order), features in range
+    const int *rt = (const int *)(blob + root->offset), *fv = (const int *)(blob + fe->offset), *lv = (const int *)(blob + le->offset), *rv = (const int *)(blob + ri->offset);
+    if (rt[0] != 0 || rt[F.n_trees] != F.n_nodes) { h->err = "grasp forest: bad tree_root"; return KG_EMODEL; }
+    for (int t = 0; t < F.n_trees; t++) {
+        const int b = rt[t], n = rt[t + 1] - b;
+        if (n < 1) { h->err = "grasp forest: empty tree"; return KG_EMODEL; }
+        for (int i = 0; i < n; i++) {
+            if (lv[b + i] < 0) continue;
+            if (lv[b + i] <= i || lv[b + i] >= n || rv[b + i] <= i || rv[b + i] >= n || fv[b + i] < 0 || fv[b + i] >= F.n_features) { h->err = "grasp forest: bad node"; return KG_EMODEL; }
+        }
+    }
+    void *p[7] = {};
+    const Sec *all[7] = {root, fe, le, ri, th, pr, cl};
+    for (int k = 0; k < 7; k++) {
+        const size_t bytes = (size_t)all[k]->count * (all[k]->dtype == 0 ? 8 : 4);
+        TRY(be_alloc(h, &p[k], bytes));
+        TRY(be_h2d(h, p[k], blob + all[k]->offset, bytes));
+    }
+    TRY(be_alloc(h, (void **)&h->d_leaf, (size_t)F.n_trees * h->n * 4));
+    TRY(be_sync(h));
+    F.root = (const int *)p[0]; F.feature = (const int *)p[1]; F.left = (const int *)p[2]; F.right = (const int *)p[3];
+    F.thresh = (const double *)p[4]; F.proba = (const double *)p[5]; F.classes = (const double *)p[6];
+    h->forest = F;      // (a replaced forest's tables stay allocated until kg_destroy)
+    h->cfg_version++;
+    return KG_OK;
+}
+// set_with_grasp_reward (ENV:791; reset(with_grasp=...) ENV:1327).  The per-episode Grasp_Reward flag is cleared by every reset.
+int kg_set_grasp_reward(kg_handle h, int on) {
+    if (!h) return KG_EINVAL;
+    if (on && !h->forest.n_trees) { h->err = "kg_set_grasp_reward: no forest loaded (kg_set_grasp_forest)"; return KG_EINVAL; }
+    h->grasp_on = on ? 1 : 0; h->cfg_version++;
+    return KG_OK;
+}
+// info["grasp_reward"] of the last kg_step (ENV:684) and the Grasp_Reward flags (ENV:103); either pointer may be NULL
+int kg_get_grasp_reward_host(kg_handle h, float *grasp_host, int *given_host) {
+    if (!h) return KG_EINVAL;
+    if (grasp_host) TRY(be_d2h(h, grasp_host, h->d_grasp, (size_t)h->n * 4));
+    if (given_host) TRY(be_d2h(h, given_host, h->A.grasp_given, (size_t)h->n * 4));
+    return be_sync(h);
+}
+// Grasp_net.predict on caller-supplied feature vectors (the same kernels the step uses): x_host float[n_features][m], m <= n
+int kg_grasp_predict_host(kg_handle h, const float *x_host, int m, float *label_host) {
+    if (!h || !x_host || !label_host || m < 1 || m > h->n) { if (h) h->err = "kg_grasp_predict_host: need 1 <= m <= n_envs"; return KG_EINVAL; }
+    if (!h->forest.n_trees) { h->err = "kg_grasp_predict_host: no forest loaded (kg_set_grasp_forest)"; return KG_EINVAL; }
+    TRY(be_h2d(h, h->d_obs, x_host, (size_t)h->forest.n_features * m * 4));
+#ifdef KG_EMU
+    for (int t = 0; t < h->forest.n_trees; t++) for (int i = 0; i < m; i++) h->d_leaf[(size_t)t * m + i] = kg_forest_leaf(h->forest, t, h->d_obs, m, i);
+    for (int i = 0; i < m; i++) h->d_reward[i] = (float)kg_forest_label(h->forest, h->d_leaf, m, i);
+#else
+    cudaStream_t st = (cudaStream_t)h->stream;
+    kg_forest_leaf_kernel<<<(h->forest.n_trees * m + 255) / 256, 256, 0, st>>>(h->forest, h->d_obs, m, h->d_leaf);
+    kg_forest_label_kernel<<<(m + 255) / 256, 256, 0, st>>>(h->forest, h->d_leaf, m, h->d_reward);
+    CUDA_TRY(h, cudaGetLastError());
+#endif
+    TRY(be_d2h(h, label_host, h->d_reward, (size_t)m * 4));
+    return be_sync(h);
 }
 int kg_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {
     if (!h || mode < 0 || mode > 2) { if (h) h->err = "kg_step: expert_mode must be 0, 1 or 2"; return KG_EINVAL; }

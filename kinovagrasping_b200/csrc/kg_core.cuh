@@ -2234,6 +2234,7 @@ struct KgEnvArrays {
     float *obs_global;            // [74][N] or NULL: _get_obs(state_rep="global") of the same step (kg_set_obs_global)
     float *ranges;                // [KG_NSITE][N] rangefinder readings of the current RL step, written by the batch-wide ray kernel (GPU path)
     unsigned char *ccache;        // [N][KG_CCACHE_BYTES] collision caches (warm-start vertices, separating axes) kept across RL steps
+    int *grasp_given;             // [N] Grasp_Reward: the grasp-classifier reward was paid in this episode (ENV:103, 655-657; cleared by reset ENV:1372)
     int N, max_steps;
     int act_dim;                  // 4 = [wrist, f1, f2, f3], 6 = [slide_x, slide_y, slide_z, f1, f2, f3] (ENV:1502-1503)
 };
@@ -2525,7 +2526,7 @@ template <class WS> KG_DEV void kg_env_reset(const KgModel &m, WS &ws, const KgE
         for (int i = l; i < KG_NOBS; i += 32) { float v = KG_WSOBS(ws)[i]; A.obs[i * N + env] = v; if (obs_out) obs_out[i * N + env] = v; }
         if (l < 4) A.hand_quat[l * N + env] = hq[l];
         if (l == 0) {
-            A.shape[env] = shape; A.elapsed[env] = 0;
+            A.shape[env] = shape; A.elapsed[env] = 0; A.grasp_given[env] = 0;
             A.ex_f[env] = KG_WSOBS(ws)[21]; A.ex_f[N + env] = KG_WSOBS(ws)[81];
             A.ex_f[2 * N + env] = 0.f; A.ex_f[3 * N + env] = 0.f; A.ex_f[4 * N + env] = 0.f;
             A.ex_i[env] = 0; A.ex_i[N + env] = 0; A.ex_i[2 * N + env] = 0;

@@ -133,8 +133,18 @@ class VecKinovaGripperEnv:
             a_ptr = self.action_soa.data_ptr()
         self.h.step(a_ptr, EXPERT_MODES[expert_mode] if isinstance(expert_mode, str) else int(expert_mode),
                     self.obs_soa.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self.action_out.data_ptr())
-        info = {"lift_reward": self.reward, "finger_reward": 0.0, "grasp_reward": 0.0, "action": self.action_out.t()}
+        if getattr(self, "with_grasp_reward", False):      # reward = lift (0 | 50) + grasp (0 | 5), both exact in fp32 (ENV:682)
+            lift = (self.reward >= 50.0).to(self.reward.dtype) * 50.0
+            info = {"lift_reward": lift, "finger_reward": 0.0, "grasp_reward": self.reward - lift, "action": self.action_out.t()}
+        else:
+            info = {"lift_reward": self.reward, "finger_reward": 0.0, "grasp_reward": 0.0, "action": self.action_out.t()}
         return self.obs_soa.t(), self.reward, self.done.bool(), info
+
+    def set_with_grasp_reward(self, with_grasp):
+        """ENV:791 for the whole batch: the grasp classifier's +5.0 (ENV:643-659, on-device decision forest) is added to the
+        reward of the first step of each episode whose obs[0:75] it labels a grasp."""
+        self.h.set_grasp_reward(bool(with_grasp))
+        self.with_grasp_reward = bool(with_grasp)
 
     def state(self):
         t = self.torch
@@ -192,7 +202,7 @@ class KinovaGripper_Env:
         self._elapsed_steps = 0
         self.pid = False
         self.state_rep = "local"
-        self.with_grasp_reward = False
+        self._with_grasp_reward = False
         self.Grasp_Reward = False
         self.obj_size = "m"                         # ENV:62; never changed on the Latin-square path
         self.filename = "/kinova_description/j2s7s300_end_effector_v1_mbox.xml"
@@ -231,13 +241,18 @@ class KinovaGripper_Env:
     def set_orientation(self, orientation): self.orientation = orientation
     def get_with_grasp_reward(self): return self.with_grasp_reward
     def set_with_grasp_reward(self, with_grasp):
-        """ENV:643-659 adds +5 once per episode when the pickled sklearn forest (KD/gc_model.pkl) predicts >= 0.3 on
-        local_obs[0:75].  That reward is outside this path (off by default, ENV:104 / MAIN:906) and is NOT built:
-        asking for it fails here instead of quietly returning the lift reward alone."""
-        if with_grasp:
-            raise NotImplementedError("grasp-classifier reward (ENV:643-659, gc_model.pkl) is not part of kinovagrasping_b200; "
-                                      "reset(..., with_grasp=False) is the reference's default")
-        self.with_grasp_reward = False
+        """ENV:791.  ENV:643-659 adds +5 once per episode when the sklearn forest of KD/gc_model.pkl labels local_obs[0:75]
+        >= 0.3; here the forest is a device table walked by two small kernels behind the step (csrc/kg_forest.cuh)."""
+        self.with_grasp_reward = with_grasp
+    # MAIN:283,302 assign env.with_grasp_reward directly, so the attribute itself switches the kernels
+    @property
+    def with_grasp_reward(self): return self._with_grasp_reward
+    @with_grasp_reward.setter
+    def with_grasp_reward(self, with_grasp):
+        on = with_grasp is True          # `if with_grasp_reward is True` (ENV:643): only the bool True enables it
+        if on != (self._with_grasp_reward is True):
+            self.h.set_grasp_reward(on)
+        self._with_grasp_reward = with_grasp
     def get_coords_filename(self): return self.coords_filename
     def set_coords_filename(self, coords_filename): self.coords_filename = coords_filename
     def get_all_objects(self): return self.all_objects
@@ -465,7 +480,11 @@ class KinovaGripper_Env:
             action = [0, 0, action[0], action[1], action[2], action[3]]      # ENV:1502-1503
         obs, rew, done = self.h.step_host(np.array(action[0:6], dtype=np.float32).reshape(6, 1), 0)
         self._elapsed_steps += 1
-        lift = float(rew[0])
+        grasp = 0.0
+        if self._with_grasp_reward is True:
+            g, given = self.h.get_grasp_reward_host()
+            grasp, self.Grasp_Reward = float(g[0]), bool(given[0])
+        lift = float(rew[0]) - grasp
         d = bool(lift > 0)
         if self._elapsed_steps >= self._max_episode_steps:
             d = True
@@ -474,8 +493,8 @@ class KinovaGripper_Env:
         states = [float(v) for v in obs[:, 0]]
         if self.pid:
             states = states + [states[81]]
-        info = {"finger_reward": 0.0, "grasp_reward": 0.0, "lift_reward": lift}
-        return states, lift, d, info
+        info = {"finger_reward": 0.0, "grasp_reward": grasp, "lift_reward": lift}
+        return states, 0.2 * 0.0 + lift + grasp, d, info      # ENV:682
 
     def _get_obs(self, state_rep=None):
         """ENV:438-534: the observation of the current state, 82 values in the wrist frame ("local") or 74 in the world

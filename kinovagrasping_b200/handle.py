@@ -67,6 +67,36 @@ class Handle:
         a = np.ascontiguousarray(shape_ids, dtype=np.int32).reshape(-1)
         self._chk(self.lib.kg_set_shape_cycle(self.h, _np_ptr(a) if a.size else None, int(a.size)), "kg_set_shape_cycle")
 
+    def load_grasp_forest(self, forest_path=None):
+        """Upload the grasp classifier's trees (assets/gc_forest.bin, tools/extract_forest.py; ENV:248) once."""
+        if not getattr(self, "_forest_loaded", False):
+            import os
+            path = forest_path or os.path.join(os.path.dirname(DEFAULT_PATH), "gc_forest.bin")
+            with open(path, "rb") as f:
+                blob = f.read()
+            self._chk(self.lib.kg_set_grasp_forest(self.h, blob, len(blob)), "kg_set_grasp_forest")
+            self._forest_loaded = True
+
+    def set_grasp_reward(self, on, forest_path=None):
+        """set_with_grasp_reward (ENV:791): the grasp classifier's +5.0 (ENV:643-659) is added by every step."""
+        if on:
+            self.load_grasp_forest(forest_path)
+        self._chk(self.lib.kg_set_grasp_reward(self.h, 1 if on else 0), "kg_set_grasp_reward")
+
+    def grasp_predict_host(self, x):
+        """Grasp_net.predict(x) (ENV:651) by the step's own forest kernels; x: [m, n_features], m <= n_envs."""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32).T)
+        out = np.zeros(x.shape[1], dtype=np.float32)
+        self._chk(self.lib.kg_grasp_predict_host(self.h, _np_ptr(x), int(x.shape[1]), _np_ptr(out)), "kg_grasp_predict_host")
+        return out
+
+    def get_grasp_reward_host(self):
+        """(info["grasp_reward"] of the last step float[n], Grasp_Reward flags bool[n])"""
+        g = np.zeros(self.n, dtype=np.float32)
+        f = np.zeros(self.n, dtype=np.int32)
+        self._chk(self.lib.kg_get_grasp_reward_host(self.h, _np_ptr(g), _np_ptr(f)), "kg_get_grasp_reward_host")
+        return g, f != 0
+
     def set_action_dim(self, dim):
         """4 = [wrist, f1, f2, f3]; 6 = [slide_x, slide_y, slide_z, f1, f2, f3] (ENV:1502-1503)."""
         self._chk(self.lib.kg_set_action_dim(self.h, int(dim)), "kg_set_action_dim")

@@ -69,7 +69,7 @@ def run_episode(env, act_fn, replay=None, shapes=("CubeS",), orientation="normal
             rec = alive & ~lifting
             replay.add_batch(obs, action, nxt, rew, done & alive, record=rec, replace=alive & lifting & done, defer=True)
             stored = stored + rec.sum()
-        success |= alive & done & (rew > 0)
+        success |= alive & done & (rew >= 50.0)          # the lift reward (a grasp-classifier +5 alone is not a success)
         alive &= ~done
         prev, obs = obs, nxt
     if replay is not None:
@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the updates eagerly instead of replaying captured CUDA graphs")
     ap.add_argument("--fp32-matmul", action="store_true", help="keep the actor/critic GEMMs in IEEE fp32 instead of TF32 tensor cores")
     ap.add_argument("--save", default=None)
+    ap.add_argument("--with-grasp-reward", action="store_true", help="add the grasp classifier's +5 (MAIN:906 --with_grasp_reward, ENV:643-659)")
     args = ap.parse_args()
 
     rank, local, world = dist_env()
@@ -166,6 +167,8 @@ def main():
         torch.set_float32_matmul_precision("high")            # TF32 tensor cores for the 20k x 400 x 300 GEMMs of an update
     torch.manual_seed(args.seed)                              # same initial weights on every rank
     env = make_sharded_env(args.envs, rank, world, local)
+    if args.with_grasp_reward:
+        env.set_with_grasp_reward(True)
     shapes = tuple(args.shapes.split(","))
     max_action = 0.8                                          # action_space.high (ENV:128)
     graphed = not args.no_graph

@@ -123,11 +123,38 @@ def test_vector_env_global_obs_view():
     assert torch.equal(g[:, 24:67], obs[:, 24:67]) and float(g[:, 23].min()) > 0.0      # object centre above the floor
 
 
-def test_grasp_classifier_reward_is_refused_not_faked(facade):
-    """ENV:643-659: the +5 classifier reward is not built; asking for it must fail loudly, never degrade to lift-only."""
-    with pytest.raises(NotImplementedError):
-        facade.set_with_grasp_reward(True)
-    with pytest.raises(NotImplementedError):
-        facade.reset(shape_keys=["CubeS"], hand_orientation="normal", with_grasp=True)
-    facade.set_with_grasp_reward(False)
-    assert facade.get_with_grasp_reward() is False
+def test_grasp_classifier_reward_through_the_facade(facade):
+    """ENV:643-659 / 791 / 1327 / 1372 and MAIN:283 (`env.with_grasp_reward = ...` assigned as an attribute): reward =
+    lift + grasp, info carries both, +5.0 once per episode, against oracle/forest.py on the states the facade returned."""
+    import os
+    from oracle.forest import Forest, grasp_reward
+    forest = Forest(os.path.join(os.path.dirname(kenv.__file__), "assets", "gc_forest.bin"))
+    e = facade
+    e._max_episode_steps = 30
+    total = 0.0
+    for episode, how in enumerate(("reset", "setter", "attribute")):
+        if how == "reset":
+            state = e.reset(shape_keys=["CubeS"], hand_orientation="normal", with_grasp=True, start_pos=[0.0, 0.02, 0.05])
+        else:
+            state = e.reset(shape_keys=["CubeS"], hand_orientation="normal", start_pos=[0.0, 0.02, 0.05])      # with_grasp=False (ENV:1327)
+            assert e.get_with_grasp_reward() is False
+            if how == "setter":
+                e.set_with_grasp_reward(True)
+            else:
+                e.with_grasp_reward = True
+        assert e.get_with_grasp_reward() is True and e.Grasp_Reward is False
+        # the code-faithful start poses never close on the object (SURVEY 8d variant A); put the hand in the side-grasp pose of
+        # variant B underneath the facade so that the classifier has a grasp to recognise
+        e.h.reset_host(np.array([0], dtype=np.int32), np.array([-1.57, 0, -1.57], dtype=np.float32).reshape(3, 1),
+                       np.array([-0.03, 0.02, 0.05], dtype=np.float32).reshape(3, 1))
+        given = False
+        for step in range(14):
+            state, reward, done, info = e.step([0.0, 0.6, 0.6, 0.6])
+            want, given = grasp_reward(forest, np.asarray(state), given)
+            assert info["grasp_reward"] == want and e.Grasp_Reward == given
+            assert reward == info["lift_reward"] + info["grasp_reward"] and info["finger_reward"] == 0.0
+            total += want
+    assert total == 15.0, total            # closing the fingers on the cube is recognised as a grasp, once per episode
+    e.with_grasp_reward = "True"           # `is True` (ENV:643): a truthy non-bool does not enable it
+    state, reward, done, info = e.step([0.0, 0.6, 0.6, 0.6])
+    assert info["grasp_reward"] == 0.0
