@@ -10,8 +10,8 @@
 #include <string>
 #include <vector>
 
-#define KG_NSHAPE 14
-#define KG_NMESH 17
+#define KG_NSHAPE 21
+#define KG_NMESH 24
 #define KG_NSITE 17
 
 struct KgMesh {

@@ -167,6 +167,8 @@ _MEM_FILES = {}
 # euler of body j2s7s300_link_7 as the shipped XMLs hold it (XML:59 of each file); write_xml overwrites it
 _XML_EULER = {k: [-1.57, 0.0, -1.57] for k in SHAPES}
 _XML_EULER["CubeS"] = [-0.06, -0.16, -0.13]
+for _k in ("CubeM", "CylinderM", "Cube45M", "Cone2M", "Vase1M", "Vase2M"):      # the committed XMLs of the medium sizes (Cone1M has the side pose)
+    _XML_EULER[_k] = [0.0, 0.0, 0.0]
 
 
 def truncate_euler(rot):
@@ -367,7 +369,7 @@ class KinovaGripper_Env:
 
     def _get_obj_size(self):
         """ENV:706-746 for a single-geom object: the mesh geom's box half sizes with the axis re-ordering heuristic."""
-        size = [float(v) for v in self.card.get("mesh_geom").reshape(17, 15)[3 + self._shape_id, 8:11]]
+        size = [float(v) for v in self.card.get("mesh_geom").reshape(-1, 15)[3 + self._shape_id, 8:11]]
         if size[2] == 0:
             size[2] = size[1]; size[1] = size[0]
         diffs = [abs(size[0] - size[1]), abs(size[1] - size[2]), abs(size[0] - size[2])]

@@ -23,7 +23,7 @@ def hand_frame_from_euler(card, euler, slides):
     Rh = euler2mat(np.asarray(euler, dtype=np.float64))
     axes = card.get("slide_axes").reshape(3, 3)
     hp = card.get("l7_pos") + Rh @ (axes.T @ np.asarray(slides, dtype=np.float64))
-    mg = card.get("mesh_geom").reshape(17, 15)[0]
+    mg = card.get("mesh_geom").reshape(-1, 15)[0]
     palm_pos = hp + Rh @ mg[0:3]
     Rfa = Rh @ _q2m(mg[3:7])
     temp = (Rfa @ np.array([[0, 0, 1], [-1, 0, 0], [0, -1, 0]])).T

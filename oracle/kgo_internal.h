@@ -7,7 +7,7 @@
 #include <stdlib.h>
 #include <stdio.h>
 
-#define NMESH 17
+#define NMESH 24
 typedef struct {
     int vert0, nvert, adj0, tri0, ntri, bvh0, nbvh, nface;
 } MeshIndex;

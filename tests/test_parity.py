@@ -38,8 +38,8 @@ def _obs_err(a, b):
 
 
 def test_reset_obs_parity_all_shapes_orientations(backend, oracle, card):
-    n = 84
-    shape, euler, objp = _poses(card, n, 1)
+    n = 126                                         # 21 shapes (the 14 of Exp1 + the 7 medium sizes) x 3 orientations x 2 rows
+    shape, euler, objp = _poses(card, n, 1, shapes=range(21))
     h = Handle(n, lib=backend)
     obs = h.reset_host(shape, euler, objp)
     ref = _oracle_reset(oracle, shape, euler, objp)
@@ -91,21 +91,21 @@ def test_smooth_dynamics_parity(backend, oracle, card):
 _LOCKSTEP_CACHE = {}
 
 
-def _lockstep(backend, oracle, card, n, seed, steps, mode=0):
-    key = (backend._name, n, seed, steps, mode)
+def _lockstep(backend, oracle, card, n, seed, steps, mode=0, shapes=(0, 1)):
+    key = (backend._name, n, seed, steps, mode, tuple(shapes))
     if key not in _LOCKSTEP_CACHE:
-        _LOCKSTEP_CACHE[key] = _lockstep_run(backend, oracle, card, n, seed, steps, mode)
+        _LOCKSTEP_CACHE[key] = _lockstep_run(backend, oracle, card, n, seed, steps, mode, shapes)
     return _LOCKSTEP_CACHE[key]
 
 
-def _lockstep_run(backend, oracle, card, n, seed, steps, mode=0):
+def _lockstep_run(backend, oracle, card, n, seed, steps, mode=0, shapes=(0, 1)):
     """Oracle-driven side-grasp rollouts.  Before EVERY physics substep the kernel state is overwritten with the
     oracle's (fp32-rounded) state, so each record is a true one-step (one mj_step) error from identical
     qpos/qvel/ctrl, which is what the north_star tolerance is stated on.  With frame_skip = 1 every call also runs the
     obs epilogue (rangefinder BVH, _get_obs local + global, experimental_sensor) on the kinematics of that same state, so
     each record also carries the post-step observation error of all 82 / 74 entries against the oracle's _get_obs."""
-    shape, _, objp = _poses(card, n, seed, orient_idx=(0,), shapes=(0, 1))
-    _, euler, _ = _poses(card, n, seed, orient_idx=(2,), shapes=(0, 1))
+    shape, _, objp = _poses(card, n, seed, orient_idx=(0,), shapes=shapes)
+    _, euler, _ = _poses(card, n, seed, orient_idx=(2,), shapes=shapes)
     h = Handle(n, lib=backend)
     h.set_max_episode_steps(10 ** 6)
     h.set_frame_skip(1)
@@ -208,6 +208,25 @@ def test_one_step_parity_every_substep_on_identical_contacts(backend, oracle, ca
     print(f"identical contacts: {len(got)} substeps ({int((ncon > 0).sum())} with contacts, up to {ncon.max()}): qvel err max {ev.max():.2e}, "
           f"p99 {np.percentile(ev, 99):.2e}; qpos err max {eq.max():.2e}")
     assert ev.max() < 1e-4 and eq.max() < 1e-4, (ev.max(), eq.max())
+
+
+def test_medium_size_shapes_lockstep(backend, oracle, card):
+    """SURVEY 8(f4) 'remaining shapes': the seven medium sizes (CubeM ... Vase2M, ENV:150-178; MAIN:1271 tests on them) through
+    the same two gates as the Exp1 shapes -- one mj_step on identical contacts within 1e-4 on every substep, and the 60 smooth
+    post-step obs entries within 1e-5 on every substep (rangefinders >= 99.5 %)."""
+    recs = _lockstep(backend, oracle, card, n=7, seed=11, steps=20, shapes=tuple(range(14, 21)))
+    got = [r for r in recs if r["evg"] is not None]
+    assert len(got) > 0.99 * len(recs)
+    ev = np.array([r["evg"] / max(1.0, r["vs"]) for r in got]); eq = np.array([r["eqg"] for r in got])
+    ncon = np.array([r["ncon"] for r in got])
+    oerr = np.stack([r["oerr"] for r in recs])
+    smooth = [k for k in range(82) if k not in list(range(50, 67)) + list(range(70, 75))]
+    print(f"medium shapes: {len(got)} substeps ({int((ncon > 0).sum())} with contacts, up to {ncon.max()}): qvel err max {ev.max():.2e}, "
+          f"qpos {eq.max():.2e}, smooth obs {oerr[:, smooth].max():.2e}, rays within 1e-5 {np.mean(oerr[:, 50:67] < 1e-5):.4f}")
+    assert (ncon > 0).sum() > 1000
+    assert ev.max() < 1e-4 and eq.max() < 1e-4, (ev.max(), eq.max())
+    assert oerr[:, smooth].max() < 1e-5, oerr[:, smooth].max()
+    assert (oerr[:, 50:67] < 1e-5).mean() >= 0.995
 
 
 RAY_ENTRIES = list(range(50, 67)) + list(range(70, 75))     # rangefinders and what experimental_sensor derives from them

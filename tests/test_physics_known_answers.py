@@ -104,7 +104,7 @@ def make(request, oracle, backend):
 
 
 def _obj_inertia(card, shape):
-    c = card.get("mesh_geom").reshape(17, 15)[3 + shape]
+    c = card.get("mesh_geom").reshape(-1, 15)[3 + shape]
     return c[12:15] * MOBJ / c[11]            # principal inertias at geom mass 0.1 (XML:153); CubeS/CubeB: geom frame = body frame
 
 
@@ -150,9 +150,9 @@ def test_resting_contact_balances_gravity(make, card):
     K = 1 / (dmax^2 tc^2), D = impratio / (2 mu^2 R), R = (1 - d)/d * invweight * (1 + mu^2): solving that for r predicts the
     equilibrium height of the lowest hull vertices, margin + r (XML:9,40; solref / solimp defaults; pair friction 0.3)."""
     shape = 0
-    mg = card.get("mesh_geom").reshape(17, 15)[3 + shape]
+    mg = card.get("mesh_geom").reshape(-1, 15)[3 + shape]
     hv = card.get("hull_vert").reshape(-1, 3)
-    mi = card.get("mesh_index").reshape(17, 8)[3 + shape]
+    mi = card.get("mesh_index").reshape(-1, 8)[3 + shape]
     zmin = hv[mi[0]:mi[0] + mi[1], 2].min()
     r = make(shape, SIDE, [0.4, 0.4, -zmin + 0.0009])
     f0 = r.forward(np.zeros(9))
@@ -167,7 +167,7 @@ def test_resting_contact_balances_gravity(make, card):
     # the predicted soft-constraint offset
     tc, dmax, impratio, mu, margin = 0.02, 0.95, 5.0, 0.3, 0.001
     K = 1.0 / (dmax * dmax * tc * tc)
-    invw = float(card.get("obj_invw0").reshape(14, 4)[shape, 0])
+    invw = float(card.get("obj_invw0").reshape(-1, 4)[shape, 0])
 
     def weight_carried(pen):
         d = _impedance(pen)
@@ -193,7 +193,7 @@ def test_sliding_friction_is_coulomb_inside_the_pyramid(make, card):
     cube STICKS: opposing rows hold it, F_t ~ 0, F_n = m g."""
     shape = 1
     hv = card.get("hull_vert").reshape(-1, 3)
-    mi = card.get("mesh_index").reshape(17, 8)[3 + shape]
+    mi = card.get("mesh_index").reshape(-1, 8)[3 + shape]
     zmin = hv[mi[0]:mi[0] + mi[1], 2].min()
     r = make(shape, SIDE, [0.4, 0.4, -zmin + 0.0008])
     r.run(300)
@@ -354,8 +354,8 @@ def test_obj_size_reordering_matches_the_meshes(card, oracle):
     third is the full height -- compared with the hull's own extents (the inertia box of a cone / vase is not its bounding
     box, hence the 35 % band; prisms and cylinders are within 15 %)."""
     hv = card.get("hull_vert").reshape(-1, 3)
-    mi = card.get("mesh_index").reshape(17, 8)
-    for shape in range(14):
+    mi = card.get("mesh_index").reshape(-1, 8)
+    for shape in range(21):
         e, obs = oracle.env_reset(shape, SIDE.astype(np.float64), np.array([0.0, 0.0, 0.06]))
         v = hv[mi[3 + shape][0]:mi[3 + shape][0] + mi[3 + shape][1]]
         ext = v.max(0) - v.min(0)

@@ -28,7 +28,9 @@ from scipy.spatial import ConvexHull
 
 REF = "/root/reference/gym-kinova-gripper/gym_kinova_gripper/envs/kinova_description"
 SHAPES = ["CubeS", "CubeB", "CylinderS", "CylinderB", "Cube45S", "Cube45B", "Cone1S", "Cone1B",
-          "Cone2S", "Cone2B", "Vase1S", "Vase1B", "Vase2S", "Vase2B"]
+          "Cone2S", "Cone2B", "Vase1S", "Vase1B", "Vase2S", "Vase2B",
+          # the medium sizes (ENV:150-178; MAIN:1271 test_sizes = ["M"]) are appended so that the ids of the 14 above never change
+          "CubeM", "CylinderM", "Cube45M", "Cone1M", "Cone2M", "Vase1M", "Vase2M"]
 ORIENTS = ["normal", "rotated", "top"]
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "kinovagrasping_b200", "assets",
                    "model_card.bin")
@@ -113,6 +115,12 @@ def eig3(mat):
 # ----------------------------------------------------------------------------- meshes
 def load_stl(path, scale=1.0):
     b = open(path, "rb").read()
+    if b[:5] == b"solid" and b"facet normal" in b[:400]:
+        # ASCII STL (only CubeM.stl, written by stlwrite.m).  MuJoCo's loader is documented as binary-only, so whether the
+        # reference's CubeM ever loaded under MuJoCo 1.50 is unknown; its triangles are taken as written, in float32.
+        v = np.array([ln.split()[1:4] for ln in b.decode("ascii", "replace").splitlines() if ln.strip().startswith("vertex")], dtype=np.float64)
+        assert len(v) % 3 == 0 and len(v) > 0, path
+        return (v.reshape(-1, 3, 3).astype(np.float32) * np.float32(scale)).astype(np.float64)
     n = struct.unpack("<I", b[80:84])[0]
     assert 84 + 50 * n == len(b), path
     a = np.frombuffer(b[84:], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))

@@ -146,7 +146,7 @@ def main():
         gx = D.arr("geom_xpos", (9, 3)); gm = D.arr("geom_xmat", (9, 9)); sx = D.arr("site_xpos", (17, 3))
         hx = D.arr("xpos", (9, 3))[1]; sd = D.arr("sensordata")
         gs = np.zeros((9, 3)); gs[0] = [2, 2, 1]
-        sizes = m.section("mesh_geom").reshape(17, 15)
+        sizes = m.section("mesh_geom").reshape(-1, 15)
         for g, mesh in zip(range(1, 8), (0, 1, 2, 1, 2, 1, 2)):
             gs[g] = sizes[mesh, 8:11]
         gs[8] = sizes[3 + shape, 8:11]
