@@ -59,6 +59,9 @@ int kg_reset_pose_host(kg_handle h, const int *mask_host, const int *shape_host,
  * objects.csv, kinova_gripper_env.py:895-999): episode e of global env i gets keys[(i + e) mod nkeys], shape ids in model-card
  * order; every env cycles through the keys and every episode index sees them uniformly.  nkeys = 0: envs keep their shape. */
 int kg_set_shape_cycle(kg_handle h, const int *keys_host, int nkeys);
+/* env.get_orientation() per env (kinova_gripper_env.py:1180-1222 select_orienation): the hand orientation the last
+ * kg_reset_sampled drew for each env -- 0 normal, 1 rotated, 2 top; -1 after a reset with explicit poses.  int[n]. */
+int kg_get_orientation_host(kg_handle h, int *orient_host);
 /* determine_hand_location for kg_reset_sampled: 0 (default) = slides start at 0 -- what main_DDPGfD.py gets, because it
  * builds a new env per episode (MAIN:381) and a new env's Tfw is all zeros (ENV:110); 1 = what expert_data.py gets, which
  * reuses one env (EXP:696): the offsets are computed from the Tfw of the env's PREVIOUS episode (none for its first). */

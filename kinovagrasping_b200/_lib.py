@@ -31,6 +31,7 @@ SIGNATURES = {
     "kg_reset_pose_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kg_set_hand_location": (C.c_int, [_vp, C.c_int]),
     "kg_set_shape_cycle": (C.c_int, [_vp, _vp, C.c_int]),
+    "kg_get_orientation_host": (C.c_int, [_vp, _vp]),
     "kg_set_action_dim": (C.c_int, [_vp, C.c_int]),
     "kg_get_state": (C.c_int, [_vp, _vp, _vp]),
     "kg_set_state": (C.c_int, [_vp, _vp, _vp]),

@@ -549,9 +549,11 @@ __global__ void __launch_bounds__(KG_LWARPS * 32) kg_reset_kernel(KgEnvArrays A,
     // keys, every episode index sees them uniformly -- Generate_Latin_Square's property, ENV:895-964), or unchanged
     int sh = shape ? shape[env] : (sampled && cycle_n > 0 ? cycle[(unsigned)(env + env_offset + ep_count[env]) % (unsigned)cycle_n] : A.shape[env]);
     float e[3], p[3], hp[3] = {0.f, 0.f, 0.f};
+    int drawn = -1;
     if (sampled) {
         KgSample s = kg_sample_pose(c_model, seed, env + env_offset, ep_count[env], sh, orient, variant, test_table);
         for (int c = 0; c < 3; c++) { e[c] = s.euler[c]; p[c] = s.objp[c]; }
+        drawn = s.orient;
         if (hand_location) {
             const float hq[4] = {A.hand_quat[env], A.hand_quat[A.N + env], A.hand_quat[2 * A.N + env], A.hand_quat[3 * A.N + env]};
             kg_hand_location(c_model, hq, ep_count[env] > 0, s.orient, hp);
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(KG_LWARPS * 32) kg_reset_kernel(KgEnvArrays A,
         for (int c = 0; c < 3; c++) { e[c] = euler[c * A.N + env]; p[c] = objp[c * A.N + env]; if (handp) hp[c] = handp[c * A.N + env]; }
     }
     __syncwarp();
-    if (lane == 0) ep_count[env] += 1;
+    if (lane == 0) { ep_count[env] += 1; A.orient[env] = drawn; }
     kg_env_reset(c_model, ws, A, env, sh, e, p, hp, obs, lane);
 }
 __global__ void kg_debug_begin_kernel(KgEnvArrays A, int env, const float *ctrl, unsigned char *carry, int *q, unsigned *tasks) {
@@ -776,16 +778,18 @@ static int launch_reset(kg_handle h, const int *mask, const int *shape, const fl
         if (mask && mask[env] == 0) continue;
         int sh = shape ? shape[env] : (sampled && h->cycle_n > 0 ? h->cycle[(unsigned)(env + h->env_offset + h->ep_count[env]) % (unsigned)h->cycle_n] : h->A.shape[env]);
         float e[3], p[3], hp[3] = {0.f, 0.f, 0.f};
+        int drawn = -1;
         if (sampled) {
             KgSample s = kg_sample_pose(h->model, seed, env + h->env_offset, h->ep_count[env], sh, orient, variant, test_table);
             for (int c = 0; c < 3; c++) { e[c] = s.euler[c]; p[c] = s.objp[c]; }
+            drawn = s.orient;
             if (h->hand_location) {
                 const int N = h->n;
                 const float hq[4] = {h->A.hand_quat[env], h->A.hand_quat[N + env], h->A.hand_quat[2 * N + env], h->A.hand_quat[3 * N + env]};
                 kg_hand_location(h->model, hq, h->ep_count[env] > 0, s.orient, hp);
             }
         } else for (int c = 0; c < 3; c++) { e[c] = euler[c * h->n + env]; p[c] = objp[c * h->n + env]; if (handp) hp[c] = handp[c * h->n + env]; }
-        h->ep_count[env] += 1;
+        h->ep_count[env] += 1; h->A.orient[env] = drawn;
         kg_env_reset(h->model, g_ws, h->A, env, sh, e, p, hp, obs, 0);
     }
     return 0;
@@ -934,7 +938,7 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
     A.N = n_envs; A.max_steps = 30; A.act_dim = 4;
     TRY(be_alloc(h, (void **)&A.qpos, 16 * N * 4)); TRY(be_alloc(h, (void **)&A.qvel, 15 * N * 4)); TRY(be_alloc(h, (void **)&A.qwarm, 15 * N * 4));
     TRY(be_alloc(h, (void **)&A.hand_quat, 4 * N * 4)); TRY(be_alloc(h, (void **)&A.shape, N * 4)); TRY(be_alloc(h, (void **)&A.elapsed, N * 4));
-    TRY(be_alloc(h, (void **)&A.grasp_given, N * 4)); TRY(be_alloc(h, (void **)&h->d_grasp, N * 4));
+    TRY(be_alloc(h, (void **)&A.orient, N * 4)); TRY(be_alloc(h, (void **)&A.grasp_given, N * 4)); TRY(be_alloc(h, (void **)&h->d_grasp, N * 4));
     TRY(be_alloc(h, (void **)&A.ex_f, 5 * N * 4)); TRY(be_alloc(h, (void **)&A.ex_i, 3 * N * 4)); TRY(be_alloc(h, (void **)&A.obs, KG_NOBS * N * 4)); TRY(be_alloc(h, (void **)&A.last_action, 4 * N * 4));
     TRY(be_alloc(h, (void **)&A.stats, 8 * 8));
 #ifdef KG_TRACE
@@ -1101,6 +1105,12 @@ int kg_set_grasp_reward(kg_handle h, int on) {
     if (on && !h->forest.n_trees) { h->err = "kg_set_grasp_reward: no forest loaded (kg_set_grasp_forest)"; return KG_EINVAL; }
     h->grasp_on = on ? 1 : 0; h->cfg_version++;
     return KG_OK;
+}
+// env.get_orientation() per env (ENV:1180-1222): what the last sampled reset drew, 0 normal / 1 rotated / 2 top; -1 = reset with explicit poses
+int kg_get_orientation_host(kg_handle h, int *orient_host) {
+    if (!h || !orient_host) return KG_EINVAL;
+    TRY(be_d2h(h, orient_host, h->A.orient, (size_t)h->n * 4));
+    return be_sync(h);
 }
 // info["grasp_reward"] of the last kg_step (ENV:684) and the Grasp_Reward flags (ENV:103); either pointer may be NULL
 int kg_get_grasp_reward_host(kg_handle h, float *grasp_host, int *given_host) {

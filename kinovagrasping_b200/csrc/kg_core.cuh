@@ -2234,6 +2234,7 @@ struct KgEnvArrays {
     float *obs_global;            // [74][N] or NULL: _get_obs(state_rep="global") of the same step (kg_set_obs_global)
     float *ranges;                // [KG_NSITE][N] rangefinder readings of the current RL step, written by the batch-wide ray kernel (GPU path)
     unsigned char *ccache;        // [N][KG_CCACHE_BYTES] collision caches (warm-start vertices, separating axes) kept across RL steps
+    int *orient;                  // [N] hand orientation of the current episode as the sampler drew it: 0 normal, 1 rotated, 2 top (env.get_orientation(), ENV:1180-1222); -1 after a reset with explicit poses
     int *grasp_given;             // [N] Grasp_Reward: the grasp-classifier reward was paid in this episode (ENV:103, 655-657; cleared by reset ENV:1372)
     int N, max_steps;
     int act_dim;                  // 4 = [wrist, f1, f2, f3], 6 = [slide_x, slide_y, slide_z, f1, f2, f3] (ENV:1502-1503)

@@ -97,6 +97,12 @@ class Handle:
         self._chk(self.lib.kg_get_grasp_reward_host(self.h, _np_ptr(g), _np_ptr(f)), "kg_get_grasp_reward_host")
         return g, f != 0
 
+    def orientation_host(self):
+        """Hand orientation each env's last sampled reset drew: 0 normal, 1 rotated, 2 top (-1: explicit-pose reset)."""
+        o = np.zeros(self.n, dtype=np.int32)
+        self._chk(self.lib.kg_get_orientation_host(self.h, _np_ptr(o)), "kg_get_orientation_host")
+        return o
+
     def set_action_dim(self, dim):
         """4 = [wrist, f1, f2, f3]; 6 = [slide_x, slide_y, slide_z, f1, f2, f3] (ENV:1502-1503)."""
         self._chk(self.lib.kg_set_action_dim(self.h, int(dim)), "kg_set_action_dim")

@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the updates eagerly instead of replaying captured CUDA graphs")
     ap.add_argument("--fp32-matmul", action="store_true", help="keep the actor/critic GEMMs in IEEE fp32 instead of TF32 tensor cores")
     ap.add_argument("--save", default=None)
+    ap.add_argument("--eval-out", default=None, help="directory for the reference's eval outputs (heatmap coordinates, boxplot arrays) of every evaluation")
     ap.add_argument("--with-grasp-reward", action="store_true", help="add the grasp classifier's +5 (MAIN:906 --with_grasp_reward, ENV:643-659)")
     args = ap.parse_args()
 
@@ -195,6 +196,14 @@ def main():
     assert held > 2, f"a rank holds only {held:.0f} expert episodes: pre-training would sample an empty shard"
 
     def evaluate(tag, sweep):
+        if args.eval_out:      # the reference's eval outputs (MAIN:130-272, 486-528): heatmap coordinates + boxplot arrays, per rank
+            from .evalout import eval_policy, save_eval_outputs
+            ret = eval_policy(env, lambda o: policy.select_actions(o), shapes, args.orientation, args.variant, mode="test", seed=args.seed + 99)
+            out = os.path.join(args.eval_out, f"rank{rank}")
+            save_eval_outputs(ret, sweep, os.path.join(out, "heatmap", "eval"), os.path.join(out, "boxplot", "eval"))
+            s, n = all_reduce_sum([float(ret["num_success"]), float(env.n)], dev)
+            log(phase="eval", tag=tag, sweep=sweep, success=s / n, avg_reward=ret["avg_reward"], wall_s=time.perf_counter() - t0)
+            return
         succ, _ = run_episode(env, lambda o: policy.select_actions(o), None, shapes, args.orientation, args.variant, mode="test", seed=args.seed + 99)
         log(phase="eval", tag=tag, sweep=sweep, success=count(succ), wall_s=time.perf_counter() - t0)
 
