@@ -321,13 +321,17 @@ def run_ours(args):
 
     # ---- e2e: host buffers through the C ABI (kg_step_host): pinned actions in, obs/reward/done out, every step
     act_h = torch.zeros((4, n), dtype=torch.float32).pin_memory()
-    act_h[1:] = 0.5
     obs_h = torch.zeros((82, n), dtype=torch.float32).pin_memory()
     rew_h = torch.zeros(n, dtype=torch.float32).pin_memory()
     done_h = torch.zeros(n, dtype=torch.int32).pin_memory()
     import ctypes as C
     mask_d = torch.zeros(n, dtype=torch.int32, device=dev)
+    # The reference's split, every step: action = controller.get_action(obs) (here kg_expert_action_host: the on-device
+    # controller, its action read back to pinned host memory), then env.step(action) with that HOST action (kg_step_host: H2D of
+    # the action, the step, D2H of obs / reward / done), then the masked reset of finished envs.  Same controller, same actions
+    # and therefore the same contact mix as the device-resident `value` loop, with every action crossing the bus both ways.
     def e2e_step():
+        env.h._chk(env.h.lib.kg_expert_action_host(env.h.h, 2, C.c_void_p(act_h.data_ptr())), "kg_expert_action_host")
         env.h._chk(env.h.lib.kg_step_host(env.h.h, C.c_void_p(act_h.data_ptr()), 0, C.c_void_p(obs_h.data_ptr()), C.c_void_p(rew_h.data_ptr()),
                                           C.c_void_p(done_h.data_ptr())), "kg_step_host")
         mask_d.copy_(done_h, non_blocking=True)
@@ -341,6 +345,17 @@ def run_ours(args):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    # what the e2e step consists of (untimed extra pass): device time of the step's kernel chain inside kg_step_host, the rest is
+    # copies + launch + synchronisation.  stats of the e2e workload next to it.
+    env.h.stats()
+    e2e_kernel = []
+    for _ in range(60):
+        e2e_step()
+        e2e_kernel.append(env.h.last_step_ms())
+    st_e2e = env.h.stats()
+    e2e_diag = {"device_ms_per_step_kernel_chain": float(np.mean(e2e_kernel)),
+                "mpr_pairs": st_e2e["mpr_pairs"] / max(1, st_e2e["substeps"]), "newton_iters": st_e2e["newton_iters"] / max(1, st_e2e["substeps"]),
+                "contacts": st_e2e["contacts"] / max(1, st_e2e["substeps"])}
     groups = 2 if n >= 32768 else (4 if n >= 2048 else (2 if n >= 512 else 1))          # kg_set_pipeline default
 
     # ---- extra workloads for the record (rank 0, single GPU only): the other pose-table variant and the 32768-env batch
@@ -405,7 +420,9 @@ def run_ours(args):
                                      "repetition_ms_min_max": [min(rep_ms), max(rep_ms)]},
                            "l2": "flushed between timed steps by a 256 MiB write (excluded from the timed spans); state is 2.4 MB per 4096 envs",
                            "parallelism": "env-sharded x%d, no data-path collective" % world},
-                "e2e": {"value": e2e_value, "unit": "physics substeps/s", "h2d_bytes_per_step": 16 * n + 4 * n, "d2h_bytes_per_step": (82 + 2) * 4 * n, "steps": e2e_steps},
+                "e2e": {"value": e2e_value, "unit": "physics substeps/s", "h2d_bytes_per_step": 16 * n + 4 * n, "d2h_bytes_per_step": (82 + 2 + 4) * 4 * n, "steps": e2e_steps,
+                        "ms_per_step": e2e_ms / e2e_steps, "workload": "per step: kg_expert_action_host (combined expert, action D2H) -> kg_step_host (action H2D, obs/reward/done D2H) -> masked sampled reset; same actions as the device-resident loop",
+                        **e2e_diag},
                 # kernels per step: per env group kg_schedule_kernel + kg_begin_kernel + 15 x (kg_mpr_kernel + kg_sub_kernel) + kg_rays_kernel, + kg_reset_kernel
                 # (the chain of a step is replayed as ONE CUDA graph launch)
                 "gpu_launches": (groups * (3 + 2 * SUBSTEPS) + 1) * steps_total,

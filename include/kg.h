@@ -83,7 +83,7 @@ int kg_reset_sampled(kg_handle h, const int *mask_dev, const int *shape_dev, int
 /* Replaces KinovaGripper_Env.step (kinova_gripper_env.py:1495-1552: ctrl mapping, frame_skip x sim.step(),
  * _get_obs, _get_reward) and gym's TimeLimit.  action_dev float[4][n] = [wrist, f1, f2, f3], or NULL to
  * let the on-device expert (expert_data.py:610-671; mode 0 naive, 1 position-dependent, 2 combined) act.
- * Outputs (any may be NULL): obs float[82][n], reward float[n] (= lift_reward, finger/grasp reward are 0),
+ * Outputs (any may be NULL): obs float[82][n], reward float[n] (= lift_reward; + grasp_reward after kg_set_grasp_reward(1)),
  * done int[n] (lift success OR elapsed >= max_episode_steps), action_out float[4][n]. */
 int kg_step(kg_handle h, const float *action_dev, int expert_mode, float *obs_dev, float *reward_dev,
             int *done_dev, float *action_out_dev);
@@ -92,6 +92,13 @@ int kg_step(kg_handle h, const float *action_dev, int expert_mode, float *obs_de
  * the launch, D2H of obs/reward/done, and a stream synchronise are all inside this call. */
 int kg_step_host(kg_handle h, const float *action_host, int expert_mode, float *obs_host, float *reward_host,
                  int *done_host);
+/* The expert controller alone -- controller.get_action(obs) of expert_data.py:610 (PID modes EXP:367-671) as its own call,
+ * for callers that keep the reference's split "action = controller(obs); env.step(action)": computes every env's action
+ * from the observation the last kg_step / kg_reset* produced and advances the controller's per-episode state exactly as
+ * kg_step(action = NULL, expert_mode) would (so do not mix the two within an episode step).  action: float[4][n]
+ * ([wrist, f1, f2, f3]; float[6][n] with rows 0-1 zero after kg_set_action_dim(6)), ready to be passed to kg_step. */
+int kg_expert_action(kg_handle h, int expert_mode, float *action_dev);
+int kg_expert_action_host(kg_handle h, int expert_mode, float *action_host);
 int kg_reset_host(kg_handle h, const int *mask_host, const int *shape_host, const float *euler_host,
                   const float *objpos_host, float *obs_host);
 

@@ -26,6 +26,8 @@ SIGNATURES = {
     "kg_reset_sampled": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_uint64, _vp]),
     "kg_step": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "kg_step_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "kg_expert_action": (C.c_int, [_vp, C.c_int, _vp]),
+    "kg_expert_action_host": (C.c_int, [_vp, C.c_int, _vp]),
     "kg_reset_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "kg_reset_pose": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kg_reset_pose_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -802,6 +802,30 @@ static int launch_reset(kg_handle h, const int *mask, const int *shape, const fl
 #endif
 }
 
+// The expert controller alone (EXP:610 get_action): one env's action from the observation the last step / reset left in
+// A.obs, the controller's episode state advanced exactly as kg_step_begin does for action == NULL.  out: [act_dim][N].
+KG_DEV void kg_expert_only(const KgEnvArrays &A, int env, int mode, float *out) {
+    const int N = A.N;
+    float obs[KG_NOBS];
+    for (int i = 0; i < KG_NOBS; i++) obs[i] = A.obs[(size_t)i * N + env];
+    KgExpertState e;
+    e.init_obj_x = A.ex_f[env]; e.init_dot = A.ex_f[N + env];
+    e.prev_fx[0] = A.ex_f[2 * N + env]; e.prev_fx[1] = A.ex_f[3 * N + env]; e.prev_fx[2] = A.ex_f[4 * N + env];
+    e.have_prev = A.ex_i[env]; e.num_good = A.ex_i[N + env]; e.total_steps = A.ex_i[2 * N + env];
+    float a4[4];
+    kg_expert_action(e, obs, mode, a4);
+    A.ex_f[2 * N + env] = e.prev_fx[0]; A.ex_f[3 * N + env] = e.prev_fx[1]; A.ex_f[4 * N + env] = e.prev_fx[2];
+    A.ex_i[env] = e.have_prev; A.ex_i[N + env] = e.num_good; A.ex_i[2 * N + env] = e.total_steps;
+    const int off = A.act_dim == 6 ? 2 : 0;
+    if (off) { out[env] = 0.f; out[N + env] = 0.f; }
+    for (int c = 0; c < 4; c++) out[(size_t)(c + off) * N + env] = a4[c];
+}
+#ifndef KG_EMU
+__global__ void __launch_bounds__(128) kg_expert_kernel(KgEnvArrays A, int mode, float *out) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < A.N) kg_expert_only(A, env, mode, out);
+}
+#endif
 #ifndef KG_EMU
 // FP32 FMA microbenchmark (the FP32 roofline denominator is measured on the box, not taken from a data sheet):
 // 8 independent FMA chains per thread, 1024 threads per CTA, 2 CTAs per SM.
@@ -1134,6 +1158,22 @@ int kg_grasp_predict_host(kg_handle h, const float *x_host, int m, float *label_
     CUDA_TRY(h, cudaGetLastError());
 #endif
     TRY(be_d2h(h, label_host, h->d_reward, (size_t)m * 4));
+    return be_sync(h);
+}
+int kg_expert_action(kg_handle h, int mode, float *action) {
+    if (!h || !action || mode < 0 || mode > 2) { if (h) h->err = "kg_expert_action: action buffer and expert_mode 0, 1 or 2"; return KG_EINVAL; }
+#ifdef KG_EMU
+    for (int env = 0; env < h->n; env++) kg_expert_only(h->A, env, mode, action);
+#else
+    kg_expert_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)h->stream>>>(h->A, mode, action);
+    CUDA_TRY(h, cudaGetLastError());
+#endif
+    return KG_OK;
+}
+int kg_expert_action_host(kg_handle h, int mode, float *action_host) {
+    if (!h || !action_host) return KG_EINVAL;
+    TRY(kg_expert_action(h, mode, h->d_action));
+    TRY(be_d2h(h, action_host, h->d_action, (size_t)h->A.act_dim * h->n * 4));
     return be_sync(h);
 }
 int kg_step(kg_handle h, const float *action, int mode, float *obs, float *reward, int *done, float *act_out) {

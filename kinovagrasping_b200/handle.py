@@ -116,6 +116,15 @@ class Handle:
         self._chk(self.lib.kg_step(self.h, action or None, int(expert_mode), obs or None, reward or None, done or None,
                                    action_out or None), "kg_step")
 
+    def expert_action(self, expert_mode, action):
+        """controller.get_action(obs) (EXP:610) alone, into the device buffer `action` ([4][n] / [6][n]); pass it to step()."""
+        self._chk(self.lib.kg_expert_action(self.h, int(expert_mode), action), "kg_expert_action")
+
+    def expert_action_host(self, expert_mode=0, out=None):
+        a = np.zeros((getattr(self, "act_dim", 4), self.n), dtype=np.float32) if out is None else out
+        self._chk(self.lib.kg_expert_action_host(self.h, int(expert_mode), _np_ptr(a)), "kg_expert_action_host")
+        return a
+
     def get_state(self, qpos, qvel):
         self._chk(self.lib.kg_get_state(self.h, qpos or None, qvel or None), "kg_get_state")
 

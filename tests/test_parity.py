@@ -417,6 +417,29 @@ def test_constraint_rows_and_solver_on_identical_contacts(backend, oracle, card)
     assert qerr.max() < 1e-4, (np.mean(qerr < 1e-4), qerr.max())
 
 
+def test_expert_action_as_its_own_call(backend, card):
+    """kg_expert_action + kg_step(action) == kg_step(action=NULL, mode): the reference's split `action = controller.get_action(obs);
+    env.step(action)` (EXP:745-804) through the C ABI gives bit-identical rollouts to the fused call, in 4-d and 6-d action layouts."""
+    n = 24
+    shape, _, objp = _poses(card, n, 17, orient_idx=(0,), shapes=(0, 1, 15))
+    _, euler, _ = _poses(card, n, 17, orient_idx=(2,), shapes=(0, 1, 15))
+    for mode in (0, 1, 2):
+        for dim in (4, 6):
+            a, b = Handle(n, lib=backend), Handle(n, lib=backend)
+            b.set_action_dim(dim)
+            oa, ob = a.reset_host(shape, euler, objp), b.reset_host(shape, euler, objp)
+            assert np.array_equal(oa, ob)
+            for t in range(16):
+                oa, ra, da = a.step_host(None, mode)
+                act = b.expert_action_host(mode)
+                assert act.shape == (dim, n) and (dim == 4 or not act[:2].any())
+                ob, rb, db = b.step_host(act, 0)
+                assert np.array_equal(act[dim - 4:], a.last_action_host()), (mode, dim, t)
+                assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db), (mode, dim, t)
+            assert a.last_action_host()[0].max() > 0          # the lift phase was reached
+            a.close(); b.close()
+
+
 def test_expert_modes_and_rollout_success_parity(backend, oracle, card):
     """Free-running expert episodes (on-device controller) vs the oracle: the controller's actions follow the validated
     host controller on the kernel's own observations, and lift success agrees within +-2 pp (+ small-sample slack)."""
