@@ -134,6 +134,10 @@ int kg_set_pipeline(kg_handle h, int groups);
 /* Launch path of kg_step (no effect on results): 1 (default) = the kernel chain of a step is captured once per distinct
  * argument set into a CUDA graph and replayed with one launch call; 0 = every kernel launched individually. */
 int kg_set_graph(kg_handle h, int on);
+/* Programmatic dependent launch inside a group's kernel chain (no effect on results): 1 = the narrowphase / per-env kernels
+ * that directly follow another kernel of the chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so
+ * their launch and CTA dispatch overlap the predecessor (they wait for its completion on the device, griddepcontrol.wait). */
+int kg_set_dependent_launch(kg_handle h, int on);
 /* Diagnostics (bench.py's roofline): with timing on, kg_step records a CUDA event after every kernel launch (and does
  * not pipeline groups); kg_timing_breakdown then returns the milliseconds of the last step by launch kind:
  * [1] schedule [2] begin [3] narrowphase (all launches) [4] substep kernels except the last [5] last substep kernel

@@ -51,6 +51,7 @@ SIGNATURES = {
     "kg_measure_fp32_peak": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "kg_set_timing": (C.c_int, [_vp, C.c_int]),
     "kg_set_graph": (C.c_int, [_vp, C.c_int]),
+    "kg_set_dependent_launch": (C.c_int, [_vp, C.c_int]),
     "kg_timing_breakdown": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "kg_get_last_action_host": (C.c_int, [_vp, _vp]),
     "kg_set_grasp_forest": (C.c_int, [_vp, _vp, C.c_size_t]),

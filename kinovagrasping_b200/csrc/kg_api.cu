@@ -45,6 +45,16 @@
 #error "narrowphase teams need the hull tables on the read-only L1 path (KG_MPR_L1)"
 #endif
 __constant__ KgModel c_model;
+// Programmatic dependent launch (kg_set_dependent_launch): the kernels of a group's chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization.  Every chain kernel first waits for its predecessor grid to have
+// completed and flushed (griddepcontrol.wait -- a no-op when the launch carried no such edge) and then lets ITS dependent be
+// launched right away (griddepcontrol.launch_dependents): the next kernel's launch and CTA dispatch happen while this one
+// runs, its CTAs sit at their own wait until this grid is done.  Execution order and results are unchanged.
+#ifdef KG_PDL_TRIGGER_EARLY
+#define KG_PDL_PROLOGUE() do { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); } while (0)
+#else      // no explicit trigger: the dependent is launched when every CTA of this grid has exited
+#define KG_PDL_PROLOGUE() asm volatile("griddepcontrol.wait;" ::: "memory")
+#endif
 #endif
 
 struct KgGraphKey { int cfg, full, qs0, mode; const void *action; void *obs, *reward, *done, *act_out; };
@@ -90,6 +100,7 @@ struct kg_handle_s {
     int cfg_version = 0;              // bumped by every setter that changes a kernel argument (graph cache key)
 #if !defined(KG_EMU)
     int use_graph = 1;                // kg_set_graph
+    int pdl = 0;                      // kg_set_dependent_launch
     cudaStream_t capstream = nullptr; // origin stream of graph captures (the caller's stream may be the legacy stream, which cannot capture)
     struct GraphEntry { KgGraphKey key; cudaGraphExec_t exec; unsigned long long used; };
     std::vector<GraphEntry> graphs;
@@ -275,6 +286,7 @@ __global__ void __launch_bounds__(1024) kg_schedule_kernel(const int *load, int 
 // first kernel of an RL step: action / on-device expert, kinematics and lane-parallel collision of substep 0
 __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_begin_kernel(KgEnvArrays A, int base, int cnt, const int *perm, const float *action, int mode,
                                                                                  unsigned char *carry, int *q, unsigned *tasks, int *subseq) {
+    KG_PDL_PROLOGUE();
     KG_ENV_OF_WARP(KgWSLight, KG_LWARPS, blockIdx.x);
     if (lane == 0) subseq[env] = 0;
     const unsigned mask = kg_step_begin(c_model, ws, A, env, action, mode, lane);
@@ -346,6 +358,7 @@ __device__ __forceinline__ void kg_heavy_lane(unsigned char *smem, int nwarps, i
 template <bool LAST>
 __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(KgEnvArrays A, int base, int cnt, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
                                                                                int nheavy_ctas, int *heavy_count, int *subseq, int sidx, int nsub, float *obs, float *reward, int *done, float *act_out) {
+    KG_PDL_PROLOGUE();
     if ((int)blockIdx.x < nheavy_ctas) {
         extern __shared__ __align__(16) unsigned char smem_h[];
         kg_heavy_lane<LAST>(smem_h, KG_HEAVY_WARPS, KG_MAXCON_LIGHT, A, base, cnt, carry, q, tasks, nheavy_ctas, heavy_count, subseq, sidx, nsub, obs, reward, done, act_out);
@@ -375,6 +388,7 @@ __global__ void __launch_bounds__(KG_LWARPS * 32, KG_LMINBLOCKS) kg_sub_kernel(K
 template <bool LAST>
 __global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_full_kernel(KgEnvArrays A, int base, int cnt, const int *perm, unsigned char *carry, int *q, unsigned *tasks,
                                                                                   int nheavy_ctas, int *heavy_count, int *subseq, int sidx, int nsub, float *obs, float *reward, int *done, float *act_out) {
+    KG_PDL_PROLOGUE();
     if ((int)blockIdx.x < nheavy_ctas) {
         extern __shared__ __align__(16) unsigned char smem_h[];
         kg_heavy_lane<LAST>(smem_h, KG_FHEAVY_WARPS, KG_MAXCON, A, base, cnt, carry, q, tasks, nheavy_ctas, heavy_count, subseq, sidx, nsub, obs, reward, done, act_out);
@@ -398,6 +412,7 @@ __global__ void __launch_bounds__(KG_WARPS * 32, KG_MINBLOCKS) kg_sub_full_kerne
 #define KG_MPR_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(KG_MPR_WARPS * 32, KG_MPR_MINBLOCKS) kg_mpr_kernel(unsigned char *carry, int *q, int *q_other, const unsigned *tasks, long long *prof) {
+    KG_PDL_PROLOGUE();
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) { q_other[0] = 0; q_other[1] = 0; }   // the list the next per-env kernel fills
@@ -615,6 +630,17 @@ static void emu_run_tasks(kg_handle h, int sel) {
 #define KG_TMARK(kind) ((void)0)
 #endif
 #ifndef KG_EMU
+// kernel launch with or without the programmatic-dependent-launch attribute (see KG_PDL_PROLOGUE)
+template <class... KArgs, class... Args>
+static void kg_launch(bool pdl, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 // Everything one RL step puts on a stream: the copy of the last step's heavy count to the host, then per env group
 //   [schedule] begin | nsub x ( narrowphase tasks | per-env substep kernel )     (2 nsub + 2 launches of our kernels)
 // forked over the group streams and joined back into `st` (which may be a capturing stream).
@@ -625,6 +651,10 @@ static int enqueue_step(kg_handle h, cudaStream_t st, const float *action, int m
     cudaMemsetAsync(h->heavy_count, 0, sizeof(int), st);
     size_t tix = 0;
     const int G = h->timing ? 1 : h->ngroups;
+    // programmatic edges only between kernels that follow each other directly on a group's stream: not into the last
+    // narrowphase / per-env kernel of a step (the ray fork's event record sits in front of the one, the wait for the rays in
+    // front of the other), not in timing mode (an event after every launch)
+    const bool pdl = h->pdl && !h->timing;
     // the ray kernel of group g, forked off the group's stream once its last carry records are written (timing mode: inline)
 #define KG_RAYS(g) do { const int rb_ = gbase[g], rc_ = gbase[(g) + 1] - rb_; \
         if (h->timing) { kg_rays_kernel<<<rc_, KG_RAY_WARPS * 32, 0, gs[g]>>>(h->carry, rb_, h->n, h->A.ranges); KG_TMARK(6); } \
@@ -648,7 +678,7 @@ static int enqueue_step(kg_handle h, cudaStream_t st, const float *action, int m
         KG_TMARK(0);
         if (h->schedule) kg_schedule_kernel<<<1, 1024, 0, gs[g]>>>(h->A.load + base, h->perm + base, cnt);
         KG_TMARK(1);
-        kg_begin_kernel<<<blocks, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, action, mode, h->carry, h->q + 4 * g + 2 * qs0, h->tasks + (size_t)base * 22, h->subseq);
+        kg_launch(pdl && h->schedule, kg_begin_kernel, blocks, KG_LWARPS * 32, smem, gs[g], h->A, base, cnt, perm, action, mode, h->carry, h->q + 4 * g + 2 * qs0, h->tasks + (size_t)base * 22, h->subseq);
         KG_TMARK(2);
         if (nsub == 1) KG_RAYS(g);
     }
@@ -664,22 +694,22 @@ static int enqueue_step(kg_handle h, cudaStream_t st, const float *action, int m
             // persistent narrowphase grid of this group: room for ~2 tasks per env at one task per team, at most the whole GPU
             int mgrid = (2 * cnt + KG_MPR_WARPS * KG_MPR_TEAMS - 1) / (KG_MPR_WARPS * KG_MPR_TEAMS);
             mgrid = mgrid < 8 ? 8 : (mgrid > h->mpr_grid ? h->mpr_grid : mgrid);
-            kg_mpr_kernel<<<mgrid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), gs[g]>>>(h->carry, q + 2 * qa, q + 2 * qb, tasks, h->A.prof);
+            kg_launch(pdl && s != nsub - 1, kg_mpr_kernel, mgrid, KG_MPR_WARPS * 32, KG_MPR_SMEM(h), gs[g], h->carry, q + 2 * qa, q + 2 * qb, tasks, h->A.prof);
             KG_TMARK(3);
             if (last && !h->timing) cudaStreamWaitEvent(gs[g], h->gray1[g], 0);      // this group's rays are in
             if (full) {
                 const int fblocks = (cnt + KG_WARPS - 1) / KG_WARPS;
                 const int hb = (cnt + 64 * KG_FHEAVY_WARPS - 1) / (64 * KG_FHEAVY_WARPS);      // more than KG_MAXCON contacts is rare: a thin lane
                 const int nhc = hb < 1 ? 1 : (hb < h->heavy_ctas ? hb : h->heavy_ctas);
-                if (last) kg_sub_full_kernel<true><<<fblocks + nhc, KG_WARPS * 32, hsmem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
-                else kg_sub_full_kernel<false><<<fblocks + nhc, KG_WARPS * 32, hsmem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
+                if (last) kg_launch(false, kg_sub_full_kernel<true>, fblocks + nhc, KG_WARPS * 32, hsmem, gs[g], h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
+                else kg_launch(pdl, kg_sub_full_kernel<false>, fblocks + nhc, KG_WARPS * 32, hsmem, gs[g], h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
             } else {
                 const int blocks = (cnt + KG_LWARPS - 1) / KG_LWARPS;
                 // heavy-lane CTAs at the front of the grid: one workspace per 8 envs of the group (they loop over whatever is heavy)
                 const int hb = (cnt + 8 * KG_HEAVY_WARPS - 1) / (8 * KG_HEAVY_WARPS);
                 const int nhc = hb < 1 ? 1 : (hb < h->heavy_ctas ? hb : h->heavy_ctas);
-                if (last) kg_sub_kernel<true><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
-                else kg_sub_kernel<false><<<blocks + nhc, KG_LWARPS * 32, smem, gs[g]>>>(h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
+                if (last) kg_launch(false, kg_sub_kernel<true>, blocks + nhc, KG_LWARPS * 32, smem, gs[g], h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
+                else kg_launch(pdl, kg_sub_kernel<false>, blocks + nhc, KG_LWARPS * 32, smem, gs[g], h->A, base, cnt, perm, h->carry, q + 2 * qb, tasks, nhc, h->heavy_count, h->subseq, s, nsub, obs, reward, done, act_out);
             }
             KG_TMARK(last ? 5 : 4);
             if (s == nsub - 2) KG_RAYS(g);
@@ -1323,6 +1353,13 @@ int kg_measure_fp32_peak(kg_handle h, float *tflops) {
     CUDA_TRY(h, cudaGetLastError());
     const double flop = 2.0 * 8.0 * 16.0 * (double)iters * 1024.0 * (double)grid;
     *tflops = (float)(flop / (best * 1e-3) / 1e12);
+#endif
+    return KG_OK;
+}
+int kg_set_dependent_launch(kg_handle h, int on) {
+    if (!h) return KG_EINVAL;
+#ifndef KG_EMU
+    h->pdl = on ? 1 : 0; h->cfg_version++;
 #endif
     return KG_OK;
 }

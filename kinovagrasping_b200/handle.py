@@ -177,6 +177,10 @@ class Handle:
         """1 (default) = kg_step replays a captured CUDA graph of its kernel chain; 0 = individual launches."""
         self._chk(self.lib.kg_set_graph(self.h, int(on)), "kg_set_graph")
 
+    def set_dependent_launch(self, on):
+        """1 = programmatic dependent launch between the kernels of a group's chain (launch latency hidden); results unchanged."""
+        self._chk(self.lib.kg_set_dependent_launch(self.h, int(on)), "kg_set_dependent_launch")
+
     def set_timing(self, on):
         self._chk(self.lib.kg_set_timing(self.h, int(on)), "kg_set_timing")
 

@@ -666,6 +666,39 @@ def test_cuda_graph_replay_does_not_change_results(card):
 
 
 @pytest.mark.gpu
+def test_dependent_launch_does_not_change_results(card):
+    """kg_set_dependent_launch: the chain kernels launched with programmatic stream serialisation (their launch overlaps the
+    predecessor, griddepcontrol.wait orders the data) give bit-identical obs / reward / done / state -- graph replay and
+    individual launches, split and full workspace mode, 15 substeps and frame_skip 1, contact-heavy shapes included."""
+    import torch
+    from kinovagrasping_b200 import _lib
+    lib = _lib.load()
+    n = 4096
+    shape = torch.from_numpy((np.arange(n) % 14).astype(np.int32)).cuda()
+    for graph, mode, fs in ((1, 0, 15), (0, 0, 15), (1, 2, 15), (1, 0, 1)):
+        runs = []
+        for pdl in (0, 1):
+            h = Handle(n, lib=lib)
+            h.set_graph(graph); h.set_mode(mode); h.set_frame_skip(fs); h.set_dependent_launch(pdl)
+            h.set_stream(torch.cuda.current_stream().cuda_stream)
+            obs = torch.zeros((82, n), device="cuda"); rew = torch.zeros(n, device="cuda"); done = torch.zeros(n, dtype=torch.int32, device="cuda")
+            h.reset_sampled(0, shape.data_ptr(), 3, 1, 0, 11, obs.data_ptr())
+            trace = []
+            for k in range(14 if fs == 15 else 60):
+                h.step(0, 2, obs.data_ptr(), rew.data_ptr(), done.data_ptr())
+                h.sync()
+                trace += [obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy()]
+                h.reset_sampled(done.data_ptr(), 0, 3, 1, 0, 11, 0)
+            trace += list(h.get_state_host())
+            st = h.stats()
+            assert st["contact_overflow"] == 0 and st["mpr_pairs"] > 0
+            runs.append(trace)
+            h.close()
+        for x, y in zip(*runs):
+            assert np.array_equal(x, y), (graph, mode, fs)
+
+
+@pytest.mark.gpu
 def test_pipeline_groups_do_not_change_results(card):
     """kg_set_pipeline cuts the batch into env groups whose kernel chains run on separate internal streams; an env's
     arithmetic does not depend on its group, so 1, 2 and 3 groups give bit-identical observations, rewards, dones and

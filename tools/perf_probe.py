@@ -25,6 +25,7 @@ groups = int(os.environ.get("KG_GROUPS", "0"))
 if groups: h.set_pipeline(groups)
 if os.environ.get("KG_TIMING"): h.set_timing(1)
 if os.environ.get("KG_GRAPH") is not None: h.set_graph(int(os.environ["KG_GRAPH"]))
+if os.environ.get("KG_PDL") is not None: h.set_dependent_launch(int(os.environ["KG_PDL"]))
 if os.environ.get("KG_GRASP"): h.set_grasp_reward(True)          # grasp-classifier reward kernels behind every step
 shape_set = [int(x) for x in os.environ.get("KG_SHAPES", "0,1").split(",")]
 orient = int(os.environ.get("KG_ORIENT", "0"))           # 0 normal, 1 rotated, 2 top, 3 random
@@ -50,7 +51,7 @@ lib.kg_get_prof(h.h, prof)
 prof = list(prof)
 print(f"{os.path.basename(sys.argv[1]):28s} sched {sched} envs {n} kernel ms: mean {ms[3:].mean():.3f} median {np.median(ms[3:]):.3f} min {ms[3:].min():.3f} max {ms[3:].max():.3f} "
       f"-> {n * 15 / ms[3:].mean() * 1e3:.3e} substeps/s | mpr/sub {st['mpr_pairs'] / st['substeps']:.2f} newton/sub {st['newton_iters'] / st['substeps']:.2f} ovf {st['contact_overflow']}"
-      f" mode {mode} groups {groups} graph {os.environ.get('KG_GRAPH', 'default')} grasp {os.environ.get('KG_GRASP', '0')}")
+      f" mode {mode} groups {groups} graph {os.environ.get('KG_GRAPH', 'default')} grasp {os.environ.get('KG_GRASP', '0')} pdl {os.environ.get('KG_PDL', 'default')}")
 if brk:
     names = ["", "schedule", "begin", "narrowphase", "substep", "last", "rays"]
     for t in (5, 18):
