@@ -97,6 +97,15 @@ def _cpu_worker(args):
         sh = (wid * n_env + i) % 2
         e, o = draw(sh)
         envs.append([e, o, sh])
+    # episode phases desynchronised before the clock starts, as the GPU arm does (env i has run i mod 30 steps of its
+    # episode): the timed steps see the steady-state mix of approach / grasp / lift, not a batch of contact-free episode starts
+    for i, rec in enumerate(envs):
+        for _ in range(i % 30):
+            a, _ = m.expert_action(rec[0], rec[1], 2)
+            o, r, d, _ = m.env_step(rec[0], a)
+            rec[1] = o
+            if d:
+                rec[0], rec[1] = draw(rec[2])
     t0 = time.perf_counter()
     for _ in range(n_steps):
         for rec in envs:
@@ -144,7 +153,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * max(times) / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[1] sample: CubeS/CubeB normal-orientation (pose-table variant %s) expert-PID rollouts, %d envs per core" % (args.variant, per_core),
-                       "envs": cores * per_core, "note": "mujoco-py 1.50 not installable; fp64 oracle port, rangefinders every substep as mj_step does"},
+                       "envs": cores * per_core, "note": "mujoco-py 1.50 not installable; fp64 oracle port, rangefinders every substep as mj_step does; episode phases desynchronised before timing"},
             "cpu_baseline": {"value": val, "unit": "physics substeps/s", "cores": cores, "kind": "port",
                              "sample": "%d RL steps x %d envs on %d cores" % (args.steps, cores * per_core, cores)},
             "e2e": {"value": val, "unit": "physics substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": wall}
