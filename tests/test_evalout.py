@@ -60,6 +60,33 @@ def test_eval_policy_dictionary_and_files(tmp_path):
     env.h.close()
 
 
+@pytest.mark.gpu
+def test_eval_policy_on_cuda(tmp_path):
+    """The same dictionary and files from the CUDA library, 1024 envs, all 21 shapes, with the grasp-classifier reward on; the
+    reward columns are consistent with each other and with the success count, and the orientation split covers the batch."""
+    n = 1024
+    env = shard.make_sharded_env(n, 0, 1, 0)
+    env.set_with_grasp_reward(True)
+    dev = env.device
+
+    def policy(obs):
+        a = torch.zeros((obs.shape[0], 4), device=dev)
+        a[:, 1:] = 0.6
+        return a
+    from kinovagrasping_b200.modelcard import SHAPES
+    ret = eval_policy(env, policy, tuple(SHAPES), "random", variant="B", mode="test", seed=5)
+    v = ret["all_ep_reward_values"]
+    tot = np.array(v["total_reward"]); lift = np.array(v["lift_reward"]); grasp = np.array(v["grasp_reward"])
+    assert np.array_equal(tot, lift + grasp) and set(np.unique(lift)) <= {0.0, 50.0} and set(np.unique(grasp)) <= {0.0, 5.0}
+    assert ret["num_success"] == int((lift == 50.0).sum()) and 0.05 * n < ret["num_success"] < 0.95 * n and grasp.sum() >= 5.0 * 0.05 * n
+    assert len(ret["success_coords"]["x"]) + len(ret["fail_coords"]["x"]) == n
+    ori = np.concatenate([ret["success_coords"]["orientation"], ret["fail_coords"]["orientation"]])
+    assert all(0.2 * n < int((ori == o).sum()) < 0.5 * n for o in ("normal", "rotated", "top"))      # thresholds 0.333 / 0.667 (ENV:1208-1220)
+    save_eval_outputs(ret, 0, str(tmp_path / "heatmap"), str(tmp_path / "boxplot"))
+    assert np.load(str(tmp_path / "boxplot" / "total_reward_0.npy")).shape == (1, 1, n)
+    env.h.close()
+
+
 def test_start_position_in_the_hand_frame_is_reset_obs_21_24():
     """MAIN:171-174 `np.matmul(eval_env.Tfw, np.append(obj_coords, 1))[0:3]` == the object entries of the reset observation."""
     kenv._MEM_FILES.clear()
