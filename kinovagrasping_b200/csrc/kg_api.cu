@@ -953,7 +953,9 @@ int kg_create(int n_envs, int device, const void *blob, size_t nbytes, kg_handle
 #endif
     h->fhull_bytes = 16 * (m.hnpad[1] + m.hnpad[2]);
     if (m.hpad0[2] != m.hpad0[1] + m.hnpad[1]) { h->err = "model card: finger hulls must be contiguous"; return KG_EMODEL; }
+#ifndef KG_MPR_L1      // (only a build that stages the object's hull in the narrowphase workspace has a size limit)
     for (int k = 3; k < KG_NMESH; k++) if (m.hnpad[k] > KG_MAXOBJVERT) { h->err = "model card: object hull too large"; return KG_EMODEL; }
+#endif
 #ifndef KG_EMU
     CUDA_TRY(h, cudaFuncSetAttribute(kg_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_LSMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(kg_sub_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KG_LSMEM));

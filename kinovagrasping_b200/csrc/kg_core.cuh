@@ -119,7 +119,14 @@ static inline unsigned KG_F2U(float x) { unsigned u; memcpy(&u, &x, 4); return u
 #define KG_WSOBS(ws) ((ws).J)
 #define KG_RANGE(ws) ((ws).range)
 #define KG_GROW(g) ((g) < 9 ? (g) : 9 + 3 * ((g) - 9))      // first J row of constraint group g
-#define KG_MAXOBJVERT 160     // padded to a multiple of 32
+// object hull vertices a narrowphase workspace can STAGE (padded to a multiple of 32).  Only builds without KG_MPR_L1 stage
+// the object's hull (the product reads the hull tables through the read-only L1 path and has no such limit: the lemon's hull
+// has 2434 vertices); the host emulation stages, so it gets room for every shape of the model card.
+#ifdef KG_EMU
+#define KG_MAXOBJVERT 2560
+#else
+#define KG_MAXOBJVERT 160
+#endif
 // Per-environment workspace in shared memory.  An RL step is a WAVEFRONT of kernels (kg_api.cu): the per-env kernels
 // keep one KgWS per warp; between kernels the CARRY part of it lives in global memory (one KgCarry record per env,
 // env-major so that a warp moves it with coalesced 128-bit accesses).  Carry = everything a later kernel of the same

@@ -10,8 +10,8 @@
 #include <string>
 #include <vector>
 
-#define KG_NSHAPE 21
-#define KG_NMESH 24
+#define KG_NSHAPE 24
+#define KG_NMESH 27
 #define KG_NSITE 17
 
 struct KgMesh {
@@ -155,6 +155,7 @@ inline std::string kg_load_model(const void *blob_, size_t nbytes, KgModel *m, K
         m->hand_rbound[k] = (float)c[7];
     }
     const double *oinv = D("obj_invw0", KG_NSHAPE * 4); KG_NEED(oinv);
+    const int *shape_flags = I("shape_flags", nullptr);      // optional: bit 0 = _get_obj_size always swaps (lemon)
     const double *hm = D("hand_M0", 81); KG_NEED(hm);
     double tr = 0; for (int j = 0; j < 9; j++) tr += hm[10 * j];
     for (int s = 0; s < KG_NSHAPE; s++) {
@@ -192,7 +193,7 @@ inline std::string kg_load_model(const void *blob_, size_t nbytes, KgModel *m, K
         if (sz[2] == 0) { sz[2] = sz[1]; sz[1] = sz[0]; }
         double df[3] = {std::abs(sz[0] - sz[1]), std::abs(sz[1] - sz[2]), std::abs(sz[0] - sz[2])};
         int am = 0; if (df[1] < df[am]) am = 1; if (df[2] < df[am]) am = 2;
-        if (am != 0) { double x = sz[0]; sz[0] = sz[2]; sz[2] = x; }
+        if (am != 0 || (shape_flags && (shape_flags[s] & 1))) { double x = sz[0]; sz[0] = sz[2]; sz[2] = x; }      // (`'lemon' in self.filename`, ENV:721)
         sh.obs_size[0] = (float)(sz[0] > 0 ? sz[0] : 0); sh.obs_size[1] = (float)(sz[1] > 0 ? sz[1] : 0); sh.obs_size[2] = (float)sz[2];
     }
     p = D("site_pos", KG_NSITE * 3); KG_NEED(p); for (int i = 0; i < KG_NSITE * 3; i++) m->site_pos[i] = (float)p[i];

@@ -167,6 +167,8 @@ _MEM_FILES = {}
 # euler of body j2s7s300_link_7 as the shipped XMLs hold it (XML:59 of each file); write_xml overwrites it
 _XML_EULER = {k: [-1.57, 0.0, -1.57] for k in SHAPES}
 _XML_EULER["CubeS"] = [-0.06, -0.16, -0.13]
+_XML_EULER.update({"LemonS": [-0.09, -0.16, -0.15], "LemonM": [-1.22, -0.04, 0.029], "LemonB": [-0.10, -0.17, -0.02]})
+_XML_FILE = {"LemonS": "slemon", "LemonM": "mlemon", "LemonB": "blemon"}      # ENV:198-201
 for _k in ("CubeM", "CylinderM", "Cube45M", "Cone2M", "Vase1M", "Vase2M"):      # the committed XMLs of the medium sizes (Cone1M has the side pose)
     _XML_EULER[_k] = [0.0, 0.0, 0.0]
 
@@ -216,7 +218,7 @@ class KinovaGripper_Env:
         self.obj_coords = [0, 0, 0]
         self.objects = {}
         self.obj_keys = []
-        self.all_objects = {k: f"/kinova_description/j2s7s300_end_effector_v1_{k}.xml" for k in SHAPES}
+        self.all_objects = {k: f"/kinova_description/j2s7s300_end_effector_v1_{_XML_FILE.get(k, k)}.xml" for k in SHAPES}
         self.action_space = _Box([-0.8] * 4, [0.8] * 4)
         self.Tfw = np.zeros([4, 4])                 # ENV:110: a new env has no hand frame yet
         self.wrist_pose = np.zeros(3)

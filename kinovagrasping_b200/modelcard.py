@@ -11,7 +11,8 @@ import numpy as np
 SHAPES = ["CubeS", "CubeB", "CylinderS", "CylinderB", "Cube45S", "Cube45B", "Cone1S", "Cone1B",
           "Cone2S", "Cone2B", "Vase1S", "Vase1B", "Vase2S", "Vase2B",
           # the medium sizes (ENV:150-178; MAIN:1271 test_sizes = ["M"]) are appended so that the ids of the 14 above never change
-          "CubeM", "CylinderM", "Cube45M", "Cone1M", "Cone2M", "Vase1M", "Vase2M"]
+          "CubeM", "CylinderM", "Cube45M", "Cone1M", "Cone2M", "Vase1M", "Vase2M",
+          "LemonS", "LemonM", "LemonB"]          # ENV:198-201: the single-geom object of the later additions
 ORIENTATIONS = ["normal", "rotated", "top"]
 DEFAULT_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "model_card.bin")
 _DT = {0: "<f8", 1: "<i4", 2: "<f4"}

@@ -26,7 +26,7 @@ extern "C" {
 #define KGO_NSENSOR 26
 #define KGO_MAXCON 64
 #define KGO_MAXEFC (3 + 6 + 4 * KGO_MAXCON)
-#define KGO_NSHAPE 21
+#define KGO_NSHAPE 24
 #define KGO_NOBS 82
 
 typedef struct KgoModel KgoModel;

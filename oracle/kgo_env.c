@@ -43,7 +43,7 @@ static void obj_size(const KgoModel *m, int shape, double *out) {
     int am = 0;
     if (diffs[1] < diffs[am]) am = 1;
     if (diffs[2] < diffs[am]) am = 2;
-    if (am != 0) { double t = size[0]; size[0] = size[2]; size[2] = t; }
+    if (am != 0 || (m->obj_flags[shape] & 1)) { double t = size[0]; size[0] = size[2]; size[2] = t; }
     out[0] = size[0] > 0 ? size[0] : 0; out[1] = size[1] > 0 ? size[1] : 0; out[2] = size[2];
 }
 

@@ -7,7 +7,7 @@
 #include <stdlib.h>
 #include <stdio.h>
 
-#define NMESH 24
+#define NMESH 27
 typedef struct {
     int vert0, nvert, adj0, tri0, ntri, bvh0, nbvh, nface;
 } MeshIndex;
@@ -33,6 +33,7 @@ struct KgoModel {
     double geom_pos[KGO_NGEOM][3], geom_quat[KGO_NGEOM][4], geom_rbound[KGO_NGEOM], geom_size[KGO_NGEOM][3];
     double obj_gpos[KGO_NSHAPE][3], obj_gquat[KGO_NSHAPE][4], obj_rbound[KGO_NSHAPE], obj_size[KGO_NSHAPE][3];
     double obj_inertia[KGO_NSHAPE][3], obj_invw[KGO_NSHAPE][4], meaninertia[KGO_NSHAPE];
+    int obj_flags[KGO_NSHAPE];   /* bit 0: _get_obj_size always swaps size[0] and size[2] ('lemon' in self.filename, ENV:721) */
     /* meshes */
     MeshIndex mesh[NMESH];
     const double *hull_vert;

@@ -119,6 +119,7 @@ KgoModel *kgo_model_load(const void *blob, size_t nbytes) {
         for (int i = 0; i < 3; i++) m->obj_inertia[s][i] = c[12 + i] * m->obj_mass / c[11];
     }
     memcpy(m->obj_invw, secd(m, "obj_invw0", KGO_NSHAPE * 4), sizeof m->obj_invw);
+    memcpy(m->obj_flags, seci(m, "shape_flags", KGO_NSHAPE), sizeof m->obj_flags);
     /* sites */
     memcpy(m->site_body, seci(m, "site_body", KGO_NSITE), sizeof m->site_body);
     memcpy(m->site_pos, secd(m, "site_pos", KGO_NSITE * 3), sizeof m->site_pos);

@@ -366,3 +366,11 @@ def test_obj_size_reordering_matches_the_meshes(card, oracle):
         width = ext[0] / np.sqrt(2) if shape in (4, 5) else ext[0]       # Cube45*: the prism stands turned by 45 degrees in its mesh frame
         assert abs(2 * s[0] - width) < band * width + 0.004, (shape, s, ext)
         assert s[2] > 2 * s[0]                              # taller than wide: the long axis ended up last
+    # the lemons: `'lemon' in self.filename` (ENV:721) swaps size[0] and size[2] although the two equal half sizes already come
+    # first, so the LONG half axis is reported first and twice a short one last -- the reference's behaviour, reproduced
+    mg = card.get("mesh_geom").reshape(-1, 15)
+    for shape in (21, 22, 23):
+        e, obs = oracle.env_reset(shape, SIDE.astype(np.float64), np.array([0.0, 0.0, 0.06]))
+        sz = mg[3 + shape][8:11]
+        assert abs(sz[0] - sz[1]) < 1e-4 * sz[0] and sz[2] > 1.3 * sz[0]
+        assert np.allclose(obs[33:36], [sz[2], sz[1], 2 * sz[0]], rtol=0, atol=1e-12), (shape, obs[33:36], sz)

@@ -30,7 +30,11 @@ REF = "/root/reference/gym-kinova-gripper/gym_kinova_gripper/envs/kinova_descrip
 SHAPES = ["CubeS", "CubeB", "CylinderS", "CylinderB", "Cube45S", "Cube45B", "Cone1S", "Cone1B",
           "Cone2S", "Cone2B", "Vase1S", "Vase1B", "Vase2S", "Vase2B",
           # the medium sizes (ENV:150-178; MAIN:1271 test_sizes = ["M"]) are appended so that the ids of the 14 above never change
-          "CubeM", "CylinderM", "Cube45M", "Cone1M", "Cone2M", "Vase1M", "Vase2M"]
+          "CubeM", "CylinderM", "Cube45M", "Cone1M", "Cone2M", "Vase1M", "Vase2M",
+          # the lemon (ENV:198-201): the one single-geom object among the later additions; its XMLs are named <size>lemon, the
+          # three sizes are one STL under three mesh scales, and the geom is rotated in the body (euler="1.57 0 0")
+          "LemonS", "LemonM", "LemonB"]
+XML_FILE = {"LemonS": "slemon", "LemonM": "mlemon", "LemonB": "blemon"}
 ORIENTS = ["normal", "rotated", "top"]
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "kinovagrasping_b200", "assets",
                    "model_card.bin")
@@ -258,7 +262,7 @@ class Blob:
 
 # ----------------------------------------------------------------------------- XML
 def parse_xml(shape):
-    root = ET.parse(f"{REF}/j2s7s300_end_effector_v1_{shape}.xml").getroot()
+    root = ET.parse(f"{REF}/j2s7s300_end_effector_v1_{XML_FILE.get(shape, shape)}.xml").getroot()
     fv = lambda s: np.array([float(x) for x in s.split()])
     opt = root.find("option")
     out = {"timestep": float(opt.get("timestep")), "impratio": float(opt.get("impratio"))}
@@ -298,6 +302,11 @@ def parse_xml(shape):
     out["sites"] = sites
     og = wb.find("body[@name='object']").find("geom")
     out["obj_mass"] = float(og.get("mass"))
+    assert len(wb.find("body[@name='object']").findall(".//geom")) == 1, shape + ": multi-geom objects are not supported"
+    am = {a.get("name"): a for a in root.find("asset").findall("mesh")}[og.get("mesh")]
+    out["obj_mesh_file"], out["obj_mesh_scale"] = am.get("file"), fv(am.get("scale"))
+    out["obj_geom_euler"] = fv(og.get("euler")) if og.get("euler") else np.zeros(3)
+    out["xml_file"] = f"j2s7s300_end_effector_v1_{XML_FILE.get(shape, shape)}.xml"
     pairs = []
     for p in root.find("contact").findall("pair"):
         pairs.append((p.get("geom1"), p.get("geom2"), int(p.get("condim")), fv(p.get("friction"))))
@@ -393,8 +402,20 @@ def main():
     meshes = [Mesh("palm", load_stl(f"{REF}/meshes/hand_3finger.STL")),
               Mesh("prox", load_stl(f"{REF}/meshes/finger_proximal.STL")),
               Mesh("dist", load_stl(f"{REF}/meshes/finger_distal.STL"))]
+    flags = []
     for s in SHAPES:
-        meshes.append(Mesh(s, load_stl(f"{REF}/meshes/{s}.stl", 0.001)))
+        y = parse_xml(s)
+        sc = y["obj_mesh_scale"]
+        assert sc[0] == sc[1] == sc[2]
+        if s not in XML_FILE:
+            assert y["obj_mesh_file"] == f"{s}.stl" and sc[0] == 0.001 and not y["obj_geom_euler"].any(), s
+        msh = Mesh(s, load_stl(f"{REF}/meshes/{y['obj_mesh_file']}", float(sc[0])))
+        if y["obj_geom_euler"].any():      # geom frame in the body = the geom's own (euler) frame composed with the mesh's inertial frame
+            qe = euler2quat(y["obj_geom_euler"])
+            msh.com, msh.quat = q2m(qe) @ msh.com, qmul(qe, msh.quat)
+        meshes.append(msh)
+        flags.append(1 if "lemon" in y["xml_file"] else 0)      # _get_obj_size: `'lemon' in self.filename` swaps size[0], size[2] (ENV:721)
+    blob.add("shape_flags", flags, "i32")
     mi, hv, adj_start, adj, tri_v, bvh_lo, bvh_hi, bvh_meta = [], [], [], [], [], [], [], []
     geomc = []
     for m in meshes:
