@@ -25,11 +25,15 @@ def _init(rank, world, port):
 
 
 def _rollout(env, steps):
-    out = [env.reset(("CubeS", "CubeB", "Cone1S"), "random", variant="A", seed=77).clone()]
+    """Expert rollout with the grasp-classifier reward on; every record carries obs, reward (lift + grasp), done, the expert's
+    action, the grasp part of the reward and -- in the first record -- the hand orientation the sampler drew per env."""
+    env.set_with_grasp_reward(True)
+    obs0 = env.reset(("CubeS", "CubeB", "Cone1S", "LemonM"), "random", variant="B", seed=77).clone()
+    out = [torch.cat([obs0, torch.from_numpy(env.h.orientation_host().astype(np.float32))[:, None]], 1)]
     for _ in range(steps):
         obs, rew, done, info = env.step(None, "combined")
-        out.append(torch.cat([obs, rew[:, None], done.float()[:, None], info["action"]], 1).clone())
-        env.reset(("CubeS", "CubeB", "Cone1S"), "random", variant="A", seed=77, mask=env.done)
+        out.append(torch.cat([obs, rew[:, None], done.float()[:, None], info["action"], info["grasp_reward"][:, None]], 1).clone())
+        env.reset(("CubeS", "CubeB", "Cone1S", "LemonM"), "random", variant="B", seed=77, mask=env.done)
     return out
 
 
@@ -55,7 +59,7 @@ def _env_worker(rank, world, port, n_total, steps, q):
 def test_env_sharding_two_ranks_equals_single_process():
     from conftest import _emu_lib
     from kinovagrasping_b200 import shard
-    n_total, steps = 10, 4
+    n_total, steps = 10, 14
     assert shard.shard_range(10, 0, 3) == (0, 4) and shard.shard_range(10, 2, 3) == (7, 10)
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
@@ -70,6 +74,8 @@ def test_env_sharding_two_ranks_equals_single_process():
     for lo, hi, recs in gathered:
         for a, b in zip(recs, single):
             assert np.array_equal(a, b[lo:hi].numpy()), (lo, hi)
+    assert len(set(single[0][:, -1].tolist())) >= 2                       # 'random' orientation: more than one value drawn ...
+    assert sum(float(r[:, -1].sum()) for r in single[1:]) >= 5.0          # ... and the classifier paid at least once
 
 
 def _learner_worker(rank, world, port, q):
