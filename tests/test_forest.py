@@ -63,6 +63,36 @@ def test_kernel_labels_equal_sklearn_on_all_golden_inputs(backend, golden):
     h.close()
 
 
+def test_forest_loader_rejects_walks_that_could_not_end(backend, tmp_path):
+    """kg_set_grasp_forest validates the blob before any kernel may walk it: children must lie behind their parent inside their
+    own tree (sklearn numbers nodes in construction order), features inside obs[0:75], sections consistent and inside the blob."""
+    import struct
+    raw = bytearray(open(FOREST, "rb").read())
+    n = struct.unpack_from("<I", raw, 8)[0]
+    sec = {}
+    for i in range(n):
+        name, dt, cnt, off = struct.unpack_from("<24sIIQ", raw, 16 + 40 * i)
+        sec[name.rstrip(b"\0").decode()] = (16 + 40 * i, dt, cnt, off)
+
+    def broken(edit):
+        b = bytearray(raw)
+        edit(b)
+        path = tmp_path / "bad_forest.bin"
+        path.write_bytes(bytes(b))
+        h = Handle(4, device=0, lib=backend)
+        with pytest.raises(KgError):
+            h.load_grasp_forest(str(path))
+        h.close()
+    broken(lambda b: struct.pack_into("<i", b, sec["node_left"][3], 0))                       # root's child = root: a cycle
+    broken(lambda b: struct.pack_into("<i", b, sec["node_right"][3], 10 ** 7))                # child outside the tree
+    broken(lambda b: struct.pack_into("<i", b, sec["node_feature"][3], 80))                   # feature beyond obs[0:75]
+    broken(lambda b: struct.pack_into("<I", b, sec["node_thresh"][0] + 28, sec["node_thresh"][2] - 1))      # section count mismatch
+    broken(lambda b: struct.pack_into("<Q", b, sec["node_proba"][0] + 32, len(raw) - 64))    # section runs past the end of the blob
+    h = Handle(4, device=0, lib=backend)
+    h.load_grasp_forest()                                                                      # the committed blob itself loads
+    h.close()
+
+
 def test_step_reward_with_grasp_classifier(backend, oracle, forest, card):
     """kg_step with kg_set_grasp_reward(1): total reward = lift + grasp, grasp = 5.0 the first time per episode the forest
     labels the step's obs[0:75] >= 0.3 (ENV:651-659), flag cleared by reset (ENV:1372) -- against oracle/forest.py's
